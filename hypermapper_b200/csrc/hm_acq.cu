@@ -1,0 +1,238 @@
+// K3 (stand-alone part): scalarised acquisition on precomputed mean/variance, and the stable k-smallest
+// selection that replaces utility_functions.get_min_configurations (utility_functions.py:295-316).
+//
+// Selection = the k lexicographically smallest (order_key(value), global index) pairs, ascending: exactly what
+// k rounds of np.argmin + delete produce (ties -> lowest index, NaN first).  Per CTA: a shared-memory candidate
+// buffer plus a running threshold tau = current k-th smallest pair; an element is appended only if it beats tau,
+// so after the first tile appends are rare (expected k*ln(n/k) per CTA) and the stream is read at HBM speed.
+// When the buffer could overflow it is bitonic-sorted, truncated to k and tau is tightened.  Stage 2 merges the
+// per-CTA lists with the same routine in one CTA.
+#include <algorithm>
+#include "hm_acq.cuh"
+
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) hm_acq_kernel(HmAcqDev p, const double* __restrict__ mean,
+                                                     const double* __restrict__ var, long long ldm,
+                                                     const double* __restrict__ feas, long long N,
+                                                     double* __restrict__ out) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < N;
+         i += (long long)gridDim.x * blockDim.x) {
+        double m[HM_MAX_OBJECTIVES], v[HM_MAX_OBJECTIVES];
+#pragma unroll
+        for (int o = 0; o < HM_MAX_OBJECTIVES; ++o) {
+            if (o < p.M) {
+                double mm = __ldg(mean + (size_t)o * ldm + i);
+                // models.py:762-763 (NaN mean -> sys.maxsize) is applied by the caller of the prediction in the
+                // reference; the acquisition sees the patched mean.
+                if (p.kind != HM_ACQ_TS && mm != mm) mm = 9.223372036854775807e18;
+                m[o] = mm;
+                v[o] = (p.kind == HM_ACQ_TS || var == nullptr) ? 0.0 : __ldg(var + (size_t)o * ldm + i);
+            } else {
+                m[o] = 0.0;
+                v[o] = 0.0;
+            }
+        }
+        const double f = feas ? __ldg(feas + i) : 1.0;
+        out[i] = hm_acq_value(p, m, v, f);
+    }
+}
+
+extern "C" int hm_acq_score(const hm_acq_params_t* acq, const double* mean, const double* var, int64_t ldm,
+                            const double* feas, int64_t N, double* score_out, void* stream) {
+    HM_REQUIRE(acq != nullptr && mean != nullptr && score_out != nullptr, "acq/mean/score_out");
+    HM_REQUIRE(N >= 0 && ldm >= N, "ldm >= N >= 0");
+    HM_REQUIRE(acq->kind == HM_ACQ_TS || var != nullptr, "var required for EI/UCB");
+    if (N == 0) return 0;
+    HmAcqDev d;
+    int rc = hm_acq_to_dev(acq, &d);
+    if (rc) {
+        hm_set_error("invalid acquisition parameters");
+        return rc;
+    }
+    const int block = 256;
+    long long blocks = (N + block - 1) / block;
+    int grid = (int)std::min<long long>(blocks, (long long)hm_num_sms() * 8);
+    hm_acq_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(d, mean, var, ldm, feas, N, score_out);
+    HM_CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+#define HM_TK_BLOCK 512
+#define HM_TK_CAP 2048
+#define HM_TK_TILE 1024
+#define HM_TK_MAXK 1024
+#define HM_TK_MAXGRID 512
+
+__device__ __forceinline__ HmPair hm_pad_pair() {
+    HmPair p;
+    p.key = ~0ull;
+    p.idx = 0x7fffffffffffffffll;
+    return p;
+}
+
+// bitonic sort of buf[0..n2) (n2 power of two, <= HM_TK_CAP) by (key, idx); all threads of the CTA participate
+__device__ void hm_bitonic_sort(HmPair* buf, int n2) {
+    for (int size = 2; size <= n2; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = threadIdx.x; t < (n2 >> 1); t += blockDim.x) {
+                const int lo = 2 * t - (t & (stride - 1));
+                const int hi = lo + stride;
+                const bool up = ((lo & size) == 0);
+                HmPair a = buf[lo], b = buf[hi];
+                if (hm_pair_less(b, a) == up) {
+                    buf[lo] = b;
+                    buf[hi] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+struct HmSelState {
+    HmPair* buf;      // [HM_TK_CAP] shared
+    int* count;       // shared
+    HmPair* tau;      // shared
+};
+
+// keep the k smallest of buf[0..*count); tighten tau.  Called by all threads (uniformly).
+__device__ void hm_sel_compact(HmSelState& s, int k) {
+    __syncthreads();
+    const int c = *s.count;
+    int n2 = 2;
+    while (n2 < c) n2 <<= 1;
+    for (int t = c + threadIdx.x; t < n2; t += blockDim.x) s.buf[t] = hm_pad_pair();
+    __syncthreads();
+    hm_bitonic_sort(s.buf, n2);
+    if (threadIdx.x == 0) {
+        const int nc = c < k ? c : k;
+        *s.count = nc;
+        if (nc >= k) *s.tau = s.buf[k - 1];
+    }
+    __syncthreads();
+}
+
+// returns the shared buffer whose first min(k, #elements) entries are the selection, ascending
+template <typename Load>
+__device__ const HmPair* hm_select_k(Load load, long long n, long long first_tile, long long tile_stride, int k,
+                                     int* n_selected) {
+    __shared__ HmPair buf[HM_TK_CAP];
+    __shared__ int count;
+    __shared__ HmPair tau;
+    HmSelState s = {buf, &count, &tau};
+    if (threadIdx.x == 0) {
+        count = 0;
+        tau = hm_pad_pair();
+    }
+    __syncthreads();
+    const long long n_tiles = (n + HM_TK_TILE - 1) / HM_TK_TILE;
+    for (long long tile = first_tile; tile < n_tiles; tile += tile_stride) {
+        const HmPair tl = tau;
+#pragma unroll
+        for (int r = 0; r < HM_TK_TILE / HM_TK_BLOCK; ++r) {
+            const long long p = tile * HM_TK_TILE + r * HM_TK_BLOCK + threadIdx.x;
+            if (p < n) {
+                HmPair e = load(p);
+                if (hm_pair_less(e, tl)) {
+                    const int pos = atomicAdd(&count, 1);
+                    buf[pos] = e;
+                }
+            }
+        }
+        __syncthreads();
+        const int c = count;
+        __syncthreads();   // nobody appends for the next tile before everyone has read the same count
+        if (c > HM_TK_CAP - HM_TK_TILE) hm_sel_compact(s, k);
+    }
+    hm_sel_compact(s, k);
+    *n_selected = count;
+    return buf;
+}
+
+struct HmLoadVals {
+    const double* vals;
+    long long base;
+    __device__ __forceinline__ HmPair operator()(long long p) const {
+        HmPair e;
+        e.key = hm_order_key(__ldg(vals + p));
+        e.idx = base + p;
+        return e;
+    }
+};
+struct HmLoadValIdx {
+    const double* vals;
+    const long long* idx;
+    __device__ __forceinline__ HmPair operator()(long long p) const {
+        HmPair e;
+        e.key = hm_order_key(__ldg(vals + p));
+        e.idx = __ldg(idx + p);
+        return e;
+    }
+};
+struct HmLoadPairs {
+    const HmPair* pairs;
+    __device__ __forceinline__ HmPair operator()(long long p) const { return pairs[p]; }
+};
+
+template <typename Load>
+__global__ void __launch_bounds__(HM_TK_BLOCK) hm_topk_stage1(Load load, long long n, int k, HmPair* ws) {
+    int c;
+    const HmPair* sel = hm_select_k(load, n, blockIdx.x, gridDim.x, k, &c);
+    HmPair* out = ws + (size_t)blockIdx.x * k;
+    for (int t = threadIdx.x; t < k; t += blockDim.x) out[t] = (t < c) ? sel[t] : hm_pad_pair();
+}
+
+__device__ __forceinline__ double hm_key_to_value(unsigned long long key) {
+    if (key == 0ull) return __longlong_as_double(0x7ff8000000000000ll);  // NaN
+    unsigned long long b = (key & 0x8000000000000000ull) ? (key ^ 0x8000000000000000ull) : ~key;
+    return __longlong_as_double((long long)b);
+}
+
+__global__ void __launch_bounds__(HM_TK_BLOCK) hm_topk_stage2(const HmPair* ws, long long n, int k, double* out_vals,
+                                                              long long* out_idx) {
+    HmLoadPairs load = {ws};
+    int c;
+    const HmPair* sel = hm_select_k(load, n, 0, 1, k, &c);
+    for (int t = threadIdx.x; t < k; t += blockDim.x) {
+        const HmPair e = (t < c) ? sel[t] : hm_pad_pair();
+        const bool pad = (e.key == ~0ull && e.idx == 0x7fffffffffffffffll);
+        out_vals[t] = pad ? __longlong_as_double(0x7ff0000000000000ll) : hm_key_to_value(e.key);
+        out_idx[t] = pad ? -1ll : e.idx;
+    }
+}
+
+extern "C" int64_t hm_topk_workspace_bytes(int k) {
+    if (k < 1) k = 1;
+    return (int64_t)HM_TK_MAXGRID * k * (int64_t)sizeof(HmPair) + 256;
+}
+
+template <typename Load>
+static int hm_topk_run(Load load, int64_t n, int k, double* out_vals, int64_t* out_idx, void* workspace,
+                       cudaStream_t st) {
+    HM_REQUIRE(k >= 1 && k <= HM_TK_MAXK, "1 <= k <= 1024");
+    HM_REQUIRE(out_vals && out_idx && workspace, "outputs/workspace");
+    HM_REQUIRE(n >= 0, "n >= 0");
+    HmPair* ws = reinterpret_cast<HmPair*>(workspace);
+    long long tiles = (n + HM_TK_TILE - 1) / HM_TK_TILE;
+    int grid = (int)std::max<long long>(1, std::min<long long>(tiles, std::min(HM_TK_MAXGRID, hm_num_sms() * 2)));
+    hm_topk_stage1<<<grid, HM_TK_BLOCK, 0, st>>>(load, (long long)n, k, ws);
+    HM_CUDA_TRY(cudaGetLastError());
+    hm_topk_stage2<<<1, HM_TK_BLOCK, 0, st>>>(ws, (long long)grid * k, k, out_vals, (long long*)out_idx);
+    HM_CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int hm_topk(const double* vals, int64_t N, int64_t index_base, int k, double* out_vals, int64_t* out_idx,
+                       void* workspace, void* stream) {
+    HM_REQUIRE(vals != nullptr || N == 0, "vals");
+    HmLoadVals load = {vals, (long long)index_base};
+    return hm_topk_run(load, N, k, out_vals, out_idx, workspace, (cudaStream_t)stream);
+}
+
+extern "C" int hm_topk_merge(const double* vals, const int64_t* idx, int64_t n, int k, double* out_vals,
+                             int64_t* out_idx, void* workspace, void* stream) {
+    HM_REQUIRE((vals != nullptr && idx != nullptr) || n == 0, "vals/idx");
+    HmLoadValIdx load = {vals, (const long long*)idx};
+    return hm_topk_run(load, n, k, out_vals, out_idx, workspace, (cudaStream_t)stream);
+}

@@ -1,0 +1,180 @@
+/*
+ * hm_b200.h -- C-ABI of the B200-native surrogate-prediction / acquisition-scoring hot path.
+ *
+ * One shared library (hypermapper_b200/csrc/libhm_b200.so), plain C linkage, plain pointers and
+ * sizes, no torch types.  Every `*_dev` / data-path pointer is a DEVICE pointer unless its name ends
+ * in `_host`; every launch goes on the caller's stream (`void* stream` == cudaStream_t, 0 = default).
+ * Return value: 0 on success, otherwise a CUDA error code (cudaError_t) or a negative HM_E* code;
+ * hm_last_error() returns a static description.  No entry point allocates on the data path except
+ * into the workspace that is handed in (handles own their model memory).
+ *
+ * Each entry point cites the reference (luinardi/hypermapper v2.2.12) interface it replaces.
+ */
+#ifndef HM_B200_H
+#define HM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HM_MAX_OBJECTIVES 8
+
+#define HM_E_INVALID   (-1)   /* bad argument */
+#define HM_E_NOMEM     (-2)
+#define HM_E_UNSUPPORTED (-3)
+
+/* acquisition kinds: random_scalarizations.py:109-150 */
+#define HM_ACQ_EI  0   /* EI   random_scalarizations.py:356-506 */
+#define HM_ACQ_UCB 1   /* ucb  random_scalarizations.py:160-261 */
+#define HM_ACQ_TS  2   /* thompson_sampling random_scalarizations.py:264-353 */
+/* scalarization methods (schema.json "scalarization_method") */
+#define HM_SCAL_LINEAR 0
+#define HM_SCAL_TCHEBYSHEV 1
+#define HM_SCAL_MODIFIED_TCHEBYSHEV 2
+
+const char* hm_last_error(void);
+/* library / device probe: returns the SM count of the current device (148 on B200) or <0 */
+int hm_device_sm_count(void);
+int hm_version(void);
+
+/* ------------------------------------------------------------------------------------------
+ * K1  forest traversal + per-leaf table reduction
+ * replaces: RFModel.get_leaves_per_sample (models.py:174-182 -> sklearn Tree._apply_dense),
+ *           RFModel.compute_rf_prediction (models.py:225-240),
+ *           RFModel.compute_rf_prediction_variance (models.py:242-275),
+ *           RandomForestRegressor.predict as used by thompson sampling (models.py:879-890).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct hm_forest hm_forest_t;
+
+/* Build a device-resident forest from HOST arrays in sklearn layout (all trees concatenated).
+ *   tree_offsets[T+1] : node offset of each tree
+ *   feature[n]        : split feature, <0 at leaves            (tree_.feature)
+ *   threshold[n]      : fp64 split threshold                   (tree_.threshold, after fit_RF re-randomisation)
+ *   left/right[n]     : tree-local child ids, -1 at leaves     (tree_.children_left/right)
+ *   q/s/u[n]          : per-node fp64 tables, read at leaves only, computed by the host EXACTLY as the
+ *                       reference does:  q = m/T  (models.py:238),  s = (m**2)/T (models.py:263-264),
+ *                       u = v/T (models.py:260) with m,v the Hutter per-leaf mean / variance
+ *                       (models.py:79-122).  May be NULL (then mean/var outputs are unavailable).
+ *   value[n]          : tree_.value[:,0,0] (plain sklearn prediction, used by the TS path). May be NULL.
+ * The split test is sklearn's `(float32)x <= (float64)thr`; thresholds are stored as the largest
+ * float32 <= thr, which gives the identical decision for every finite float32 x.                  */
+int hm_forest_create(int n_trees, int n_features, const int64_t* tree_offsets_host,
+                     const int32_t* feature_host, const double* threshold_host,
+                     const int32_t* left_host, const int32_t* right_host,
+                     const double* q_host, const double* s_host, const double* u_host,
+                     const double* value_host, hm_forest_t** out);
+void hm_forest_destroy(hm_forest_t* f);
+int hm_forest_n_trees(const hm_forest_t* f);
+int hm_forest_n_features(const hm_forest_t* f);
+/* 1 if the forest is streamed through shared memory, 0 if a tree was too large and it is walked in L2 */
+int hm_forest_staged(const hm_forest_t* f);
+
+/* acquisition parameters, one struct for all kinds (unused fields ignored) */
+typedef struct hm_acq_params {
+    int32_t kind;            /* HM_ACQ_*  */
+    int32_t scalarization;   /* HM_SCAL_* */
+    int32_t n_objectives;    /* M <= HM_MAX_OBJECTIVES */
+    int32_t reserved;
+    double weight[HM_MAX_OBJECTIVES]; /* objective_weights, or reciprocate_weights(...) for modified_tchebyshev
+                                         (utility_functions.py:666-681) -- the host passes the ones the branch uses */
+    double f_min[HM_MAX_OBJECTIVES];  /* EI: 1 - (min(data[obj]) - lo)/diff  (random_scalarizations.py:429-431) */
+    double beta;                       /* UCB: sqrt(0.125*log(2*iter+1))  (random_scalarizations.py:187) */
+} hm_acq_params_t;
+
+/* Candidates are a column-major float32 matrix Xcm[f*ldx + i], f < n_features, i < N (ldx >= N):
+ * the encoding of models.preprocess_data_array (models.py:941-984) cast to float32 as sklearn does.
+ *
+ * hm_rf_eval walks M forests (objectives) over the same candidates in ONE launch and emits whichever
+ * outputs are non-NULL:
+ *   leaf_out[m]  : int32 [T_m][N]  sklearn leaf node id per (tree, candidate)         (A3)
+ *   mean_out     : fp64 [M][N]     Hutter mean                                         (A4)
+ *   var_out      : fp64 [M][N]     Hutter variance (0 -> 1e-5)                         (A5)
+ *   pred_out     : fp64 [M][N]     plain RandomForestRegressor.predict                 (A12)
+ *   score_out    : fp64 [N]        scalarised acquisition value (requires acq != NULL) (A10-A12)
+ *   feas         : fp64 [N] or NULL  feasibility probability multiplied into the score
+ */
+int hm_rf_eval(const hm_forest_t* const* forests, int M, const float* Xcm, int64_t ldx, int64_t N,
+               int32_t* const* leaf_out, double* mean_out, double* var_out, double* pred_out,
+               const hm_acq_params_t* acq, const double* feas, double* score_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K3  scalarised acquisition on precomputed mean/variance (GP path, or RF mean/var API users)
+ * replaces: EI / ucb / thompson_sampling arithmetic (random_scalarizations.py:160-506)
+ *   mean, var : fp64 [M][N] (ld = ldm); for HM_ACQ_TS `mean` holds the posterior sample / prediction.
+ * ------------------------------------------------------------------------------------------ */
+int hm_acq_score(const hm_acq_params_t* acq, const double* mean, const double* var, int64_t ldm,
+                 const double* feas, int64_t N, double* score_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * stable k-smallest: replaces utility_functions.get_min_configurations (utility_functions.py:295-316)
+ * i.e. k x np.argmin-and-delete  ==  the k lexicographically smallest (value, index) pairs, ascending,
+ * NaN ordered first (np.argmin returns the first NaN), -0.0 == +0.0.
+ *   out_vals[k], out_idx[k] (device); out_idx = index_base + position.  If N < k the tail is filled
+ *   with (+inf, -1).  workspace: hm_topk_workspace_bytes(k) bytes of device memory.
+ * ------------------------------------------------------------------------------------------ */
+int64_t hm_topk_workspace_bytes(int k);
+int hm_topk(const double* vals, int64_t N, int64_t index_base, int k, double* out_vals, int64_t* out_idx,
+            void* workspace, void* stream);
+/* merge P sorted-or-unsorted candidate lists of (value, global index) pairs (e.g. the all-gathered
+ * per-rank top-k) into the global top-k with the same ordering.  n = total pairs. */
+int hm_topk_merge(const double* vals, const int64_t* idx, int64_t n, int k, double* out_vals,
+                  int64_t* out_idx, void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K2  GP posterior mean / variance
+ * replaces: GPy GPRegression.predict as called by compute_gp_prediction_mean_and_uncertainty
+ *           (models.py:997-1024): Matern52 ARD cross-covariance, mean = Kx^T alpha,
+ *           var = sf2 - ||L^-1 Kx||^2 (clip 1e-15) + noise, de-normalise, floor 1e-11.
+ *   Xs_host    : fp64 [n][D] training inputs ALREADY divided by the ARD lengthscales
+ *   inv_ls_host: fp64 [D]    1/lengthscale (applied to candidates on the device)
+ *   alpha_host : fp64 [n]    K_y^-1 y_normalised
+ *   Linv_host  : fp64 [n][n] row-major inverse of the lower Cholesky factor of K_y (lower triangular)
+ *   kernel_kind: 0 = Matern-5/2, 1 = RBF
+ * ------------------------------------------------------------------------------------------ */
+typedef struct hm_gp hm_gp_t;
+int hm_gp_create(int n, int D, const double* Xs_host, const double* inv_ls_host, const double* alpha_host,
+                 const double* Linv_host, double sf2, double noise, double y_mean, double y_std,
+                 int kernel_kind, hm_gp_t** out);
+void hm_gp_destroy(hm_gp_t* g);
+/* Xcm: fp64 column-major candidates [D][N] (ld = ldx), raw (not divided by lengthscale).
+ * mean_out/var_out: fp64 [N]; var floored at 1e-11 as models.py:1018.                       */
+int hm_gp_mean_var(const hm_gp_t* g, const double* Xcm, int64_t ldx, int64_t N, double* mean_out,
+                   double* var_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K4  Pareto dominance filter
+ * replaces: compute_pareto.sequential_is_pareto_efficient (compute_pareto.py:89-117), both passes.
+ *   costs : fp64 [N][M] row-major (device), M <= HM_MAX_OBJECTIVES
+ *   mask  : uint8 [N] (device) 1 = Pareto efficient
+ *   workspace: hm_pareto_workspace_bytes(N, M) bytes of device memory
+ *   n_front_out_host: optional host int64 receiving the number of efficient points
+ * The call synchronises the stream internally (the sweep is data dependent).
+ * ------------------------------------------------------------------------------------------ */
+int64_t hm_pareto_workspace_bytes(int64_t N, int M);
+int hm_pareto_filter(const double* costs, int64_t N, int M, uint8_t* mask, void* workspace,
+                     int64_t* n_front_out_host, void* stream);
+/* pass 1 only (the order-independent weak front, compute_pareto.py:100-104): used by the sharded
+ * path, which exchanges pass-1 survivors between ranks before the sequential pass 2. */
+int hm_pareto_pass1(const double* costs, int64_t N, int M, uint8_t* mask, void* workspace,
+                    int64_t* n_alive_out_host, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Host-buffer convenience entry points (what a reference-side ctypes/cffi binding calls when its
+ * data lives in numpy arrays): pinned staging + H2D/D2H copies happen inside.  Used for `e2e`.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct hm_host_ctx hm_host_ctx_t;
+int hm_host_ctx_create(int64_t max_candidates_per_chunk, int max_features, hm_host_ctx_t** out);
+void hm_host_ctx_destroy(hm_host_ctx_t* c);
+/* X_host: float32 column-major [n_features][N] (ld = ldx) in host memory (pinned or pageable).
+ * Scores all N candidates through M forests + acquisition, chunked and double-buffered across two
+ * streams; writes score_out_host[N] if non-NULL and the stable top-k (values + indices) if k > 0. */
+int hm_rf_score_host(hm_host_ctx_t* c, const hm_forest_t* const* forests, int M, const float* X_host,
+                     int64_t ldx, int64_t N, const hm_acq_params_t* acq, double* score_out_host, int k,
+                     double* topk_vals_host, int64_t* topk_idx_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HM_B200_H */

@@ -1,0 +1,316 @@
+"""Generate golden vectors by running the UNMODIFIED reference (/root/reference) in the build container.
+
+    python tests/golden/make_golden.py          # rewrites tests/golden/*.npz / *.json
+
+The reference cannot travel to the GPU box, so its outputs are frozen here:
+  rf_mixed.npz    fitted RFModel forests (raw sklearn arrays + Hutter leaf tables), candidates, and the
+                  reference's own outputs: encoded buffer, leaves, mean/var/std, sklearn predict,
+                  run_acquisition_function for {EI,UCB,TS} x {linear,tchebyshev,modified_tchebyshev},
+                  get_min_configurations picks, compute_data_array_scalarization
+  rf_branin.npz   the bundled _branin_scenario.json shape (C1): 2 real inputs, 10 trees, 1 objective
+  pareto.npz      sequential_is_pareto_efficient masks on random / tie-heavy / duplicated / NaN inputs and the
+                  three known-answer cases of the reference's tests (tests/data/*pareto*.csv)
+  local_search.npz  local_search() trajectory end points under fixed seeds (discrete space)
+"""
+import copy
+import json
+import os
+import random
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_harness  # noqa: E402
+
+ns = ref_harness.load()
+REF = ref_harness.REFERENCE_ROOT
+
+
+def validated(config):
+    from jsonschema import Draft4Validator
+    with open(os.path.join(REF, "hypermapper", "schema.json")) as f:
+        schema = json.load(f)
+    V = ns.utility_functions.extend_with_default(Draft4Validator)
+    config = copy.deepcopy(config)
+    V(schema).validate(config)
+    return config
+
+
+MIXED = {
+    "application_name": "golden_mixed",
+    "optimization_objectives": ["obj_a", "obj_b"],
+    "optimization_iterations": 5,
+    "models": {"model": "random_forest", "number_of_trees": 8},
+    "input_parameters": {
+        "x_real": {"parameter_type": "real", "values": [-5, 10], "parameter_default": 0},
+        "x_int": {"parameter_type": "integer", "values": [0, 20], "parameter_default": 3},
+        "x_ord": {"parameter_type": "ordinal", "values": [1, 2, 4, 8, 16, 32, 64, 128], "parameter_default": 4},
+        "x_cat": {"parameter_type": "categorical", "values": ["a", "b", "c"], "parameter_default": "a"},
+        "x_ordf": {"parameter_type": "ordinal", "values": [0.5, 1.5, 2.5], "parameter_default": 1.5},
+        "x_cat2": {"parameter_type": "categorical", "values": ["p", "q"], "parameter_default": "q"},
+    },
+}
+
+BRANIN = {
+    "application_name": "golden_branin",
+    "optimization_objectives": ["Value"],
+    "optimization_iterations": 5,
+    "input_parameters": {
+        "x1": {"parameter_type": "real", "values": [-5, 10], "parameter_default": 0},
+        "x2": {"parameter_type": "real", "values": [0, 15], "parameter_default": 0},
+    },
+}
+
+DISCRETE = {
+    "application_name": "golden_discrete",
+    "optimization_objectives": ["Value"],
+    "optimization_iterations": 5,
+    "models": {"model": "random_forest", "number_of_trees": 6},
+    "local_search_random_points": 300,
+    "local_search_starting_points": 4,
+    "number_of_cpus": 1,
+    "input_parameters": {
+        "a": {"parameter_type": "ordinal", "values": list(range(1, 33)), "parameter_default": 1},
+        "b": {"parameter_type": "ordinal", "values": [1, 2, 4, 8, 16, 32, 64], "parameter_default": 1},
+        "c": {"parameter_type": "categorical", "values": ["u", "v", "w", "x"], "parameter_default": "u"},
+        "d": {"parameter_type": "ordinal", "values": [0, 1, 2], "parameter_default": 0},
+    },
+}
+
+
+def params_desc(config):
+    out = []
+    for name, p in config["input_parameters"].items():
+        vals = p["values"]
+        if p["parameter_type"] == "ordinal":
+            vals = sorted(vals, key=float)
+        out.append({"name": name, "type": p["parameter_type"], "values": vals})
+    return out
+
+
+def objective_mixed(cfg):
+    x, i, o, c, of, c2 = cfg["x_real"], cfg["x_int"], cfg["x_ord"], cfg["x_cat"], cfg["x_ordf"], cfg["x_cat2"]
+    a = (x - 2.0) ** 2 + 0.3 * i + np.log2(o) * (1 + c) + of * 2 - 3 * c2
+    b = 50 - 3 * x + (i - 10) ** 2 / 4.0 + 20.0 / o + 5 * (c == 1) + of ** 2
+    return float(a), float(b)
+
+
+def branin(cfg):
+    x1, x2 = cfg["x1"], cfg["x2"]
+    a, b, c, r, s, t = 1.0, 5.1 / (4 * np.pi ** 2), 5 / np.pi, 6.0, 10.0, 1 / (8 * np.pi)
+    return float(a * (x2 - b * x1 ** 2 + c * x1 - r) ** 2 + s * (1 - t) * np.cos(x1) + s)
+
+
+def objective_discrete(cfg):
+    return float((cfg["a"] - 11) ** 2 / 10.0 + abs(np.log2(cfg["b"]) - 3) * 2 + [3, 0, 1, 2][cfg["c"]] + cfg["d"])
+
+
+def to_native(v):
+    return v.item() if hasattr(v, "item") else v
+
+
+def sample_data_array(space, n, fn, objectives):
+    cfgs = space.get_random_configuration(size=n, use_priors=False)
+    data = {k: [] for k in space.get_input_parameters()}
+    for o in objectives:
+        data[o] = []
+    for c in cfgs:
+        for k in space.get_input_parameters():
+            data[k].append(to_native(c[k]))
+        vals = fn(c)
+        if not isinstance(vals, tuple):
+            vals = (vals,)
+        for o, v in zip(objectives, vals):
+            data[o].append(v)
+    return data
+
+
+def fit(config, space, data, objectives):
+    with ref_harness.logger_stdout():
+        models, _, _ = ns.models.generate_mono_output_regression_models(
+            data, space, space.get_input_parameters(), objectives, 1.0, config, model_type="random_forest", number_of_cpus=1)
+    return models
+
+
+def rf_case(config, fn, n_train, n_cand, seed, fname):
+    from oracle import oracle
+    config = validated(config)
+    np.random.seed(seed)
+    random.seed(seed)
+    space = ns.space.Space(config)
+    objectives = config["optimization_objectives"]
+    inputs = space.get_input_parameters()
+    data = sample_data_array(space, n_train, fn, objectives)
+    models = fit(config, space, data, objectives)
+
+    cand = space.get_random_configuration(size=n_cand, use_priors=False, return_as_array=True)
+    configurations = ns.utility_functions.array_to_list_of_dicts(cand, inputs)
+    bufferx = [tuple(to_native(c[k]) for k in inputs) for c in configurations]
+
+    out = {}
+    out["params_json"] = np.array(json.dumps(params_desc(config)))
+    out["objectives_json"] = np.array(json.dumps(objectives))
+    out["config_json"] = np.array(json.dumps(config))
+    out["candidates"] = np.array([[float(v) for v in row] for row in bufferx], dtype=np.float64)
+    out["data_inputs"] = np.array([[float(data[k][r]) for k in inputs] for r in range(n_train)], dtype=np.float64)
+    for o in objectives:
+        out["data_" + o] = np.array(data[o], dtype=np.float64)
+
+    with ref_harness.logger_stdout():
+        enc = ns.models.preprocess_data_buffer(bufferx, space)
+        out["encoded"] = np.array(enc, dtype=np.float64)
+        for o in objectives:
+            fa = oracle.forest_arrays_from_model(models[o])
+            out.update(fa.to_npz_dict("forest_%s_" % o))
+            out["leaves_" + o] = models[o].get_leaves_per_sample(enc, space)
+            out["sk_predict_" + o] = models[o].predict(enc)
+        mean, var = ns.models.compute_model_mean_and_uncertainty(bufferx, models, "random_forest", space, var=True)
+        _, std = ns.models.compute_model_mean_and_uncertainty(bufferx, models, "random_forest", space, var=False)
+        for o in objectives:
+            out["mean_" + o] = mean[o]
+            out["var_" + o] = var[o]
+            out["std_" + o] = std[o]
+
+        weights = {o: w for o, w in zip(objectives, [0.37, 0.63][: len(objectives)] if len(objectives) > 1 else [1.0])}
+        limits = {o: [float("inf"), float("-inf")] for o in objectives}
+        for o in objectives:
+            limits[o] = [min(data[o]), max(data[o])]
+        # make the running-limit update matter: shrink the stored limits a little
+        stored_limits = {o: [limits[o][0] + 0.1 * (limits[o][1] - limits[o][0]), limits[o][1]] for o in objectives}
+        out["weights"] = np.array([weights[o] for o in objectives])
+        out["stored_limits"] = np.array([stored_limits[o] for o in objectives])
+        iteration_number = 7
+        out["iteration_number"] = np.int64(iteration_number)
+        for scal in ("linear", "tchebyshev", "modified_tchebyshev"):
+            s, lim = ns.utility_functions.compute_data_array_scalarization(data, weights, copy.deepcopy(stored_limits), scal)
+            out["data_scalarization_" + scal] = np.array(s)
+            out["data_scalarization_limits_" + scal] = np.array([lim[o] for o in objectives])
+            for acq in ("EI", "UCB", "TS"):
+                vals, feas = ns.random_scalarizations.run_acquisition_function(
+                    acq, configurations, weights, models, space, scal, copy.deepcopy(stored_limits), iteration_number,
+                    data, "random_forest", None, 1)
+                out["acq_%s_%s" % (acq, scal)] = np.array(vals, dtype=np.float64)
+                assert feas == [1] * len(vals)
+        # get_min_configurations in index form
+        vals = out["acq_EI_tchebyshev"]
+        d = {"__index": list(range(len(vals))), "scal": list(vals)}
+        for k in (1, 20, 64):
+            best = ns.utility_functions.get_min_configurations(d, k, "scal")
+            out["topk_idx_%d" % k] = np.array(best["__index"], dtype=np.int64)
+            out["topk_val_%d" % k] = np.array(best["scal"], dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, fname), **out)
+    print(fname, {k: (v.shape if hasattr(v, "shape") else v) for k, v in list(out.items())[:6]},
+          "distinct EI", len(np.unique(out["acq_EI_tchebyshev"])))
+
+
+def pareto_case():
+    out = {}
+    f = ns.compute_pareto.sequential_is_pareto_efficient
+    rng = np.random.default_rng(7)
+    cases = {
+        "uniform3": rng.random((4000, 3)),
+        "uniform2": rng.random((4000, 2)),
+        "uniform4": rng.random((1500, 4)),
+        "ties3": np.floor(rng.random((3000, 3)) * 16) / 16,
+        "ties2": np.floor(rng.random((3000, 2)) * 32) / 32,
+        "anticorr2": None,
+        "dups3": None,
+        "nan3": None,
+        "single": np.array([[1.0, 2.0, 3.0]]),
+        "quirk3": np.array([[1.0, 5.0, 9.0], [1.0, 4.0, 10.0]]),
+        "quirk3_swapped": np.array([[1.0, 4.0, 10.0], [1.0, 5.0, 9.0]]),
+    }
+    x = rng.random(2000)
+    cases["anticorr2"] = np.stack([x, 1 - x + 0.01 * rng.random(2000)], 1)
+    base = rng.random((500, 3))
+    cases["dups3"] = np.concatenate([base, base[:200], base[100:300]], 0)
+    n3 = rng.random((1500, 3))
+    n3[rng.integers(0, 1500, 25), rng.integers(0, 3, 25)] = np.nan
+    n3[7] = np.nan
+    cases["nan3"] = n3
+    for k, c in cases.items():
+        with np.errstate(all="ignore"):
+            out["costs_" + k] = c
+            out["mask_" + k] = f(c.copy())
+    # the reference's own known-answer cases (tests/test_system.py + tests/data/*.csv)
+    import csv
+    rows = list(csv.DictReader(open(os.path.join(REF, "tests/data/BlackScholes_exhaustive_search_data.csv"))))
+    valid = [r for r in rows if r["Valid"].strip().lower() == "true"]
+    costs = np.array([[float(r["ALMs"]), float(r["Cycles"])] for r in valid])
+    out["costs_blackscholes"] = costs
+    out["mask_blackscholes"] = f(costs.copy())
+    gold = list(csv.DictReader(open(os.path.join(REF, "tests/data/BlackScholes_real_pareto.csv"))))
+    out["kat_blackscholes"] = np.array(sorted([[float(r["ALMs"]), float(r["Cycles"])] for r in gold]))
+    got = np.array(sorted(costs[out["mask_blackscholes"]].tolist()))
+    assert got.shape == out["kat_blackscholes"].shape and np.array_equal(got, out["kat_blackscholes"]), "BlackScholes KAT"
+
+    # 100x100 Branin grid of the quick-start example -> branin_grid_search_pareto.csv
+    sys.path.insert(0, os.path.join(REF, "example_scenarios", "quick_start"))
+    gold = list(csv.DictReader(open(os.path.join(REF, "tests/data/branin_grid_search_pareto.csv"))))
+    keys = list(gold[0].keys())
+    out["kat_branin_grid_cols"] = np.array(json.dumps(keys))
+    out["kat_branin_grid"] = np.array([[float(r[k]) for k in keys] for r in gold])
+    gold = list(csv.DictReader(open(os.path.join(REF, "tests/data/ordinal_branin_real_pareto.csv"))))
+    keys = list(gold[0].keys())
+    out["kat_ordinal_branin_cols"] = np.array(json.dumps(keys))
+    out["kat_ordinal_branin"] = np.array([[float(r[k]) for k in keys] for r in gold])
+    np.savez_compressed(os.path.join(HERE, "pareto.npz"), **out)
+    print("pareto.npz", {k: int(v.sum()) for k, v in out.items() if k.startswith("mask_")})
+
+
+def local_search_case():
+    """local_search() on a discrete space (deterministic given the seeds): frozen models + picked configuration."""
+    from oracle import oracle
+    config = validated(DISCRETE)
+    out = {}
+    np.random.seed(11)
+    random.seed(11)
+    space = ns.space.Space(config)
+    objectives = config["optimization_objectives"]
+    inputs = space.get_input_parameters()
+    data = sample_data_array(space, 60, objective_discrete, objectives)
+    models = fit(config, space, data, objectives)
+    fa = oracle.forest_arrays_from_model(models["Value"])
+    out.update(fa.to_npz_dict("forest_Value_"))
+    out["params_json"] = np.array(json.dumps(params_desc(config)))
+    out["config_json"] = np.array(json.dumps(config))
+    out["data_inputs"] = np.array([[float(data[k][r]) for k in inputs] for r in range(60)])
+    out["data_Value"] = np.array(data["Value"])
+    fast = {}
+    for r in range(60):
+        fast[space.get_unique_hash_string_from_values({k: data[k][r] for k in inputs})] = r
+    weights = {"Value": 1.0}
+    limits = {"Value": [min(data["Value"]), max(data["Value"])]}
+    for trial, seed in enumerate((3, 4, 5)):
+        for acq in ("EI", "UCB"):
+            np.random.seed(seed)
+            random.seed(seed)
+            state = np.random.get_state()
+            d2 = copy.deepcopy(data)
+            scal, _ = ns.utility_functions.compute_data_array_scalarization(d2, weights, copy.deepcopy(limits), "tchebyshev")
+            d2[config["scalarization_key"]] = scal.tolist()
+            cfg2 = copy.deepcopy(config)
+            cfg2["acquisition_function"] = acq
+            with ref_harness.logger_stdout():
+                best = ns.random_scalarizations.random_scalarizations(
+                    cfg2, d2, space, fast, models, 3 + trial, weights, copy.deepcopy(limits), None, None, "local_search")
+            out["best_%s_%d" % (acq, seed)] = np.array([float(best[k]) for k in inputs])
+            # the pools the reference drew (same RNG state -> same draws), for pool-level parity
+            np.random.set_state(state)
+            uni = space.get_random_configuration(size=config["local_search_random_points"], use_priors=False, return_as_array=True)
+            pri = space.get_random_configuration(size=config["local_search_random_points"], use_priors=True, return_as_array=True)
+            out["pool_uniform_%s_%d" % (acq, seed)] = uni.astype(np.float64)
+            out["pool_prior_%s_%d" % (acq, seed)] = pri.astype(np.float64)
+    np.savez_compressed(os.path.join(HERE, "local_search.npz"), **out)
+    print("local_search.npz", {k: v.tolist() for k, v in out.items() if k.startswith("best_")})
+
+
+if __name__ == "__main__":
+    rf_case(MIXED, objective_mixed, 90, 700, 1, "rf_mixed.npz")
+    rf_case(BRANIN, branin, 40, 1500, 2, "rf_branin.npz")
+    pareto_case()
+    local_search_case()
