@@ -1,0 +1,193 @@
+"""Fitted forest -> device-resident structure-of-arrays forest (hm_forest_create) and the launch wrappers.
+
+Model fitting is out of scope (stays with sklearn / the reference's RFModel.fit_RF, models.py:184-223); this
+module only reads the fitted model: sklearn's tree arrays plus the Hutter per-leaf tables
+(tree_means_per_leaf / tree_vars_per_leaf, models.py:79-122).
+"""
+import ctypes
+import weakref
+
+import numpy as np
+
+from . import _lib
+
+
+def forest_tables(model):
+    """Flatten `model` (reference RFModel, or any sklearn forest) into the host arrays hm_forest_create takes.
+
+    The three per-leaf fp64 tables are computed here with the reference's own scalar arithmetic so that the
+    device only has to add them up in tree order:
+        q = m / T                (models.py:237-239)
+        s = (m ** 2) / T         (models.py:262-264; `**` on a float scalar is libm pow, not m*m)
+        u = v / T                (models.py:259-261)
+    """
+    ests = model.estimators_
+    T = len(ests)
+    means = getattr(model, "tree_means_per_leaf", None) or None
+    vars_ = getattr(model, "tree_vars_per_leaf", None) or None
+    offs = np.zeros(T + 1, dtype=np.int64)
+    for t, est in enumerate(ests):
+        offs[t + 1] = offs[t] + est.tree_.node_count
+    n = int(offs[-1])
+    left = np.empty(n, dtype=np.int32)
+    right = np.empty(n, dtype=np.int32)
+    feature = np.empty(n, dtype=np.int32)
+    threshold = np.empty(n, dtype=np.float64)
+    value = np.empty(n, dtype=np.float64)
+    q = s = u = None
+    if means is not None:
+        q = np.zeros(n, dtype=np.float64)
+        s = np.zeros(n, dtype=np.float64)
+        u = np.zeros(n, dtype=np.float64)
+    for t, est in enumerate(ests):
+        tr = est.tree_
+        b, e = int(offs[t]), int(offs[t + 1])
+        left[b:e] = tr.children_left
+        right[b:e] = tr.children_right
+        feature[b:e] = tr.feature
+        threshold[b:e] = tr.threshold
+        value[b:e] = np.asarray(tr.value, dtype=np.float64).reshape(e - b, -1)[:, 0]
+        if means is not None:
+            for leaf, m in means[t].items():
+                q[b + int(leaf)] = m / T
+                s[b + int(leaf)] = (m ** 2) / T
+            for leaf, v in vars_[t].items():
+                u[b + int(leaf)] = v / T
+    return {"T": T, "n_features": int(model.n_features_in_), "tree_off": offs, "left": left, "right": right,
+            "feature": feature, "threshold": threshold, "q": q, "s": s, "u": u, "value": value}
+
+
+def tables_from_arrays(tree_off, left, right, feature, threshold, leaf_mean, leaf_var, value, n_features):
+    """Same as forest_tables but from already-flattened arrays (golden fixtures / synthetic workloads):
+    leaf_mean / leaf_var are per-node arrays holding the Hutter tables at leaf positions."""
+    T = len(tree_off) - 1
+    q = s = u = None
+    if leaf_mean is not None:
+        lm = np.asarray(leaf_mean, dtype=np.float64)
+        is_leaf = np.asarray(left) < 0
+        q = np.where(is_leaf, lm / T, 0.0)
+        s = np.zeros_like(lm)
+        for i in np.nonzero(is_leaf)[0]:
+            s[i] = (float(lm[i]) ** 2) / T      # scalar pow, as the reference
+        u = np.where(is_leaf, np.asarray(leaf_var, dtype=np.float64) / T, 0.0)
+    return {"T": T, "n_features": int(n_features), "tree_off": np.asarray(tree_off, dtype=np.int64),
+            "left": np.asarray(left, dtype=np.int32), "right": np.asarray(right, dtype=np.int32),
+            "feature": np.asarray(feature, dtype=np.int32), "threshold": np.asarray(threshold, dtype=np.float64),
+            "q": q, "s": s, "u": u, "value": None if value is None else np.asarray(value, dtype=np.float64)}
+
+
+class DeviceForest:
+    """Owns one hm_forest handle on the current CUDA device."""
+
+    def __init__(self, tables):
+        _lib.require_cuda()
+        L = _lib.lib()
+        c = np.ascontiguousarray
+        self._keep = [c(tables["tree_off"], dtype=np.int64), c(tables["feature"], dtype=np.int32),
+                      c(tables["threshold"], dtype=np.float64), c(tables["left"], dtype=np.int32),
+                      c(tables["right"], dtype=np.int32)]
+        opt = [None if tables.get(k) is None else c(tables[k], dtype=np.float64) for k in ("q", "s", "u", "value")]
+        h = ctypes.c_void_p()
+        rc = L.hm_forest_create(int(tables["T"]), int(tables["n_features"]), *[_lib.hptr(a) for a in self._keep],
+                                *[_lib.hptr(a) for a in opt], ctypes.byref(h))
+        _lib.check(rc, "hm_forest_create")
+        self.handle = h
+        self.n_trees = int(tables["T"])
+        self.n_features = int(tables["n_features"])
+        self.has_hutter_tables = tables.get("q") is not None
+        self.staged = bool(L.hm_forest_staged(h))
+        self._keep = None
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h is not None and h.value:
+            try:
+                _lib.lib().hm_forest_destroy(h)
+            except Exception:
+                pass
+            self.handle = None
+
+
+_cache = weakref.WeakKeyDictionary()
+
+
+def device_forest(model):
+    """DeviceForest for a fitted model, cached on the model object (a new fit creates new estimator objects,
+    which invalidates the entry)."""
+    if isinstance(model, DeviceForest):
+        return model
+    ests = model.estimators_
+    stamp = (id(ests), len(ests), id(ests[0].tree_), id(ests[-1].tree_))
+    try:
+        hit = _cache.get(model)
+    except TypeError:
+        hit = None
+    if hit is not None and hit[0] == stamp:
+        return hit[1]
+    df = DeviceForest(forest_tables(model))
+    try:
+        _cache[model] = (stamp, df)
+    except TypeError:
+        pass
+    return df
+
+
+def rf_eval(forests, Xcm, want_leaves=False, want_mean=False, want_var=False, want_pred=False, acq=None, feas=None):
+    """One launch of hm_rf_eval.  forests: list of DeviceForest; Xcm: float32 CUDA tensor [D_enc][N].
+    Returns a dict of CUDA tensors."""
+    torch = _lib.require_cuda()
+    L = _lib.lib()
+    M = len(forests)
+    assert Xcm.dtype == torch.float32 and Xcm.is_cuda and Xcm.dim() == 2 and Xcm.is_contiguous()
+    D, N = Xcm.shape
+    if D != forests[0].n_features:
+        raise ValueError("X has %d features, but the forest is expecting %d features as input" % (D, forests[0].n_features))
+    dev = Xcm.device
+    out = {}
+    handles = (ctypes.c_void_p * M)(*[f.handle for f in forests])
+    leaf_ptrs = None
+    if want_leaves:
+        out["leaves"] = [torch.empty((f.n_trees, N), dtype=torch.int32, device=dev) for f in forests]
+        leaf_ptrs = (ctypes.c_void_p * M)(*[t.data_ptr() for t in out["leaves"]])
+    for key, flag in (("mean", want_mean), ("var", want_var), ("pred", want_pred)):
+        if flag:
+            out[key] = torch.empty((M, N), dtype=torch.float64, device=dev)
+    acq_ref = None
+    if acq is not None:
+        out["score"] = torch.empty((N,), dtype=torch.float64, device=dev)
+        acq_ref = ctypes.byref(acq)
+    if N == 0:
+        return out
+    rc = L.hm_rf_eval(handles, M, _lib.dptr(Xcm), N, N, leaf_ptrs, _lib.dptr(out.get("mean")), _lib.dptr(out.get("var")),
+                      _lib.dptr(out.get("pred")), acq_ref, _lib.dptr(feas), _lib.dptr(out.get("score")), _lib.stream_ptr())
+    _lib.check(rc, "hm_rf_eval")
+    return out
+
+
+def topk(values, k, index_base=0):
+    """Stable k smallest of a CUDA fp64 vector: (values[k], indices[k]) CUDA tensors, (+inf,-1) padded."""
+    torch = _lib.require_cuda()
+    L = _lib.lib()
+    assert values.dtype == torch.float64 and values.is_cuda and values.is_contiguous()
+    N = values.numel()
+    ws = torch.empty((int(L.hm_topk_workspace_bytes(k)),), dtype=torch.uint8, device=values.device)
+    ov = torch.empty((k,), dtype=torch.float64, device=values.device)
+    oi = torch.empty((k,), dtype=torch.int64, device=values.device)
+    rc = L.hm_topk(_lib.dptr(values), N, int(index_base), int(k), _lib.dptr(ov), _lib.dptr(oi), _lib.dptr(ws), _lib.stream_ptr())
+    _lib.check(rc, "hm_topk")
+    return ov, oi
+
+
+def topk_merge(values, indices, k):
+    torch = _lib.require_cuda()
+    L = _lib.lib()
+    assert values.dtype == torch.float64 and indices.dtype == torch.int64 and values.is_cuda and indices.is_cuda
+    values = values.contiguous().view(-1)
+    indices = indices.contiguous().view(-1)
+    ws = torch.empty((int(L.hm_topk_workspace_bytes(k)),), dtype=torch.uint8, device=values.device)
+    ov = torch.empty((k,), dtype=torch.float64, device=values.device)
+    oi = torch.empty((k,), dtype=torch.int64, device=values.device)
+    rc = L.hm_topk_merge(_lib.dptr(values), _lib.dptr(indices), values.numel(), int(k), _lib.dptr(ov), _lib.dptr(oi),
+                         _lib.dptr(ws), _lib.stream_ptr())
+    _lib.check(rc, "hm_topk_merge")
+    return ov, oi

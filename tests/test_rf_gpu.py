@@ -1,0 +1,233 @@
+"""GPU parity: the CUDA forest / acquisition / top-k path (through the C-ABI) against the reference's golden
+vectors and against the CPU oracle on seeded inputs."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+REL_VAR = 1e-10   # variance: mean**2 is libm pow(x,2) in the reference, x*x on the device (<= 1 ulp apart)
+REL_ACQ = 1e-5    # north_star tolerance for acquisition values
+
+
+def _torch():
+    import torch
+    assert torch.cuda.is_available()
+    return torch
+
+
+def load(name):
+    return np.load(os.path.join(GOLDEN, name), allow_pickle=False)
+
+
+def device_forests(z):
+    from hypermapper_b200 import forest
+    objectives = json.loads(str(z["objectives_json"]))
+    out = []
+    for o in objectives:
+        pre = "forest_%s_" % o
+        tabs = forest.tables_from_arrays(z[pre + "tree_off"], z[pre + "left"], z[pre + "right"], z[pre + "feature"],
+                                         z[pre + "threshold"], z[pre + "leaf_mean"], z[pre + "leaf_var"],
+                                         z[pre + "value"], int(z[pre + "n_features"]))
+        out.append(forest.DeviceForest(tabs))
+    return objectives, out
+
+
+def xcm(z):
+    torch = _torch()
+    enc32 = np.ascontiguousarray(z["encoded"].astype(np.float32).T)
+    return torch.from_numpy(enc32).cuda()
+
+
+def assert_rel(a, b, rel):
+    a = np.asarray(a)
+    b = np.asarray(b)
+    assert a.shape == b.shape
+    both_nan = np.isnan(a) & np.isnan(b)
+    with np.errstate(all="ignore"):
+        err = np.abs(a - b) / np.maximum(np.abs(b), 1e-300)
+    err[both_nan] = 0
+    err[(a == b)] = 0
+    assert np.all(err <= rel), "max rel err %g" % np.max(err)
+
+
+@pytest.mark.parametrize("name", ["rf_mixed.npz", "rf_branin.npz"])
+def test_leaves_mean_var_vs_reference_golden(name):
+    from hypermapper_b200 import forest
+    z = load(name)
+    objectives, forests = device_forests(z)
+    out = forest.rf_eval(forests, xcm(z), want_leaves=True, want_mean=True, want_var=True, want_pred=True)
+    for m, o in enumerate(objectives):
+        assert np.array_equal(out["leaves"][m].cpu().numpy().astype(np.int64), z["leaves_" + o])   # bit-exact
+        assert np.array_equal(out["mean"][m].cpu().numpy(), z["mean_" + o])                       # bit-exact
+        assert_rel(out["var"][m].cpu().numpy(), z["var_" + o], REL_VAR)
+        assert np.array_equal(out["pred"][m].cpu().numpy(), z["sk_predict_" + o])                 # bit-exact
+
+
+@pytest.mark.parametrize("name", ["rf_mixed.npz", "rf_branin.npz"])
+@pytest.mark.parametrize("acq", ["EI", "UCB", "TS"])
+@pytest.mark.parametrize("scal", ["linear", "tchebyshev", "modified_tchebyshev"])
+def test_fused_acquisition_vs_reference_golden(name, acq, scal):
+    from hypermapper_b200 import forest, _lib
+    from oracle import oracle
+    z = load(name)
+    objectives, forests = device_forests(z)
+    data = {o: z["data_" + o].tolist() for o in objectives}
+    weights = {o: float(w) for o, w in zip(objectives, z["weights"])}
+    limits = {o: [float(a), float(b)] for o, (a, b) in zip(objectives, z["stored_limits"])}
+    _, lim = oracle.compute_data_array_scalarization(data, weights, limits, scal)
+    w = oracle.reciprocate_weights(weights) if scal == "modified_tchebyshev" else weights
+    fmin = [oracle.ei_f_min(data, o, lim) for o in objectives]
+    it = int(z["iteration_number"])
+    beta = float(np.sqrt(0.125 * np.log(2 * it + 1)))
+    p = _lib.make_acq_params(acq, scal, [w[o] for o in objectives], fmin, beta)
+    out = forest.rf_eval(forests, xcm(z), acq=p)
+    assert_rel(out["score"].cpu().numpy(), z["acq_%s_%s" % (acq, scal)], REL_ACQ)
+
+
+@pytest.mark.parametrize("k", [1, 20, 64])
+def test_topk_matches_get_min_configurations_golden(k):
+    from hypermapper_b200 import forest
+    torch = _torch()
+    z = load("rf_mixed.npz")
+    vals = torch.from_numpy(z["acq_EI_tchebyshev"]).cuda()
+    ov, oi = forest.topk(vals, k)
+    assert np.array_equal(oi.cpu().numpy(), z["topk_idx_%d" % k])
+    assert np.array_equal(ov.cpu().numpy(), z["topk_val_%d" % k])
+
+
+@pytest.mark.parametrize("n,k", [(1, 1), (5, 20), (1000, 20), (100000, 20), (3_000_000, 64), (3_000_000, 1024)])
+def test_topk_vs_oracle_ties_nan(n, k):
+    from hypermapper_b200 import forest
+    from oracle import oracle
+    torch = _torch()
+    rng = np.random.default_rng(n + k)
+    v = np.round(rng.standard_normal(n), 2)      # heavy ties
+    if n > 100:
+        v[rng.integers(0, n, 3)] = np.nan
+        v[rng.integers(0, n, 5)] = -0.0
+        v[rng.integers(0, n, 2)] = -np.inf
+    ov, oi = forest.topk(torch.from_numpy(v).cuda(), k, index_base=7)
+    want = oracle.get_min_indices_fast(v, k)
+    got = oi.cpu().numpy()
+    assert np.array_equal(got[: len(want)] - 7, want)
+    assert np.all(got[len(want):] == -1)
+    gv = ov.cpu().numpy()[: len(want)]
+    assert np.array_equal(np.isnan(gv), np.isnan(v[want]))
+    assert np.array_equal(gv[~np.isnan(gv)], v[want][~np.isnan(gv)] + 0.0)
+
+
+def test_topk_descending_input_worst_case():
+    from hypermapper_b200 import forest
+    torch = _torch()
+    n = 1_000_000
+    v = torch.arange(n, 0, -1, dtype=torch.float64, device="cuda")
+    ov, oi = forest.topk(v, 20)
+    assert oi.cpu().tolist() == list(range(n - 1, n - 21, -1))
+
+
+def test_topk_merge_equals_global_topk():
+    from hypermapper_b200 import forest
+    torch = _torch()
+    rng = np.random.default_rng(5)
+    v = np.round(rng.standard_normal(400_000), 3)
+    vals = torch.from_numpy(v).cuda()
+    k = 20
+    gv, gi = forest.topk(vals, k)
+    parts_v, parts_i = [], []
+    for r in range(4):     # four "ranks", contiguous shards, global indices
+        lo, hi = r * 100_000, (r + 1) * 100_000
+        pv, pi = forest.topk(vals[lo:hi].contiguous(), k, index_base=lo)
+        parts_v.append(pv)
+        parts_i.append(pi)
+    mv, mi = forest.topk_merge(torch.cat(parts_v), torch.cat(parts_i), k)
+    assert torch.equal(mi, gi) and torch.equal(mv, gv)
+
+
+def _synthetic_forest(rng, T, D, depth_lo, depth_hi):
+    """random binary trees in sklearn layout with random Hutter tables"""
+    offs, left, right, feat, thr, lm, lv, val = [0], [], [], [], [], [], [], []
+    for _ in range(T):
+        l, r, f, th = [], [], [], []
+
+        def grow(depth):
+            i = len(l)
+            l.append(-1)
+            r.append(-1)
+            f.append(-2)
+            th.append(-2.0)
+            if depth < depth_lo or (depth < depth_hi and rng.random() < 0.7):
+                f[i] = int(rng.integers(0, D))
+                th[i] = float(rng.random())
+                l[i] = grow(depth + 1)
+                r[i] = grow(depth + 1)
+            return i
+
+        grow(0)
+        n = len(l)
+        offs.append(offs[-1] + n)
+        left += l
+        right += r
+        feat += f
+        thr += th
+        lm += list(rng.standard_normal(n))
+        lv += list(rng.random(n) * (rng.random(n) > 0.2))
+        val += list(rng.standard_normal(n))
+    return dict(tree_off=np.array(offs), left=np.array(left), right=np.array(right), feature=np.array(feat),
+                threshold=np.array(thr), leaf_mean=np.array(lm), leaf_var=np.array(lv), value=np.array(val), n_features=D)
+
+
+@pytest.mark.parametrize("T,D,dlo,dhi,N", [(3, 2, 1, 3, 5000), (64, 23, 4, 11, 20000), (300, 32, 6, 12, 6000),
+                                           (17, 60, 2, 9, 3001), (2, 150, 1, 5, 777), (4, 5, 13, 15, 4000)])
+def test_forest_kernel_vs_oracle_synthetic(T, D, dlo, dhi, N):
+    """streamed (multi-group), resident, narrow-block and wide-feature configurations against the C oracle"""
+    from hypermapper_b200 import forest
+    from oracle import oracle
+    torch = _torch()
+    rng = np.random.default_rng(T * 1000 + D)
+    fs = [_synthetic_forest(rng, T, D, dlo, dhi) for _ in range(2)]
+    X = rng.random((N, D))
+    X[:, 0] = np.round(X[:, 0], 1)
+    fas = [oracle.ForestArrays(f["tree_off"], f["left"], f["right"], f["feature"], f["threshold"], f["leaf_mean"],
+                               f["leaf_var"], f["value"], D) for f in fs]
+    dfs = [forest.DeviceForest(forest.tables_from_arrays(**f)) for f in fs]
+    Xd = torch.from_numpy(np.ascontiguousarray(X.astype(np.float32).T)).cuda()
+    out = forest.rf_eval(dfs, Xd, want_leaves=True, want_mean=True, want_var=True, want_pred=True)
+    for m, fa in enumerate(fas):
+        leaf = oracle.rf_apply(fa, X)
+        assert np.array_equal(out["leaves"][m].cpu().numpy().astype(np.int64), leaf)
+        mean = oracle.rf_prediction(fa, leaf)
+        assert np.array_equal(out["mean"][m].cpu().numpy(), mean)
+        assert_rel(out["var"][m].cpu().numpy(), oracle.rf_prediction_variance(fa, leaf, mean), 1e-9)
+        assert np.array_equal(out["pred"][m].cpu().numpy(), oracle.rf_sklearn_predict(fa, leaf))
+
+
+def test_threshold_rounding_edge_cases():
+    """x32 <= thr32 must equal (double)x32 <= thr64 for thresholds that are not float32-representable."""
+    from hypermapper_b200 import forest
+    from oracle import oracle
+    torch = _torch()
+    xs = np.array([0.1, 0.3, 1.0, 1e-30, 16777217.0, -0.7], dtype=np.float32)
+    thr, X = [], []
+    for x in xs:
+        d = float(x)
+        for t in (d, np.nextafter(d, np.inf), np.nextafter(d, -np.inf), float(np.nextafter(x, np.float32(np.inf))),
+                  float(np.nextafter(x, np.float32(-np.inf)))):
+            thr.append(t)
+            X.append(x)
+    T = len(thr)
+    # every tree tests every candidate, so each (x, threshold) pairing above is covered on the diagonal and more
+    f = dict(tree_off=np.arange(0, 3 * T + 1, 3), left=np.tile([1, -1, -1], T), right=np.tile([2, -1, -1], T),
+             feature=np.tile([0, -2, -2], T), threshold=np.repeat(thr, 3), leaf_mean=np.zeros(3 * T),
+             leaf_var=np.zeros(3 * T), value=np.zeros(3 * T), n_features=1)
+    Xn = np.array(X, dtype=np.float64).reshape(-1, 1)
+    fa = oracle.ForestArrays(f["tree_off"], f["left"], f["right"], f["feature"], f["threshold"], f["leaf_mean"],
+                             f["leaf_var"], f["value"], 1)
+    df = forest.DeviceForest(forest.tables_from_arrays(**f))
+    Xd = torch.from_numpy(np.ascontiguousarray(Xn.astype(np.float32).T)).cuda()
+    out = forest.rf_eval([df], Xd, want_leaves=True)
+    assert np.array_equal(out["leaves"][0].cpu().numpy().astype(np.int64), oracle.rf_apply(fa, Xn))
