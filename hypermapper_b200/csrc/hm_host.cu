@@ -1,13 +1,112 @@
-// host-buffer entry points placeholder (implemented next)
+// Host-buffer entry point: what a reference-side binding calls when the candidates live in host memory
+// (numpy arrays).  Candidates are streamed H2D in column-major chunks on two streams so that the copy of chunk
+// c+1 overlaps the fused forest/acquisition kernel of chunk c; scores stream back D2H the same way; the stable
+// top-k runs once over the device-resident score vector.
+#include <algorithm>
+#include <new>
 #include "hm_common.cuh"
-extern "C" int hm_host_ctx_create(int64_t, int, hm_host_ctx_t** out) {
-    if (out) *out = nullptr;
-    hm_set_error("hm_host_ctx_create: not implemented yet");
-    return HM_E_UNSUPPORTED;
+
+struct hm_host_ctx {
+    int64_t chunk;          // candidates per chunk
+    int max_features;
+    cudaStream_t st[2];
+    cudaEvent_t ev[2];
+    float* d_x[2];          // [max_features][chunk]
+    double* d_scores;       // [cap_scores]
+    int64_t cap_scores;
+    void* d_topk_ws;
+    int64_t topk_ws_bytes;
+    double* d_topk_vals;
+    int64_t* d_topk_idx;
+};
+
+extern "C" int hm_host_ctx_create(int64_t max_candidates_per_chunk, int max_features, hm_host_ctx_t** out) {
+    HM_REQUIRE(out != nullptr, "out");
+    *out = nullptr;
+    HM_REQUIRE(max_candidates_per_chunk > 0 && max_features > 0, "chunk/features > 0");
+    hm_host_ctx* c = new (std::nothrow) hm_host_ctx();
+    if (!c) return HM_E_NOMEM;
+    memset(c, 0, sizeof(*c));
+    c->chunk = (max_candidates_per_chunk + 1023) / 1024 * 1024;
+    c->max_features = max_features;
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        e = cudaStreamCreateWithFlags(&c->st[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&c->d_x[i], (size_t)c->chunk * max_features * sizeof(float));
+    }
+    c->topk_ws_bytes = hm_topk_workspace_bytes(1024);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_topk_ws, (size_t)c->topk_ws_bytes);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&c->d_topk_vals, 1024 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&c->d_topk_idx, 1024 * sizeof(int64_t));
+    if (e != cudaSuccess) {
+        hm_set_error("hm_host_ctx_create: %s", cudaGetErrorString(e));
+        hm_host_ctx_destroy(c);
+        return (int)e;
+    }
+    *out = c;
+    return 0;
 }
-extern "C" void hm_host_ctx_destroy(hm_host_ctx_t*) {}
-extern "C" int hm_rf_score_host(hm_host_ctx_t*, const hm_forest_t* const*, int, const float*, int64_t, int64_t,
-                                const hm_acq_params_t*, double*, int, double*, int64_t*) {
-    hm_set_error("hm_rf_score_host: not implemented yet");
-    return HM_E_UNSUPPORTED;
+
+extern "C" void hm_host_ctx_destroy(hm_host_ctx_t* c) {
+    if (!c) return;
+    for (int i = 0; i < 2; ++i) {
+        if (c->d_x[i]) cudaFree(c->d_x[i]);
+        if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+        if (c->st[i]) cudaStreamDestroy(c->st[i]);
+    }
+    if (c->d_scores) cudaFree(c->d_scores);
+    if (c->d_topk_ws) cudaFree(c->d_topk_ws);
+    if (c->d_topk_vals) cudaFree(c->d_topk_vals);
+    if (c->d_topk_idx) cudaFree(c->d_topk_idx);
+    delete c;
+}
+
+extern "C" int hm_rf_score_host(hm_host_ctx_t* c, const hm_forest_t* const* forests, int M, const float* X_host,
+                                int64_t ldx, int64_t N, const hm_acq_params_t* acq, double* score_out_host, int k,
+                                double* topk_vals_host, int64_t* topk_idx_host) {
+    HM_REQUIRE(c != nullptr && forests != nullptr && acq != nullptr, "ctx/forests/acq");
+    HM_REQUIRE(N >= 0 && ldx >= N, "ldx >= N >= 0");
+    HM_REQUIRE(k >= 0 && k <= 1024, "0 <= k <= 1024");
+    HM_REQUIRE(k == 0 || (topk_vals_host && topk_idx_host), "top-k outputs");
+    const int D = hm_forest_n_features(forests[0]);
+    HM_REQUIRE(D > 0 && D <= c->max_features, "n_features exceeds the context's max_features");
+    if (N > c->cap_scores) {
+        if (c->d_scores) cudaFree(c->d_scores);
+        c->d_scores = nullptr;
+        c->cap_scores = 0;
+        HM_CUDA_TRY(cudaMalloc((void**)&c->d_scores, (size_t)N * sizeof(double)));
+        c->cap_scores = N;
+    }
+    int n_chunks = 0;
+    for (int64_t lo = 0; lo < N; lo += c->chunk, ++n_chunks) {
+        const int b = n_chunks & 1;
+        const int64_t n = std::min<int64_t>(c->chunk, N - lo);
+        cudaStream_t st = c->st[b];
+        // [D][n] slab of the column-major host matrix -> dense [D][n] device buffer
+        HM_CUDA_TRY(cudaMemcpy2DAsync(c->d_x[b], (size_t)n * sizeof(float), X_host + lo, (size_t)ldx * sizeof(float),
+                                      (size_t)n * sizeof(float), (size_t)D, cudaMemcpyHostToDevice, st));
+        int rc = hm_rf_eval(forests, M, c->d_x[b], n, n, nullptr, nullptr, nullptr, nullptr, acq, nullptr,
+                            c->d_scores + lo, (void*)st);
+        if (rc) return rc;
+        if (score_out_host)
+            HM_CUDA_TRY(cudaMemcpyAsync(score_out_host + lo, c->d_scores + lo, (size_t)n * sizeof(double),
+                                        cudaMemcpyDeviceToHost, st));
+    }
+    if (k > 0) {
+        // stream 0 waits for stream 1's kernels, then selects over the whole score vector
+        if (n_chunks > 1) {
+            HM_CUDA_TRY(cudaEventRecord(c->ev[1], c->st[1]));
+            HM_CUDA_TRY(cudaStreamWaitEvent(c->st[0], c->ev[1], 0));
+        }
+        int rc = hm_topk(c->d_scores, N, 0, k, c->d_topk_vals, c->d_topk_idx, c->d_topk_ws, (void*)c->st[0]);
+        if (rc) return rc;
+        HM_CUDA_TRY(cudaMemcpyAsync(topk_vals_host, c->d_topk_vals, (size_t)k * sizeof(double), cudaMemcpyDeviceToHost,
+                                    c->st[0]));
+        HM_CUDA_TRY(cudaMemcpyAsync(topk_idx_host, c->d_topk_idx, (size_t)k * sizeof(int64_t), cudaMemcpyDeviceToHost,
+                                    c->st[0]));
+    }
+    HM_CUDA_TRY(cudaStreamSynchronize(c->st[0]));
+    HM_CUDA_TRY(cudaStreamSynchronize(c->st[1]));
+    return 0;
 }

@@ -12,7 +12,7 @@ import numpy as np
 from . import _lib
 
 
-def forest_tables(model):
+def forest_tables(model, value_column=0):
     """Flatten `model` (reference RFModel, or any sklearn forest) into the host arrays hm_forest_create takes.
 
     The three per-leaf fp64 tables are computed here with the reference's own scalar arithmetic so that the
@@ -46,7 +46,7 @@ def forest_tables(model):
         right[b:e] = tr.children_right
         feature[b:e] = tr.feature
         threshold[b:e] = tr.threshold
-        value[b:e] = np.asarray(tr.value, dtype=np.float64).reshape(e - b, -1)[:, 0]
+        value[b:e] = np.asarray(tr.value, dtype=np.float64).reshape(e - b, -1)[:, value_column]
         if means is not None:
             for leaf, m in means[t].items():
                 q[b + int(leaf)] = m / T
@@ -130,6 +130,34 @@ def device_forest(model):
     except TypeError:
         pass
     return df
+
+
+_clf_cache = weakref.WeakKeyDictionary()
+
+
+def classifier_forest(clf, cls):
+    """Feasibility classifier (RandomForestClassifier, models.py:574-578) as a traversal forest whose leaf payload is
+    the class fraction of `cls`: predict_proba = sum_t tree_.value[leaf, 0, class] / T (sklearn/ensemble/_forest.py),
+    which is exactly the `pred` output of hm_rf_eval."""
+    col = list(clf.classes_).index(cls)
+    ests = clf.estimators_
+    stamp = (id(ests), len(ests), id(ests[0].tree_), col)
+    hit = _clf_cache.get(clf)
+    if hit is not None and stamp in hit:
+        return hit[stamp]
+    df = DeviceForest(forest_tables(_NoHutter(clf), value_column=col))
+    _clf_cache.setdefault(clf, {})[stamp] = df
+    return df
+
+
+class _NoHutter:
+    """view of a plain sklearn forest without Hutter tables"""
+
+    def __init__(self, model):
+        self.estimators_ = model.estimators_
+        self.n_features_in_ = model.n_features_in_
+        self.tree_means_per_leaf = None
+        self.tree_vars_per_leaf = None
 
 
 def rf_eval(forests, Xcm, want_leaves=False, want_mean=False, want_var=False, want_pred=False, acq=None, feas=None):

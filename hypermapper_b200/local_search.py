@@ -1,0 +1,326 @@
+"""Acquisition optimiser of the hot path: same entry points as the reference's local_search.py
+(get_neighbors :83-161, local_search :389-833), with the two hot loops on the GPU:
+
+  A. the two big random pools are encoded as arrays, scored in one fused launch each and reduced to the
+     2*starting_points best seeds by the stable device top-k -- no per-candidate Python dict is built
+     (the reference explodes the (N, D) sample array into N dicts, local_search.py:446-451);
+  B. the hill climb scores every neighbour batch through the same fused kernel with the model resident.
+
+`optimization_function` keeps the reference's plug-in contract
+    f(configurations=[dict, ...], **optimization_function_parameters) -> (values, feasibility_indicators)
+(local_search.py:468-473, 346-348); any callable works.  When it is this package's run_acquisition_function the
+pools bypass the list-of-dicts form.  The multi-process branches of the reference (number_of_cpus != 1) are not
+reproduced: a CUDA context must not be forked, and the GPU replaces the worker pool.
+
+Known non-determinism of the reference that cannot be matched bit for bit: the column order used by the
+duplicate filter comes from iterating a Python `set` of key strings (utility_functions.py:237-239 via
+local_search.py:666-675), which changes with the interpreter's hash seed; input-parameter order is used here.
+"""
+import copy
+import datetime
+import sys
+
+import numpy as np
+from scipy import stats
+
+from .utility_functions import (
+    are_configurations_equal,
+    concatenate_data_dictionaries,
+    concatenate_list_of_dictionaries,
+    data_tuples_to_dict_list,
+    dict_of_lists_to_list_of_dicts,
+    get_min_configurations,
+    get_min_feasible_configurations,
+    min_indices,
+)
+
+# pools larger than this are not materialised as Python lists in the returned data_array
+MATERIALISE_LIMIT = 262144
+
+
+def _log(msg, verbose=False):
+    w = getattr(sys.stdout, "write_to_logfile", None)
+    if w is not None:
+        try:
+            w(msg, msg_is_verbose=verbose) if verbose else w(msg)
+        except TypeError:
+            w(msg)
+
+
+def get_neighbors(configuration, param_space):
+    """SMAC-style one-exchange neighbourhood (local_search.py:83-161), same enumeration order, same RNG draws."""
+    neighbors = []
+    objects = param_space.get_input_parameters_objects()
+    inputs = param_space.get_input_parameters()
+    numeric_neighbors = 4
+    base = [configuration[p] for p in inputs]
+
+    def push(pos, value):
+        cand = list(base)
+        cand[pos] = value
+        if cand not in neighbors:
+            neighbors.append(cand)
+
+    for pos, name in enumerate(inputs):
+        kind = param_space.get_type(name)
+        obj = objects[name]
+        if kind == "categorical" or (kind == "ordinal" and len(obj.get_discrete_values()) <= 5):
+            for value in obj.get_discrete_values():
+                push(pos, value)
+        elif kind == "ordinal":
+            values = obj.get_discrete_values()
+            idx = values.index(configuration[name])
+            if idx < numeric_neighbors / 2:
+                window = values[: numeric_neighbors + 1]
+            elif (len(values) - idx) <= numeric_neighbors / 2:
+                window = values[-(numeric_neighbors + 1):]
+            else:
+                window = values[int(idx - numeric_neighbors / 2): int(idx + numeric_neighbors / 2 + 1)]
+            for value in window:
+                push(pos, value)
+        elif kind in ("real", "integer"):
+            lo, hi = obj.get_min(), obj.get_max()
+            mean = (configuration[name] - lo) / (hi - lo)
+            draws = stats.truncnorm.rvs(0, 1, loc=mean, scale=0.2, size=numeric_neighbors).tolist()
+            draws.append(mean)
+            for value in draws:
+                value = 0 if value < 0 else (1 if value > 1 else value)
+                push(pos, obj.from_range_0_1_to_parameter_value(value))
+        else:
+            print("Unsupported parameter type:", kind)
+            raise SystemExit
+    return neighbors
+
+
+def _is_device_scorer(optimization_function):
+    from . import random_scalarizations as rs
+    return optimization_function is rs.run_acquisition_function
+
+
+def _score_pool(pool, inputs, optimization_function, params, device_scorer):
+    """pool: object/float array [N][D] (or list of dicts when the whole space was enumerated).
+    Returns (values, n_evaluated) where values is a CUDA tensor (device scorer) or a host list."""
+    if device_scorer:
+        from .random_scalarizations import acquisition_scores_device
+        p = {k: v for k, v in params.items() if k != "number_of_cpus"}
+        cand = pool if isinstance(pool, list) else np.asarray(pool, dtype=np.float64)
+        scores = acquisition_scores_device(p["acquisition_function"], cand, p["objective_weights"],
+                                           p["regression_models"], p["param_space"], p["scalarization_method"],
+                                           p["objective_limits"], p["iteration_number"], p["data_array"],
+                                           p["model_type"], p.get("classification_model"))
+        return scores, scores.numel()
+    configs = pool if isinstance(pool, list) else _rows_to_dicts(pool, inputs, range(len(pool)))
+    values, _ = optimization_function(configurations=configs, **params)
+    return list(values), len(values)
+
+
+def _rows_to_dicts(pool, inputs, rows):
+    if isinstance(pool, list):
+        return [pool[r] for r in rows]
+    return [{k: pool[r, j] for j, k in enumerate(inputs)} for r in rows]
+
+
+def _values_at(values, rows):
+    if isinstance(values, list):
+        return [values[r] for r in rows]
+    if len(rows) == 0:
+        return []
+    import torch
+    return values[torch.as_tensor(np.asarray(rows, dtype=np.int64), device=values.device)].cpu().tolist()
+
+
+def _hill_climb(start, param_space, inputs, optimization_function, params, enable_feasible_predictor,
+                scalarization_key, feasible_parameter):
+    """One start of the multi-start local search (local_search.py:337-386)."""
+    iteration_data = {}
+    configuration = start
+    log = "Starting local search on configuration: " + str(configuration) + "\n"
+    while configuration is not None:
+        neighbors = data_tuples_to_dict_list(get_neighbors(configuration, param_space), inputs)
+        values, feas = optimization_function(configurations=neighbors, **params)
+        m = len(values)
+        batch = concatenate_list_of_dictionaries(neighbors[:m])
+        batch[scalarization_key] = values
+        if enable_feasible_predictor:
+            batch[feasible_parameter] = feas
+        iteration_data = concatenate_data_dictionaries(iteration_data, batch)
+        if enable_feasible_predictor:
+            best = get_min_feasible_configurations(batch, 1, scalarization_key, feasible_parameter)
+        else:
+            best = get_min_configurations(batch, 1, scalarization_key)
+        current = {k: [v] for k, v in configuration.items()}
+        if are_configurations_equal(best, current, inputs):
+            log += "Local minimum found: " + str(dict(best)) + "\n"
+            configuration = None
+        else:
+            log += "Replacing configuration by best neighbor: " + str(dict(best)) + "\n"
+            configuration = {k: v[0] for k, v in best.items()}
+    return iteration_data, log
+
+
+def local_search(local_search_starting_points, local_search_random_points, param_space,
+                 fast_addressing_of_data_array, enable_feasible_predictor, optimization_function,
+                 optimization_function_parameters, scalarization_key, number_of_cpus, previous_points=None,
+                 profiling=None, noise=False):
+    """Random pools + multi-start hill climb on the acquisition function; returns (data_array, best_configuration).
+    Mirrors local_search.py:389-833 (single-process branch)."""
+    t0 = datetime.datetime.now()
+    inputs = param_space.get_input_parameters()
+    feasible_parameter = param_space.get_feasible_parameter()[0]
+    params = optimization_function_parameters
+    device_scorer = _is_device_scorer(optimization_function) and not enable_feasible_predictor
+    oversampling_factor = 2
+
+    # (kept for RNG / side-effect parity with local_search.py:429-432; the hash table copy is not used afterwards)
+    default_configuration = param_space.get_default_or_random_configuration()
+    param_space.get_unique_hash_string_from_values(default_configuration)
+
+    if param_space.get_space_size() < local_search_random_points:
+        everything = dict_of_lists_to_list_of_dicts(param_space.get_space())
+        half = int(len(everything) / 2)
+        pool_u, pool_p = everything[0:half], everything[half::]
+    else:
+        pool_u = param_space.get_random_configuration(size=local_search_random_points, use_priors=False, return_as_array=True)
+        pool_p = param_space.get_random_configuration(size=local_search_random_points, use_priors=True, return_as_array=True)
+    sampling_time = datetime.datetime.now()
+    _log("Total RS time %10.4f sec\n" % ((sampling_time - t0).total_seconds()))
+
+    # ---- hot loop A: score both pools --------------------------------------------------------------------
+    val_u, n_u = _score_pool(pool_u, inputs, optimization_function, params, device_scorer)
+    val_p, n_p = _score_pool(pool_p, inputs, optimization_function, params, device_scorer)
+    acquisition_time = datetime.datetime.now()
+    _log("Optimization function time %10.4f sec\n" % (acquisition_time - sampling_time).total_seconds())
+    end_of_search = (n_u < len(pool_u)) or (n_p < len(pool_p))
+    if end_of_search:
+        _log("Out of budget, not all configurations were evaluated, stopping local search\n")
+
+    # ---- seeds: 2*starting_points best of each pool, ranked separately (local_search.py:625-645) ------------
+    k = local_search_starting_points * oversampling_factor
+
+    def best_of(pool, values, n_eval):
+        if enable_feasible_predictor:
+            d = concatenate_list_of_dictionaries(_rows_to_dicts(pool, inputs, range(n_eval)))
+            d[scalarization_key] = list(values)
+            # the plug-in reports every point feasible (random_scalarizations.py:154-155)
+            d[feasible_parameter] = [1] * n_eval
+            return get_min_feasible_configurations(d, k, scalarization_key, feasible_parameter)
+        vals = values if not isinstance(values, list) else values[:n_eval]
+        rows = [int(i) for i in min_indices(vals, k)]
+        d = concatenate_list_of_dictionaries(_rows_to_dicts(pool, inputs, rows)) if rows else {p: [] for p in inputs}
+        d[scalarization_key] = _values_at(values, rows)
+        return d
+
+    seeds_u = best_of(pool_u, val_u, n_u)
+    seeds_p = best_of(pool_p, val_p, n_p)
+    keys = inputs + [scalarization_key]
+    seeds = {key: list(seeds_u[key]) + list(seeds_p[key]) for key in keys}
+    n_seed_u, n_seed_p = len(seeds_u[scalarization_key]), len(seeds_p[scalarization_key])
+
+    best_previous = None
+    if previous_points is not None:
+        if enable_feasible_predictor:
+            best_previous = get_min_feasible_configurations(previous_points, local_search_starting_points,
+                                                            scalarization_key, feasible_parameter)
+        else:
+            best_previous = get_min_configurations(previous_points, local_search_starting_points, scalarization_key)
+        seeds = {key: seeds[key] + list(best_previous[key]) for key in keys}
+
+    # duplicate filter (local_search.py:673-699 -> space.remove_duplicate_configs): first occurrence wins in the order
+    # previous > prior > uniform; every group comes back sorted lexicographically by parameter values.
+    table = np.zeros((len(seeds[scalarization_key]), len(keys)), dtype=np.dtype(object))
+    for j, key in enumerate(keys):
+        table[:, j] = seeds[key]
+    grp_u = table[0:n_seed_u]
+    grp_p = table[n_seed_u:n_seed_u + n_seed_p]
+    grp_prev = table[n_seed_u + n_seed_p:]
+    grp_prev, grp_p, grp_u = param_space.remove_duplicate_configs(grp_prev, grp_p, grp_u, ignore_columns=len(inputs))
+    chosen = np.concatenate((grp_u[0:local_search_starting_points], grp_p[0:local_search_starting_points],
+                             grp_prev[0:local_search_starting_points]), axis=0)
+    starts = {key: chosen[:, j].tolist() for j, key in enumerate(keys)}
+    data_collection_time = datetime.datetime.now()
+    n_starts = len(starts[scalarization_key])
+    _log("Starting local search iteration: " + ", #configs:" + str(n_starts) + "\n")
+
+    # ---- hot loop B: multi-start hill climb, starts in order (keeps the RNG order of get_neighbors) ----------
+    result_array = {}
+    for s in range(n_starts):
+        start = {key: starts[key][s] for key in keys}
+        it_data, log = _hill_climb(start, param_space, inputs, optimization_function, params, enable_feasible_predictor,
+                                   scalarization_key, feasible_parameter)
+        _log(log, verbose=True)
+        result_array = concatenate_data_dictionaries(result_array, it_data)
+    local_search_time = datetime.datetime.now()
+    _log("Multi-start LS time %10.4f sec\n" % (local_search_time - acquisition_time).total_seconds())
+
+    # ---- final pick: argmin over [LS results, uniform pool, prior pool, previous points] skipping configurations
+    #      that were already evaluated (local_search.py:789-807); ties -> first in that order -------------------
+    ls_vals = list(result_array.get(scalarization_key, []))
+    prev_vals = list(previous_points[scalarization_key]) if previous_points is not None else []
+    off_u = len(ls_vals)
+    off_p = off_u + n_u
+    off_prev = off_p + n_p
+
+    def config_at(pos):
+        if pos < off_u:
+            return {p: result_array[p][pos] for p in inputs}
+        if pos < off_p:
+            return _rows_to_dicts(pool_u, inputs, [pos - off_u])[0]
+        if pos < off_prev:
+            return _rows_to_dicts(pool_p, inputs, [pos - off_p])[0]
+        return {p: previous_points[p][pos - off_prev] for p in inputs}
+
+    def rank_key(v, pos):
+        return (0, 0.0, pos) if v != v else (1, v + 0.0, pos)      # NaN first, -0.0 == +0.0, then position
+
+    best_configuration = None
+    want = 32
+    while best_configuration is None:
+        cand = [(v, i) for i, v in enumerate(ls_vals)]
+        horizons = []
+        for values, n_eval, off in ((val_u, n_u, off_u), (val_p, n_p, off_p)):
+            vals = values if not isinstance(values, list) else values[:n_eval]
+            rows = [int(i) for i in min_indices(vals, min(want, n_eval))]
+            fetched = [(v, off + r) for v, r in zip(_values_at(values, rows), rows)]
+            cand += fetched
+            if n_eval > want and fetched:
+                horizons.append(rank_key(*fetched[-1]))     # unfetched entries of this pool rank after this pair
+        cand += [(v, off_prev + i) for i, v in enumerate(prev_vals)]
+        cand.sort(key=lambda c: rank_key(*c))
+        need_more = False
+        for v, pos in cand:
+            if any(rank_key(v, pos) > h for h in horizons):
+                need_more = True
+                break
+            conf = config_at(pos)
+            if param_space.get_unique_hash_string_from_values(conf) not in fast_addressing_of_data_array:
+                best_configuration = conf
+                break
+        if best_configuration is None:
+            if not need_more:
+                raise ValueError("attempt to get argmin of an empty sequence")   # what np.argmin raises in the reference
+            want *= 8
+    post_time = datetime.datetime.now()
+    _log("MSLS time %10.4f sec\n" % (post_time - acquisition_time).total_seconds())
+
+    # ---- returned data_array: [LS results, pools, previous] as dict of lists (pools only when small) ---------
+    data_array = {}
+    if n_u + n_p <= MATERIALISE_LIMIT:
+        du = concatenate_list_of_dictionaries(_rows_to_dicts(pool_u, inputs, range(n_u))) if n_u else {p: [] for p in inputs}
+        du[scalarization_key] = _values_at(val_u, list(range(n_u)))
+        dp = concatenate_list_of_dictionaries(_rows_to_dicts(pool_p, inputs, range(n_p))) if n_p else {p: [] for p in inputs}
+        dp[scalarization_key] = _values_at(val_p, list(range(n_p)))
+        data_array = {key: list(du[key]) + list(dp[key]) for key in keys}
+    else:
+        data_array = {key: list(seeds_u[key]) + list(seeds_p[key]) for key in keys}
+    if previous_points is not None:
+        data_array = {key: data_array[key] + list(previous_points[key]) for key in keys}
+    if result_array:
+        data_array = {key: list(result_array[key]) + data_array[key] for key in keys}
+
+    if profiling is not None:
+        profiling.add("(LS) Random sampling time", (sampling_time - t0).total_seconds())
+        profiling.add("(LS) Acquisition evaluation time", (acquisition_time - sampling_time).total_seconds())
+        profiling.add("(LS) Data collection time", (data_collection_time - acquisition_time).total_seconds())
+        profiling.add("(LS) Multi-start LS time", (local_search_time - data_collection_time).total_seconds())
+        profiling.add("(LS) Post-MSLS data treatment time", (post_time - local_search_time).total_seconds())
+    return data_array, best_configuration

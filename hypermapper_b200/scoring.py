@@ -1,0 +1,49 @@
+"""Host-buffer scoring: the call a reference-side binding makes when candidates live in host memory.
+Wraps hm_host_ctx_* / hm_rf_score_host (include/hm_b200.h): chunked, double-buffered H2D -> fused forest +
+acquisition kernel -> D2H, plus the stable device top-k."""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+
+class HostScorer:
+    def __init__(self, max_features, chunk=1 << 21):
+        _lib.require_cuda()
+        h = ctypes.c_void_p()
+        _lib.check(_lib.lib().hm_host_ctx_create(int(chunk), int(max_features), ctypes.byref(h)), "hm_host_ctx_create")
+        self.handle = h
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h is not None and h.value:
+            try:
+                _lib.lib().hm_host_ctx_destroy(h)
+            except Exception:
+                pass
+            self.handle = None
+
+    def score(self, forests, x_host, acq, k=0, scores_out=None):
+        """forests: list of DeviceForest; x_host: float32 column-major [D_enc][N] host array (numpy, or a pinned torch
+        CPU tensor for full-speed async copies); acq: AcqParams.  scores_out: optional float64 [N] host buffer.
+        Returns (scores_out, topk_values[k], topk_indices[k])."""
+        if hasattr(x_host, "data_ptr"):
+            D, N = x_host.shape
+            assert x_host.is_contiguous() and not x_host.is_cuda and str(x_host.dtype) == "torch.float32"
+            xp = ctypes.c_void_p(x_host.data_ptr())
+        else:
+            assert x_host.dtype == np.float32 and x_host.flags.c_contiguous
+            D, N = x_host.shape
+            xp = _lib.hptr(x_host)
+        sp = None
+        if scores_out is not None:
+            sp = ctypes.c_void_p(scores_out.data_ptr()) if hasattr(scores_out, "data_ptr") else _lib.hptr(scores_out)
+        tv = np.empty(max(k, 1), dtype=np.float64)
+        ti = np.empty(max(k, 1), dtype=np.int64)
+        M = len(forests)
+        handles = (ctypes.c_void_p * M)(*[f.handle for f in forests])
+        rc = _lib.lib().hm_rf_score_host(self.handle, handles, M, xp, N, N, ctypes.byref(acq), sp, int(k),
+                                         _lib.hptr(tv), _lib.hptr(ti))
+        _lib.check(rc, "hm_rf_score_host")
+        return scores_out, tv[:k], ti[:k]
