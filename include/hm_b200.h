@@ -128,13 +128,13 @@ int hm_topk_merge(const double* vals, const int64_t* idx, int64_t n, int k, doub
  *           (models.py:997-1024): Matern52 ARD cross-covariance, mean = Kx^T alpha,
  *           var = sf2 - ||L^-1 Kx||^2 (clip 1e-15) + noise, de-normalise, floor 1e-11.
  *   Xs_host    : fp64 [n][D] training inputs ALREADY divided by the ARD lengthscales
- *   inv_ls_host: fp64 [D]    1/lengthscale (applied to candidates on the device)
+ *   ls_host    : fp64 [D]    ARD lengthscales (candidates are divided by them on the device, as GPy does)
  *   alpha_host : fp64 [n]    K_y^-1 y_normalised
  *   Linv_host  : fp64 [n][n] row-major inverse of the lower Cholesky factor of K_y (lower triangular)
- *   kernel_kind: 0 = Matern-5/2, 1 = RBF
+ *   kernel_kind: 0 = Matern-5/2, 1 = RBF;  n <= 768 training points, D <= 64
  * ------------------------------------------------------------------------------------------ */
 typedef struct hm_gp hm_gp_t;
-int hm_gp_create(int n, int D, const double* Xs_host, const double* inv_ls_host, const double* alpha_host,
+int hm_gp_create(int n, int D, const double* Xs_host, const double* ls_host, const double* alpha_host,
                  const double* Linv_host, double sf2, double noise, double y_mean, double y_std,
                  int kernel_kind, hm_gp_t** out);
 void hm_gp_destroy(hm_gp_t* g);

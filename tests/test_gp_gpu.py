@@ -1,0 +1,75 @@
+"""GPU parity for K2 (GP posterior mean / variance + EI) against the numpy/scipy oracle restatement of GPy's
+exact inference.  GP parity is UNPINNED against the real GPy (not installable here) -- see oracle/__init__.py.
+Tolerance: 1e-5 relative (north_star) on mean, variance and acquisition values."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-5
+
+
+def _setup(n, D, noise, seed, kernel="matern52"):
+    from hypermapper_b200 import gp, workloads
+    from oracle import oracle
+    rng = np.random.default_rng(seed)
+    X = rng.random((n, D))
+    y = workloads.hartmann6(X) if D == 6 else np.sin(3 * X[:, 0]) + (X ** 2).sum(1)
+    ls = np.random.default_rng(seed + 1).uniform(0.3, 1.0, D)
+    st_o = oracle.gp_fit(X, y, ls, 1.0, noise, kernel=kernel)
+    st = gp.GPState.from_hyperparameters(X, y, ls, 1.0, noise, kernel=kernel)
+    return st_o, st
+
+
+def rel_err(a, b):
+    return np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))
+
+
+@pytest.mark.parametrize("n,D,noise,N,kernel", [(256, 6, 1e-4, 20000, "matern52"), (256, 6, 0.0, 20000, "matern52"),
+                                                (200, 6, 1e-4, 5001, "matern52"), (17, 3, 1e-2, 1000, "matern52"),
+                                                (512, 32, 1e-4, 4000, "matern52"), (700, 10, 1e-3, 2000, "matern52"),
+                                                (300, 4, 1e-4, 3000, "rbf"), (3, 2, 1e-2, 100, "matern52")])
+def test_gp_mean_var_vs_oracle(n, D, noise, N, kernel):
+    import torch
+    from hypermapper_b200 import gp
+    from oracle import oracle
+    st_o, st = _setup(n, D, noise, seed=n + D, kernel=kernel)
+    Xs = np.random.default_rng(4).random((N, D))
+    Xs[:5] = st.X[:5]                      # candidates ON training points: the ill-conditioned end of the variance
+    mean_o, var_o = oracle.gp_predict(st_o, Xs)
+    X64 = torch.from_numpy(np.ascontiguousarray(Xs.T)).cuda()
+    mean = torch.empty(N, dtype=torch.float64, device="cuda")
+    var = torch.empty_like(mean)
+    gp.gp_mean_var(gp.device_gp(st), X64, mean, var)
+    m, v = mean.cpu().numpy(), var.cpu().numpy()
+    # mean: relative to the scale of the data (mu = Kx.alpha cancels; the oracle's own BLAS summation order has the
+    # same absolute error)
+    assert np.max(np.abs(m - mean_o)) <= REL * max(1.0, np.max(np.abs(mean_o)))
+    # variance: 1e-5 relative, plus the rounding floor of the cancellation sf2 - ||L^-1 k||^2 (n * eps * sf2 * std^2)
+    floor = 64 * n * np.finfo(np.float64).eps * st.variance * st.y_std ** 2
+    assert np.all(np.abs(v - var_o) <= REL * var_o + floor)
+    assert np.all(v >= 1e-11)
+
+
+def test_gp_ei_matches_oracle_c2_shape():
+    """C2: Hartmann-6, n = 256, EI single objective, through run_acquisition_function-level plumbing."""
+    import torch
+    from hypermapper_b200 import gp, models, _lib
+    from oracle import oracle
+    st_o, st = _setup(256, 6, 1e-4, seed=2)
+    N = 50000
+    Xs = np.random.default_rng(9).random((N, 6))
+    mean_o, var_o = oracle.gp_predict(st_o, Xs)
+    y = (st_o.alpha * 0).tolist()
+    data = {"Value": (np.random.default_rng(1).standard_normal(50)).tolist()}
+    w = {"Value": 1.0}
+    lim = {"Value": [min(data["Value"]), max(data["Value"])]}
+    want = oracle.EI({"Value": mean_o}, {"Value": var_o}, data, w, "tchebyshev", lim)
+    X64 = torch.from_numpy(np.ascontiguousarray(Xs.T)).cuda()
+    mean = torch.empty((1, N), dtype=torch.float64, device="cuda")
+    var = torch.empty_like(mean)
+    gp.gp_mean_var(gp.device_gp(st), X64, mean[0], var[0])
+    _, lim2 = oracle.compute_data_array_scalarization(data, w, lim, "tchebyshev")
+    p = _lib.make_acq_params("EI", "tchebyshev", [1.0], [oracle.ei_f_min(data, "Value", lim2)], 0.0)
+    got = models.acq_score_device(p, mean, var).cpu().numpy()
+    assert rel_err(got, want) <= REL
