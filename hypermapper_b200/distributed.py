@@ -37,10 +37,10 @@ def allgather_topk(local_vals, local_idx, k, group=None):
     world = dist.get_world_size(group)
     if world == 1:
         return local_vals, local_idx
-    gv = torch.empty((world, local_vals.numel()), dtype=local_vals.dtype, device=local_vals.device)
-    gi = torch.empty((world, local_idx.numel()), dtype=local_idx.dtype, device=local_idx.device)
-    dist.all_gather_into_tensor(gv, local_vals.contiguous(), group=group)
-    dist.all_gather_into_tensor(gi, local_idx.contiguous(), group=group)
+    gv = torch.empty((world * local_vals.numel(),), dtype=local_vals.dtype, device=local_vals.device)
+    gi = torch.empty((world * local_idx.numel(),), dtype=local_idx.dtype, device=local_idx.device)
+    dist.all_gather_into_tensor(gv, local_vals.contiguous().view(-1), group=group)
+    dist.all_gather_into_tensor(gi, local_idx.contiguous().view(-1), group=group)
     if gv.is_cuda:
         from .forest import topk_merge
         return topk_merge(gv, gi, k)

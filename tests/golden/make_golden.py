@@ -309,8 +309,33 @@ def local_search_case():
     print("local_search.npz", {k: v.tolist() for k, v in out.items() if k.startswith("best_")})
 
 
+def neighbors_case():
+    """get_neighbors (local_search.py:83-161) on the discrete and the mixed scenario, RNG seeded per call."""
+    out = {}
+    for tag, cfg in (("discrete", DISCRETE), ("mixed", MIXED)):
+        config = validated(cfg)
+        space = ns.space.Space(config)
+        inputs = space.get_input_parameters()
+        np.random.seed(21)
+        starts = space.get_random_configuration(size=6, use_priors=False, return_as_array=True)
+        out["params_json_" + tag] = np.array(json.dumps(params_desc(config)))
+        out["config_json_" + tag] = np.array(json.dumps(config))
+        out["starts_" + tag] = starts.astype(np.float64)
+        for r in range(len(starts)):
+            conf = {k: to_native(starts[r, j]) for j, k in enumerate(inputs)}
+            np.random.seed(100 + r)
+            nb = ns.local_search.get_neighbors(conf, space)
+            out["neighbors_%s_%d" % (tag, r)] = np.array([[float(v) for v in row] for row in nb], dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, "neighbors.npz"), **out)
+    print("neighbors.npz", {k: v.shape for k, v in out.items() if k.startswith("neighbors_")})
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "neighbors":
+        neighbors_case()
+        sys.exit(0)
     rf_case(MIXED, objective_mixed, 90, 700, 1, "rf_mixed.npz")
     rf_case(BRANIN, branin, 40, 1500, 2, "rf_branin.npz")
     pareto_case()
     local_search_case()
+    neighbors_case()

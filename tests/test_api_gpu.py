@@ -1,0 +1,236 @@
+"""GPU parity through the reference-facing Python API (the drop-in boundary): the functions named like the
+reference's, called the way the reference calls them, against golden vectors produced by the reference itself."""
+import copy
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-5
+
+
+def load(name):
+    return np.load(os.path.join(GOLDEN, name), allow_pickle=False)
+
+
+class FrozenForest:
+    """A fitted model as the exporter sees it (estimators_ with a tree_, Hutter tables), rebuilt from the golden file."""
+
+    class _Tree:
+        def __init__(self, left, right, feature, threshold, value):
+            self.children_left, self.children_right, self.feature, self.threshold = left, right, feature, threshold
+            self.value = value.reshape(-1, 1, 1)
+            self.node_count = len(left)
+
+    class _Est:
+        def __init__(self, tree):
+            self.tree_ = tree
+
+    def __init__(self, z, prefix):
+        off = z[prefix + "tree_off"]
+        self.estimators_ = []
+        self.tree_means_per_leaf, self.tree_vars_per_leaf = [], []
+        for t in range(len(off) - 1):
+            b, e = int(off[t]), int(off[t + 1])
+            left = z[prefix + "left"][b:e]
+            self.estimators_.append(self._Est(self._Tree(left, z[prefix + "right"][b:e], z[prefix + "feature"][b:e],
+                                                         z[prefix + "threshold"][b:e], z[prefix + "value"][b:e])))
+            leaves = np.nonzero(left < 0)[0]
+            self.tree_means_per_leaf.append({int(l): float(z[prefix + "leaf_mean"][b + l]) for l in leaves})
+            self.tree_vars_per_leaf.append({int(l): float(z[prefix + "leaf_var"][b + l]) for l in leaves})
+        self.n_features_in_ = int(z[prefix + "n_features"])
+
+
+def setup_case(name):
+    from hypermapper_b200.space_lite import SpaceLite
+    z = load(name)
+    config = json.loads(str(z["config_json"]))
+    space = SpaceLite(config)
+    objectives = json.loads(str(z["objectives_json"]))
+    params = json.loads(str(z["params_json"]))
+    models = {o: FrozenForest(z, "forest_%s_" % o) for o in objectives}
+    cand = z["candidates"]
+    bufferx = []
+    for row in cand:
+        t = []
+        for p, v in zip(params, row):
+            if p["type"] in ("integer", "categorical"):
+                t.append(int(v))
+            elif p["type"] == "ordinal" and all(float(x).is_integer() for x in p["values"]):
+                t.append(int(v))
+            else:
+                t.append(float(v))
+        bufferx.append(tuple(t))
+    data = {o: z["data_" + o].tolist() for o in objectives}
+    weights = {o: float(w) for o, w in zip(objectives, z["weights"])}
+    limits = {o: [float(a), float(b)] for o, (a, b) in zip(objectives, z["stored_limits"])}
+    return z, space, objectives, models, bufferx, data, weights, limits
+
+
+def rel_ok(a, b, rel):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    err = np.abs(a - b) / np.maximum(np.abs(b), 1e-300)
+    err[a == b] = 0
+    return np.all(err <= rel)
+
+
+@pytest.mark.parametrize("name", ["rf_mixed.npz", "rf_branin.npz"])
+def test_preprocess_and_mean_uncertainty(name):
+    from hypermapper_b200 import models as hm
+    z, space, objectives, models, bufferx, *_ = setup_case(name)
+    enc = hm.preprocess_data_buffer(bufferx, space)
+    assert np.array_equal(np.array(enc), z["encoded"])
+    mean, var = hm.compute_model_mean_and_uncertainty(bufferx, models, "random_forest", space, var=True)
+    _, std = hm.compute_model_mean_and_uncertainty(bufferx, models, "random_forest", space, var=False)
+    assert list(mean.keys()) == objectives
+    for o in objectives:
+        assert np.array_equal(mean[o], z["mean_" + o])
+        assert rel_ok(var[o], z["var_" + o], 1e-10)
+        assert rel_ok(std[o], z["std_" + o], 1e-10)
+        leaves = hm.rf_get_leaves_per_sample(models[o], z["encoded"])
+        assert leaves.dtype == np.int64 and np.array_equal(leaves, z["leaves_" + o])
+        assert np.array_equal(hm.rf_compute_rf_prediction(models[o], leaves), z["mean_" + o])
+        assert np.array_equal(hm.rf_compute_rf_prediction_variance(models[o], leaves, z["mean_" + o]), z["var_" + o])
+    pred = hm.model_prediction(bufferx, models, space)
+    for o in objectives:
+        assert np.array_equal(pred[o], z["sk_predict_" + o])
+    # 2-D array input takes the same path
+    mean2, _ = hm.compute_model_mean_and_uncertainty(z["candidates"], models, "random_forest", space, var=True)
+    for o in objectives:
+        assert np.array_equal(mean2[o], z["mean_" + o])
+
+
+@pytest.mark.parametrize("name", ["rf_mixed.npz", "rf_branin.npz"])
+@pytest.mark.parametrize("acq", ["EI", "UCB", "TS"])
+@pytest.mark.parametrize("scal", ["linear", "tchebyshev", "modified_tchebyshev"])
+def test_run_acquisition_function_list_of_dicts(name, acq, scal):
+    from hypermapper_b200 import random_scalarizations as rs
+    z, space, objectives, models, bufferx, data, weights, limits = setup_case(name)
+    inputs = space.get_input_parameters()
+    configurations = [dict(zip(inputs, row)) for row in bufferx]
+    lim_before = copy.deepcopy(limits)
+    vals, feas = rs.run_acquisition_function(acq, configurations, weights, models, space, scal, limits,
+                                             int(z["iteration_number"]), data, "random_forest", None, 1)
+    assert isinstance(vals, list) and feas == [1] * len(configurations)
+    assert limits == lim_before                       # inputs are not mutated
+    assert rel_ok(vals, z["acq_%s_%s" % (acq, scal)], REL)
+
+
+def test_unknown_enums_raise_system_exit():
+    from hypermapper_b200 import random_scalarizations as rs
+    z, space, objectives, models, bufferx, data, weights, limits = setup_case("rf_branin.npz")
+    cfgs = [dict(zip(space.get_input_parameters(), bufferx[0]))]
+    with pytest.raises(SystemExit):
+        rs.run_acquisition_function("PI", cfgs, weights, models, space, "linear", limits, 1, data, "random_forest")
+    with pytest.raises(SystemExit):
+        rs.run_acquisition_function("EI", cfgs, weights, models, space, "chebyshev", limits, 1, data, "random_forest")
+
+
+@pytest.mark.parametrize("k", [1, 20, 64])
+def test_get_min_configurations_dict_api(k):
+    from hypermapper_b200 import utility_functions as uf
+    z = load("rf_mixed.npz")
+    vals = z["acq_EI_tchebyshev"]
+    d = {"__index": list(range(len(vals))), "scal": list(vals)}
+    best = uf.get_min_configurations(d, k, "scal")
+    assert best["__index"] == z["topk_idx_%d" % k].tolist()
+    assert best["scal"] == z["topk_val_%d" % k].tolist()
+    assert len(d["scal"]) == len(vals)                # input not consumed
+
+
+def test_feasibility_classifier_probability_matches_sklearn():
+    """N1: P(feasible) through the traversal kernel == RandomForestClassifier.predict_proba (class_weight etc. as
+    models.py:574-578), and it multiplies the acquisition value."""
+    from sklearn.ensemble import RandomForestClassifier
+    from hypermapper_b200 import models as hm, random_scalarizations as rs
+    from hypermapper_b200.space_lite import SpaceLite
+    z, space, objectives, models, bufferx, data, weights, limits = setup_case("rf_mixed.npz")
+    config = json.loads(str(z["config_json"]))
+    config["feasible_output"] = {"enable_feasible_predictor": True, "name": "Valid", "true_value": "True", "false_value": "False"}
+    space = SpaceLite(config)
+    Xtr = z["encoded"][:300]
+    ytr = (Xtr[:, 0] + Xtr[:, 1] > np.median(Xtr[:, 0] + Xtr[:, 1]))
+    clf = RandomForestClassifier(class_weight={True: 0.9, False: 0.1}, n_estimators=10, max_features=0.75, random_state=0)
+    clf.fit(Xtr, ytr)
+    probs = hm.model_probabilities(bufferx, {"Valid": clf}, space)["Valid"]
+    want = clf.predict_proba(z["encoded"])
+    assert np.array_equal(probs, want)
+    inputs = space.get_input_parameters()
+    configurations = [dict(zip(inputs, row)) for row in bufferx]
+    vals, _ = rs.run_acquisition_function("EI", configurations, weights, models, space, "tchebyshev", limits,
+                                          int(z["iteration_number"]), data, "random_forest", {"Valid": clf}, 1)
+    true_idx = clf.classes_.tolist().index(True)
+    assert rel_ok(vals, z["acq_EI_tchebyshev"] * want[:, true_idx], REL)
+
+
+def test_local_search_matches_reference_golden():
+    """local_search() end point on the discrete golden scenario: same pools (frozen from the reference's RNG draws),
+    same fitted forest -> same best configuration as the reference picked."""
+    from hypermapper_b200 import random_scalarizations as rs, utility_functions as uf
+    from hypermapper_b200.space_lite import SpaceLite
+    z = load("local_search.npz")
+    config = json.loads(str(z["config_json"]))
+    space = SpaceLite(config)
+    inputs = space.get_input_parameters()
+    models = {"Value": FrozenForest(z, "forest_Value_")}
+    data = {k: [int(v) for v in z["data_inputs"][:, j]] for j, k in enumerate(inputs)}
+    data["Value"] = z["data_Value"].tolist()
+    fast = {space.get_unique_hash_string_from_values({k: data[k][r] for k in inputs}): r for r in range(60)}
+    weights = {"Value": 1.0}
+    limits = {"Value": [min(data["Value"]), max(data["Value"])]}
+    for trial, seed in enumerate((3, 4, 5)):
+        for acq in ("EI", "UCB"):
+            pools = [z["pool_uniform_%s_%d" % (acq, seed)], z["pool_prior_%s_%d" % (acq, seed)]]
+
+            def frozen_pools(use_priors=True, size=1, return_as_array=False, _p=pools):
+                arr = _p.pop(0)
+                out = np.array([[None] * arr.shape[1]] * arr.shape[0])
+                for j in range(arr.shape[1]):
+                    out[:, j] = arr[:, j].astype(np.int64)
+                return out
+
+            space.get_random_configuration = frozen_pools
+            d2 = copy.deepcopy(data)
+            scal, _ = uf.compute_data_array_scalarization(d2, weights, copy.deepcopy(limits), "tchebyshev")
+            d2[config["scalarization_key"]] = scal.tolist()
+            cfg2 = copy.deepcopy(config)
+            cfg2["acquisition_function"] = acq
+            np.random.seed(seed)
+            random.seed(seed)
+            best = rs.random_scalarizations(cfg2, d2, space, fast, models, 3 + trial, weights, copy.deepcopy(limits),
+                                            None, None, "local_search")
+            assert [float(best[k]) for k in inputs] == z["best_%s_%d" % (acq, seed)].tolist()
+            assert space.get_unique_hash_string_from_values(best) not in fast
+
+
+def test_local_search_generic_callable_and_return_shape():
+    """the plug-in seam: any f(configurations=[dict], **params) -> (values, feasibility) works, and the returned
+    data_array holds every evaluated point (LS points first, then both pools, then previous points)."""
+    from hypermapper_b200 import local_search as ls
+    from hypermapper_b200.space_lite import SpaceLite
+    config = {"optimization_objectives": ["v"], "input_parameters": {
+        "a": {"parameter_type": "ordinal", "values": list(range(40)), "parameter_default": 0},
+        "b": {"parameter_type": "integer", "values": [0, 30], "parameter_default": 0},
+        "c": {"parameter_type": "real", "values": [0, 1], "parameter_default": 0.5}}}
+    space = SpaceLite(config)
+    calls = []
+
+    def f(configurations, offset):
+        calls.append(len(configurations))
+        return [abs(c["a"] - 17) + abs(c["b"] - 4) + abs(c["c"] - 0.25) + offset for c in configurations], [1] * len(configurations)
+
+    np.random.seed(0)
+    data_array, best = ls.local_search(3, 200, space, {}, False, f, {"offset": 1.0}, "scalarization", 1)
+    assert calls[0] == 200 and calls[1] == 200
+    assert set(data_array.keys()) == {"a", "b", "c", "scalarization"}
+    n = len(data_array["scalarization"])
+    assert n == sum(calls)
+    i = int(np.argmin(data_array["scalarization"]))
+    assert [data_array[k][i] for k in ("a", "b", "c")] == [best[k] for k in ("a", "b", "c")]
+    assert best["a"] == 17 and best["b"] == 4

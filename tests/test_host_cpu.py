@@ -1,0 +1,239 @@
+"""CPU tests of the host-side logic (no GPU, no compute calls): encoding, scalarisation constants, neighbour
+generation, selection order, the C-ABI surface, and the world_size-2 top-k merge over gloo."""
+import ctypes
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT
+
+
+def load(name):
+    return np.load(os.path.join(GOLDEN, name), allow_pickle=False)
+
+
+def space_of(z, key="config_json"):
+    from hypermapper_b200.space_lite import SpaceLite
+    return SpaceLite(json.loads(str(z[key])))
+
+
+def typed_rows(params, arr):
+    rows = []
+    for row in arr:
+        t = []
+        for p, v in zip(params, row):
+            if p["type"] in ("integer", "categorical") or (p["type"] == "ordinal" and all(float(x).is_integer() for x in p["values"])):
+                t.append(int(v))
+            else:
+                t.append(float(v))
+        rows.append(tuple(t))
+    return rows
+
+
+@pytest.mark.parametrize("name", ["rf_mixed.npz", "rf_branin.npz"])
+def test_encoder_matches_reference_preprocess(name):
+    from hypermapper_b200.encoding import Encoder
+    z = load(name)
+    space = space_of(z)
+    enc = Encoder(space)
+    params = json.loads(str(z["params_json"]))
+    rows = typed_rows(params, z["candidates"])
+    assert np.array_equal(enc.encode(rows).T, z["encoded"])                     # list of tuples
+    assert np.array_equal(enc.encode(z["candidates"]).T, z["encoded"])          # 2-D float array
+    cfgs = [dict(zip(space.get_input_parameters(), r)) for r in rows]
+    assert np.array_equal(enc.encode_configurations(cfgs).T, z["encoded"])      # list of dicts
+    assert enc.n_encoded == z["encoded"].shape[1]
+
+
+def test_encoder_rejects_unknown_values():
+    from hypermapper_b200.encoding import Encoder
+    z = load("rf_mixed.npz")
+    enc = Encoder(space_of(z))
+    bad = z["candidates"][:3].copy()
+    bad[1, 2] = 3.0                 # not one of the ordinal's values
+    with pytest.raises(ValueError):
+        enc.encode(bad)
+    bad = z["candidates"][:3].copy()
+    bad[0, 3] = 7                   # categorical index out of range
+    with pytest.raises(ValueError):
+        enc.encode(bad)
+
+
+def test_encoder_normalize_inputs():
+    from hypermapper_b200.encoding import Encoder
+    from hypermapper_b200.space_lite import SpaceLite
+    from oracle import oracle
+    z = load("rf_mixed.npz")
+    cfg = json.loads(str(z["config_json"]))
+    cfg["normalize_inputs"] = True
+    space = SpaceLite(cfg)
+    params = json.loads(str(z["params_json"]))
+    means, stds = {}, {}
+    for j, p in enumerate(params):
+        means[p["name"]] = float(np.mean(z["candidates"][:, j]))
+        stds[p["name"]] = float(np.std(z["candidates"][:, j]))
+        space.set_parameter_mean(p["name"], means[p["name"]])
+        space.set_parameter_std(p["name"], stds[p["name"]])
+    rows = typed_rows(params, z["candidates"])
+    cols = {p["name"]: [r[j] for r in rows] for j, p in enumerate(params)}
+    want, _ = oracle.encode(cols, params, normalize_inputs=True, means=means, stds=stds)
+    assert np.array_equal(Encoder(space).encode(rows).T, want)
+
+
+@pytest.mark.parametrize("name", ["rf_mixed.npz", "rf_branin.npz"])
+@pytest.mark.parametrize("scal", ["linear", "tchebyshev", "modified_tchebyshev"])
+def test_scalarization_and_constants_match_reference(name, scal):
+    from hypermapper_b200 import utility_functions as uf
+    from hypermapper_b200.random_scalarizations import acquisition_constants
+    from oracle import oracle
+    z = load(name)
+    objectives = json.loads(str(z["objectives_json"]))
+    data = {o: z["data_" + o].tolist() for o in objectives}
+    weights = {o: float(w) for o, w in zip(objectives, z["weights"])}
+    limits = {o: [float(a), float(b)] for o, (a, b) in zip(objectives, z["stored_limits"])}
+    s, lim = uf.compute_data_array_scalarization(data, weights, limits, scal)
+    assert np.array_equal(s, z["data_scalarization_" + scal])
+    assert np.array_equal(np.array([lim[o] for o in objectives]), z["data_scalarization_limits_" + scal])
+    w, fmin, beta = acquisition_constants("EI", scal, objectives, weights, limits, data, 7)
+    assert fmin == [oracle.ei_f_min(data, o, lim) for o in objectives]
+    rw = oracle.reciprocate_weights(weights)
+    assert w == [(rw if scal == "modified_tchebyshev" else weights)[o] for o in objectives]
+    _, _, beta = acquisition_constants("UCB", scal, objectives, weights, limits, data, 7)
+    assert beta == float(np.sqrt(0.125 * np.log(2 * 7 + 1)))
+
+
+def test_min_indices_host_order():
+    from hypermapper_b200 import utility_functions as uf
+    from oracle import oracle
+    rng = np.random.default_rng(0)
+    v = np.round(rng.standard_normal(3000), 1)
+    v[[17, 400]] = np.nan
+    v[[3, 9]] = -0.0
+    for k in (1, 7, 100, 5000):
+        assert np.array_equal(uf.min_indices(v.tolist(), k), oracle.get_min_indices(v, k))
+    d = {"x": list(range(10)), "s": [3, 1, 2, 1, 5, 1, 0, 9, 0, 4], "Valid": [1, 0, 1, 1, 0, 1, 0, 1, 1, 1]}
+    best = uf.get_min_feasible_configurations(d, 3, "s", "Valid")
+    assert best["x"] == [8, 3, 5]
+    best = uf.get_min_feasible_configurations(d, 9, "s", "Valid")       # not enough feasible: all feasible + best infeasible
+    assert best["x"] == [0, 2, 3, 5, 7, 8, 9, 6, 1]
+
+
+@pytest.mark.parametrize("tag", ["discrete", "mixed"])
+def test_get_neighbors_matches_reference(tag):
+    """same enumeration order and the same truncnorm draws as local_search.get_neighbors of the reference"""
+    from hypermapper_b200 import local_search as ls
+    z = load("neighbors.npz")
+    space = space_of(z, "config_json_" + tag)
+    params = json.loads(str(z["params_json_" + tag]))
+    inputs = space.get_input_parameters()
+    starts = typed_rows(params, z["starts_" + tag])
+    for r, row in enumerate(starts):
+        np.random.seed(100 + r)
+        nb = ls.get_neighbors(dict(zip(inputs, row)), space)
+        got = np.array([[float(v) for v in x] for x in nb], dtype=np.float64)
+        assert np.array_equal(got, z["neighbors_%s_%d" % (tag, r)])
+
+
+def test_space_lite_accessors():
+    z = load("rf_mixed.npz")
+    space = space_of(z)
+    assert space.get_input_parameters() == ["x_real", "x_int", "x_ord", "x_cat", "x_ordf", "x_cat2"]
+    assert space.get_input_categorical_parameters(space.get_input_parameters()) == ["x_cat", "x_cat2"]
+    assert space.get_type("x_ord") == "ordinal" and space.get_space_size() == float("inf")
+    np.random.seed(0)
+    arr = space.get_random_configuration(size=50, use_priors=False, return_as_array=True)
+    assert arr.shape == (50, 6) and arr.dtype == object
+    conf = space.get_default_or_random_configuration()
+    assert conf["x_cat"] == 0 and conf["x_ordf"] == 1.5
+    assert space.get_unique_hash_string_from_values({"x_real": 1.5, "x_int": 3}) == "1.5_3_____"
+
+
+def test_library_exports_every_declared_symbol():
+    from hypermapper_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "hm_b200.h")).read()
+    declared = set(re.findall(r"\b(hm_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
+    if not os.path.exists(_lib.SO_PATH):
+        _lib.build()
+    L = ctypes.CDLL(_lib.SO_PATH)          # loads without a GPU
+    for sym in declared:
+        assert getattr(L, sym) is not None
+    L.hm_version.restype = ctypes.c_int
+    assert L.hm_version() >= 100
+    L.hm_topk_workspace_bytes.restype = ctypes.c_int64
+    assert L.hm_topk_workspace_bytes(20) > 0
+
+
+def test_product_never_imports_the_oracle():
+    """the oracle is the checker: nothing under hypermapper_b200/ may import it"""
+    pkg = os.path.join(ROOT, "hypermapper_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+                assert "hm_oracle" not in src, f
+
+
+def test_no_cuda_means_loud_failure():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from hypermapper_b200 import _lib, compute_pareto
+    with pytest.raises(_lib.HmError):
+        compute_pareto.sequential_is_pareto_efficient(np.random.rand(10, 2))
+
+
+def test_shard_bounds_cover_the_pool():
+    from hypermapper_b200.distributed import shard_bounds
+    for n, g in ((10, 3), (64, 8), (7, 8), (1 << 26, 8)):
+        b = [shard_bounds(n, r, g) for r in range(g)]
+        assert b[0][0] == 0 and b[-1][1] == n
+        assert all(b[i][1] == b[i + 1][0] for i in range(g - 1))
+
+
+GLOO_WORKER = r"""
+import os, sys
+import numpy as np
+import torch
+import torch.distributed as dist
+sys.path.insert(0, %r)
+from hypermapper_b200.distributed import allgather_topk, shard_bounds, merge_topk_host
+from oracle import oracle
+rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+rng = np.random.default_rng(11)
+vals = np.round(rng.standard_normal(50001), 2)       # heavy ties across the shard boundary
+vals[[5, 40000]] = np.nan
+k = 20
+lo, hi = shard_bounds(len(vals), rank, world)
+local = oracle.get_min_indices_fast(vals[lo:hi], k)
+lv = torch.full((k,), float("inf"), dtype=torch.float64); li = torch.full((k,), -1, dtype=torch.int64)
+lv[:len(local)] = torch.from_numpy(vals[lo:hi][local]); li[:len(local)] = torch.from_numpy(local + lo)
+gv, gi = allgather_topk(lv, li, k)
+want = oracle.get_min_indices_fast(vals, k)
+assert np.array_equal(gi.numpy(), want), (rank, gi.numpy(), want)
+gathered = [None] * world
+dist.all_gather_object(gathered, gi.tolist())
+assert all(g == gathered[0] for g in gathered)        # identical on every rank
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_two_rank_topk_merge_over_gloo(tmp_path):
+    """N > 1 path on CPU: contiguous shards, per-rank stable top-k with global indices, all-gather, merge ->
+    every rank holds the single-process top-k (ties resolved by lowest global index)."""
+    script = tmp_path / "worker.py"
+    script.write_text(GLOO_WORKER % ROOT)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29531", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
