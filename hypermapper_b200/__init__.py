@@ -8,3 +8,53 @@ from . import _lib  # noqa: F401
 from ._lib import HmError, build  # noqa: F401
 
 __all__ = ["HmError", "build"]
+
+
+def install(hypermapper_package=None):
+    """Drop this package in underneath an importable reference `hypermapper` package: rebinds the hot-path entry points
+    of hypermapper.models / random_scalarizations / local_search / compute_pareto (and the RFModel methods) to the
+    B200 implementations.  Call it after `import hypermapper...` and before `optimizer.optimize(...)`; the scenario JSON
+    and schema.json are untouched (backend selection must not add JSON keys: schema.json:441 additionalProperties=false).
+    Returns the list of rebound names."""
+    import importlib
+
+    from . import compute_pareto as b_cp
+    from . import local_search as b_ls
+    from . import models as b_models
+    from . import random_scalarizations as b_rs
+
+    def mod(name):
+        if hypermapper_package is not None:
+            return getattr(hypermapper_package, name)
+        return importlib.import_module("hypermapper." + name)
+
+    done = []
+
+    def bind(target, name, fn):
+        setattr(target, name, fn)
+        done.append("%s.%s" % (getattr(target, "__name__", target), name))
+
+    r_models = mod("models")
+    for name in ("compute_model_mean_and_uncertainty", "compute_rf_prediction_mean_and_uncertainty",
+                 "compute_gp_prediction_mean_and_uncertainty", "model_prediction", "model_probabilities"):
+        bind(r_models, name, getattr(b_models, name))
+    bind(r_models.RFModel, "get_leaves_per_sample", b_models.rf_get_leaves_per_sample)
+    bind(r_models.RFModel, "compute_rf_prediction", b_models.rf_compute_rf_prediction)
+    bind(r_models.RFModel, "compute_rf_prediction_variance", b_models.rf_compute_rf_prediction_variance)
+    r_rs = mod("random_scalarizations")
+    for name in ("run_acquisition_function", "EI", "ucb", "thompson_sampling", "random_scalarizations"):
+        bind(r_rs, name, getattr(b_rs, name))
+    r_ls = mod("local_search")
+    bind(r_ls, "local_search", b_ls.local_search)
+    bind(r_ls, "get_neighbors", b_ls.get_neighbors)
+    bind(r_models, "local_search", b_ls.local_search)          # models.minimize_posterior_mean imports it by name
+    r_cp = mod("compute_pareto")
+    for name in ("sequential_is_pareto_efficient", "sequential_is_pareto_efficient_dumb", "parallel_is_pareto_efficient",
+                 "compute_pareto"):
+        bind(r_cp, name, getattr(b_cp, name))
+    # bo.py binds `random_scalarizations` at import time (bo.py:43-60) -> rebind there too if it is loaded
+    import sys
+    bo = sys.modules.get("hypermapper.bo")
+    if bo is not None and hasattr(bo, "random_scalarizations"):
+        bind(bo, "random_scalarizations", b_rs.random_scalarizations)
+    return done

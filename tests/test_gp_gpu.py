@@ -35,7 +35,7 @@ def test_gp_mean_var_vs_oracle(n, D, noise, N, kernel):
     from oracle import oracle
     st_o, st = _setup(n, D, noise, seed=n + D, kernel=kernel)
     Xs = np.random.default_rng(4).random((N, D))
-    Xs[:5] = st.X[:5]                      # candidates ON training points: the ill-conditioned end of the variance
+    Xs[:min(5, n)] = st.X[:5]                      # candidates ON training points: the ill-conditioned end of the variance
     mean_o, var_o = oracle.gp_predict(st_o, Xs)
     X64 = torch.from_numpy(np.ascontiguousarray(Xs.T)).cuda()
     mean = torch.empty(N, dtype=torch.float64, device="cuda")

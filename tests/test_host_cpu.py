@@ -237,3 +237,44 @@ def test_two_rank_topk_merge_over_gloo(tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+def test_install_rebinds_reference_entry_points():
+    """with the real reference importable (build container only): install() rebinds every hot-path name"""
+    from oracle import ref_harness
+    if not ref_harness.available():
+        pytest.skip("reference tree not present on this box")
+    ns = ref_harness.load()
+    import hypermapper_b200
+    from hypermapper_b200 import models as b_models, random_scalarizations as b_rs, local_search as b_ls, compute_pareto as b_cp
+    saved = {}
+    targets = [(ns.models, ["compute_model_mean_and_uncertainty", "compute_rf_prediction_mean_and_uncertainty",
+                            "compute_gp_prediction_mean_and_uncertainty", "model_prediction", "model_probabilities",
+                            "local_search"]),
+               (ns.models.RFModel, ["get_leaves_per_sample", "compute_rf_prediction", "compute_rf_prediction_variance"]),
+               (ns.random_scalarizations, ["run_acquisition_function", "EI", "ucb", "thompson_sampling", "random_scalarizations"]),
+               (ns.local_search, ["local_search", "get_neighbors"]),
+               (ns.compute_pareto, ["sequential_is_pareto_efficient", "sequential_is_pareto_efficient_dumb",
+                                    "parallel_is_pareto_efficient", "compute_pareto"])]
+    for tgt, names in targets:
+        for n in names:
+            saved[(tgt, n)] = getattr(tgt, n)
+    try:
+        done = hypermapper_b200.install()
+        assert len(done) >= 20
+        assert ns.models.compute_model_mean_and_uncertainty is b_models.compute_model_mean_and_uncertainty
+        assert ns.random_scalarizations.run_acquisition_function is b_rs.run_acquisition_function
+        assert ns.local_search.local_search is b_ls.local_search
+        assert ns.compute_pareto.sequential_is_pareto_efficient is b_cp.sequential_is_pareto_efficient
+        assert ns.models.RFModel.get_leaves_per_sample is b_models.rf_get_leaves_per_sample
+        # signatures keep the reference's positional parameter names
+        import inspect
+        for (tgt, n), ref_fn in saved.items():
+            if tgt is ns.models.RFModel:
+                continue
+            ref_params = list(inspect.signature(ref_fn).parameters)
+            new_params = list(inspect.signature(getattr(tgt, n)).parameters)
+            assert new_params[: len(ref_params)] == ref_params, (n, ref_params, new_params)
+    finally:
+        for (tgt, n), fn in saved.items():
+            setattr(tgt, n, fn)
