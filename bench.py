@@ -1,21 +1,25 @@
 #!/usr/bin/env python
-"""bench.py -- acquisition evaluations / second on the RF + EI hot path (BASELINE.json metric).
+"""bench.py -- acquisition evaluations / second on the surrogate-prediction + acquisition hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c3|c1|c5rf] [--candidates n]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--workload c3|c1|c5rf|c2|c5gp|c4] [--candidates n]
 
-Default workload = BASELINE.json configs[2] ("C3"): 2-objective mixed ordinal/categorical space (D_enc = 23),
-256-tree Hutter forests, random_scalarizations EI + tchebyshev over 16 777 216 candidates per GPU, stable top-20.
-One "step" = one pass of the hot path over the whole pool: fused forest traversal + EI scalarisation (hm_rf_eval)
--> stable top-k (hm_topk) [-> all-gather + merge of the per-rank top-k when N > 1].  Weak scaling: every rank
-scores its own 16M-candidate shard (seed + rank), model replicated, the only collective is the k-pair all-gather.
+Default workload = BASELINE.json configs[2] ("C3"), the configuration the north-star's RF+EI target is quoted on:
+2-objective mixed ordinal/categorical space (D_enc = 23), two 256-tree Hutter forests, random_scalarizations
+EI + tchebyshev over 16 777 216 candidates per GPU, stable top-20.
+One "step" = one pass of the hot path over the whole pool:
+  RF : fused forest traversal + Hutter reduction + EI scalarisation (hm_rf_eval) -> stable top-k (hm_topk)
+  GP : hm_gp_mean_var -> hm_acq_score -> hm_topk                      (c2: Hartmann-6, n=256; c5gp: 20-D, n=512)
+  c4 : hm_pareto_filter on 10^7 x 3 points (metric: points/s)
+[-> all-gather + merge of the per-rank top-k when N > 1].  Weak scaling: every rank owns its own shard (seed + rank),
+model replicated, the only collective is the k-pair all-gather.
 
-value  : evaluations/s with the encoded candidates already resident in HBM (CUDA events, max over ranks)
-e2e    : the same through the host-buffer C-ABI call (hm_rf_score_host): pinned host candidates -> H2D -> kernels ->
-         D2H of every score + the top-k, all inside the timed region
-roofline: the dominant kernel (hm_forest_kernel) against the measured HBM copy bandwidth, algorithmic bytes =
-         (4*D_enc + 8) per evaluation (fp32 encoded candidate in, fp64 score out)
-cpu_baseline: the CPU oracle port (oracle/hm_oracle.c, OpenMP over all host threads + numpy EI) on a bounded sample
---impl reference: times that CPU port alone (the reference itself is Python on sklearn and cannot travel to the box)
+value   : units/s with the inputs already resident in HBM (CUDA events on the launching stream, max over ranks)
+e2e     : the same through host buffers: pinned host inputs -> H2D -> kernels -> D2H of the results, all timed
+roofline: the dominant kernel against the measured peak (HBM copy bandwidth from MEASURED_PEAKS.json; FP64 DFMA rate
+          measured in-process for the GP kernel)
+cpu_baseline / --impl reference: the CPU oracle port on all host threads, bounded sample (the reference itself is
+          Python on sklearn/GPy and cannot travel to the GPU box; kind = "port")
 """
 import argparse
 import json
@@ -31,8 +35,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "acquisition_evals_per_sec"
-UNIT = "evals/s"
+WORKLOADS = ["c3", "c1", "c5rf", "c2", "c5gp", "c4"]
 
 
 def parse():
@@ -41,32 +44,17 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c3", choices=["c3", "c1", "c5rf"])
-    ap.add_argument("--candidates", type=int, default=0, help="candidates per GPU (default: the workload's)")
-    ap.add_argument("--cpu-sample", type=int, default=0, help="candidates in the CPU baseline sample")
+    ap.add_argument("--workload", default="c3", choices=WORKLOADS)
+    ap.add_argument("--candidates", type=int, default=0, help="units per GPU (default: the workload's)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="units in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
 
 
-def make_workload(name):
-    from hypermapper_b200 import workloads
-    if name == "c3":
-        return workloads.RFWorkload(workloads.scenario_c3(), n_train=2000, seed=5), 1 << 24, \
-            "C3: 2-objective mixed ordinal/categorical (D_enc=23), 256-tree RF x2, EI+tchebyshev, top-20"
-    if name == "c1":
-        return workloads.RFWorkload(workloads.scenario_c1(), n_train=15, seed=0), 1 << 26, \
-            "C1 shape: 2 real inputs (Branin), 10-tree RF, EI+tchebyshev, top-20"
-    if name == "c5rf":
-        return workloads.RFWorkload(workloads.scenario_c5(), n_train=4000, seed=9), 1 << 24, \
-            "C5-RF: 20-D mixed space (D_enc=32), 256-tree RF, EI+tchebyshev, top-20"
-    raise SystemExit("unknown workload")
-
-
-def measured_hbm_peak():
-    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+def measured_peaks():
     try:
-        with open(p) as f:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
@@ -78,17 +66,14 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index = index
-        self.rows = []
-        self.proc = None
+        self.index, self.rows, self.proc = index, [], None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
+            threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
@@ -123,50 +108,338 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_port_rate(wl, sample, repeats=1):
-    """The CPU port of the hot path on `sample` candidates with all host threads: OpenMP forest traversal +
-    Hutter reduction (oracle/hm_oracle.c) per objective, numpy/scipy EI scalarisation, stable top-k."""
-    from oracle import oracle
-    from hypermapper_b200.forest import forest_tables
-    fas = {}
-    for o, m in wl.models.items():
-        fas[o] = oracle.forest_arrays_from_model(m)
-    Xcm = wl.candidates_encoded(sample, seed=1234)
-    X = np.ascontiguousarray(Xcm.T)          # the reference's row-major float32 layout
-    best = None
-    for _ in range(repeats):
+# =====================================================================================================================
+# workloads: each exposes  cpu_port(sample) -> seconds  (no GPU),  and on the GPU side  setup_device(N, rank),
+# step(record) -> ((topk values, topk indices), events),  e2e_step() -> (values, indices)
+# =====================================================================================================================
+class RFBench:
+    metric, unit, dtype = "acquisition_evals_per_sec", "evals/s", "f64"
+    cpu_desc = "OpenMP C port of models.py:174-275 + numpy/scipy EI + top-20"
+    e2e_api = "hm_rf_score_host (C-ABI, pinned host candidates, 2M-candidate double-buffered chunks)"
+
+    def __init__(self, name):
+        from hypermapper_b200 import workloads
+        self.name = name
+        cache = os.path.join(os.environ.get("HM_BENCH_CACHE", "/tmp"), "hm_bench_wl_%s.pkl" % name)
+        cached = None
+        if os.path.exists(cache):
+            import pickle
+            try:
+                with open(cache, "rb") as f:
+                    cached = pickle.load(f)
+            except Exception:
+                cached = None
+        if cached is not None:
+            self.wl = cached
+        if name == "c3":
+            self.wl = cached or workloads.RFWorkload(workloads.scenario_c3(), n_train=2000, seed=5)
+            self.n_default = 1 << 24
+            self.desc = "C3: 2-objective mixed ordinal/categorical (D_enc=23), 256-tree RF x2, EI+tchebyshev, top-20"
+        elif name == "c1":
+            self.wl = cached or workloads.RFWorkload(workloads.scenario_c1(), n_train=15, seed=0)
+            self.n_default = 1 << 26
+            self.desc = "C1 shape: 2 real inputs (Branin), 10-tree RF, EI+tchebyshev, top-20"
+        else:
+            self.wl = cached or workloads.RFWorkload(workloads.scenario_c5(), n_train=4000, seed=9)
+            self.n_default = 1 << 24
+            self.desc = "C5-RF: 20-D mixed space (D_enc=32), 256-tree RF, EI+tchebyshev, top-20"
+        if cached is None:
+            try:
+                import pickle
+                with open(cache, "wb") as f:
+                    pickle.dump(self.wl, f)
+            except Exception:
+                pass
+        self.k = 20
+        self.cpu_sample_default = 200000 if name != "c1" else 2000000
+
+    def config(self, N, world):
+        wl = self.wl
+        return {"workload": self.desc, "candidates_per_gpu": N, "D_enc": wl.D_enc, "trees": wl.n_trees,
+                "objectives": len(wl.objectives), "k": self.k, "parallelism": "candidate-sharded x%d" % world,
+                "l2": "inputs (%.2f GB per GPU) larger than L2, no flush needed" % (4 * wl.D_enc * N / 1e9)}
+
+    def cpu_port(self, sample):
+        """OpenMP forest traversal + Hutter reduction (oracle/hm_oracle.c) per objective, numpy/scipy EI, top-k."""
+        from oracle import oracle
+        wl = self.wl
+        if not hasattr(self, "_fas"):
+            self._fas = {o: oracle.forest_arrays_from_model(m) for o, m in wl.models.items()}
+            self._Xcpu = {}
+        if sample not in self._Xcpu:
+            self._Xcpu = {sample: np.ascontiguousarray(wl.candidates_encoded(sample, seed=1234).T)}
+        X = self._Xcpu[sample]
         t0 = time.perf_counter()
         means, variances = {}, {}
-        for o, fa in fas.items():
+        for o, fa in self._fas.items():
             means[o], variances[o], _ = oracle.rf_mean_var_omp(fa, X)
         vals = oracle.EI(means, variances, wl.data_array, wl.objective_weights, wl.scalarization, wl.objective_limits)
-        oracle.get_min_indices_fast(vals, 20)
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    return sample / best, best, oracle.num_threads()
+        oracle.get_min_indices_fast(vals, self.k)
+        return time.perf_counter() - t0
+
+    def setup_device(self, N, rank):
+        import torch
+        from hypermapper_b200 import forest
+        from hypermapper_b200.scoring import HostScorer
+        wl = self.wl
+        self.N, self.rank = N, rank
+        self.forests = [forest.device_forest(wl.models[o]) for o in wl.objectives]
+        self.acq = wl.acq_params()
+        self.x_host = torch.empty((wl.D_enc, N), dtype=torch.float32).pin_memory()
+        wl.candidates_encoded(N, seed=6 + rank, out=self.x_host.numpy())
+        self.x_dev = self.x_host.cuda()
+        self.scores_host = torch.empty((N,), dtype=torch.float64).pin_memory()
+        self.scorer = HostScorer(wl.D_enc, chunk=1 << 21)
+        self.launches_per_step = 3
+
+    def step(self, record):
+        import torch
+        from hypermapper_b200 import forest
+        ev = None
+        if record:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
+        out = forest.rf_eval(self.forests, self.x_dev, acq=self.acq)
+        if record:
+            ev[1].record()
+        tv, ti = forest.topk(out["score"], self.k, index_base=self.rank * self.N)
+        return (tv, ti), ev
+
+    def e2e_step(self):
+        import torch
+        _, tv, ti = self.scorer.score(self.forests, self.x_host, self.acq, k=self.k, scores_out=self.scores_host)
+        return torch.from_numpy(tv).cuda(), torch.from_numpy(ti + self.rank * self.N).cuda()
+
+    def e2e_bytes(self, N):
+        return 4 * self.wl.D_enc * N, 8 * N + 16 * self.k
+
+    def roofline(self, N, kernel_ms):
+        peak, src = measured_peaks()
+        b = 4 * self.wl.D_enc + 8
+        ach = b * N / (kernel_ms / 1e3) / 1e9
+        return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "kernel": "hm_forest_kernel<false>", "kernel_ms": kernel_ms, "algorithmic_bytes_per_eval": b,
+                "peak_source": src,
+                "note": "forests with thousands of node visits per evaluation are bound by the L1/shared-memory data "
+                        "pipe, not HBM (profiles/, DESIGN.md section 3)"}
 
 
-def run_reference(args, rank, world):
-    """--impl reference: the CPU port alone (rank 0 only)."""
+class GPBench:
+    metric, unit, dtype = "acquisition_evals_per_sec", "evals/s", "f64"
+    cpu_desc = "numpy/scipy (BLAS) restatement of GPy predict, not GPy itself + EI + top-20"
+    e2e_api = "GP path: pinned host candidates -> H2D -> hm_gp_mean_var + hm_acq_score + hm_topk -> D2H scores + top-k"
+
+    def __init__(self, name):
+        from hypermapper_b200 import gp, workloads
+        self.name = name
+        if name == "c2":
+            n, D, self.n_default = 256, 6, 1 << 20
+            X = np.random.default_rng(2).random((n, D))
+            y = workloads.hartmann6(X)
+            scale = 1.0
+            self.desc = "C2: Hartmann-6, GP Matern-5/2 ARD (n=256), EI over a 1M-candidate pool, top-20"
+        else:
+            n, D, self.n_default = 512, 32, 1 << 22
+            X = np.random.default_rng(12).random((n, D))
+            y = np.sin(X[:, :8].sum(1)) + (X[:, 8:] ** 2).sum(1) * 0.1
+            scale = 3.0
+            self.desc = "C5-GP: 20-D mixed space encoded to D_enc=32, GP Matern-5/2 ARD (n=512), EI, top-20"
+        self.n, self.D = n, D
+        self.X, self.y = X, y
+        self.ls = np.random.default_rng(3).uniform(0.3, 1.0, D) * scale
+        self.state = gp.GPState.from_hyperparameters(X, y, self.ls, 1.0, 1e-4)
+        self.k = 20
+        self.data = {"Value": [float(v) for v in y]}
+        self.weights = {"Value": 1.0}
+        self.limits = {"Value": [float(y.min()), float(y.max())]}
+        self.cpu_sample_default = 200000 if name == "c2" else 50000
+
+    def small(self, N):
+        return 8 * self.D * N < 200e6
+
+    def config(self, N, world):
+        return {"workload": self.desc, "candidates_per_gpu": N, "D_enc": self.D, "n_train": self.n, "k": self.k,
+                "parallelism": "candidate-sharded x%d" % world,
+                "l2": "flushed between timed steps (256 MB write)" if self.small(N) else "inputs larger than L2"}
+
+    def candidates(self, N, seed):
+        return np.ascontiguousarray(np.random.default_rng(seed).random((self.D, N)))
+
+    def cpu_port(self, sample):
+        """numpy/scipy restatement of GPy's exact-inference predict (BLAS, all threads) + EI + top-k"""
+        from oracle import oracle
+        if not hasattr(self, "_st"):
+            self._st = oracle.gp_fit(self.X, self.y, self.ls, 1.0, 1e-4)
+            self._Xs = np.ascontiguousarray(self.candidates(sample, 1234).T)
+        t0 = time.perf_counter()
+        mean, var = oracle.gp_predict(self._st, self._Xs)
+        vals = oracle.EI({"Value": mean}, {"Value": var}, self.data, self.weights, "tchebyshev", self.limits)
+        oracle.get_min_indices_fast(vals, self.k)
+        return time.perf_counter() - t0
+
+    def setup_device(self, N, rank):
+        import torch
+        from hypermapper_b200 import gp, _lib
+        from hypermapper_b200.random_scalarizations import acquisition_constants
+        self.N, self.rank = N, rank
+        self.dgp = gp.device_gp(self.state)
+        w, fmin, beta = acquisition_constants("EI", "tchebyshev", ["Value"], self.weights, self.limits, self.data, 5)
+        self.acq = _lib.make_acq_params("EI", "tchebyshev", w, fmin, beta)
+        self.x_host = torch.from_numpy(self.candidates(N, 6 + rank)).pin_memory()
+        self.x_dev = self.x_host.cuda()
+        self.x_stage = torch.empty_like(self.x_dev)
+        self.mean = torch.empty((1, N), dtype=torch.float64, device="cuda")
+        self.var = torch.empty_like(self.mean)
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if self.small(N) else None
+        self.scores_host = torch.empty((N,), dtype=torch.float64).pin_memory()
+        self.launches_per_step = 4
+        self.fp64_peak = float(_lib.lib().hm_fp64_peak_tflops())
+
+    def step(self, record):
+        import torch
+        from hypermapper_b200 import forest, gp, models
+        if self.flush is not None:
+            self.flush.fill_(1)                    # evict the (small) candidate matrix from L2 between steps
+        ev = None
+        if record:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
+        gp.gp_mean_var(self.dgp, self.x_dev, self.mean[0], self.var[0])
+        if record:
+            ev[1].record()
+        scores = models.acq_score_device(self.acq, self.mean, self.var)
+        tv, ti = forest.topk(scores, self.k, index_base=self.rank * self.N)
+        return (tv, ti), ev
+
+    def e2e_step(self):
+        from hypermapper_b200 import forest, gp, models
+        self.x_stage.copy_(self.x_host, non_blocking=True)
+        gp.gp_mean_var(self.dgp, self.x_stage, self.mean[0], self.var[0])
+        scores = models.acq_score_device(self.acq, self.mean, self.var)
+        self.scores_host.copy_(scores, non_blocking=True)
+        tv, ti = forest.topk(scores, self.k, index_base=self.rank * self.N)
+        ti.cpu()
+        return tv, ti
+
+    def e2e_bytes(self, N):
+        return 8 * self.D * N, 8 * N + 16 * self.k
+
+    def roofline(self, N, kernel_ms):
+        n_pad = (self.n + 15) // 16 * 16
+        # cross-covariance (2D-flop dot + ~40 for the Matern transform) + lower-triangular contraction (n^2 flops) + squares
+        flops = n_pad * (2 * self.D + 40) + n_pad * n_pad + 17 * n_pad
+        ach = flops * N / (kernel_ms / 1e3) / 1e12
+        peak = self.fp64_peak if self.fp64_peak > 0 else 37.0
+        return {"bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                "kernel": "hm_gp_kernel", "kernel_ms": kernel_ms, "algorithmic_flops_per_eval": flops,
+                "peak_source": "FP64 DFMA burst measured in-process (hm_fp64_peak_tflops)" if self.fp64_peak > 0
+                else "datasheet 37 TFLOP/s",
+                "note": "tcgen05 has no f64 kind and tf32/3xtf32 miss the 1e-5 tolerance (DESIGN.md section 3, K2): the "
+                        "contraction runs on the FP64 pipe"}
+
+
+class ParetoBench:
+    metric, unit, dtype = "pareto_points_per_sec", "points/s", "f64"
+    cpu_desc = "single-thread C port of compute_pareto.py:89-117 (the sweep is sequential by definition)"
+    e2e_api = "compute_pareto path: pinned host costs -> H2D -> hm_pareto_filter -> D2H mask"
+
+    def __init__(self, name):
+        self.name = name
+        self.M = 3
+        self.n_default = 10_000_000
+        self.desc = "C4: compute_pareto dominance filter, 10M uniform 3-objective points (both passes)"
+        self.cpu_sample_default = 10_000_000
+        self.k = 0
+
+    def config(self, N, world):
+        return {"workload": self.desc, "points_per_gpu": N, "objectives": self.M,
+                "parallelism": "replicas x%d (each rank filters its own chunk)" % world,
+                "l2": "inputs (%.2f GB) larger than L2" % (8 * self.M * N / 1e9)}
+
+    def cpu_port(self, sample):
+        from oracle import oracle
+        c = np.random.default_rng(7).random((sample, self.M))
+        t0 = time.perf_counter()
+        oracle.pareto(c)
+        return time.perf_counter() - t0
+
+    def setup_device(self, N, rank):
+        import torch
+        self.N, self.rank = N, rank
+        c = np.random.default_rng(7 + rank).random((N, self.M))
+        self.c_host = torch.from_numpy(c).pin_memory()
+        self.c_dev = self.c_host.cuda()
+        self.c_stage = torch.empty_like(self.c_dev)
+        self.mask_host = torch.empty((N,), dtype=torch.uint8).pin_memory()
+        self.launches_per_step = 5 * 4 + 4
+
+    def step(self, record):
+        import torch
+        from hypermapper_b200 import compute_pareto
+        ev = None
+        if record:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
+        mask = compute_pareto.pareto_mask_device(self.c_dev)
+        if record:
+            ev[1].record()
+        return (mask, None), ev
+
+    def e2e_step(self):
+        from hypermapper_b200 import compute_pareto
+        self.c_stage.copy_(self.c_host, non_blocking=True)
+        mask = compute_pareto.pareto_mask_device(self.c_stage)
+        self.mask_host.copy_(mask, non_blocking=True)
+        return mask, None
+
+    def e2e_bytes(self, N):
+        return 8 * self.M * N, N
+
+    def roofline(self, N, kernel_ms):
+        peak, src = measured_peaks()
+        b = 8 * self.M + 1
+        ach = b * N / (kernel_ms / 1e3) / 1e9
+        return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "kernel": "hm_pareto_* (whole filter call: rounds x {resolve, filter, scan, scatter} + pass 2)",
+                "kernel_ms": kernel_ms, "algorithmic_bytes_per_point": b, "peak_source": src}
+
+
+def make_bench(name):
+    if name in ("c3", "c1", "c5rf"):
+        return RFBench(name)
+    if name in ("c2", "c5gp"):
+        return GPBench(name)
+    return ParetoBench(name)
+
+
+def cpu_threads(workload):
+    from oracle import oracle
+    n = oracle.use_all_host_threads()
+    return 1 if workload == "c4" else n
+
+
+def run_reference(args, rank):
+    """--impl reference: the CPU port alone, rank 0 only, bounded sample per step."""
     if rank != 0:
         return
-    wl, n_default, desc = make_workload(args.workload)
-    sample = args.cpu_sample or 200000
+    b = make_bench(args.workload)
+    threads = cpu_threads(args.workload)
+    sample = args.cpu_sample or b.cpu_sample_default
     times = []
     for s in range(args.warmup + args.steps):
-        rate, dt, threads = cpu_port_rate(wl, sample)
+        dt = b.cpu_port(sample)
         if s >= args.warmup:
             times.append(dt)
     ms = 1000.0 * sum(times) / len(times)
     value = sample / (ms / 1000.0)
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "impl": "reference",
-        "config": {"workload": desc, "candidates_per_step": sample, "note": "bounded sample of the same workload"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": "%d candidates per step, OpenMP C port of models.py:174-275 + numpy EI" % sample},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "metric": b.metric, "value": value, "unit": b.unit, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": b.dtype, "data": "synthetic", "impl": "reference",
+        "config": {"workload": b.desc, "units_per_step": sample, "note": "bounded sample of the same workload"},
+        "cpu_baseline": {"value": value, "unit": b.unit, "cores": threads, "kind": "port",
+                         "sample": "%d units per step; %s" % (sample, b.cpu_desc)},
+        "e2e": {"value": value, "unit": b.unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
@@ -178,49 +451,29 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank)
         return
 
     import torch
     import torch.distributed as dist
-    from hypermapper_b200 import forest, _lib
     from hypermapper_b200.distributed import allgather_topk
-    from hypermapper_b200.scoring import HostScorer
 
-    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    wl, n_default, desc = make_workload(args.workload)
-    N = args.candidates or n_default
-    k = 20
-    forests = [forest.device_forest(wl.models[o]) for o in wl.objectives]
-    acq = wl.acq_params()
-    D = wl.D_enc
-
-    # candidates of this rank: pinned host copy (for e2e) + HBM-resident copy (for value)
-    x_host = torch.empty((D, N), dtype=torch.float32).pin_memory()
-    wl.candidates_encoded(N, seed=6 + rank, out=x_host.numpy())
-    x_dev = x_host.cuda(non_blocking=False)
-    index_base = rank * N
-    L = _lib.lib()
-    ws = torch.empty((int(L.hm_topk_workspace_bytes(k)),), dtype=torch.uint8, device="cuda")
-
-    kernel_ms = []
+    b = make_bench(args.workload)
+    N = args.candidates or b.n_default
+    b.setup_device(N, rank)
     ev_pairs = []
 
-    def step(record):
-        if record:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-        out = forest.rf_eval(forests, x_dev, acq=acq)
-        if record:
-            e1.record()
-            ev_pairs.append((e0, e1))
-        tv, ti = forest.topk(out["score"], k, index_base=index_base)
-        if world > 1:
-            tv, ti = allgather_topk(tv, ti, k)
+    def full_step(record):
+        (tv, ti), ev = b.step(record)
+        if ev is not None:
+            ev_pairs.append(ev)
+        if world > 1 and ti is not None:
+            tv, ti = allgather_topk(tv, ti, b.k)
         return tv, ti
 
     def barrier():
@@ -229,7 +482,7 @@ def main():
         torch.cuda.synchronize()
 
     for _ in range(args.warmup):
-        res = step(False)
+        res = full_step(False)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -237,81 +490,60 @@ def main():
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start.record()
     for _ in range(args.steps):
-        res = step(True)
+        res = full_step(True)
     t_end.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     elapsed_ms = t_start.elapsed_time(t_end)
-    kernel_ms = [a.elapsed_time(b) for a, b in ev_pairs]
+    kernel_ms = statistics.mean(a.elapsed_time(c) for a, c in ev_pairs)
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(t.item())
-    ms_per_step = elapsed_ms / args.steps
+    ms_per_step = float(t.item()) / args.steps
     value = world * N / (ms_per_step / 1000.0)
-    launches_per_step = 3 + (2 if world > 1 else 0)    # forest kernel + top-k stage 1/2 (+ merge stage 1/2)
+    launches = b.launches_per_step + (2 if (world > 1 and b.k) else 0)
 
-    # e2e: host buffers through the C-ABI host entry point
     e2e = None
     if not args.no_e2e:
-        scorer = HostScorer(D, chunk=1 << 21)
-        scores_host = torch.empty((N,), dtype=torch.float64).pin_memory()
-        for _ in range(max(1, min(args.warmup, 2))):
-            scorer.score(forests, x_host, acq, k=k, scores_out=scores_host)
+        for _ in range(2):
+            b.e2e_step()
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            _, tv_h, ti_h = scorer.score(forests, x_host, acq, k=k, scores_out=scores_host)
-            if world > 1:
-                gv, gi = allgather_topk(torch.from_numpy(tv_h).cuda(), torch.from_numpy(ti_h + index_base).cuda(), k)
-                gi.cpu()
+            tv, ti = b.e2e_step()
+            if world > 1 and ti is not None:
+                tv, ti = allgather_topk(tv, ti, b.k)
+                ti.cpu()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         td = torch.tensor([dt], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(td, op=dist.ReduceOp.MAX)
         dt = float(td.item())
-        e2e = {"value": world * N * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": 4 * D * N * world,
-               "d2h_bytes_per_step": (8 * N + 16 * k) * world, "ms_per_step": 1000.0 * dt / args.steps,
-               "api": "hm_rf_score_host (C-ABI, pinned host candidates, 2M-candidate double-buffered chunks)"}
-        # cross-check: same top-k as the HBM-resident path
-        if world == 1:
-            assert np.array_equal(ti_h, res[1].cpu().numpy()), "e2e and device-resident top-k differ"
+        h2d, d2h = b.e2e_bytes(N)
+        e2e = {"value": world * N * args.steps / dt, "unit": b.unit, "h2d_bytes_per_step": h2d * world,
+               "d2h_bytes_per_step": d2h * world, "ms_per_step": 1000.0 * dt / args.steps, "api": b.e2e_api}
+        if world == 1 and ti is not None:
+            assert torch.equal(ti.cpu(), res[1].cpu()), "e2e and device-resident top-k differ"
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    peak, peak_src = measured_hbm_peak()
-    kms = statistics.mean(kernel_ms)
-    alg_bytes = (4 * D + 8) * N
-    achieved = alg_bytes / (kms / 1000.0) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "hm_forest_kernel<false>", "kernel_ms": kms,
-                "algorithmic_bytes_per_eval": 4 * D + 8, "peak_source": peak_src,
-                "share_of_step": kms / ms_per_step,
-                "note": "large forests are shared-memory/issue bound, not HBM bound (SURVEY 8(d)); see DESIGN.md, profiles/"}
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "impl": "b200",
-        "config": {"workload": desc, "candidates_per_gpu": N, "D_enc": D, "trees": wl.n_trees,
-                   "objectives": len(wl.objectives), "k": k, "parallelism": "candidate-sharded x%d" % world,
-                   "l2": "inputs (%.2f GB per GPU) larger than L2, no flush needed" % (4 * D * N / 1e9)},
-        "roofline": roofline,
-        "clocks": clocks,
-        "gpu_launches": launches_per_step * args.steps,
-    }
-    if e2e is not None:
-        line["e2e"] = e2e
-    if world == 1 and not args.no_cpu_baseline:
-        sample = args.cpu_sample or 200000
-        rate, dt, threads = cpu_port_rate(wl, sample)
-        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": "%d candidates of the same pool (%.1f s), OpenMP C port of models.py:174-275 "
-                                          "+ numpy EI + top-20" % (sample, dt)}
-    print(json.dumps(line), flush=True)
+    if rank == 0:
+        roof = b.roofline(N, kernel_ms)
+        roof["share_of_step"] = kernel_ms / ms_per_step
+        line = {
+            "metric": b.metric, "value": value, "unit": b.unit, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": b.dtype, "data": "synthetic", "impl": "b200", "config": b.config(N, world),
+            "roofline": roof, "clocks": clocks, "gpu_launches": launches * args.steps,
+        }
+        if e2e is not None:
+            line["e2e"] = e2e
+        if world == 1 and not args.no_cpu_baseline:
+            threads = cpu_threads(args.workload)
+            sample = args.cpu_sample or b.cpu_sample_default
+            dt = b.cpu_port(sample)
+            line["cpu_baseline"] = {"value": sample / dt, "unit": b.unit, "cores": threads, "kind": "port",
+                                    "sample": "%d units of the same workload (%.1f s); %s" % (sample, dt, b.cpu_desc)}
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

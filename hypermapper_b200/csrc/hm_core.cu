@@ -42,3 +42,41 @@ extern "C" int hm_device_sm_count(void) {
 }
 
 extern "C" int hm_version(void) { return 100; }
+
+// ---- FP64 pipe probe: measures the DFMA rate the same way the driver measured the HBM / bf16 peaks (a burst of the
+// plain operation), so K2's roofline has a measured denominator.  Not on any data path.
+__global__ void __launch_bounds__(256) hm_fp64_probe_kernel(double* out, int iters, double seed) {
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+// returns measured FP64 TFLOP/s (2 flops per DFMA), or a negative error code
+extern "C" double hm_fp64_peak_tflops(void) {
+    const int grid = hm_num_sms() * 8, block = 256, iters = 1 << 14;
+    double* d = nullptr;
+    if (cudaMalloc((void**)&d, (size_t)grid * block * sizeof(double)) != cudaSuccess) return -1.0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0);
+        hm_fp64_probe_kernel<<<grid, block>>>(d, iters, 1.0 + rep);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { best = -1.f; break; }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    if (best <= 0.f) return -1.0;
+    const double flops = 2.0 * 8.0 * (double)iters * (double)grid * (double)block;
+    return flops / (best * 1e-3) / 1e12;
+}

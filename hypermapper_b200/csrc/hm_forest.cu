@@ -15,7 +15,7 @@
 //               trees are re-laid out breadth-first so the two children are adjacent and the hot top levels
 //               share a few shared-memory lines.
 //   groups    : descriptor per group (offset/bytes/first tree/#trees)
-//   leaf_tab  : 4 fp64 per leaf  [q = m/T, s = m**2/T, u = v/T, value]  (32 B -> one sector per leaf visit)
+//   leaf_tab  : 4 fp64 per leaf  [q = m/T, s = m**2/T, u = v/T, value]  (32 B -> one sector, one 256-bit load per leaf visit)
 //   leaf_node : sklearn node id per leaf (for the apply output)
 //
 // Kernel: one thread = one candidate, trees visited in tree order so the fp64 accumulation order is the
@@ -286,13 +286,15 @@ __device__ __forceinline__ void hm_walk_group(const uint32_t* __restrict__ roots
             const uint32_t nxt = (nd.y & HM_LEFT_MASK) + ((xv <= __uint_as_float(nd.x)) ? 0u : 1u);
             nd = nodes[nxt];
         }
-        const double2* lt = reinterpret_cast<const double2*>(leaf_tab) + 2 * (size_t)nd.x;
-        const double2 qs = __ldg(lt);
-        const double2 uv = __ldg(lt + 1);
-        acc.q = hm_add(acc.q, qs.x);
-        acc.s = hm_add(acc.s, qs.y);
-        acc.u = hm_add(acc.u, uv.x);
-        acc.v = hm_add(acc.v, uv.y);
+        // one 256-bit load of the 32-byte leaf record (LDG.E.256): one L1 wavefront pass instead of two
+        double lq, ls, lu, lv;
+        asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+                     : "=d"(lq), "=d"(ls), "=d"(lu), "=d"(lv)
+                     : "l"(leaf_tab + 4 * (size_t)nd.x));
+        acc.q = hm_add(acc.q, lq);
+        acc.s = hm_add(acc.s, ls);
+        acc.u = hm_add(acc.u, lu);
+        acc.v = hm_add(acc.v, lv);
         if (APPLY) {
             if (valid && leaf_out) leaf_out[(size_t)(first_tree + t) * (size_t)N + (size_t)i] = __ldg(leaf_node + nd.x);
         }

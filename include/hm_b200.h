@@ -38,6 +38,8 @@ const char* hm_last_error(void);
 /* library / device probe: returns the SM count of the current device (148 on B200) or <0 */
 int hm_device_sm_count(void);
 int hm_version(void);
+/* burst FP64 DFMA rate of the current device in TFLOP/s (roofline denominator for K2; not on a data path) */
+double hm_fp64_peak_tflops(void);
 
 /* ------------------------------------------------------------------------------------------
  * K1  forest traversal + per-leaf table reduction

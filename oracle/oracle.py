@@ -36,6 +36,17 @@ def num_threads():
     return int(lib().oracle_num_threads())
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU baseline is meant to use every host core"""
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    lib().oracle_set_num_threads(ctypes.c_int(n))
+    return num_threads()
+
+
 def _p(a):
     return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
 
