@@ -11,14 +11,17 @@
 // 1e6 when the reference fixes the noise to 0 (models.py:451-453), so tf32 / 3xtf32 cannot meet the 1e-5 relative
 // tolerance (DESIGN.md has the measured error); tcgen05 has no f64 kind, so the contraction runs on the FP64 pipe.
 //
-// Structure (v2): a SIMT fp64 "GEMM" micro-kernel used twice per candidate tile.  A warp owns a 32 x 32 output tile
-// (32 candidates x 32 training points / rows of L^-1); lanes are an 8 x 4 grid, each thread a 4 x 8 register tile
-// (32 fp64 accumulators), so one k-step is 6 shared-memory wavefronts for 32 DFMA warp-instructions.
-//   phase A  dot[i][k] = sum_d xs[d][i] * Xs[k][d]  ->  r^2  ->  Matern/RBF  ->  Kt[k][i] (shared memory), partial mu
-//   phase B  T[i][m]   = sum_{k<=m} Kt[k][i] * Linv[m][k]   per 32-row panel of L^-1;  ||T||^2 accumulated per candidate.
-//            L^-1 is pre-tiled on the host into per-panel contiguous [k][32] slabs, streamed by each warp through its
-//            own ring of shared-memory stages with cp.async.bulk (TMA 1-D) + mbarrier, so the DFMA stream never waits
-//            on L2.  Panels (cost ~ r+1) are dealt boustrophedon to the warp slots so the triangle balances.
+// Structure (v3): both contractions run on the FP64 tensor path (mma.sync m8n8k4 f64 -> DMMA.8x8x4; same peak as DFMA
+// on B200 but 8x fewer instructions and 3x fewer operand loads, so the FP64 pipe is the only busy unit).
+//   phase A  dot[i][k] = sum_d xs[d][i] * Xs[k][d]  (DMMA)  ->  r^2  ->  Matern/RBF in the accumulator registers ->
+//            Kt (shared memory, stored directly in the A-fragment order phase B reads), partial mu.
+//   phase B  T[i][m]   = sum_{k<=m} Kx[i][k] * Linv[m][k]   per 32-row panel of L^-1; a warp owns 32 candidates x 32 rows
+//            (16 accumulator tiles); ||T||^2 accumulated per candidate.  L^-1 is pre-tiled on the host into per-panel
+//            contiguous B-fragment order, streamed by each warp through its own ring of shared-memory stages with
+//            cp.async.bulk (TMA 1-D) + mbarrier.  Panels (cost ~ r+1) are dealt boustrophedon to the warp slots so the
+//            triangle balances; the all-zero tiles above the diagonal are skipped.
+// Fragment order (m8n8k4, lane l, gid = l >> 2, tig = l & 3):  A[i = gid][k = tig],  B[k = tig][n = gid],
+//            C[i = gid][n = 2 tig + {0,1}].
 #include <math.h>
 #include <string.h>
 #include <algorithm>
@@ -39,18 +42,18 @@ struct hm_gp {
     int G, stage_k, n_stages, aliased;
     size_t smem_bytes;
     double sf2, noise, y_mean, y_std, y_std2;
-    double* d_XsB;     // [R][D][32]  training inputs / lengthscale, blocked by 32 points (zero padded)
+    double* d_XsF;     // [n_pad/8][Dp/4][32]  training inputs / lengthscale in B-fragment order (zero padded)
     double* d_b2;      // [n_pad]     |Xs_j|^2
     double* d_alpha;   // [n_pad]     (zero padded)
-    double* d_Lp;      // panels r = 0..R-1, panel r = [(r+1)*32 k][32 rows]: Lp[k][p] = Linv[32 r + p][k]
+    double* d_LpF;     // panels r = 0..R-1, panel r = [(r+1)*8 k4][4 nb][32 lanes] in B-fragment order
     double* d_ls;      // [D]
 };
 
 struct HmGpArgs {
-    const double* XsB;
+    const double* XsF;
     const double* b2;
     const double* alpha;
-    const double* Lp;
+    const double* LpF;
     const double* ls;
     const double* X;     // [D][N] column-major candidates
     double* mean;
@@ -64,28 +67,31 @@ struct HmGpArgs {
 // shared-memory plan: candidate groups per CTA (G), ring geometry.  Returns 0 if nothing fits.
 static int hm_gp_plan(int n_pad, int D, int* G_out, int* stage_k_out, int* n_stages_out, int* aliased_out,
                       size_t* smem_out) {
+    const int Dp = (D + 3) & ~3;
     for (int G = 8; G >= 1; G >>= 1) {
         const size_t BM = 32 * (size_t)G;
         const size_t fixed = HM_GP_SMEM_HEADER + 8 * ((size_t)n_pad * BM      // Kt
                                                        + BM                     // a2s
                                                        + HM_GP_WARPS * 32       // red
                                                        + (size_t)(n_pad / HM_GP_BLK) * BM);   // mur
-        const size_t xs = 8 * (size_t)D * BM;
-        // first choice: xs and the ring side by side (the ring can prefetch during phase A), 8 k-steps per stage
+        const size_t xs = 8 * (size_t)Dp * BM;
+        // ring geometries in order of preference: (k-steps per stage, stages); 16-step stages halve the per-chunk
+        // bookkeeping, deeper rings only help when the stage is short.  First with xs and the ring side by side
+        // (the ring prefetches during phase A), then aliased (large n).
+        static const int geom[][2] = {{16, 3}, {16, 2}, {8, 4}, {8, 3}, {4, 4}, {4, 3}, {8, 2}, {4, 2}};
         for (int aliased = 0; aliased <= 1; ++aliased) {
-            for (int stage_k = 8; stage_k >= 4; stage_k >>= 1) {
-                const size_t stage = (size_t)HM_GP_WARPS * stage_k * 32 * 8;
-                for (int ns = HM_GP_MAX_STAGES; ns >= (aliased ? 2 : 3); --ns) {
-                    const size_t ring = stage * ns;
-                    const size_t total = fixed + (aliased ? std::max(xs, ring) : xs + ring);
-                    if (total <= HM_GP_SMEM_LIMIT) {
-                        *G_out = G;
-                        *stage_k_out = stage_k;
-                        *n_stages_out = ns;
-                        *aliased_out = aliased;
-                        *smem_out = total;
-                        return 1;
-                    }
+            for (const auto& gm : geom) {
+                const int stage_k = gm[0], ns = gm[1];
+                if (!aliased && ns < 3 && stage_k < 16) continue;
+                const size_t ring = (size_t)HM_GP_WARPS * stage_k * 32 * 8 * ns;
+                const size_t total = fixed + (aliased ? std::max(xs, ring) : xs + ring);
+                if (total <= HM_GP_SMEM_LIMIT) {
+                    *G_out = G;
+                    *stage_k_out = stage_k;
+                    *n_stages_out = ns;
+                    *aliased_out = aliased;
+                    *smem_out = total;
+                    return 1;
                 }
             }
         }
@@ -123,20 +129,24 @@ extern "C" int hm_gp_create(int n, int D, const double* Xs, const double* ls, co
         return HM_E_UNSUPPORTED;
     }
     const int R = n_pad / HM_GP_BLK;
-    std::vector<double> hXs((size_t)n_pad * D, 0.0), hb2(n_pad, 0.0), ha(n_pad, 0.0);
-    std::vector<double> hLp((size_t)1024 * R * (R + 1) / 2, 0.0);
+    const int Dp = (D + 3) & ~3, D4 = Dp / 4;
+    std::vector<double> hXs((size_t)n_pad * Dp, 0.0), hb2(n_pad, 0.0), ha(n_pad, 0.0);
+    std::vector<double> hLp((size_t)512 * R * (R + 1), 0.0);
     for (int j = 0; j < n; ++j) {
         double s = 0.0;
-        const int kb = j / HM_GP_BLK, p = j % HM_GP_BLK;
+        const int kb8 = j / 8, gid = j % 8;
         for (int d = 0; d < D; ++d) {
-            hXs[((size_t)kb * D + d) * HM_GP_BLK + p] = Xs[(size_t)j * D + d];
+            // B fragment of the dot product: B[k = d % 4][n = training point % 8]
+            hXs[((size_t)kb8 * D4 + d / 4) * 32 + gid * 4 + (d & 3)] = Xs[(size_t)j * D + d];
             s += Xs[(size_t)j * D + d] * Xs[(size_t)j * D + d];
         }
         hb2[j] = s;
         ha[j] = alpha[j];
-        // row m = j of L^-1 lives in panel r = kb at column p
-        double* panel = hLp.data() + (size_t)1024 * kb * (kb + 1) / 2;
-        for (int k = 0; k <= j; ++k) panel[(size_t)k * HM_GP_BLK + p] = Linv[(size_t)j * n + k];
+        // row m = j of L^-1 lives in panel r = j / 32, column block nb = (j % 32) / 8, fragment column gid = j % 8
+        const int r = j / HM_GP_BLK, nb = (j % HM_GP_BLK) / 8;
+        double* panel = hLp.data() + (size_t)512 * r * (r + 1);
+        for (int k = 0; k <= j; ++k)
+            panel[((size_t)(k / 4) * 4 + nb) * 32 + gid * 4 + (k & 3)] = Linv[(size_t)j * n + k];
     }
     cudaError_t e;
 #define HM_G_TRY(x)                                             \
@@ -145,15 +155,15 @@ extern "C" int hm_gp_create(int n, int D, const double* Xs, const double* ls, co
         hm_gp_destroy(g);                                       \
         return (int)e;                                          \
     }
-    HM_G_TRY(cudaMalloc((void**)&g->d_XsB, hXs.size() * 8));
+    HM_G_TRY(cudaMalloc((void**)&g->d_XsF, hXs.size() * 8));
     HM_G_TRY(cudaMalloc((void**)&g->d_b2, hb2.size() * 8));
     HM_G_TRY(cudaMalloc((void**)&g->d_alpha, ha.size() * 8));
-    HM_G_TRY(cudaMalloc((void**)&g->d_Lp, hLp.size() * 8));
+    HM_G_TRY(cudaMalloc((void**)&g->d_LpF, hLp.size() * 8));
     HM_G_TRY(cudaMalloc((void**)&g->d_ls, (size_t)D * 8));
-    HM_G_TRY(cudaMemcpy(g->d_XsB, hXs.data(), hXs.size() * 8, cudaMemcpyHostToDevice));
+    HM_G_TRY(cudaMemcpy(g->d_XsF, hXs.data(), hXs.size() * 8, cudaMemcpyHostToDevice));
     HM_G_TRY(cudaMemcpy(g->d_b2, hb2.data(), hb2.size() * 8, cudaMemcpyHostToDevice));
     HM_G_TRY(cudaMemcpy(g->d_alpha, ha.data(), ha.size() * 8, cudaMemcpyHostToDevice));
-    HM_G_TRY(cudaMemcpy(g->d_Lp, hLp.data(), hLp.size() * 8, cudaMemcpyHostToDevice));
+    HM_G_TRY(cudaMemcpy(g->d_LpF, hLp.data(), hLp.size() * 8, cudaMemcpyHostToDevice));
     HM_G_TRY(cudaMemcpy(g->d_ls, ls, (size_t)D * 8, cudaMemcpyHostToDevice));
 #undef HM_G_TRY
     *out = g;
@@ -162,36 +172,85 @@ extern "C" int hm_gp_create(int n, int D, const double* Xs, const double* ls, co
 
 extern "C" void hm_gp_destroy(hm_gp_t* g) {
     if (!g) return;
-    cudaFree(g->d_XsB);
+    cudaFree(g->d_XsF);
     cudaFree(g->d_b2);
     cudaFree(g->d_alpha);
-    cudaFree(g->d_Lp);
+    cudaFree(g->d_LpF);
     cudaFree(g->d_ls);
     delete g;
 }
 
-// stationary kernel value from the squared scaled distance (GPy Matern52.K_of_r / RBF.K_of_r)
-__device__ __forceinline__ double hm_gp_k_of_r2(double r2, int kind, double sf2) {
-    const double SQRT5 = 2.23606797749979;     // np.sqrt(5.)
-    if (kind == 0) {
-        const double r = sqrt(r2);
-        const double poly = 1.0 + SQRT5 * r + (5.0 / 3) * (r * r);
-        return sf2 * poly * exp(-SQRT5 * r);
-    }
-    return sf2 * exp(-0.5 * r2);
+// ---- lean fp64 elementary functions for the covariance transform ------------------------------------------------
+// The CUDA library sqrt()/exp() carry inline slow paths (denormals, infinities, huge arguments) and cost ~160 SASS
+// instructions per covariance entry; here the argument ranges are known (r2 >= 0, exponent argument <= 0), so
+// branch-free versions with <= 1-2 ulp error do the same job in ~40.
+// sqrt(x) for x >= 1e-30 (callers clamp): fp32 rsqrt seed + two coupled Newton steps (Goldschmidt form) + one residual
+// correction.
+__device__ __forceinline__ double hm_sqrt_pos(double x) {
+    float yf;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(yf) : "f"((float)x));
+    const double y = (double)yf;                     // ~2^-22
+    double g = __dmul_rn(x, y);                      // ~ sqrt(x)
+    double h = __dmul_rn(0.5, y);                    // ~ 1 / (2 sqrt(x))
+    double e = fma(-g, h, 0.5);
+    g = fma(g, e, g);
+    h = fma(h, e, h);                                // ~2^-43
+    e = fma(-g, h, 0.5);
+    g = fma(g, e, g);                                // rounding-limited
+    const double d = fma(-g, g, x);                  // exact residual
+    return fma(d, h, g);
+}
+// exp(x) for -708 <= x <= 0 (callers clamp): n = rint(x log2 e), f = x - n ln2 (two-constant Cody-Waite), degree-13
+// Taylor polynomial on |f| <= ln2/2 (truncation 4e-18), scaled by 2^n through the exponent field (result stays normal).
+__device__ __forceinline__ double hm_exp_neg(double x) {
+    const double MAGIC = 6755399441055744.0;         // 1.5 * 2^52: the low mantissa word of (t + MAGIC) is rint(t)
+    const double t = fma(x, 1.4426950408889634, MAGIC);
+    const int n = __double2loint(t);
+    const double nf = __dsub_rn(t, MAGIC);
+    double f = fma(nf, -6.93147180559945290e-01, x);
+    f = fma(nf, -2.31904681384629956e-17, f);
+    double p = 1.6059043836821613e-10;               // 1/13!
+    p = fma(p, f, 2.08767569878681e-09);             // 1/12!
+    p = fma(p, f, 2.505210838544172e-08);            // 1/11!
+    p = fma(p, f, 2.755731922398589e-07);            // 1/10!
+    p = fma(p, f, 2.7557319223985893e-06);           // 1/9!
+    p = fma(p, f, 2.48015873015873e-05);             // 1/8!
+    p = fma(p, f, 1.984126984126984e-04);            // 1/7!
+    p = fma(p, f, 1.388888888888889e-03);            // 1/6!
+    p = fma(p, f, 8.333333333333333e-03);            // 1/5!
+    p = fma(p, f, 4.1666666666666664e-02);           // 1/4!
+    p = fma(p, f, 1.6666666666666666e-01);           // 1/3!
+    p = fma(p, f, 0.5);
+    p = fma(p, f, 1.0);
+    p = fma(p, f, 1.0);
+    return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
 }
 
-// one k-step of the 32 x 32 warp tile: acc[c][m] += a[c] * b[m]   (4 candidates x 8 columns per thread)
-__device__ __forceinline__ void hm_gp_mac(double (&acc)[4][8], const double2& a01, const double2& a23,
-                                          const double2 (&b)[4]) {
-    const double av[4] = {a01.x, a01.y, a23.x, a23.y};
-#pragma unroll
-    for (int c = 0; c < 4; ++c)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            acc[c][2 * j] = fma(av[c], b[j].x, acc[c][2 * j]);
-            acc[c][2 * j + 1] = fma(av[c], b[j].y, acc[c][2 * j + 1]);
-        }
+// min(x, cap) for x >= 0 and a cap whose low word is zero: non-negative doubles order like their high words
+__device__ __forceinline__ double hm_cap_pos(double x, double cap) {
+    return __hiloint2double(min(__double2hiint(x), __double2hiint(cap)), __double2loint(x));
+}
+
+// stationary kernel value from the squared scaled distance (GPy Matern52.K_of_r / RBF.K_of_r).  r2 >= 0 and finite:
+// candidates with NaN / inf coordinates are patched in the epilogue.
+template <int KIND>
+__device__ __forceinline__ double hm_gp_k_of_r2(double r2, double sf2) {
+    const double SQRT5 = 2.23606797749979;     // np.sqrt(5.)
+    if (KIND == 0) {
+        // r2 < 1e-30 is treated as r = 1e-15: k'(0) = 0, so the value differs from k(0) by < 1e-29 relative;
+        // r is capped at 316 (exp(-sqrt5 * 316) ~ 1e-307: the smallest normal result, 0 for every purpose here)
+        const double r = hm_cap_pos(hm_sqrt_pos(r2 > 1e-30 ? r2 : 1e-30), 316.0);
+        const double poly = fma(r, fma(r, 5.0 / 3, SQRT5), 1.0);
+        return __dmul_rn(__dmul_rn(sf2, poly), hm_exp_neg(__dmul_rn(-SQRT5, r)));
+    }
+    return __dmul_rn(sf2, hm_exp_neg(__dmul_rn(-0.5, hm_cap_pos(r2, 1408.0))));
+}
+
+// D(8x8) += A(8x4) * B(4x8), fp64 tensor path (DMMA.8x8x4)
+__device__ __forceinline__ void hm_dmma(double (&c)[2], double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c[0]), "+d"(c[1])
+        : "d"(a), "d"(b));
 }
 
 // Panel order of warp slot `slot` (of S): rounds j = 0, 1, ...; panels dealt in descending size, direction alternating.
@@ -200,20 +259,24 @@ __device__ __forceinline__ int hm_gp_panel(int j, int slot, int S, int R) {
     return R - 1 - idx;      // < 0: no panel in this round
 }
 
+template <int KIND>
 __global__ void __launch_bounds__(HM_GP_THREADS, 1) hm_gp_kernel(const __grid_constant__ HmGpArgs a) {
     extern __shared__ __align__(128) unsigned char gp_smem[];
-    const int G = a.G, BM = 32 * G, S = HM_GP_WARPS / G, R = a.n_pad / HM_GP_BLK;
+    const int G = a.G, BM = 32 * G, NBt = 4 * G, S = HM_GP_WARPS / G, R = a.n_pad / HM_GP_BLK;
+    const int D4 = (a.D + 3) >> 2;
     uint64_t* bars = reinterpret_cast<uint64_t*>(gp_smem);
-    double* Kt = reinterpret_cast<double*>(gp_smem + HM_GP_SMEM_HEADER);   // [n_pad][BM]
-    double* a2s = Kt + (size_t)a.n_pad * BM;                                 // [BM]
+    double* KtF = reinterpret_cast<double*>(gp_smem + HM_GP_SMEM_HEADER);  // [n_pad/4][NBt][32]  A fragments of Kx
+    double* a2s = KtF + (size_t)a.n_pad * BM;                                // [BM]
     double* red = a2s + BM;                                                  // [S][BM] == [8][32] partial ||T||^2
     double* mur = red + HM_GP_WARPS * 32;                                    // [R][BM] partial mu
-    double* xs = mur + (size_t)R * BM;                                       // [D][BM] scaled candidates
+    double* xsF = mur + (size_t)R * BM;                                      // [D4][NBt][32]  A fragments of x / ls
+    const int stage_shift = (a.stage_k == 16) ? 4 : (a.stage_k == 8) ? 3 : 2;
     const size_t stage_dbl = (size_t)a.stage_k * 32;
-    double* ring_all = a.aliased ? xs : xs + (size_t)a.D * BM;               // [8 warps][n_stages][stage_k][32]
+    const uint32_t stage_bytes = (uint32_t)(stage_dbl * 8);
+    double* ring_all = a.aliased ? xsF : xsF + (size_t)D4 * 4 * BM;          // [8 warps][n_stages][stage_k/4][4][32]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int cg = lane & 7, rg = lane >> 3;
+    const int gid = lane >> 2, tig = lane & 3;
     const long long n_tiles = (a.N + BM - 1) / BM;
     const int NS = a.n_stages;
     uint64_t* wbar = bars + warp * HM_GP_MAX_STAGES;
@@ -228,30 +291,28 @@ __global__ void __launch_bounds__(HM_GP_THREADS, 1) hm_gp_kernel(const __grid_co
     // phase-B role of this warp
     const int gB = warp % G, slot = warp / G;
     int chunks_per_tile = 0;
-    for (int j = 0;; ++j) {
+    for (int j = 0; j * S < R; ++j) {
         const int r = hm_gp_panel(j, slot, S, R);
-        if (j * S >= R) break;
-        if (r >= 0) chunks_per_tile += (r + 1) * HM_GP_BLK / a.stage_k;
+        if (r >= 0) chunks_per_tile += ((r + 1) * HM_GP_BLK) >> stage_shift;
     }
     // ring cursors (warp uniform)
     int c_stage = 0, c_par = 0, p_stage = 0;
 
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long long i0 = tile * BM;
-        // producer state for this tile
-        int p_round = 0, p_chunk = 0, p_left = chunks_per_tile;
-        auto produce = [&]() {      // lane 0 only: issue the next chunk of this warp's panel sequence
-            int r = hm_gp_panel(p_round, slot, S, R);
-            while (r < 0 || p_chunk >= (r + 1) * HM_GP_BLK / a.stage_k) {
-                ++p_round;
-                p_chunk = 0;
-                r = hm_gp_panel(p_round, slot, S, R);
+        // producer state for this tile (lane 0 only): round, chunks left in the current panel, source cursor
+        int p_round = -1, p_in_panel = 0, p_left = chunks_per_tile;
+        const double* p_src = a.LpF;
+        auto produce = [&]() {      // issue the next chunk of this warp's panel sequence into stage p_stage
+            if (p_in_panel == 0) {
+                const int r = hm_gp_panel(++p_round, slot, S, R);      // valid while p_left > 0
+                p_in_panel = ((r + 1) * HM_GP_BLK) >> stage_shift;
+                p_src = a.LpF + (size_t)512 * r * (r + 1);
             }
-            const double* src = a.Lp + (size_t)1024 * r * (r + 1) / 2 + (size_t)p_chunk * stage_dbl;
-            const uint32_t bytes = (uint32_t)(stage_dbl * 8);
-            hm_mbar_expect_tx(&wbar[p_stage], bytes);
-            hm_bulk_g2s(ring + (size_t)p_stage * stage_dbl, src, bytes, &wbar[p_stage]);
-            ++p_chunk;
+            hm_mbar_expect_tx(&wbar[p_stage], stage_bytes);
+            hm_bulk_g2s(ring + (size_t)p_stage * stage_dbl, p_src, stage_bytes, &wbar[p_stage]);
+            p_src += stage_dbl;
+            --p_in_panel;
             --p_left;
             if (++p_stage == NS) p_stage = 0;
         };
@@ -259,83 +320,72 @@ __global__ void __launch_bounds__(HM_GP_THREADS, 1) hm_gp_kernel(const __grid_co
             for (int s = 0; s < NS && p_left > 0; ++s) produce();
         }
 
-        // ---- scaled candidates + squared norms ----------------------------------------------------------
-        for (int e = tid; e < a.D * BM; e += HM_GP_THREADS) {
+        // ---- scaled candidates (A-fragment order) + squared norms ------------------------------------------
+        for (int e = tid; e < D4 * 4 * BM; e += HM_GP_THREADS) {
             const int d = e / BM, i = e - d * BM;
-            const long long gi = min(i0 + i, a.N - 1);
-            xs[e] = __ldg(a.X + (size_t)d * a.ldx + gi) / __ldg(a.ls + d);
+            double v = 0.0;
+            if (d < a.D) {
+                const long long gi = min(i0 + i, a.N - 1);
+                v = __ldg(a.X + (size_t)d * a.ldx + gi) / __ldg(a.ls + d);
+            }
+            xsF[((size_t)(d >> 2) * NBt + (i >> 3)) * 32 + (i & 7) * 4 + (d & 3)] = v;
         }
         __syncthreads();
         if (tid < BM) {
             double s = 0.0;
-            for (int d = 0; d < a.D; ++d) s = __dadd_rn(s, __dmul_rn(xs[d * BM + tid], xs[d * BM + tid]));
+            const double* col = xsF + (size_t)(tid >> 3) * 32 + (tid & 7) * 4;
+            for (int d = 0; d < a.D; ++d) {
+                const double x = col[(size_t)(d >> 2) * NBt * 32 + (d & 3)];
+                s = __dadd_rn(s, __dmul_rn(x, x));
+            }
             a2s[tid] = s;
         }
         __syncthreads();
 
-        // ---- phase A: Kt[k][i] = k(x_i, X_k), partial mu --------------------------------------------------
-        for (int u = warp; u < G * R; u += HM_GP_WARPS) {
-            const int g = u % G, kb = u / G;
-            double acc[4][8];
+        // ---- phase A: Kx[i][k] = k(x_i, X_k) into KtF, partial mu ------------------------------------------
+        // item = (8 candidates, 32 training points): 4 accumulator tiles, the transform runs in registers
+        for (int item = warp; item < NBt * R; item += HM_GP_WARPS) {
+            const int iblk = item % NBt, kb = item / NBt;
+            double c[4][2];
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
-#pragma unroll
-                for (int m = 0; m < 8; ++m) acc[c][m] = 0.0;
-            const double* xb = a.XsB + (size_t)kb * a.D * HM_GP_BLK + rg * 2;
-            const double* xa = xs + g * 32 + cg * 2;
+            for (int t = 0; t < 4; ++t) c[t][0] = c[t][1] = 0.0;
+            const double* xa = xsF + (size_t)iblk * 32 + lane;
+            const double* xb = a.XsF + (size_t)kb * 4 * D4 * 32 + lane;
 #pragma unroll 2
-            for (int d = 0; d < a.D; ++d) {
-                const double2 a01 = *reinterpret_cast<const double2*>(xa + (size_t)d * BM);
-                const double2 a23 = *reinterpret_cast<const double2*>(xa + (size_t)d * BM + 16);
-                double2 b[4];
+            for (int d4 = 0; d4 < D4; ++d4) {
+                const double av = xa[(size_t)d4 * NBt * 32];
+                double bv[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) b[j] = __ldg(reinterpret_cast<const double2*>(xb + d * HM_GP_BLK + j * 8));
-                hm_gp_mac(acc, a01, a23, b);
-            }
-            // r^2 = -2 a.b + (|b|^2 + |a|^2), clipped at 0 (GPy Stationary._unscaled_dist)
-            const double2 q01 = *reinterpret_cast<const double2*>(a2s + g * 32 + cg * 2);
-            const double2 q23 = *reinterpret_cast<const double2*>(a2s + g * 32 + cg * 2 + 16);
-            const double a2v[4] = {q01.x, q01.y, q23.x, q23.y};
+                for (int t = 0; t < 4; ++t) bv[t] = __ldg(xb + ((size_t)t * D4 + d4) * 32);
 #pragma unroll
-            for (int m = 0; m < 8; ++m) {
-                const int k = kb * HM_GP_BLK + (m >> 1) * 8 + rg * 2 + (m & 1);
-                const double b2k = __ldg(a.b2 + k);
-                double r2[4];
+                for (int t = 0; t < 4; ++t) hm_dmma(c[t], av, bv[t]);
+            }
+            // thread holds dot[i = iblk*8 + gid][k = kb*32 + t*8 + 2 tig + e]
+            const double a2 = a2s[iblk * 8 + gid];
+            double mu = 0.0;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const double v = __dadd_rn(__dmul_rn(-2.0, acc[c][m]), __dadd_rn(b2k, a2v[c]));
-                    r2[c] = v > 0.0 ? v : 0.0;
-                }
-                double* row = Kt + (size_t)k * BM + g * 32 + cg * 2;
-                *reinterpret_cast<double2*>(row) = make_double2(r2[0], r2[1]);
-                *reinterpret_cast<double2*>(row + 16) = make_double2(r2[2], r2[3]);
+            for (int t = 0; t < 4; ++t) {
+                const int k = kb * HM_GP_BLK + t * 8 + 2 * tig;
+                const double2 b2k = __ldg(reinterpret_cast<const double2*>(a.b2 + k));
+                const double2 alk = __ldg(reinterpret_cast<const double2*>(a.alpha + k));     // zero in the padding
+                // r^2 = -2 a.b + (|b|^2 + |a|^2), clipped at 0 (GPy Stationary._unscaled_dist)
+                double r0 = __dadd_rn(__dmul_rn(-2.0, c[t][0]), __dadd_rn(b2k.x, a2));
+                double r1 = __dadd_rn(__dmul_rn(-2.0, c[t][1]), __dadd_rn(b2k.y, a2));
+                r0 = r0 > 0.0 ? r0 : 0.0;
+                r1 = r1 > 0.0 ? r1 : 0.0;
+                double v0 = hm_gp_k_of_r2<KIND>(r0, a.sf2);
+                double v1 = hm_gp_k_of_r2<KIND>(r1, a.sf2);
+                if (k >= a.n) v0 = 0.0;                                 // padding rows contribute nothing
+                if (k + 1 >= a.n) v1 = 0.0;
+                mu = fma(v0, alk.x, mu);
+                mu = fma(v1, alk.y, mu);
+                // A-fragment order for phase B: k4 = k / 4, lane' = gid * 4 + k % 4
+                double* dst = KtF + ((size_t)((kb * 8 + t * 2 + (tig >> 1)) * NBt + iblk)) * 32 + gid * 4 + 2 * (tig & 1);
+                *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
             }
-            __syncwarp();
-            // transform pass over the 32 x 32 block this warp just wrote: lane = (candidate pair, k parity)
-            {
-                const int p = lane & 15, h = lane >> 4;
-                double mu0 = 0.0, mu1 = 0.0;
-#pragma unroll 1
-                for (int t = 0; t < 16; ++t) {
-                    const int k = kb * HM_GP_BLK + h + 2 * t;
-                    double2* cell = reinterpret_cast<double2*>(Kt + (size_t)k * BM + g * 32 + p * 2);
-                    double2 v = *cell;
-                    if (k < a.n) {
-                        v.x = hm_gp_k_of_r2(v.x, a.kind, a.sf2);
-                        v.y = hm_gp_k_of_r2(v.y, a.kind, a.sf2);
-                        const double al = __ldg(a.alpha + k);
-                        mu0 = fma(v.x, al, mu0);
-                        mu1 = fma(v.y, al, mu1);
-                    } else {
-                        v.x = 0.0;
-                        v.y = 0.0;
-                    }
-                    *cell = v;
-                }
-                mu0 += __shfl_xor_sync(0xffffffffu, mu0, 16);
-                mu1 += __shfl_xor_sync(0xffffffffu, mu1, 16);
-                if (h == 0) *reinterpret_cast<double2*>(mur + (size_t)kb * BM + g * 32 + p * 2) = make_double2(mu0, mu1);
-            }
+            mu += __shfl_xor_sync(0xffffffffu, mu, 1);
+            mu += __shfl_xor_sync(0xffffffffu, mu, 2);
+            if (tig == 0) mur[(size_t)kb * BM + iblk * 8 + gid] = mu;
         }
         if (a.aliased) hm_fence_proxy_async();
         __syncthreads();
@@ -345,31 +395,37 @@ __global__ void __launch_bounds__(HM_GP_THREADS, 1) hm_gp_kernel(const __grid_co
 
         // ---- phase B: T = Kx . Linv^T panel by panel, ||T||^2 per candidate --------------------------------
         double ss[4] = {0.0, 0.0, 0.0, 0.0};
-        const double* ka = Kt + gB * 32 + cg * 2;
+        const double* ka = KtF + (size_t)gB * 4 * 32 + lane;
+        const int k4_per_chunk = a.stage_k >> 2;
         for (int j = 0; j * S < R; ++j) {
             const int r = hm_gp_panel(j, slot, S, R);
             if (r < 0) continue;
-            double acc[4][8];
+            double c[4][4][2];
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
+            for (int ib = 0; ib < 4; ++ib)
 #pragma unroll
-                for (int m = 0; m < 8; ++m) acc[c][m] = 0.0;
-            const int nch = (r + 1) * HM_GP_BLK / a.stage_k;
+                for (int nb = 0; nb < 4; ++nb) c[ib][nb][0] = c[ib][nb][1] = 0.0;
+            const int nch = ((r + 1) * HM_GP_BLK) >> stage_shift;
+            int k4 = 0;
             for (int ch = 0; ch < nch; ++ch) {
                 hm_mbar_wait(&wbar[c_stage], (uint32_t)c_par);
-                const double* sb = ring + (size_t)c_stage * stage_dbl + rg * 2;
-                const double* kr = ka + (size_t)ch * a.stage_k * BM;
-                for (int k4 = 0; k4 < a.stage_k; k4 += 4) {
+                const double* sb = ring + (size_t)c_stage * stage_dbl + lane;
+                for (int q = 0; q < k4_per_chunk; ++q, ++k4) {
+                    // tiles strictly above the diagonal of the last block are all zero: rows nb*8.. < k
+                    const int k4l = k4 - 8 * r;
+                    const int nb0 = (k4l >= 2) ? (k4l >> 1) : 0;
+                    double av[4], bv[4];
+                    const double* kr = ka + (size_t)k4 * NBt * 32;
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        const double* krow = kr + (size_t)(k4 + kk) * BM;
-                        const double2 a01 = *reinterpret_cast<const double2*>(krow);
-                        const double2 a23 = *reinterpret_cast<const double2*>(krow + 16);
-                        double2 b[4];
+                    for (int ib = 0; ib < 4; ++ib) av[ib] = kr[ib * 32];
 #pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            b[q] = *reinterpret_cast<const double2*>(sb + (k4 + kk) * 32 + q * 8);
-                        hm_gp_mac(acc, a01, a23, b);
+                    for (int nb = 0; nb < 4; ++nb) bv[nb] = sb[(q * 4 + nb) * 32];
+#pragma unroll
+                    for (int nb = 0; nb < 4; ++nb) {
+                        if (nb >= nb0) {
+#pragma unroll
+                            for (int ib = 0; ib < 4; ++ib) hm_dmma(c[ib][nb], av[ib], bv[nb]);
+                        }
                     }
                 }
                 if (++c_stage == NS) {
@@ -377,25 +433,26 @@ __global__ void __launch_bounds__(HM_GP_THREADS, 1) hm_gp_kernel(const __grid_co
                     c_par ^= 1;
                 }
                 __syncwarp();
-                if (lane == 0 && p_left > 0) {
-                    hm_fence_proxy_async();
-                    produce();
-                }
+                // every lane's reads of this stage have completed (their DMMAs were issued above), so the
+                // stage can be handed back to the TMA engine without a cross-proxy fence
+                if (lane == 0 && p_left > 0) produce();
             }
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
+            for (int ib = 0; ib < 4; ++ib)
 #pragma unroll
-                for (int m = 0; m < 8; ++m) ss[c] = fma(acc[c][m], acc[c][m], ss[c]);
+                for (int nb = 0; nb < 4; ++nb) {
+                    ss[ib] = fma(c[ib][nb][0], c[ib][nb][0], ss[ib]);
+                    ss[ib] = fma(c[ib][nb][1], c[ib][nb][1], ss[ib]);
+                }
         }
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            ss[c] += __shfl_xor_sync(0xffffffffu, ss[c], 8);
-            ss[c] += __shfl_xor_sync(0xffffffffu, ss[c], 16);
+        for (int ib = 0; ib < 4; ++ib) {
+            ss[ib] += __shfl_xor_sync(0xffffffffu, ss[ib], 1);
+            ss[ib] += __shfl_xor_sync(0xffffffffu, ss[ib], 2);
         }
-        if (rg == 0) {
-            double* rr = red + slot * BM + gB * 32 + cg * 2;
-            *reinterpret_cast<double2*>(rr) = make_double2(ss[0], ss[1]);
-            *reinterpret_cast<double2*>(rr + 16) = make_double2(ss[2], ss[3]);
+        if (tig == 0) {
+#pragma unroll
+            for (int ib = 0; ib < 4; ++ib) red[slot * BM + gB * 32 + ib * 8 + gid] = ss[ib];
         }
         __syncthreads();
         // ---- epilogue -----------------------------------------------------------------------------------
@@ -410,8 +467,10 @@ __global__ void __launch_bounds__(HM_GP_THREADS, 1) hm_gp_kernel(const __grid_co
             const double mean = mu * a.y_std + a.y_mean;
             double var = v * a.y_std2;
             if (var < 1e-11) var = 1e-11;                   // models.py:1018
-            a.mean[i0 + tid] = mean;
-            a.var[i0 + tid] = var;
+            const double a2 = a2s[tid];
+            const bool bad = !(a2 < 1.7976931348623157e308);   // NaN / inf coordinates: GPy's K is NaN, so are mean and var
+            a.mean[i0 + tid] = bad ? a2 - a2 : mean;
+            a.var[i0 + tid] = bad ? a2 - a2 : var;
         }
         __syncthreads();
     }
@@ -424,10 +483,10 @@ extern "C" int hm_gp_mean_var(const hm_gp_t* g, const double* Xcm, int64_t ldx, 
     if (N == 0) return 0;
     HM_REQUIRE(Xcm && mean_out && var_out, "Xcm/mean/var");
     HmGpArgs a;
-    a.XsB = g->d_XsB;
+    a.XsF = g->d_XsF;
     a.b2 = g->d_b2;
     a.alpha = g->d_alpha;
-    a.Lp = g->d_Lp;
+    a.LpF = g->d_LpF;
     a.ls = g->d_ls;
     a.X = Xcm;
     a.mean = mean_out;
@@ -451,8 +510,13 @@ extern "C" int hm_gp_mean_var(const hm_gp_t* g, const double* Xcm, int64_t ldx, 
     const int BM = 32 * g->G;
     const long long n_tiles = (N + BM - 1) / BM;
     const int grid = (int)std::min<long long>(n_tiles, hm_num_sms());
-    HM_CUDA_TRY(cudaFuncSetAttribute(hm_gp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem_bytes));
-    hm_gp_kernel<<<grid, HM_GP_THREADS, g->smem_bytes, st>>>(a);
+    if (g->kind == 0) {
+        HM_CUDA_TRY(cudaFuncSetAttribute(hm_gp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem_bytes));
+        hm_gp_kernel<0><<<grid, HM_GP_THREADS, g->smem_bytes, st>>>(a);
+    } else {
+        HM_CUDA_TRY(cudaFuncSetAttribute(hm_gp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem_bytes));
+        hm_gp_kernel<1><<<grid, HM_GP_THREADS, g->smem_bytes, st>>>(a);
+    }
     HM_CUDA_TRY(cudaGetLastError());
     return 0;
 }

@@ -47,6 +47,31 @@ __global__ void __launch_bounds__(256) dmma16816_k(double* out, int iters) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// even warps run the DFMA loop, odd warps the DMMA loop: do the two paths share one execution unit?
+__global__ void __launch_bounds__(256) mixed_k(double* out, int iters) {
+    double s = 0;
+    if ((threadIdx.x >> 5) & 1) {
+        double c[8][2];
+        for (int j = 0; j < 8; ++j) c[j][0] = c[j][1] = 0.0;
+        double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+        for (int i = 0; i < iters; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                             : "+d"(c[j][0]), "+d"(c[j][1]) : "d"(a), "d"(b));
+        for (int j = 0; j < 8; ++j) s += c[j][0] + c[j][1];
+    } else {
+        double a[8];
+        for (int j = 0; j < 8; ++j) a[j] = threadIdx.x + j;
+        const double m = 1.0000001, c = 1e-9;
+        for (int i = 0; i < 8 * iters; ++i)      // 8 DFMA = the flops of one DMMA per thread
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] = fma(a[j], m, c);
+        for (int j = 0; j < 8; ++j) s += a[j];
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 template <typename K>
 double timeit(K k, int grid, int iters, double flops_per_thread_iter, double* d) {
     cudaEvent_t e0, e1;
@@ -72,6 +97,9 @@ int main() {
     // m8n8k4: 8*8*4 FMA per warp -> 2*256/32 flops per thread per mma
     printf("DMMA m8n8k4     : %.2f TFLOP/s\n", timeit(dmma884_k, grid, iters, 8 * 2.0 * 256 / 32, d));
     printf("DMMA m16n8k16   : %.2f TFLOP/s\n", timeit(dmma16816_k, grid, iters, 4 * 2.0 * 2048 / 32, d));
+    // every warp does `iters * 8 * 16` flops per thread in both branches
+    printf("mixed DFMA+DMMA : %.2f TFLOP/s (sum of both halves; ~37 => one shared unit, ~74 => separate units)\n",
+           timeit(mixed_k, grid, iters, 8 * 2.0 * 256 / 32, d));
     printf("err %s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
 }
