@@ -1,18 +1,33 @@
 // K4: Pareto dominance filter = compute_pareto.sequential_is_pareto_efficient (compute_pareto.py:89-117).
 //
 // Pass 1 of the reference sweeps the points in index order; every point that is still efficient when its turn
-// comes ("pivot") kills every efficient point j with  NOT any(c_j <= c_pivot).  The sweep is reproduced exactly,
-// a batch of B pivot candidates at a time:
+// comes ("pivot") kills every efficient point j with  NOT any(c_j <= c_pivot),  i.e.  all(c_j > c_pivot).
+//
+// FAST PATH (NaN-free input).  Strict dominance in every coordinate is transitive, so the survivors of the sweep are
+// exactly the points that NO other point kills -- independent of the order, and ANY subset of the points may be used
+// as pivots to thin the set out first.  Two thinning levels, then an exact all-pairs test on what is left:
+//   sample  : a strided sample of the (remaining) points is gathered, its own exact front computed (all-pairs, tiled
+//             through shared memory, one candidate per warp) and sorted by coordinate sum -> <= 1024 strong pivots.
+//   stream  : every point is tested against the 8 strongest pivots unconditionally (branch-free), block survivors are
+//             compacted in shared memory and tested warp-cooperatively against the remaining pivots; survivors'
+//             indices are appended to a list.  Level 1 streams the cost matrix once at HBM speed (8 M + 1 bytes/point
+//             algorithmic), level 2 re-filters the ~1 % survivors against pivots sampled from among them.
+//   exact   : all-pairs on the level-2 survivors -> mask.
+// Everything is sized by device-side counters: no host round trip until the final (count, NaN flag) read-back.
+// Pass 2 (compute_pareto.py:107-115; sequential and order dependent by definition): at point i's turn every later point
+// still has its pass-1 state and every earlier point its final state, so  dead(i) = A(i) or B(i)  with
+// A(i) = exists j > i: rel(j, i)  (fully parallel) and B(i) = exists j < i alive: rel(j, i)  (one CTA walks only the
+// points that have such a candidate, in index order);  rel(j, i) = any(c_j == c_i) and any(c_j < c_i).
+//
+// EXACT PATH (input contains NaN: the kill relation is no longer transitive, the sweep order matters).  The sweep is
+// reproduced literally, a batch of B pivot candidates at a time:
 //   resolve : one CTA builds the BxB "i kills j" bit matrix of the batch in shared memory (tiled pairwise
 //             dominance), then one warp replays the sequential sweep over the bit rows -> which batch members are
-//             pivots (efficient at their turn).  Exact even for NaN inputs, where the relation is not transitive.
+//             pivots (efficient at their turn).
 //   filter  : every efficient point (already-processed pivots, the batch, the not-yet-reached rest) is tested
 //             against the <= B pivots held in shared memory; survivors are compacted in index order (block
 //             counts -> scan -> scatter), so the next batch is again "the next B efficient points in index order".
-// For random data ~(ln N)^M/M! points are ever pivots, so a handful of rounds suffices (10^7 x 3: 5 rounds); the
-// first round streams the cost matrix once (HBM bound), later rounds touch only survivors.
-// Pass 2 (compute_pareto.py:107-115) is sequential and order dependent by definition; it runs on the survivor set
-// in one CTA, one block-wide vote per surviving point.
+// The fast path raises a device flag when it meets a NaN and the call is redone on the exact path.
 #include <algorithm>
 #include <vector>
 #include "hm_common.cuh"
@@ -247,14 +262,405 @@ __global__ void hm_pareto_write_mask(const unsigned* __restrict__ alive, const u
     if (i < S && (state == nullptr || state[i])) mask[alive[i]] = 1;
 }
 
+// ============================================================================================================
+// fast path kernels
+// ============================================================================================================
+#define HM_PX_THREADS 256
+#define HM_PX_WARPS 8
+#define HM_PX_CPW 4                 // candidates per warp
+#define HM_PX_GROUP (HM_PX_WARPS * HM_PX_CPW)
+#define HM_PX_TILE 1024             // points per shared-memory tile
+#define HM_PIV_MAX 1024
+#define HM_PIV_FIRST 8              // pivots every point is tested against before block compaction
+#define HM_SAMPLE1 4096
+#define HM_SAMPLE2 8192
+#define HM_PS_ITEMS 8
+#define HM_PS_CHUNK (HM_PX_THREADS * HM_PS_ITEMS)
+
+struct HmParetoCtl {
+    unsigned n_sample;      // gathered sample size
+    unsigned n_piv_raw;     // front of the sample (unsorted)
+    unsigned n_piv;         // pivots after sort / cap
+    unsigned n_list1;       // survivors of level 1
+    unsigned n_list2;       // survivors of level 2
+    unsigned n_front1;      // pass-1 survivors
+    unsigned nan_flag;
+    unsigned n_dead2;       // points removed by pass 2
+    unsigned n_uncertain;
+    unsigned pad[7];
+};
+
+__global__ void hm_px_ctl_init(HmParetoCtl* ctl) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        ctl->n_sample = ctl->n_piv_raw = ctl->n_piv = 0;
+        ctl->n_list1 = ctl->n_list2 = ctl->n_front1 = 0;
+        ctl->nan_flag = ctl->n_dead2 = ctl->n_uncertain = 0;
+    }
+}
+
+// strided sample of a point list (idx == nullptr: the identity list 0..n_total-1) into a compact [S][M] array
+template <int M>
+__global__ void hm_px_gather_sample(const double* __restrict__ costs, const unsigned* __restrict__ idx,
+                                    const unsigned* __restrict__ count_ptr, unsigned n_total, unsigned s_max,
+                                    double* __restrict__ sample, HmParetoCtl* ctl) {
+    const unsigned count = count_ptr ? *count_ptr : n_total;
+    const unsigned S = min(s_max, count);
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        ctl->n_sample = S;
+        ctl->n_piv_raw = 0;
+    }
+    if (i >= S) return;
+    const unsigned pos = (unsigned)(((unsigned long long)i * count) / S);
+    const size_t src = idx ? (size_t)idx[pos] : (size_t)pos;
+#pragma unroll
+    for (int d = 0; d < M; ++d) sample[(size_t)i * M + d] = costs[src * M + d];
+}
+
+// exact front of a point list: every candidate is tested against every point of the list (tiles staged in shared
+// memory, SoA, one candidate per warp at a time, lanes stride over the tile).
+//   TO_MASK = false : survivors' costs are appended to out_costs (count in *out_count)       [sample -> pivots]
+//   TO_MASK = true  : mask[index] = 1 for survivors, *out_count += survivors                  [final exact step]
+template <int M, bool TO_MASK>
+__global__ void __launch_bounds__(HM_PX_THREADS) hm_px_exact(const double* __restrict__ costs,
+                                                             const unsigned* __restrict__ idx,
+                                                             const unsigned* __restrict__ count_ptr,
+                                                             double* __restrict__ out_costs, unsigned char* __restrict__ mask,
+                                                             unsigned* __restrict__ out_count,
+                                                             const unsigned* __restrict__ abort_flag) {
+    extern __shared__ __align__(16) unsigned char exact_smem[];
+    if (*abort_flag) return;        // a NaN was seen: the exact path will redo the call
+    double (*tile)[HM_PX_TILE] = reinterpret_cast<double (*)[HM_PX_TILE]>(exact_smem);   // [M][HM_PX_TILE]
+    const unsigned count = *count_ptr;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (unsigned g0 = blockIdx.x * HM_PX_GROUP; g0 < count; g0 += gridDim.x * HM_PX_GROUP) {
+        double cc[HM_PX_CPW][M];
+        unsigned alive = 0;          // bit c: candidate c exists and is not killed yet (warp uniform)
+#pragma unroll
+        for (int c = 0; c < HM_PX_CPW; ++c) {
+            const unsigned q = g0 + warp * HM_PX_CPW + c;
+            const bool ok = q < count;
+            const size_t src = ok ? (idx ? (size_t)idx[q] : (size_t)q) : 0;
+#pragma unroll
+            for (int d = 0; d < M; ++d) cc[c][d] = costs[src * M + d];
+            if (ok) alive |= 1u << c;
+        }
+        for (unsigned t0 = 0; t0 < count; t0 += HM_PX_TILE) {
+            if (!__syncthreads_or(alive != 0)) break;        // also: everyone is done with the previous tile
+            const unsigned tn = min((unsigned)HM_PX_TILE, count - t0);
+            for (unsigned t = threadIdx.x; t < tn; t += HM_PX_THREADS) {
+                const size_t src = idx ? (size_t)idx[t0 + t] : (size_t)(t0 + t);
+#pragma unroll
+                for (int d = 0; d < M; ++d) tile[d][t] = costs[src * M + d];
+            }
+            __syncthreads();
+            if (alive) {
+                unsigned killed = 0;
+                for (unsigned j = lane; j < tn; j += 32) {
+                    double p[M];
+#pragma unroll
+                    for (int d = 0; d < M; ++d) p[d] = tile[d][j];
+#pragma unroll
+                    for (int c = 0; c < HM_PX_CPW; ++c)
+                        if (hm_kills<M>(p, cc[c])) killed |= 1u << c;
+                }
+#pragma unroll
+                for (int c = 0; c < HM_PX_CPW; ++c)
+                    if (__any_sync(0xffffffffu, (killed >> c) & 1u)) alive &= ~(1u << c);
+            }
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int c = 0; c < HM_PX_CPW; ++c) {
+                if (!((alive >> c) & 1u)) continue;
+                const unsigned q = g0 + warp * HM_PX_CPW + c;
+                if (TO_MASK) {
+                    mask[idx ? idx[q] : q] = 1;
+                    atomicAdd(out_count, 1u);
+                } else {
+                    const unsigned pos = atomicAdd(out_count, 1u);
+#pragma unroll
+                    for (int d = 0; d < M; ++d) out_costs[(size_t)pos * M + d] = cc[c][d];
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// sort the raw pivots by coordinate sum (strongest killers first) and keep at most HM_PIV_MAX of them.  One CTA.
+template <int M>
+__global__ void __launch_bounds__(1024, 1) hm_px_sort_pivots(const double* __restrict__ raw, double* __restrict__ sorted,
+                                                             HmParetoCtl* ctl) {
+    extern __shared__ __align__(16) unsigned char sort_smem[];
+    double* key = reinterpret_cast<double*>(sort_smem);                                  // [HM_SAMPLE2]
+    unsigned short* ord = reinterpret_cast<unsigned short*>(key + HM_SAMPLE2);           // [HM_SAMPLE2]
+    const unsigned n = ctl->n_piv_raw;
+    unsigned n2 = 1;
+    while (n2 < n) n2 <<= 1;
+    for (unsigned i = threadIdx.x; i < n2; i += 1024) {
+        double s = INFINITY;
+        if (i < n) {
+            s = 0.0;
+#pragma unroll
+            for (int d = 0; d < M; ++d) s += raw[(size_t)i * M + d];
+            if (s != s) s = INFINITY;       // inf - inf
+        }
+        key[i] = s;
+        ord[i] = (unsigned short)i;
+    }
+    __syncthreads();
+    for (unsigned k = 2; k <= n2; k <<= 1) {
+        for (unsigned j = k >> 1; j > 0; j >>= 1) {
+            for (unsigned i = threadIdx.x; i < n2; i += 1024) {
+                const unsigned l = i ^ j;
+                if (l > i) {
+                    const bool up = (i & k) == 0;
+                    const double a = key[i], b = key[l];
+                    const unsigned short oa = ord[i], ob = ord[l];
+                    const bool gt = (a > b) || (a == b && oa > ob);
+                    if (gt == up) {
+                        key[i] = b;
+                        key[l] = a;
+                        ord[i] = ob;
+                        ord[l] = oa;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    const unsigned P = min(n, (unsigned)HM_PIV_MAX);
+    for (unsigned i = threadIdx.x; i < P; i += 1024) {
+        const unsigned src = ord[i];
+#pragma unroll
+        for (int d = 0; d < M; ++d) sorted[(size_t)i * M + d] = raw[(size_t)src * M + d];
+    }
+    if (threadIdx.x == 0) ctl->n_piv = P;
+}
+
+// streaming filter of a point list against the sorted pivots; survivors' indices are appended to out_list.
+template <int M>
+__global__ void __launch_bounds__(HM_PX_THREADS) hm_px_stream(const double* __restrict__ costs,
+                                                              const unsigned* __restrict__ idx,
+                                                              const unsigned* __restrict__ count_ptr, unsigned n_total,
+                                                              const double* __restrict__ pivots, HmParetoCtl* ctl,
+                                                              unsigned* __restrict__ out_list,
+                                                              unsigned* __restrict__ out_count) {
+    extern __shared__ __align__(16) unsigned char stream_smem[];
+    double* sp = reinterpret_cast<double*>(stream_smem);                    // [M][HM_PIV_MAX]  (SoA)
+    unsigned* s1 = reinterpret_cast<unsigned*>(sp + (size_t)M * HM_PIV_MAX);  // [HM_PS_CHUNK] stage-1 survivors (source index)
+    unsigned* s2 = s1 + HM_PS_CHUNK;                                        // [HM_PS_CHUNK] stage-2 survivors
+    __shared__ unsigned n1, n2, base_out;
+    if (*(volatile unsigned*)&ctl->nan_flag) return;      // uniform enough: the whole call is void once the flag is up
+    const unsigned count = count_ptr ? *count_ptr : n_total;
+    const unsigned P = ctl->n_piv;
+    for (unsigned i = threadIdx.x; i < P * M; i += HM_PX_THREADS) {
+        const unsigned p = i / M, d = i - p * M;
+        sp[(size_t)d * HM_PIV_MAX + p] = pivots[i];
+    }
+    const unsigned K1 = min(P, (unsigned)HM_PIV_FIRST);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    bool saw_nan = false;
+    for (unsigned base = blockIdx.x * HM_PS_CHUNK; base < count; base += gridDim.x * HM_PS_CHUNK) {
+        if (threadIdx.x == 0) {
+            n1 = 0;
+            n2 = 0;
+        }
+        __syncthreads();            // also covers the pivot staging on the first trip
+        // ---- stage 1: the strongest pivots, branch-free ----
+#pragma unroll
+        for (int r = 0; r < HM_PS_ITEMS; ++r) {
+            const unsigned pos = base + r * HM_PX_THREADS + threadIdx.x;
+            bool keep = false;
+            unsigned src = 0;
+            if (pos < count) {
+                src = idx ? idx[pos] : pos;
+                double cj[M];
+#pragma unroll
+                for (int d = 0; d < M; ++d) cj[d] = __ldg(costs + (size_t)src * M + d);
+#pragma unroll
+                for (int d = 0; d < M; ++d) saw_nan = saw_nan || (cj[d] != cj[d]);
+                bool dead = false;
+                for (unsigned p = 0; p < K1; ++p) {
+                    bool all = true;
+#pragma unroll
+                    for (int d = 0; d < M; ++d) all = all && (cj[d] > sp[(size_t)d * HM_PIV_MAX + p]);
+                    dead = dead || all;
+                }
+                keep = !dead;
+            }
+            const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+            if (ballot) {
+                unsigned wbase = 0;
+                if (lane == 0) wbase = atomicAdd(&n1, (unsigned)__popc(ballot));
+                wbase = __shfl_sync(0xffffffffu, wbase, 0);
+                if (keep) s1[wbase + __popc(ballot & ((1u << lane) - 1u))] = src;
+            }
+        }
+        __syncthreads();
+        // ---- stage 2: the remaining pivots, one survivor per warp, lanes over pivots ----
+        const unsigned ns = n1;
+        for (unsigned s = warp; s < ns; s += HM_PX_WARPS) {
+            const unsigned src = s1[s];
+            double cj[M];
+#pragma unroll
+            for (int d = 0; d < M; ++d) cj[d] = __ldg(costs + (size_t)src * M + d);
+            bool dead = false;
+            for (unsigned p0 = K1; p0 < P && !dead; p0 += 32) {
+                const unsigned p = p0 + lane;
+                bool all = p < P;
+#pragma unroll
+                for (int d = 0; d < M; ++d) all = all && (cj[d] > sp[(size_t)d * HM_PIV_MAX + (p < P ? p : 0)]);
+                dead = __any_sync(0xffffffffu, all);
+            }
+            if (!dead && lane == 0) s2[atomicAdd(&n2, 1u)] = src;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && n2) base_out = atomicAdd(out_count, n2);
+        __syncthreads();
+        for (unsigned i = threadIdx.x; i < n2; i += HM_PX_THREADS) out_list[base_out + i] = s2[i];
+        __syncthreads();
+    }
+    if (saw_nan) ctl->nan_flag = 1;
+}
+
+// per-block counts of set flags (feeds hm_pareto_scan / hm_pareto_scatter: ordered compaction of the mask)
+__global__ void __launch_bounds__(HM_PF_THREADS) hm_px_count_flags(const unsigned char* __restrict__ flags, unsigned n,
+                                                                   unsigned* __restrict__ block_counts) {
+    __shared__ unsigned blk;
+    if (threadIdx.x == 0) blk = 0;
+    __syncthreads();
+    const unsigned base = blockIdx.x * HM_PF_CHUNK;
+    unsigned kept = 0;
+#pragma unroll
+    for (int r = 0; r < HM_PF_ITEMS; ++r) {
+        const unsigned pos = base + r * HM_PF_THREADS + threadIdx.x;
+        if (pos < n) kept += flags[pos] ? 1u : 0u;
+    }
+    for (int o = 16; o > 0; o >>= 1) kept += __shfl_down_sync(0xffffffffu, kept, o);
+    if ((threadIdx.x & 31) == 0 && kept) atomicAdd(&blk, kept);
+    __syncthreads();
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = blk;
+}
+
+template <int M>
+__device__ __forceinline__ bool hm_rel2(const double* __restrict__ cj, const double* __restrict__ ci) {
+    bool eq = false, lt = false;
+#pragma unroll
+    for (int d = 0; d < M; ++d) {
+        eq = eq || (cj[d] == ci[d]);
+        lt = lt || (cj[d] < ci[d]);
+    }
+    return eq && lt;
+}
+
+// pass 2, parallel part: state[i] = 0 (killed by a later point), 2 (a earlier point may kill it), 1 (efficient)
+template <int M>
+__global__ void __launch_bounds__(HM_PX_THREADS) hm_px_pass2_a(const double* __restrict__ costs,
+                                                               const unsigned* __restrict__ sorted,
+                                                               const unsigned* __restrict__ count_ptr,
+                                                               unsigned char* __restrict__ state,
+                                                               const unsigned* __restrict__ abort_flag) {
+    if (*abort_flag) return;
+    const unsigned S = *count_ptr;
+    const int lane = threadIdx.x & 31;
+    const unsigned gw = (blockIdx.x * HM_PX_THREADS + threadIdx.x) >> 5, nw = (gridDim.x * HM_PX_THREADS) >> 5;
+    for (unsigned i = gw; i < S; i += nw) {
+        double ci[M];
+        const size_t si = sorted[i];
+#pragma unroll
+        for (int d = 0; d < M; ++d) ci[d] = __ldg(costs + si * M + d);
+        bool later = false, earlier = false;
+        for (unsigned j0 = 0; j0 < S; j0 += 32) {
+            const unsigned j = j0 + lane;
+            if (j < S) {
+                double cj[M];
+                const size_t sj = sorted[j];
+#pragma unroll
+                for (int d = 0; d < M; ++d) cj[d] = __ldg(costs + sj * M + d);
+                if (hm_rel2<M>(cj, ci)) {
+                    later = later || (j > i);
+                    earlier = earlier || (j < i);
+                }
+            }
+            if (__any_sync(0xffffffffu, later)) break;
+        }
+        const bool a = __any_sync(0xffffffffu, later), b = __any_sync(0xffffffffu, earlier);
+        if (lane == 0) state[i] = a ? 0 : (b ? 2 : 1);
+    }
+}
+
+// pass 2, sequential part (one CTA): resolve the state-2 points in index order, clear the mask of the dead.
+template <int M>
+__global__ void __launch_bounds__(1024, 1) hm_px_pass2_b(const double* __restrict__ costs,
+                                                         const unsigned* __restrict__ sorted,
+                                                         const unsigned* __restrict__ count_ptr,
+                                                         volatile unsigned char* state, unsigned char* __restrict__ mask,
+                                                         HmParetoCtl* ctl) {
+    if (ctl->nan_flag) return;
+    const unsigned S = *count_ptr;
+    __shared__ unsigned pending[1024];
+    __shared__ unsigned n_pending;
+    unsigned dead_count = 0;
+    for (unsigned c0 = 0; c0 < S; c0 += 1024) {
+        if (threadIdx.x == 0) n_pending = 0;
+        __syncthreads();
+        // ordered list of the undecided points of this chunk
+        const unsigned i = c0 + threadIdx.x;
+        const bool und = i < S && state[i] == 2;
+        const unsigned ballot = __ballot_sync(0xffffffffu, und);
+        __shared__ unsigned wcount[32];
+        if ((threadIdx.x & 31) == 0) wcount[threadIdx.x >> 5] = __popc(ballot);
+        __syncthreads();
+        unsigned before = 0;
+        for (unsigned w = 0; w < (threadIdx.x >> 5); ++w) before += wcount[w];
+        if (und) pending[before + __popc(ballot & ((1u << (threadIdx.x & 31)) - 1u))] = i;
+        if (threadIdx.x == 1023) n_pending = before + __popc(ballot);
+        __syncthreads();
+        const unsigned np = n_pending;
+        for (unsigned q = 0; q < np; ++q) {
+            const unsigned ii = pending[q];
+            double ci[M];
+            const size_t si = sorted[ii];
+#pragma unroll
+            for (int d = 0; d < M; ++d) ci[d] = costs[si * M + d];
+            int found = 0;
+            for (unsigned j = threadIdx.x; j < ii && !found; j += 1024) {
+                if (state[j] != 1) continue;
+                double cj[M];
+                const size_t sj = sorted[j];
+#pragma unroll
+                for (int d = 0; d < M; ++d) cj[d] = costs[sj * M + d];
+                found = hm_rel2<M>(cj, ci) ? 1 : 0;
+            }
+            const int kill = __syncthreads_or(found);
+            if (threadIdx.x == 0) state[ii] = kill ? 0 : 1;
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    for (unsigned i = threadIdx.x; i < S; i += 1024) {
+        if (state[i] == 0) {
+            mask[sorted[i]] = 0;
+            ++dead_count;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) dead_count += __shfl_down_sync(0xffffffffu, dead_count, o);
+    if ((threadIdx.x & 31) == 0 && dead_count) atomicAdd(&ctl->n_dead2, dead_count);
+}
+
 // ------------------------------------------------------------------------------------------------------------
 struct HmParetoWs {
-    unsigned* alive[2];
+    unsigned* alive[2];          // exact path: ping-pong index lists; fast path: level-1 / level-2 survivor lists
     unsigned char* flags;
     unsigned* block_counts;
-    double* pivots;
+    double* pivots;              // exact path: batch pivots; fast path: sorted pivots   [HM_PB][M]
     unsigned char* state;
     HmParetoRound* round;
+    double* sample;              // [HM_SAMPLE2][M]
+    double* piv_raw;             // [HM_SAMPLE2][M]
+    HmParetoCtl* ctl;
 };
 
 static size_t hm_align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -275,6 +681,9 @@ static size_t hm_pareto_layout(int64_t N, int M, unsigned char* base, HmParetoWs
     unsigned char* pv = take((size_t)HM_PB * M * 8);
     unsigned char* stt = take(n);
     unsigned char* rd = take(sizeof(HmParetoRound));
+    unsigned char* sm = take((size_t)HM_SAMPLE2 * M * 8);
+    unsigned char* pr = take((size_t)HM_SAMPLE2 * M * 8);
+    unsigned char* ct = take(sizeof(HmParetoCtl));
     if (ws) {
         ws->alive[0] = (unsigned*)a0;
         ws->alive[1] = (unsigned*)a1;
@@ -283,6 +692,9 @@ static size_t hm_pareto_layout(int64_t N, int M, unsigned char* base, HmParetoWs
         ws->pivots = (double*)pv;
         ws->state = stt;
         ws->round = (HmParetoRound*)rd;
+        ws->sample = (double*)sm;
+        ws->piv_raw = (double*)pr;
+        ws->ctl = (HmParetoCtl*)ct;
     }
     return off;
 }
@@ -293,7 +705,7 @@ extern "C" int64_t hm_pareto_workspace_bytes(int64_t N, int M) {
 }
 
 template <int M>
-static int hm_pareto_run(const double* costs, int64_t N, uint8_t* mask, void* workspace, int64_t* n_out, bool pass2,
+static int hm_pareto_run_exact(const double* costs, int64_t N, uint8_t* mask, void* workspace, int64_t* n_out, bool pass2,
                          cudaStream_t st) {
     HmParetoWs ws;
     unsigned char* base = (unsigned char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
@@ -350,6 +762,78 @@ static int hm_pareto_run(const double* costs, int64_t N, uint8_t* mask, void* wo
         *n_out = n_front;
     }
     return 0;
+}
+
+// NaN-free fast path; *saw_nan_out = 1 means the result is void and the exact path must run.
+template <int M>
+static int hm_pareto_run_fast(const double* costs, int64_t N, uint8_t* mask, void* workspace, int64_t* n_out, bool pass2,
+                              cudaStream_t st, int* saw_nan_out) {
+    HmParetoWs ws;
+    unsigned char* base = (unsigned char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    hm_pareto_layout(N, M, base, &ws);
+    static_assert(HM_PIV_MAX <= HM_PB, "sorted pivots share the exact path's pivot buffer");
+    const size_t exact_smem = sizeof(double) * M * HM_PX_TILE;
+    const size_t sort_smem = (sizeof(double) + sizeof(unsigned short)) * HM_SAMPLE2;
+    const size_t stream_smem = sizeof(double) * M * HM_PIV_MAX + 2 * sizeof(unsigned) * HM_PS_CHUNK;
+    HM_CUDA_TRY(cudaFuncSetAttribute(hm_px_exact<M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)exact_smem));
+    HM_CUDA_TRY(cudaFuncSetAttribute(hm_px_exact<M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)exact_smem));
+    HM_CUDA_TRY(cudaFuncSetAttribute(hm_px_sort_pivots<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
+    HM_CUDA_TRY(cudaFuncSetAttribute(hm_px_stream<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_smem));
+    const unsigned n = (unsigned)N;
+    const int sms = hm_num_sms();
+    HmParetoCtl* ctl = ws.ctl;
+    unsigned* list1 = ws.alive[0];
+    unsigned* list2 = ws.alive[1];
+
+    hm_px_ctl_init<<<1, 32, 0, st>>>(ctl);
+    HM_CUDA_TRY(cudaMemsetAsync(mask, 0, (size_t)N, st));
+    // ---- level 1: pivots from a strided sample of everything, stream the whole cost matrix ----
+    hm_px_gather_sample<M><<<(HM_SAMPLE1 + 255) / 256, 256, 0, st>>>(costs, nullptr, nullptr, n, HM_SAMPLE1, ws.sample, ctl);
+    hm_px_exact<M, false><<<(HM_SAMPLE1 + HM_PX_GROUP - 1) / HM_PX_GROUP, HM_PX_THREADS, exact_smem, st>>>(
+        ws.sample, nullptr, &ctl->n_sample, ws.piv_raw, nullptr, &ctl->n_piv_raw, &ctl->nan_flag);
+    hm_px_sort_pivots<M><<<1, 1024, sort_smem, st>>>(ws.piv_raw, ws.pivots, ctl);
+    {
+        const unsigned chunks = (n + HM_PS_CHUNK - 1) / HM_PS_CHUNK;
+        const unsigned grid = std::min<unsigned>(chunks, (unsigned)sms * 8);
+        hm_px_stream<M><<<grid, HM_PX_THREADS, stream_smem, st>>>(costs, nullptr, nullptr, n, ws.pivots, ctl, list1,
+                                                               &ctl->n_list1);
+    }
+    // ---- level 2: pivots sampled from the survivors, re-filter the survivors ----
+    hm_px_gather_sample<M><<<(HM_SAMPLE2 + 255) / 256, 256, 0, st>>>(costs, list1, &ctl->n_list1, 0, HM_SAMPLE2, ws.sample, ctl);
+    hm_px_exact<M, false><<<(HM_SAMPLE2 + HM_PX_GROUP - 1) / HM_PX_GROUP, HM_PX_THREADS, exact_smem, st>>>(
+        ws.sample, nullptr, &ctl->n_sample, ws.piv_raw, nullptr, &ctl->n_piv_raw, &ctl->nan_flag);
+    hm_px_sort_pivots<M><<<1, 1024, sort_smem, st>>>(ws.piv_raw, ws.pivots, ctl);
+    hm_px_stream<M><<<sms * 4, HM_PX_THREADS, stream_smem, st>>>(costs, list1, &ctl->n_list1, 0, ws.pivots, ctl, list2,
+                                                              &ctl->n_list2);
+    // ---- exact all-pairs on what is left -> mask ----
+    hm_px_exact<M, true><<<sms * 4, HM_PX_THREADS, exact_smem, st>>>(costs, list2, &ctl->n_list2, nullptr, mask, &ctl->n_front1,
+                                                                     &ctl->nan_flag);
+    HM_CUDA_TRY(cudaGetLastError());
+    if (pass2) {
+        // survivors in index order (ordered compaction of the mask), then the order-dependent clean-up pass
+        const unsigned nblk = (n + HM_PF_CHUNK - 1) / HM_PF_CHUNK;
+        hm_px_count_flags<<<nblk, HM_PF_THREADS, 0, st>>>(mask, n, ws.block_counts);
+        hm_pareto_scan<<<1, 1024, 0, st>>>(ws.block_counts, nblk, ws.round);
+        hm_pareto_scatter<<<nblk, HM_PF_THREADS, 0, st>>>(nullptr, n, mask, ws.block_counts, list1, 0xffffffffu, ws.round);
+        hm_px_pass2_a<M><<<sms * 4, HM_PX_THREADS, 0, st>>>(costs, list1, &ctl->n_front1, ws.state, &ctl->nan_flag);
+        hm_px_pass2_b<M><<<1, 1024, 0, st>>>(costs, list1, &ctl->n_front1, ws.state, mask, ctl);
+        HM_CUDA_TRY(cudaGetLastError());
+    }
+    HmParetoCtl h;
+    HM_CUDA_TRY(cudaMemcpyAsync(&h, ctl, sizeof(h), cudaMemcpyDeviceToHost, st));
+    HM_CUDA_TRY(cudaStreamSynchronize(st));
+    *saw_nan_out = h.nan_flag ? 1 : 0;
+    if (n_out) *n_out = (int64_t)h.n_front1 - (int64_t)h.n_dead2;
+    return 0;
+}
+
+template <int M>
+static int hm_pareto_run(const double* costs, int64_t N, uint8_t* mask, void* workspace, int64_t* n_out, bool pass2,
+                         cudaStream_t st) {
+    int saw_nan = 0;
+    int rc = hm_pareto_run_fast<M>(costs, N, mask, workspace, n_out, pass2, st, &saw_nan);
+    if (rc || !saw_nan) return rc;
+    return hm_pareto_run_exact<M>(costs, N, mask, workspace, n_out, pass2, st);
 }
 
 static int hm_pareto_dispatch(const double* costs, int64_t N, int M, uint8_t* mask, void* workspace, int64_t* n_out,
