@@ -157,8 +157,9 @@ __global__ void __launch_bounds__(HM_PF_THREADS) hm_pareto_filter_k(const double
 
 // exclusive scan of the block counts (single CTA), total -> round->total
 __global__ void __launch_bounds__(1024) hm_pareto_scan(unsigned* __restrict__ block_counts, unsigned n_blocks,
-                                                       HmParetoRound* round) {
+                                                       HmParetoRound* round, const unsigned* __restrict__ run_flag) {
     __shared__ unsigned warp_sums[32];
+    if (run_flag && !*run_flag) return;
     __shared__ unsigned carry;
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
@@ -196,8 +197,10 @@ __global__ void __launch_bounds__(HM_PF_THREADS) hm_pareto_scatter(const unsigne
                                                                    const unsigned char* __restrict__ flags,
                                                                    const unsigned* __restrict__ block_offsets,
                                                                    unsigned* __restrict__ alive_out, unsigned boundary,
-                                                                   HmParetoRound* round) {
+                                                                   HmParetoRound* round,
+                                                                   const unsigned* __restrict__ run_flag) {
     __shared__ unsigned warp_sums[HM_PF_THREADS / 32];
+    if (run_flag && !*run_flag) return;
     __shared__ unsigned running;
     if (threadIdx.x == 0) running = block_offsets[blockIdx.x];
     __syncthreads();
@@ -267,15 +270,15 @@ __global__ void hm_pareto_write_mask(const unsigned* __restrict__ alive, const u
 // ============================================================================================================
 #define HM_PX_THREADS 256
 #define HM_PX_WARPS 8
-#define HM_PX_CPW 4                 // candidates per warp
+#define HM_PX_CPW 2                 // candidates per warp
 #define HM_PX_GROUP (HM_PX_WARPS * HM_PX_CPW)
 #define HM_PX_TILE 1024             // points per shared-memory tile
 #define HM_PIV_MAX 1024
-#define HM_PIV_FIRST 8              // pivots every point is tested against before block compaction
 #define HM_SAMPLE1 4096
-#define HM_SAMPLE2 8192
-#define HM_PS_ITEMS 8
-#define HM_PS_CHUNK (HM_PX_THREADS * HM_PS_ITEMS)
+#define HM_SAMPLE2 4096
+#define HM_SORT_MAX 8192            // longest list the one-CTA sorts take
+#define HM_PS_ITEMS1 4              // points per thread, level-1 stream
+#define HM_PS_ITEMS2 1              // level 2: few points, spread them over many CTAs
 
 struct HmParetoCtl {
     unsigned n_sample;      // gathered sample size
@@ -286,7 +289,7 @@ struct HmParetoCtl {
     unsigned n_front1;      // pass-1 survivors
     unsigned nan_flag;
     unsigned n_dead2;       // points removed by pass 2
-    unsigned n_uncertain;
+    unsigned need_scan;     // pass-1 front too long for the one-CTA index sort
     unsigned pad[7];
 };
 
@@ -294,7 +297,7 @@ __global__ void hm_px_ctl_init(HmParetoCtl* ctl) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         ctl->n_sample = ctl->n_piv_raw = ctl->n_piv = 0;
         ctl->n_list1 = ctl->n_list2 = ctl->n_front1 = 0;
-        ctl->nan_flag = ctl->n_dead2 = ctl->n_uncertain = 0;
+        ctl->nan_flag = ctl->n_dead2 = ctl->need_scan = 0;
     }
 }
 
@@ -320,7 +323,7 @@ __global__ void hm_px_gather_sample(const double* __restrict__ costs, const unsi
 // exact front of a point list: every candidate is tested against every point of the list (tiles staged in shared
 // memory, SoA, one candidate per warp at a time, lanes stride over the tile).
 //   TO_MASK = false : survivors' costs are appended to out_costs (count in *out_count)       [sample -> pivots]
-//   TO_MASK = true  : mask[index] = 1 for survivors, *out_count += survivors                  [final exact step]
+//   TO_MASK = true  : mask[index] = 1 for survivors, their indices appended to (unsigned*)out_costs [final exact step]
 template <int M, bool TO_MASK>
 __global__ void __launch_bounds__(HM_PX_THREADS) hm_px_exact(const double* __restrict__ costs,
                                                              const unsigned* __restrict__ idx,
@@ -375,8 +378,9 @@ __global__ void __launch_bounds__(HM_PX_THREADS) hm_px_exact(const double* __res
                 if (!((alive >> c) & 1u)) continue;
                 const unsigned q = g0 + warp * HM_PX_CPW + c;
                 if (TO_MASK) {
-                    mask[idx ? idx[q] : q] = 1;
-                    atomicAdd(out_count, 1u);
+                    const unsigned gi = idx ? idx[q] : q;
+                    mask[gi] = 1;
+                    reinterpret_cast<unsigned*>(out_costs)[atomicAdd(out_count, 1u)] = gi;     // front list (indices)
                 } else {
                     const unsigned pos = atomicAdd(out_count, 1u);
 #pragma unroll
@@ -393,8 +397,8 @@ template <int M>
 __global__ void __launch_bounds__(1024, 1) hm_px_sort_pivots(const double* __restrict__ raw, double* __restrict__ sorted,
                                                              HmParetoCtl* ctl) {
     extern __shared__ __align__(16) unsigned char sort_smem[];
-    double* key = reinterpret_cast<double*>(sort_smem);                                  // [HM_SAMPLE2]
-    unsigned short* ord = reinterpret_cast<unsigned short*>(key + HM_SAMPLE2);           // [HM_SAMPLE2]
+    double* key = reinterpret_cast<double*>(sort_smem);                                  // [HM_SORT_MAX]
+    unsigned short* ord = reinterpret_cast<unsigned short*>(key + HM_SORT_MAX);          // [HM_SORT_MAX]
     const unsigned n = ctl->n_piv_raw;
     unsigned n2 = 1;
     while (n2 < n) n2 <<= 1;
@@ -440,18 +444,27 @@ __global__ void __launch_bounds__(1024, 1) hm_px_sort_pivots(const double* __res
 }
 
 // streaming filter of a point list against the sorted pivots; survivors' indices are appended to out_list.
-template <int M>
-__global__ void __launch_bounds__(HM_PX_THREADS) hm_px_stream(const double* __restrict__ costs,
+// Warp-autonomous (no block barrier after the pivot staging), so every warp's DRAM latency overlaps the others' work:
+//   stage 1: the K1 (2..8, by M) strongest pivots live in registers; every point of the warp's 32 x ITEMS sub-chunk is
+//            tested against all of them (branch-free); all loads of the sub-chunk are issued up front.
+//   stage 2: stage-1 survivors queue up in a per-warp shared-memory buffer; whenever 32 are waiting (and at the end)
+//            they walk the remaining pivots, one per lane (shared memory, broadcast reads), until killed.
+//   output : stage-2 survivors queue up in a second per-warp buffer, flushed 32 at a time with one global atomic.
+#define HM_PS_Q1 (32 + 32 * 8)
+#define HM_PS_Q2 64
+template <int M, int ITEMS>
+__global__ void __launch_bounds__(HM_PX_THREADS, 3) hm_px_stream(const double* __restrict__ costs,
                                                               const unsigned* __restrict__ idx,
                                                               const unsigned* __restrict__ count_ptr, unsigned n_total,
                                                               const double* __restrict__ pivots, HmParetoCtl* ctl,
                                                               unsigned* __restrict__ out_list,
                                                               unsigned* __restrict__ out_count) {
+    static_assert(ITEMS <= 8, "queue sizing");
+    // register-resident pivots: as many as ~36 registers hold
+    constexpr int K1 = M <= 2 ? 8 : (M == 3 ? 6 : (M == 4 ? 4 : 2));
     extern __shared__ __align__(16) unsigned char stream_smem[];
     double* sp = reinterpret_cast<double*>(stream_smem);                    // [M][HM_PIV_MAX]  (SoA)
-    unsigned* s1 = reinterpret_cast<unsigned*>(sp + (size_t)M * HM_PIV_MAX);  // [HM_PS_CHUNK] stage-1 survivors (source index)
-    unsigned* s2 = s1 + HM_PS_CHUNK;                                        // [HM_PS_CHUNK] stage-2 survivors
-    __shared__ unsigned n1, n2, base_out;
+    unsigned* qall = reinterpret_cast<unsigned*>(sp + (size_t)M * HM_PIV_MAX);
     if (*(volatile unsigned*)&ctl->nan_flag) return;      // uniform enough: the whole call is void once the flag is up
     const unsigned count = count_ptr ? *count_ptr : n_total;
     const unsigned P = ctl->n_piv;
@@ -459,76 +472,135 @@ __global__ void __launch_bounds__(HM_PX_THREADS) hm_px_stream(const double* __re
         const unsigned p = i / M, d = i - p * M;
         sp[(size_t)d * HM_PIV_MAX + p] = pivots[i];
     }
-    const unsigned K1 = min(P, (unsigned)HM_PIV_FIRST);
+    double pv[K1][M];                            // +inf padding never kills
+#pragma unroll
+    for (int p = 0; p < K1; ++p)
+#pragma unroll
+        for (int d = 0; d < M; ++d) pv[p][d] = ((unsigned)p < P) ? __ldg(pivots + (size_t)p * M + d) : INFINITY;
+    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned* q1 = qall + warp * (HM_PS_Q1 + HM_PS_Q2);   // stage-1 survivors waiting for stage 2
+    unsigned* q2 = q1 + HM_PS_Q1;                          // stage-2 survivors waiting for the flush
+    unsigned n1 = 0, n2 = 0;                               // queue fill (warp uniform)
     bool saw_nan = false;
-    for (unsigned base = blockIdx.x * HM_PS_CHUNK; base < count; base += gridDim.x * HM_PS_CHUNK) {
-        if (threadIdx.x == 0) {
-            n1 = 0;
-            n2 = 0;
+
+    auto flush = [&](unsigned m) {                         // write the first m (<= 32) entries of q2 to the list
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(out_count, m);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if ((unsigned)lane < m) out_list[base + lane] = q2[lane];
+        __syncwarp();
+        if ((unsigned)lane + 32 < n2) {                    // move the tail down (n2 <= 64)
+            const unsigned v = q2[lane + 32];
+            q2[lane] = v;
         }
-        __syncthreads();            // also covers the pivot staging on the first trip
-        // ---- stage 1: the strongest pivots, branch-free ----
+        __syncwarp();
+        n2 -= m;
+    };
+    auto stage2 = [&](unsigned m) {                        // the LAST m (<= 32) entries of q1 walk the remaining pivots
+        const bool have = (unsigned)lane < m;
+        const unsigned sidx = have ? q1[n1 - m + lane] : 0;
+        double c2[M];
 #pragma unroll
-        for (int r = 0; r < HM_PS_ITEMS; ++r) {
-            const unsigned pos = base + r * HM_PX_THREADS + threadIdx.x;
-            bool keep = false;
-            unsigned src = 0;
-            if (pos < count) {
-                src = idx ? idx[pos] : pos;
-                double cj[M];
+        for (int d = 0; d < M; ++d) c2[d] = have ? __ldg(costs + (size_t)sidx * M + d) : 0.0;
+        bool dead = !have;
+        for (unsigned p = K1; p < P; ++p) {
+            if (__all_sync(0xffffffffu, dead)) break;
+            bool all = true;
 #pragma unroll
-                for (int d = 0; d < M; ++d) cj[d] = __ldg(costs + (size_t)src * M + d);
-#pragma unroll
-                for (int d = 0; d < M; ++d) saw_nan = saw_nan || (cj[d] != cj[d]);
-                bool dead = false;
-                for (unsigned p = 0; p < K1; ++p) {
-                    bool all = true;
-#pragma unroll
-                    for (int d = 0; d < M; ++d) all = all && (cj[d] > sp[(size_t)d * HM_PIV_MAX + p]);
-                    dead = dead || all;
-                }
-                keep = !dead;
-            }
-            const unsigned ballot = __ballot_sync(0xffffffffu, keep);
-            if (ballot) {
-                unsigned wbase = 0;
-                if (lane == 0) wbase = atomicAdd(&n1, (unsigned)__popc(ballot));
-                wbase = __shfl_sync(0xffffffffu, wbase, 0);
-                if (keep) s1[wbase + __popc(ballot & ((1u << lane) - 1u))] = src;
-            }
+            for (int d = 0; d < M; ++d) all = all && (c2[d] > sp[(size_t)d * HM_PIV_MAX + p]);
+            dead = dead || all;
         }
-        __syncthreads();
-        // ---- stage 2: the remaining pivots, one survivor per warp, lanes over pivots ----
-        const unsigned ns = n1;
-        for (unsigned s = warp; s < ns; s += HM_PX_WARPS) {
-            const unsigned src = s1[s];
-            double cj[M];
+        n1 -= m;
+        const unsigned ballot = __ballot_sync(0xffffffffu, !dead);
+        if (!dead) q2[n2 + __popc(ballot & ((1u << lane) - 1u))] = sidx;
+        n2 += __popc(ballot);
+        __syncwarp();
+        if (n2 >= 32) flush(32);
+    };
+
+    const unsigned gw = blockIdx.x * HM_PX_WARPS + warp, nw = gridDim.x * HM_PX_WARPS;
+    constexpr unsigned SUB = 32 * ITEMS;
+    for (unsigned long long base = (unsigned long long)gw * SUB; base < count; base += (unsigned long long)nw * SUB) {
+        double cj[ITEMS][M];
+        unsigned src[ITEMS];
 #pragma unroll
-            for (int d = 0; d < M; ++d) cj[d] = __ldg(costs + (size_t)src * M + d);
+        for (int r = 0; r < ITEMS; ++r) {
+            const unsigned long long pos = base + r * 32 + lane;
+            const unsigned pc = pos < count ? (unsigned)pos : count - 1;
+            src[r] = idx ? idx[pc] : pc;
+        }
+#pragma unroll
+        for (int r = 0; r < ITEMS; ++r)
+#pragma unroll
+            for (int d = 0; d < M; ++d) cj[r][d] = __ldg(costs + (size_t)src[r] * M + d);
+#pragma unroll
+        for (int r = 0; r < ITEMS; ++r) {
+            const unsigned long long pos = base + r * 32 + lane;
+            double sum = cj[r][0];
+#pragma unroll
+            for (int d = 1; d < M; ++d) sum += cj[r][d];
+            saw_nan = saw_nan || (sum != sum);             // (+inf) + (-inf) also lands here: merely takes the exact path
             bool dead = false;
-            for (unsigned p0 = K1; p0 < P && !dead; p0 += 32) {
-                const unsigned p = p0 + lane;
-                bool all = p < P;
 #pragma unroll
-                for (int d = 0; d < M; ++d) all = all && (cj[d] > sp[(size_t)d * HM_PIV_MAX + (p < P ? p : 0)]);
-                dead = __any_sync(0xffffffffu, all);
+            for (int p = 0; p < K1; ++p) {
+                bool all = true;
+#pragma unroll
+                for (int d = 0; d < M; ++d) all = all && (cj[r][d] > pv[p][d]);
+                dead = dead || all;
             }
-            if (!dead && lane == 0) s2[atomicAdd(&n2, 1u)] = src;
+            const bool keep = !dead && pos < count;
+            const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+            if (keep) q1[n1 + __popc(ballot & ((1u << lane) - 1u))] = src[r];
+            n1 += __popc(ballot);
         }
-        __syncthreads();
-        if (threadIdx.x == 0 && n2) base_out = atomicAdd(out_count, n2);
-        __syncthreads();
-        for (unsigned i = threadIdx.x; i < n2; i += HM_PX_THREADS) out_list[base_out + i] = s2[i];
-        __syncthreads();
+        __syncwarp();
+        while (n1 >= 32) stage2(32);
     }
+    if (n1) stage2(n1);
+    while (n2) flush(n2 < 32 ? n2 : 32);
     if (saw_nan) ctl->nan_flag = 1;
+}
+
+// sort the (usually tiny) list of pass-1 survivors by index so that pass 2 can walk it in index order.  One CTA.
+// Lists longer than HM_SORT_MAX are left to the ordered mask compaction (count -> scan -> scatter).
+__global__ void __launch_bounds__(1024, 1) hm_px_sort_front(unsigned* __restrict__ list, HmParetoCtl* ctl) {
+    __shared__ unsigned key[HM_SORT_MAX];
+    const unsigned n = ctl->n_front1;
+    if (ctl->nan_flag) return;
+    if (n > HM_SORT_MAX) {
+        if (threadIdx.x == 0) ctl->need_scan = 1;
+        return;
+    }
+    unsigned n2 = 1;
+    while (n2 < n) n2 <<= 1;
+    for (unsigned i = threadIdx.x; i < n2; i += 1024) key[i] = i < n ? list[i] : 0xffffffffu;
+    __syncthreads();
+    for (unsigned k = 2; k <= n2; k <<= 1) {
+        for (unsigned j = k >> 1; j > 0; j >>= 1) {
+            for (unsigned i = threadIdx.x; i < n2; i += 1024) {
+                const unsigned l = i ^ j;
+                if (l > i) {
+                    const bool up = (i & k) == 0;
+                    const unsigned a = key[i], b = key[l];
+                    if ((a > b) == up) {
+                        key[i] = b;
+                        key[l] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (unsigned i = threadIdx.x; i < n; i += 1024) list[i] = key[i];
 }
 
 // per-block counts of set flags (feeds hm_pareto_scan / hm_pareto_scatter: ordered compaction of the mask)
 __global__ void __launch_bounds__(HM_PF_THREADS) hm_px_count_flags(const unsigned char* __restrict__ flags, unsigned n,
-                                                                   unsigned* __restrict__ block_counts) {
+                                                                   unsigned* __restrict__ block_counts,
+                                                                   const unsigned* __restrict__ run_flag) {
     __shared__ unsigned blk;
+    if (!*run_flag) return;
     if (threadIdx.x == 0) blk = 0;
     __syncthreads();
     const unsigned base = blockIdx.x * HM_PF_CHUNK;
@@ -725,9 +797,9 @@ static int hm_pareto_run_exact(const double* costs, int64_t N, uint8_t* mask, vo
         const unsigned nblk = (n_alive + HM_PF_CHUNK - 1) / HM_PF_CHUNK;
         hm_pareto_filter_k<M><<<nblk, HM_PF_THREADS, filter_smem, st>>>(costs, cur, n_alive, ws.pivots, ws.round, ws.flags,
                                                              ws.block_counts);
-        hm_pareto_scan<<<1, 1024, 0, st>>>(ws.block_counts, nblk, ws.round);
+        hm_pareto_scan<<<1, 1024, 0, st>>>(ws.block_counts, nblk, ws.round, nullptr);
         unsigned* nxt = ws.alive[flip];
-        hm_pareto_scatter<<<nblk, HM_PF_THREADS, 0, st>>>(cur, n_alive, ws.flags, ws.block_counts, nxt, done + b, ws.round);
+        hm_pareto_scatter<<<nblk, HM_PF_THREADS, 0, st>>>(cur, n_alive, ws.flags, ws.block_counts, nxt, done + b, ws.round, nullptr);
         HM_CUDA_TRY(cudaGetLastError());
         HM_CUDA_TRY(cudaMemcpyAsync(&h, ws.round, sizeof(h), cudaMemcpyDeviceToHost, st));
         HM_CUDA_TRY(cudaStreamSynchronize(st));
@@ -769,16 +841,19 @@ template <int M>
 static int hm_pareto_run_fast(const double* costs, int64_t N, uint8_t* mask, void* workspace, int64_t* n_out, bool pass2,
                               cudaStream_t st, int* saw_nan_out) {
     HmParetoWs ws;
+    constexpr int IT1 = (M <= 4) ? HM_PS_ITEMS1 : 2;      // level-1 points per lane (register budget)
     unsigned char* base = (unsigned char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     hm_pareto_layout(N, M, base, &ws);
     static_assert(HM_PIV_MAX <= HM_PB, "sorted pivots share the exact path's pivot buffer");
     const size_t exact_smem = sizeof(double) * M * HM_PX_TILE;
-    const size_t sort_smem = (sizeof(double) + sizeof(unsigned short)) * HM_SAMPLE2;
-    const size_t stream_smem = sizeof(double) * M * HM_PIV_MAX + 2 * sizeof(unsigned) * HM_PS_CHUNK;
+    const size_t sort_smem = (sizeof(double) + sizeof(unsigned short)) * HM_SORT_MAX;
+    const size_t stream_smem1 = sizeof(double) * M * HM_PIV_MAX + sizeof(unsigned) * HM_PX_WARPS * (HM_PS_Q1 + HM_PS_Q2);
+    const size_t stream_smem2 = stream_smem1;
     HM_CUDA_TRY(cudaFuncSetAttribute(hm_px_exact<M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)exact_smem));
     HM_CUDA_TRY(cudaFuncSetAttribute(hm_px_exact<M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)exact_smem));
     HM_CUDA_TRY(cudaFuncSetAttribute(hm_px_sort_pivots<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
-    HM_CUDA_TRY(cudaFuncSetAttribute(hm_px_stream<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_smem));
+    HM_CUDA_TRY(cudaFuncSetAttribute(hm_px_stream<M, IT1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_smem1));
+    HM_CUDA_TRY(cudaFuncSetAttribute(hm_px_stream<M, HM_PS_ITEMS2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_smem2));
     const unsigned n = (unsigned)N;
     const int sms = hm_num_sms();
     HmParetoCtl* ctl = ws.ctl;
@@ -793,28 +868,32 @@ static int hm_pareto_run_fast(const double* costs, int64_t N, uint8_t* mask, voi
         ws.sample, nullptr, &ctl->n_sample, ws.piv_raw, nullptr, &ctl->n_piv_raw, &ctl->nan_flag);
     hm_px_sort_pivots<M><<<1, 1024, sort_smem, st>>>(ws.piv_raw, ws.pivots, ctl);
     {
-        const unsigned chunks = (n + HM_PS_CHUNK - 1) / HM_PS_CHUNK;
-        const unsigned grid = std::min<unsigned>(chunks, (unsigned)sms * 8);
-        hm_px_stream<M><<<grid, HM_PX_THREADS, stream_smem, st>>>(costs, nullptr, nullptr, n, ws.pivots, ctl, list1,
-                                                               &ctl->n_list1);
+        const unsigned chunk = HM_PX_THREADS * IT1;
+        const unsigned chunks = (n + chunk - 1) / chunk;
+        const unsigned grid = std::min<unsigned>(chunks, (unsigned)sms * 4);
+        hm_px_stream<M, IT1><<<grid, HM_PX_THREADS, stream_smem1, st>>>(costs, nullptr, nullptr, n, ws.pivots, ctl,
+                                                                              list1, &ctl->n_list1);
     }
     // ---- level 2: pivots sampled from the survivors, re-filter the survivors ----
     hm_px_gather_sample<M><<<(HM_SAMPLE2 + 255) / 256, 256, 0, st>>>(costs, list1, &ctl->n_list1, 0, HM_SAMPLE2, ws.sample, ctl);
     hm_px_exact<M, false><<<(HM_SAMPLE2 + HM_PX_GROUP - 1) / HM_PX_GROUP, HM_PX_THREADS, exact_smem, st>>>(
         ws.sample, nullptr, &ctl->n_sample, ws.piv_raw, nullptr, &ctl->n_piv_raw, &ctl->nan_flag);
     hm_px_sort_pivots<M><<<1, 1024, sort_smem, st>>>(ws.piv_raw, ws.pivots, ctl);
-    hm_px_stream<M><<<sms * 4, HM_PX_THREADS, stream_smem, st>>>(costs, list1, &ctl->n_list1, 0, ws.pivots, ctl, list2,
-                                                              &ctl->n_list2);
-    // ---- exact all-pairs on what is left -> mask ----
-    hm_px_exact<M, true><<<sms * 4, HM_PX_THREADS, exact_smem, st>>>(costs, list2, &ctl->n_list2, nullptr, mask, &ctl->n_front1,
-                                                                     &ctl->nan_flag);
+    hm_px_stream<M, HM_PS_ITEMS2><<<sms * 4, HM_PX_THREADS, stream_smem2, st>>>(costs, list1, &ctl->n_list1, 0, ws.pivots,
+                                                                             ctl, list2, &ctl->n_list2);
+    // ---- exact all-pairs on what is left -> mask, and the front's indices into list1 ----
+    hm_px_exact<M, true><<<sms * 4, HM_PX_THREADS, exact_smem, st>>>(costs, list2, &ctl->n_list2, (double*)list1, mask,
+                                                                     &ctl->n_front1, &ctl->nan_flag);
     HM_CUDA_TRY(cudaGetLastError());
     if (pass2) {
-        // survivors in index order (ordered compaction of the mask), then the order-dependent clean-up pass
+        // survivors in index order (one-CTA sort of the front list; the ordered mask compaction only runs, device
+        // side decision, when the front is too long for that), then the order-dependent clean-up pass
         const unsigned nblk = (n + HM_PF_CHUNK - 1) / HM_PF_CHUNK;
-        hm_px_count_flags<<<nblk, HM_PF_THREADS, 0, st>>>(mask, n, ws.block_counts);
-        hm_pareto_scan<<<1, 1024, 0, st>>>(ws.block_counts, nblk, ws.round);
-        hm_pareto_scatter<<<nblk, HM_PF_THREADS, 0, st>>>(nullptr, n, mask, ws.block_counts, list1, 0xffffffffu, ws.round);
+        hm_px_sort_front<<<1, 1024, 0, st>>>(list1, ctl);
+        hm_px_count_flags<<<nblk, HM_PF_THREADS, 0, st>>>(mask, n, ws.block_counts, &ctl->need_scan);
+        hm_pareto_scan<<<1, 1024, 0, st>>>(ws.block_counts, nblk, ws.round, &ctl->need_scan);
+        hm_pareto_scatter<<<nblk, HM_PF_THREADS, 0, st>>>(nullptr, n, mask, ws.block_counts, list1, 0xffffffffu, ws.round,
+                                                          &ctl->need_scan);
         hm_px_pass2_a<M><<<sms * 4, HM_PX_THREADS, 0, st>>>(costs, list1, &ctl->n_front1, ws.state, &ctl->nan_flag);
         hm_px_pass2_b<M><<<1, 1024, 0, st>>>(costs, list1, &ctl->n_front1, ws.state, mask, ctl);
         HM_CUDA_TRY(cudaGetLastError());
