@@ -23,9 +23,20 @@
 // [feature][thread] shared-memory tile (bank = lane: conflict free).  Tree groups are streamed through two
 // shared-memory buffers with 1-D TMA bulk copies (cp.async.bulk + mbarrier); a forest that fits in the two
 // buffers is loaded once per CTA and stays resident.  Persistent grid: one 1024-thread CTA per SM.
+//
+// Coherence pre-pass (large forests, large pools).  A forest that streams through shared memory is bound by the
+// L1/shared-memory data pipe: with candidates in arrival order the 32 lanes of a warp sit in 12 different nodes per
+// visit (2.5-way bank conflicts) and 30 % of the lanes idle behind the deepest path.  The forest itself is a spatial
+// index: candidates that land in the same leaves of two "key" trees follow nearly the same path in every other tree.
+// So the pool is bucketed by (leaf of key tree A, leaf of key tree B) -- key kernel + histogram, scan, scatter: a
+// counting sort on <= 2^22 bins -- and the traversal kernel visits candidates through that permutation (gather on
+// load, scatter on store; every candidate's arithmetic is untouched, so results stay bit-identical).  Measured on
+// the C3 shape this cuts distinct nodes per warp visit 12.5 -> 2.3 and raises lane utilisation 0.70 -> 0.86.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <utility>
 #include <vector>
 #include "hm_acq.cuh"
 
@@ -56,6 +67,14 @@ struct HmForestDev {
     int pad;
 };
 
+// a tree the coherence pre-pass walks in global memory
+struct HmKeyTree {
+    const uint2* nodes;          // node array of the tree's group
+    const unsigned* leaf_rank;   // forest-wide: DFS rank of a leaf among the leaves of its own tree
+    unsigned root;               // group-relative index of the root
+    unsigned n_leaves;
+};
+
 struct hm_forest {
     HmForestDev dev;
     int n_trees, n_features, n_leaves, staged, block, nodebuf;
@@ -64,6 +83,9 @@ struct hm_forest {
     void* d_groups;
     void* d_leaf_tab;
     void* d_leaf_node;
+    void* d_leaf_rank;
+    int n_key;
+    HmKeyTree key[2];
 };
 
 struct HmEvalArgs {
@@ -77,6 +99,7 @@ struct HmEvalArgs {
     double* pred_out;
     double* score_out;
     const double* feas;
+    const unsigned* perm;     // coherence order (nullptr: arrival order)
     HmAcqDev acq;
     int has_acq;
 };
@@ -155,6 +178,9 @@ extern "C" int hm_forest_create(int n_trees, int n_features, const int64_t* off,
     std::vector<unsigned char> blob;
     std::vector<double> leaf_tab((size_t)n_leaves * 4, 0.0);
     std::vector<int> leaf_node((size_t)n_leaves, 0);
+    std::vector<unsigned> leaf_rank((size_t)n_leaves, 0);
+    std::vector<long long> tree_leaf_base(n_trees + 1, 0), tree_nodes_off(n_trees, 0);
+    std::vector<unsigned> tree_root(n_trees, 0);
     long long leaf_ord = 0;
     int t = 0;
     while (t < n_trees) {
@@ -190,6 +216,9 @@ extern "C" int hm_forest_create(int n_trees, int n_features, const int64_t* off,
             const TreeLay& L = lay[tt];
             const long long b = off[tt];
             roots[tt - t] = base;
+            tree_root[tt] = base;
+            tree_nodes_off[tt] = (long long)(g.blob_off + hdr);
+            tree_leaf_base[tt] = leaf_ord;
             for (size_t h = 0; h < L.order.size(); ++h) {
                 int nd = L.order[h];
                 int l = left[b + nd], r = right[b + nd];
@@ -212,6 +241,15 @@ extern "C" int hm_forest_create(int n_trees, int n_features, const int64_t* off,
                 }
             }
             base += (uint32_t)L.order.size();
+            // DFS (= sklearn node id) rank of every leaf of this tree: neighbouring ranks are neighbouring regions
+            {
+                const long long lb = tree_leaf_base[tt], le = leaf_ord;
+                std::vector<std::pair<int, long long>> byid;
+                byid.reserve((size_t)(le - lb));
+                for (long long o = lb; o < le; ++o) byid.push_back(std::make_pair(leaf_node[o], o));
+                std::sort(byid.begin(), byid.end());
+                for (size_t r = 0; r < byid.size(); ++r) leaf_rank[byid[r].second] = (unsigned)r;
+            }
         }
         groups.push_back(g);
         t = t1;
@@ -238,10 +276,12 @@ extern "C" int hm_forest_create(int n_trees, int n_features, const int64_t* off,
     HM_F_TRY(cudaMalloc(&F->d_groups, groups.size() * sizeof(HmGroupDesc)));
     HM_F_TRY(cudaMalloc(&F->d_leaf_tab, leaf_tab.size() * sizeof(double)));
     HM_F_TRY(cudaMalloc(&F->d_leaf_node, leaf_node.size() * sizeof(int)));
+    HM_F_TRY(cudaMalloc(&F->d_leaf_rank, leaf_rank.size() * sizeof(unsigned)));
     HM_F_TRY(cudaMemcpy(F->d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
     HM_F_TRY(cudaMemcpy(F->d_groups, groups.data(), groups.size() * sizeof(HmGroupDesc), cudaMemcpyHostToDevice));
     HM_F_TRY(cudaMemcpy(F->d_leaf_tab, leaf_tab.data(), leaf_tab.size() * sizeof(double), cudaMemcpyHostToDevice));
     HM_F_TRY(cudaMemcpy(F->d_leaf_node, leaf_node.data(), leaf_node.size() * sizeof(int), cudaMemcpyHostToDevice));
+    HM_F_TRY(cudaMemcpy(F->d_leaf_rank, leaf_rank.data(), leaf_rank.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
 #undef HM_F_TRY
     F->dev.blob = (const unsigned char*)F->d_blob;
     F->dev.groups = (const HmGroupDesc*)F->d_groups;
@@ -250,6 +290,14 @@ extern "C" int hm_forest_create(int n_trees, int n_features, const int64_t* off,
     F->dev.n_groups = (int)groups.size();
     F->dev.n_trees = n_trees;
     F->dev.staged = staged;
+    tree_leaf_base[n_trees] = leaf_ord;
+    F->n_key = std::min(n_trees, 2);
+    for (int kk = 0; kk < F->n_key; ++kk) {
+        F->key[kk].nodes = (const uint2*)((const unsigned char*)F->d_blob + tree_nodes_off[kk]);
+        F->key[kk].leaf_rank = (const unsigned*)F->d_leaf_rank;
+        F->key[kk].root = tree_root[kk];
+        F->key[kk].n_leaves = (unsigned)(tree_leaf_base[kk + 1] - tree_leaf_base[kk]);
+    }
     *out = F;
     return 0;
 }
@@ -260,6 +308,7 @@ extern "C" void hm_forest_destroy(hm_forest_t* F) {
     cudaFree(F->d_groups);
     cudaFree(F->d_leaf_tab);
     cudaFree(F->d_leaf_node);
+    cudaFree(F->d_leaf_rank);
     delete F;
 }
 extern "C" int hm_forest_n_trees(const hm_forest_t* f) { return f ? f->n_trees : 0; }
@@ -271,34 +320,100 @@ struct HmAcc {
     double q, s, u, v;
 };
 
-// Walk `ntrees` trees whose roots/nodes are at the given pointers (shared or global), in tree order.
-template <bool APPLY>
+// Walk NCH consecutive trees of a group at once.  The walk is a chain of dependent loads (node -> feature -> node
+// ...); the chains of different trees are independent, so their loads overlap; a chain that has reached its leaf
+// idles (predicated off) until the slowest of the NCH is done.  The leaf records are then added in tree order, so the
+// fp64 sums are unchanged.
+template <bool APPLY, bool SMEM, int NCH>
+__device__ __forceinline__ void hm_walk_round(const uint32_t* __restrict__ roots, const uint2* __restrict__ nodes,
+                                              int t0, const float* __restrict__ xs_t, int BD,
+                                              const double* __restrict__ leaf_tab, const int* __restrict__ leaf_node,
+                                              HmAcc& acc, int* __restrict__ leaf_out, long long N, long long i,
+                                              bool valid, int first_tree) {
+    uint2 nd[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) nd[c] = nodes[roots[t0 + c]];
+    bool any = false;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) any = any || (nd[c].y & HM_LEFT_MASK);
+    if (SMEM) {
+        // shared-memory forest: predicated ld.shared (a finished chain issues no load and no branch)
+        const uint32_t xs_a = hm_smem_u32(xs_t), nodes_a = hm_smem_u32(nodes);
+        while (any) {
+            float xv[NCH];
+            uint32_t left[NCH];
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                left[c] = nd[c].y & HM_LEFT_MASK;
+                xv[c] = 0.0f;
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p ld.shared.f32 %0, [%2];\n\t}"
+                             : "+f"(xv[c])
+                             : "r"(left[c]), "r"(xs_a + (nd[c].y >> HM_LEFT_BITS) * (uint32_t)(BD * 4)));
+            }
+            any = false;
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                // sklearn: go left iff x <= threshold (NaN -> right)
+                const uint32_t nxt = left[c] + ((xv[c] <= __uint_as_float(nd[c].x)) ? 0u : 1u);
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.shared.v2.u32 {%0, %1}, [%3];\n\t}"
+                             : "+r"(nd[c].x), "+r"(nd[c].y)
+                             : "r"(left[c]), "r"(nodes_a + nxt * 8u));
+                any = any || (nd[c].y & HM_LEFT_MASK);
+            }
+        }
+    } else {
+        while (any) {
+            any = false;
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                if (nd[c].y & HM_LEFT_MASK) {
+                    const float xv = xs_t[(nd[c].y >> HM_LEFT_BITS) * BD];
+                    const uint32_t nxt = (nd[c].y & HM_LEFT_MASK) + ((xv <= __uint_as_float(nd[c].x)) ? 0u : 1u);
+                    nd[c] = nodes[nxt];
+                    any = any || (nd[c].y & HM_LEFT_MASK);
+                }
+            }
+        }
+    }
+    // one 256-bit load of each 32-byte leaf record (LDG.E.256): one L1 wavefront pass instead of two
+    double lq[NCH], ls[NCH], lu[NCH], lv[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+        asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+                     : "=d"(lq[c]), "=d"(ls[c]), "=d"(lu[c]), "=d"(lv[c])
+                     : "l"(leaf_tab + 4 * (size_t)nd[c].x));
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        acc.q = hm_add(acc.q, lq[c]);
+        acc.s = hm_add(acc.s, ls[c]);
+        acc.u = hm_add(acc.u, lu[c]);
+        acc.v = hm_add(acc.v, lv[c]);
+        if (APPLY) {
+            if (valid && leaf_out)
+                leaf_out[(size_t)(first_tree + t0 + c) * (size_t)N + (size_t)i] = __ldg(leaf_node + nd[c].x);
+        }
+    }
+}
+
+// Walk `ntrees` trees whose roots/nodes are at the given pointers (shared or global), in tree order: rounds of 3,
+// then what is left as a round of 2 and/or 1 (4 = 2 + 2).
+template <bool APPLY, bool SMEM>
 __device__ __forceinline__ void hm_walk_group(const uint32_t* __restrict__ roots, const uint2* __restrict__ nodes,
                                               int ntrees, const float* __restrict__ xs_t, int BD,
                                               const double* __restrict__ leaf_tab, const int* __restrict__ leaf_node,
                                               HmAcc& acc, int* __restrict__ leaf_out, long long N, long long i,
                                               bool valid, int first_tree) {
-    for (int t = 0; t < ntrees; ++t) {
-        uint2 nd = nodes[roots[t]];
-        while (nd.y & HM_LEFT_MASK) {
-            const float xv = xs_t[(nd.y >> HM_LEFT_BITS) * BD];
-            // sklearn: go left iff x <= threshold (NaN -> right)
-            const uint32_t nxt = (nd.y & HM_LEFT_MASK) + ((xv <= __uint_as_float(nd.x)) ? 0u : 1u);
-            nd = nodes[nxt];
-        }
-        // one 256-bit load of the 32-byte leaf record (LDG.E.256): one L1 wavefront pass instead of two
-        double lq, ls, lu, lv;
-        asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
-                     : "=d"(lq), "=d"(ls), "=d"(lu), "=d"(lv)
-                     : "l"(leaf_tab + 4 * (size_t)nd.x));
-        acc.q = hm_add(acc.q, lq);
-        acc.s = hm_add(acc.s, ls);
-        acc.u = hm_add(acc.u, lu);
-        acc.v = hm_add(acc.v, lv);
-        if (APPLY) {
-            if (valid && leaf_out) leaf_out[(size_t)(first_tree + t) * (size_t)N + (size_t)i] = __ldg(leaf_node + nd.x);
-        }
+    int t = 0;
+    while (ntrees - t >= 3 && ntrees - t != 4) {
+        hm_walk_round<APPLY, SMEM, 3>(roots, nodes, t, xs_t, BD, leaf_tab, leaf_node, acc, leaf_out, N, i, valid, first_tree);
+        t += 3;
     }
+    while (ntrees - t >= 2) {
+        hm_walk_round<APPLY, SMEM, 2>(roots, nodes, t, xs_t, BD, leaf_tab, leaf_node, acc, leaf_out, N, i, valid, first_tree);
+        t += 2;
+    }
+    if (t < ntrees)
+        hm_walk_round<APPLY, SMEM, 1>(roots, nodes, t, xs_t, BD, leaf_tab, leaf_node, acc, leaf_out, N, i, valid, first_tree);
 }
 
 template <bool APPLY>
@@ -350,10 +465,12 @@ __global__ void __launch_bounds__(1024, 1) hm_forest_kernel(const __grid_constan
     long long step = 0;
     float* xs_t = xs + tid;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const long long i = tile * BD + tid;
-        const bool valid = i < a.N;
-        const long long ii = valid ? i : a.N - 1;
-        for (int f = 0; f < a.D; ++f) xs_t[f * BD] = __ldg(a.X + (size_t)f * (size_t)a.ldx + (size_t)ii);
+        const long long slot = tile * BD + tid;
+        const bool valid = slot < a.N;
+        const long long sl = valid ? slot : a.N - 1;
+        // i = the candidate this thread evaluates: arrival order, or the coherence order of the pre-pass
+        const long long i = a.perm ? (long long)__ldg(a.perm + sl) : sl;
+        for (int f = 0; f < a.D; ++f) xs_t[f * BD] = __ldg(a.X + (size_t)f * (size_t)a.ldx + (size_t)i);
 
         double mean_l[HM_MAX_OBJECTIVES], var_l[HM_MAX_OBJECTIVES];
         int step_in_tile = 0;
@@ -370,7 +487,7 @@ __global__ void __launch_bounds__(1024, 1) hm_forest_kernel(const __grid_constan
                     const unsigned ntr = __ldg(&F.groups[g].n_trees);
                     const unsigned noff = __ldg(&F.groups[g].nodes_off);
                     const unsigned ft = __ldg(&F.groups[g].first_tree);
-                    hm_walk_group<APPLY>(reinterpret_cast<const uint32_t*>(gb),
+                    hm_walk_group<APPLY, true>(reinterpret_cast<const uint32_t*>(gb),
                                          reinterpret_cast<const uint2*>(gb + noff), (int)ntr, xs_t, BD, F.leaf_tab,
                                          F.leaf_node, acc, lo, a.N, i, valid, (int)ft);
                     if (!resident) {
@@ -384,7 +501,7 @@ __global__ void __launch_bounds__(1024, 1) hm_forest_kernel(const __grid_constan
                 for (int g = 0; g < F.n_groups; ++g) {
                     const HmGroupDesc gd = F.groups[g];
                     const unsigned char* gb = F.blob + gd.blob_off;
-                    hm_walk_group<APPLY>(reinterpret_cast<const uint32_t*>(gb),
+                    hm_walk_group<APPLY, false>(reinterpret_cast<const uint32_t*>(gb),
                                          reinterpret_cast<const uint2*>(gb + gd.nodes_off), (int)gd.n_trees, xs_t, BD,
                                          F.leaf_tab, F.leaf_node, acc, lo, a.N, i, valid, (int)gd.first_tree);
                 }
@@ -415,6 +532,157 @@ __global__ void __launch_bounds__(1024, 1) hm_forest_kernel(const __grid_constan
             a.score_out[i] = hm_acq_value(a.acq, mean_l, var_l, feas);
         }
     }
+}
+
+// ---- coherence pre-pass ----------------------------------------------------------------------------------------
+#define HM_SORT_MAX_BITS 22
+#define HM_SORT_MIN_N (1 << 17)
+
+struct HmKeyArgs {
+    HmKeyTree t[2];
+    unsigned shift[2];
+    unsigned nB;            // bins of the second component (1 if there is only one key tree)
+    int n_key;
+    const float* X;
+    long long ldx, N;
+};
+
+// key[i] = (leaf rank in tree A >> shiftA) * nB + (leaf rank in tree B >> shiftB); histogram of the keys
+__global__ void __launch_bounds__(256) hm_forest_sortkey(const HmKeyArgs a, unsigned* __restrict__ key,
+                                                         unsigned* __restrict__ hist) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.N) return;
+    unsigned k = 0;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        if (q < a.n_key) {
+            const uint2* __restrict__ nodes = a.t[q].nodes;
+            uint2 nd = __ldg(nodes + a.t[q].root);
+            while (nd.y & HM_LEFT_MASK) {
+                const float xv = __ldg(a.X + (size_t)(nd.y >> HM_LEFT_BITS) * (size_t)a.ldx + (size_t)i);
+                nd = __ldg(nodes + (nd.y & HM_LEFT_MASK) + ((xv <= __uint_as_float(nd.x)) ? 0u : 1u));
+            }
+            const unsigned r = __ldg(a.t[q].leaf_rank + nd.x) >> a.shift[q];
+            k = (q == 0) ? r : k * a.nB + r;
+        }
+    }
+    key[i] = k;
+    atomicAdd(hist + k, 1u);
+}
+
+// exclusive scan of `n` counters in place, one CTA (n <= 2^22: a few passes over an L2-resident array)
+__global__ void __launch_bounds__(1024, 1) hm_forest_scan(unsigned* __restrict__ v, unsigned n) {
+    __shared__ unsigned warp_sums[32];
+    __shared__ unsigned carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (unsigned base = 0; base < n; base += 4096) {
+        // 4 consecutive counters per thread
+        const unsigned i0 = base + threadIdx.x * 4;
+        unsigned c[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) c[q] = (i0 + q < n) ? v[i0 + q] : 0;
+        const unsigned mine = c[0] + c[1] + c[2] + c[3];
+        unsigned x = mine;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) warp_sums[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned s = warp_sums[lane];
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned y = __shfl_up_sync(0xffffffffu, s, o);
+                if (lane >= o) s += y;
+            }
+            warp_sums[lane] = s;
+        }
+        __syncthreads();
+        unsigned run = carry + (warp ? warp_sums[warp - 1] : 0) + (x - mine);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (i0 + q < n) v[i0 + q] = run;
+            run += c[q];
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = run;
+        __syncthreads();
+    }
+}
+
+// perm[offset[key[i]]++] = i   (order inside a bucket is arbitrary: it cannot influence any result)
+__global__ void __launch_bounds__(256) hm_forest_perm(const unsigned* __restrict__ key, unsigned* __restrict__ offs,
+                                                      long long N, unsigned* __restrict__ perm) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    perm[atomicAdd(offs + key[i], 1u)] = (unsigned)i;
+}
+
+static int hm_forest_sort_mode() {
+    static int mode = -2;       // -1 auto, 0 off, 1 on
+    if (mode == -2) {
+        const char* e = getenv("HM_B200_FOREST_SORT");
+        mode = e ? atoi(e) : -1;
+    }
+    return mode;
+}
+
+// builds the coherence permutation of the N candidates in *perm_out (stream-ordered allocation, freed by the caller)
+static int hm_forest_build_perm(const hm_forest_t* const* forests, int M, const float* Xcm, int64_t ldx, int64_t N,
+                                cudaStream_t st, unsigned** perm_out, void** scratch_out) {
+    HmKeyArgs ka;
+    memset(&ka, 0, sizeof(ka));
+    // key trees: one from each of the first two forests, or the first two trees of a single forest
+    if (M >= 2) {
+        ka.t[0] = forests[0]->key[0];
+        ka.t[1] = forests[1]->key[0];
+        ka.n_key = 2;
+    } else {
+        ka.n_key = forests[0]->n_key;
+        for (int q = 0; q < ka.n_key; ++q) ka.t[q] = forests[0]->key[q];
+    }
+    unsigned bits[2] = {0, 0};
+    for (int q = 0; q < ka.n_key; ++q)
+        while ((1u << bits[q]) < ka.t[q].n_leaves) ++bits[q];
+    while (bits[0] + bits[1] > HM_SORT_MAX_BITS) {          // coarsen the larger component first
+        const int q = (bits[0] - ka.shift[0] >= bits[1] - ka.shift[1]) ? 0 : 1;
+        ++ka.shift[q];
+        --bits[q];
+    }
+    const unsigned nA = ((ka.t[0].n_leaves - 1) >> ka.shift[0]) + 1;
+    ka.nB = (ka.n_key == 2) ? ((ka.t[1].n_leaves - 1) >> ka.shift[1]) + 1 : 1;
+    const size_t bins = (size_t)nA * ka.nB;
+    ka.X = Xcm;
+    ka.ldx = ldx;
+    ka.N = N;
+    static bool pool_set = false;
+    if (!pool_set) {            // keep freed blocks in the pool: the next call reuses them without a driver round trip
+        cudaMemPool_t pool;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long thr = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+        pool_set = true;
+    }
+    unsigned* buf = nullptr;
+    const size_t words = (size_t)N * 2 + bins;
+    HM_CUDA_TRY(cudaMallocAsync((void**)&buf, words * sizeof(unsigned), st));
+    unsigned* key = buf;
+    unsigned* perm = buf + N;
+    unsigned* hist = buf + 2 * (size_t)N;
+    HM_CUDA_TRY(cudaMemsetAsync(hist, 0, bins * sizeof(unsigned), st));
+    const unsigned grid = (unsigned)((N + 255) / 256);
+    hm_forest_sortkey<<<grid, 256, 0, st>>>(ka, key, hist);
+    hm_forest_scan<<<1, 1024, 0, st>>>(hist, (unsigned)bins);
+    hm_forest_perm<<<grid, 256, 0, st>>>(key, hist, N, perm);
+    HM_CUDA_TRY(cudaGetLastError());
+    *perm_out = perm;
+    *scratch_out = buf;
+    return 0;
 }
 
 extern "C" int hm_rf_eval(const hm_forest_t* const* forests, int M, const float* Xcm, int64_t ldx, int64_t N,
@@ -462,6 +730,18 @@ extern "C" int hm_rf_eval(const hm_forest_t* const* forests, int M, const float*
         HM_REQUIRE(score_out == nullptr, "score_out without acq");
     }
     const int block = forests[0]->block;
+    // coherence pre-pass: pays when the forest streams through shared memory (not resident) and the pool is large
+    void* scratch = nullptr;
+    {
+        const int mode = hm_forest_sort_mode();
+        const bool big = steps > 2 && N >= HM_SORT_MIN_N && N < 4294967295ll;
+        if (!any_leaf && (mode == 1 || (mode == -1 && big))) {
+            unsigned* perm = nullptr;
+            int rc = hm_forest_build_perm(forests, M, Xcm, ldx, N, (cudaStream_t)stream, &perm, &scratch);
+            if (rc) return rc;
+            a.perm = perm;
+        }
+    }
     const size_t smem = HM_SMEM_HEADER + 2 * (size_t)a.nodebuf + (size_t)block * a.D * 4;
     const long long n_tiles = (N + block - 1) / block;
     const int grid = (int)std::min<long long>(n_tiles, hm_num_sms());
@@ -474,5 +754,6 @@ extern "C" int hm_rf_eval(const hm_forest_t* const* forests, int M, const float*
         hm_forest_kernel<false><<<grid, block, smem, st>>>(a);
     }
     HM_CUDA_TRY(cudaGetLastError());
+    if (scratch) HM_CUDA_TRY(cudaFreeAsync(scratch, st));
     return 0;
 }
