@@ -19,6 +19,7 @@ SCALARIZATIONS = {"linear": 0, "tchebyshev": 1, "modified_tchebyshev": 2}
 EXPORTED_SYMBOLS = [
     "hm_last_error", "hm_device_sm_count", "hm_version", "hm_fp64_peak_tflops",
     "hm_forest_create", "hm_forest_destroy", "hm_forest_n_trees", "hm_forest_n_features", "hm_forest_staged",
+    "hm_forest_set_coherence_mode", "hm_forest_n_groups",
     "hm_rf_eval", "hm_acq_score",
     "hm_topk_workspace_bytes", "hm_topk", "hm_topk_merge",
     "hm_gp_create", "hm_gp_destroy", "hm_gp_mean_var",
@@ -73,8 +74,9 @@ def lib():
     L.hm_forest_create.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, ctypes.POINTER(vp)]
     L.hm_forest_destroy.argtypes = [vp]
     L.hm_forest_destroy.restype = None
-    for f in ("hm_forest_n_trees", "hm_forest_n_features", "hm_forest_staged"):
+    for f in ("hm_forest_n_trees", "hm_forest_n_features", "hm_forest_staged", "hm_forest_n_groups"):
         getattr(L, f).argtypes = [vp]
+    L.hm_forest_set_coherence_mode.argtypes = [i32]
     L.hm_rf_eval.argtypes = [ctypes.POINTER(vp), i32, vp, i64, i64, ctypes.POINTER(vp), vp, vp, vp,
                              ctypes.POINTER(AcqParams), vp, vp, vp]
     L.hm_acq_score.argtypes = [ctypes.POINTER(AcqParams), vp, vp, i64, vp, i64, vp, vp]

@@ -314,12 +314,16 @@ extern "C" void hm_forest_destroy(hm_forest_t* F) {
 extern "C" int hm_forest_n_trees(const hm_forest_t* f) { return f ? f->n_trees : 0; }
 extern "C" int hm_forest_n_features(const hm_forest_t* f) { return f ? f->n_features : 0; }
 extern "C" int hm_forest_staged(const hm_forest_t* f) { return f ? f->staged : 0; }
+extern "C" int hm_forest_n_groups(const hm_forest_t* f) { return f ? f->dev.n_groups : 0; }
 
 // ------------------------------------------------------------------------------------------------------------
 struct HmAcc {
     double q, s, u, v;
 };
 
+#ifndef HM_FOREST_MAXCH
+#define HM_FOREST_MAXCH 3
+#endif
 // Walk NCH consecutive trees of a group at once.  The walk is a chain of dependent loads (node -> feature -> node
 // ...); the chains of different trees are independent, so their loads overlap; a chain that has reached its leaf
 // idles (predicated off) until the slowest of the NCH is done.  The leaf records are then added in tree order, so the
@@ -404,16 +408,17 @@ __device__ __forceinline__ void hm_walk_group(const uint32_t* __restrict__ roots
                                               HmAcc& acc, int* __restrict__ leaf_out, long long N, long long i,
                                               bool valid, int first_tree) {
     int t = 0;
-    while (ntrees - t >= 3 && ntrees - t != 4) {
-        hm_walk_round<APPLY, SMEM, 3>(roots, nodes, t, xs_t, BD, leaf_tab, leaf_node, acc, leaf_out, N, i, valid, first_tree);
-        t += 3;
-    }
-    while (ntrees - t >= 2) {
-        hm_walk_round<APPLY, SMEM, 2>(roots, nodes, t, xs_t, BD, leaf_tab, leaf_node, acc, leaf_out, N, i, valid, first_tree);
-        t += 2;
-    }
-    if (t < ntrees)
-        hm_walk_round<APPLY, SMEM, 1>(roots, nodes, t, xs_t, BD, leaf_tab, leaf_node, acc, leaf_out, N, i, valid, first_tree);
+#define HM_ROUND(K) hm_walk_round<APPLY, SMEM, K>(roots, nodes, t, xs_t, BD, leaf_tab, leaf_node, acc, leaf_out, N, i, valid, first_tree)
+#if HM_FOREST_MAXCH >= 5
+    while (ntrees - t >= 5) { HM_ROUND(5); t += 5; }
+#endif
+#if HM_FOREST_MAXCH >= 4
+    while (ntrees - t >= 4) { HM_ROUND(4); t += 4; }
+#endif
+    while (ntrees - t >= 3 && (HM_FOREST_MAXCH >= 4 || ntrees - t != 4)) { HM_ROUND(3); t += 3; }
+    while (ntrees - t >= 2) { HM_ROUND(2); t += 2; }
+    if (t < ntrees) HM_ROUND(1);
+#undef HM_ROUND
 }
 
 template <bool APPLY>
@@ -620,13 +625,18 @@ __global__ void __launch_bounds__(256) hm_forest_perm(const unsigned* __restrict
     perm[atomicAdd(offs + key[i], 1u)] = (unsigned)i;
 }
 
+static int g_forest_sort_mode = -2;       // -1 auto, 0 off, 1 on; -2 = not read yet (env HM_B200_FOREST_SORT)
 static int hm_forest_sort_mode() {
-    static int mode = -2;       // -1 auto, 0 off, 1 on
-    if (mode == -2) {
+    if (g_forest_sort_mode == -2) {
         const char* e = getenv("HM_B200_FOREST_SORT");
-        mode = e ? atoi(e) : -1;
+        g_forest_sort_mode = e ? atoi(e) : -1;
     }
-    return mode;
+    return g_forest_sort_mode;
+}
+extern "C" int hm_forest_set_coherence_mode(int mode) {
+    HM_REQUIRE(mode >= -1 && mode <= 1, "mode in {-1 auto, 0 off, 1 on}");
+    g_forest_sort_mode = mode;
+    return 0;
 }
 
 // builds the coherence permutation of the N candidates in *perm_out (stream-ordered allocation, freed by the caller)

@@ -96,6 +96,7 @@ class DeviceForest:
         self.n_features = int(tables["n_features"])
         self.has_hutter_tables = tables.get("q") is not None
         self.staged = bool(L.hm_forest_staged(h))
+        self.n_groups = int(L.hm_forest_n_groups(h))
         self._keep = None
 
     def __del__(self):

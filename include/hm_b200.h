@@ -72,6 +72,9 @@ int hm_forest_n_trees(const hm_forest_t* f);
 int hm_forest_n_features(const hm_forest_t* f);
 /* 1 if the forest is streamed through shared memory, 0 if a tree was too large and it is walked in L2 */
 int hm_forest_staged(const hm_forest_t* f);
+/* number of shared-memory tree groups of the device layout (<= 2 summed over the forests of a call: the forests
+ * stay resident in shared memory; more: they stream through it and large pools take the coherence pre-pass) */
+int hm_forest_n_groups(const hm_forest_t* f);
 
 /* acquisition parameters, one struct for all kinds (unused fields ignored) */
 typedef struct hm_acq_params {
@@ -97,6 +100,11 @@ typedef struct hm_acq_params {
  *   score_out    : fp64 [N]        scalarised acquisition value (requires acq != NULL) (A10-A12)
  *   feas         : fp64 [N] or NULL  feasibility probability multiplied into the score
  */
+/* Coherence pre-pass of hm_rf_eval (candidates bucketed by the leaves of two key trees so that the lanes of a warp
+ * walk the same nodes): -1 = automatic (forests that stream through shared memory, N >= 2^17; the default, also
+ * settable with the environment variable HM_B200_FOREST_SORT), 0 = never, 1 = always.  Results are bit-identical
+ * either way; this only exists for tests and measurements. */
+int hm_forest_set_coherence_mode(int mode);
 int hm_rf_eval(const hm_forest_t* const* forests, int M, const float* Xcm, int64_t ldx, int64_t N,
                int32_t* const* leaf_out, double* mean_out, double* var_out, double* pred_out,
                const hm_acq_params_t* acq, const double* feas, double* score_out, void* stream);

@@ -206,6 +206,44 @@ def test_forest_kernel_vs_oracle_synthetic(T, D, dlo, dhi, N):
         assert np.array_equal(out["pred"][m].cpu().numpy(), oracle.rf_sklearn_predict(fa, leaf))
 
 
+@pytest.mark.parametrize("T,D,N", [(40, 23, 300_000), (24, 32, 200_001)])
+def test_coherence_prepass_is_invisible(T, D, N):
+    """hm_rf_eval buckets large pools by the leaves of two key trees and walks them through that permutation
+    (hm_forest.cu, coherence pre-pass).  Every output must be bit-identical with the pre-pass off, and equal the
+    C oracle on a sample."""
+    from hypermapper_b200 import forest, _lib
+    from oracle import oracle
+    torch = _torch()
+    rng = np.random.default_rng(T + D)
+    fs = [_synthetic_forest(rng, T, D, 8, 12) for _ in range(2)]
+    X = rng.random((N, D))
+    X[:, 1] = np.round(X[:, 1], 1)
+    dfs = [forest.DeviceForest(forest.tables_from_arrays(**f)) for f in fs]
+    Xd = torch.from_numpy(np.ascontiguousarray(X.astype(np.float32).T)).cuda()
+    acq = _lib.make_acq_params("EI", "tchebyshev", [0.3, 0.7], [0.1, 0.2], 0.0)
+    outs = []
+    try:
+        for mode in (0, 1):
+            _lib.check(_lib.lib().hm_forest_set_coherence_mode(mode), "hm_forest_set_coherence_mode")
+            o = forest.rf_eval(dfs, Xd, want_mean=True, want_var=True, want_pred=True, acq=acq)
+            outs.append({k: [t.cpu().numpy() for t in v] if isinstance(v, (list, tuple)) else v.cpu().numpy()
+                         for k, v in o.items() if v is not None})
+    finally:
+        _lib.lib().hm_forest_set_coherence_mode(-1)
+    for k in outs[0]:
+        a, b = outs[0][k], outs[1][k]
+        if isinstance(a, list):
+            assert all(np.array_equal(x, y, equal_nan=True) for x, y in zip(a, b)), k
+        else:
+            assert np.array_equal(a, b, equal_nan=True), k
+    sub = rng.choice(N, 4000, replace=False)
+    for m, f in enumerate(fs):
+        fa = oracle.ForestArrays(f["tree_off"], f["left"], f["right"], f["feature"], f["threshold"], f["leaf_mean"],
+                                 f["leaf_var"], f["value"], D)
+        leaf = oracle.rf_apply(fa, X[sub].astype(np.float32).astype(np.float64))
+        assert np.array_equal(outs[1]["mean"][m][sub], oracle.rf_prediction(fa, leaf))
+
+
 def test_threshold_rounding_edge_cases():
     """x32 <= thr32 must equal (double)x32 <= thr64 for thresholds that are not float32-representable."""
     from hypermapper_b200 import forest
