@@ -317,9 +317,28 @@ extern "C" int hm_forest_staged(const hm_forest_t* f) { return f ? f->staged : 0
 extern "C" int hm_forest_n_groups(const hm_forest_t* f) { return f ? f->dev.n_groups : 0; }
 
 // ------------------------------------------------------------------------------------------------------------
+// Running sums of one objective + the leaf records of the previous round of trees, still in flight: a round's leaf
+// gathers (L2 latency, ~30 % of a round when waited for on the spot) are issued when its walk ends and added -- in tree
+// order -- only after the NEXT round's walk, so their latency hides behind that walk.
+#define HM_MAX_CHAINS 3
 struct HmAcc {
     double q, s, u, v;
+    double pq[HM_MAX_CHAINS], ps[HM_MAX_CHAINS], pu[HM_MAX_CHAINS], pv[HM_MAX_CHAINS];
+    int pn;
 };
+template <bool NEED_V>
+__device__ __forceinline__ void hm_acc_flush(HmAcc& acc) {
+#pragma unroll
+    for (int c = 0; c < HM_MAX_CHAINS; ++c) {
+        if (c < acc.pn) {
+            acc.q = hm_add(acc.q, acc.pq[c]);
+            acc.s = hm_add(acc.s, acc.ps[c]);
+            acc.u = hm_add(acc.u, acc.pu[c]);
+            if (NEED_V) acc.v = hm_add(acc.v, acc.pv[c]);
+        }
+    }
+    acc.pn = 0;
+}
 
 #ifndef HM_FOREST_MAXCH
 #define HM_FOREST_MAXCH 3
@@ -328,44 +347,59 @@ struct HmAcc {
 // ...); the chains of different trees are independent, so their loads overlap; a chain that has reached its leaf
 // idles (predicated off) until the slowest of the NCH is done.  The leaf records are then added in tree order, so the
 // fp64 sums are unchanged.
-template <bool APPLY, bool SMEM, int NCH>
+template <bool APPLY, bool NEED_V, bool SMEM, int NCH>
 __device__ __forceinline__ void hm_walk_round(const uint32_t* __restrict__ roots, const uint2* __restrict__ nodes,
                                               int t0, const float* __restrict__ xs_t, int BD,
                                               const double* __restrict__ leaf_tab, const int* __restrict__ leaf_node,
                                               HmAcc& acc, int* __restrict__ leaf_out, long long N, long long i,
                                               bool valid, int first_tree) {
     uint2 nd[NCH];
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) nd[c] = nodes[roots[t0 + c]];
-    bool any = false;
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) any = any || (nd[c].y & HM_LEFT_MASK);
     if (SMEM) {
-        // shared-memory forest: predicated ld.shared (a finished chain issues no load and no branch)
-        const uint32_t xs_a = hm_smem_u32(xs_t), nodes_a = hm_smem_u32(nodes);
+        // shared-memory forest.  One visit = one PTX block per chain (ptxas interleaves the chains): both loads are
+        // predicated on "this chain is still at an internal node", so a finished chain issues no load and no branch;
+        // the node lives in one 64-bit register {threshold bits | leaf ordinal, feature << 22 | left}.
+        const uint32_t xs_a = hm_smem_u32(xs_t), nodes_a = hm_smem_u32(nodes), xstride = (uint32_t)BD * 4u;
+        unsigned long long nq[NCH];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) nq[c] = reinterpret_cast<const unsigned long long*>(nodes)[roots[t0 + c]];
+        bool any = false;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) any = any || ((uint32_t)(nq[c] >> 32) & HM_LEFT_MASK);
         while (any) {
-            float xv[NCH];
-            uint32_t left[NCH];
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
-                left[c] = nd[c].y & HM_LEFT_MASK;
-                xv[c] = 0.0f;
-                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p ld.shared.f32 %0, [%2];\n\t}"
-                             : "+f"(xv[c])
-                             : "r"(left[c]), "r"(xs_a + (nd[c].y >> HM_LEFT_BITS) * (uint32_t)(BD * 4)));
+                asm volatile(
+                    "{\n\t"
+                    ".reg .pred p, q;\n\t"
+                    ".reg .b32 th, y, left, f, xa, na;\n\t"
+                    ".reg .f32 xv, thf;\n\t"
+                    "mov.b64 {th, y}, %0;\n\t"
+                    "and.b32 left, y, 0x3fffff;\n\t"
+                    "setp.ne.u32 p, left, 0;\n\t"
+                    "shr.u32 f, y, 22;\n\t"
+                    "mad.lo.u32 xa, f, %3, %1;\n\t"
+                    "@p ld.shared.f32 xv, [xa];\n\t"
+                    "mov.b32 thf, th;\n\t"
+                    "mad.lo.u32 na, left, 8, %2;\n\t"
+                    "setp.gtu.f32 q, xv, thf;\n\t"          // sklearn: go left iff x <= threshold (NaN -> right)
+                    "@q add.u32 na, na, 8;\n\t"
+                    "@p ld.shared.b64 %0, [na];\n\t"
+                    "}"
+                    : "+l"(nq[c])
+                    : "r"(xs_a), "r"(nodes_a), "r"(xstride));
             }
             any = false;
 #pragma unroll
-            for (int c = 0; c < NCH; ++c) {
-                // sklearn: go left iff x <= threshold (NaN -> right)
-                const uint32_t nxt = left[c] + ((xv[c] <= __uint_as_float(nd[c].x)) ? 0u : 1u);
-                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.shared.v2.u32 {%0, %1}, [%3];\n\t}"
-                             : "+r"(nd[c].x), "+r"(nd[c].y)
-                             : "r"(left[c]), "r"(nodes_a + nxt * 8u));
-                any = any || (nd[c].y & HM_LEFT_MASK);
-            }
+            for (int c = 0; c < NCH; ++c) any = any || ((uint32_t)(nq[c] >> 32) & HM_LEFT_MASK);
         }
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) nd[c] = make_uint2((uint32_t)nq[c], (uint32_t)(nq[c] >> 32));
     } else {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) nd[c] = nodes[roots[t0 + c]];
+        bool any = false;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) any = any || (nd[c].y & HM_LEFT_MASK);
         while (any) {
             any = false;
 #pragma unroll
@@ -379,36 +413,38 @@ __device__ __forceinline__ void hm_walk_round(const uint32_t* __restrict__ roots
             }
         }
     }
-    // one 256-bit load of each 32-byte leaf record (LDG.E.256): one L1 wavefront pass instead of two
-    double lq[NCH], ls[NCH], lu[NCH], lv[NCH];
-#pragma unroll
-    for (int c = 0; c < NCH; ++c)
-        asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
-                     : "=d"(lq[c]), "=d"(ls[c]), "=d"(lu[c]), "=d"(lv[c])
-                     : "l"(leaf_tab + 4 * (size_t)nd[c].x));
+    // add the previous round's leaf records (they had this whole walk to arrive), then put this round's in flight:
+    // one 256-bit load per 32-byte record (LDG.E.256), or 128 + 64 bits when the `value` column is not needed
+    hm_acc_flush<NEED_V>(acc);
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
-        acc.q = hm_add(acc.q, lq[c]);
-        acc.s = hm_add(acc.s, ls[c]);
-        acc.u = hm_add(acc.u, lu[c]);
-        acc.v = hm_add(acc.v, lv[c]);
+        const double* rec = leaf_tab + 4 * (size_t)nd[c].x;
+        if (NEED_V) {
+            asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+                         : "=d"(acc.pq[c]), "=d"(acc.ps[c]), "=d"(acc.pu[c]), "=d"(acc.pv[c])
+                         : "l"(rec));
+        } else {
+            asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(acc.pq[c]), "=d"(acc.ps[c]) : "l"(rec));
+            asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(acc.pu[c]) : "l"(rec + 2));
+        }
         if (APPLY) {
             if (valid && leaf_out)
                 leaf_out[(size_t)(first_tree + t0 + c) * (size_t)N + (size_t)i] = __ldg(leaf_node + nd[c].x);
         }
     }
+    acc.pn = NCH;
 }
 
 // Walk `ntrees` trees whose roots/nodes are at the given pointers (shared or global), in tree order: rounds of 3,
 // then what is left as a round of 2 and/or 1 (4 = 2 + 2).
-template <bool APPLY, bool SMEM>
+template <bool APPLY, bool NEED_V, bool SMEM>
 __device__ __forceinline__ void hm_walk_group(const uint32_t* __restrict__ roots, const uint2* __restrict__ nodes,
                                               int ntrees, const float* __restrict__ xs_t, int BD,
                                               const double* __restrict__ leaf_tab, const int* __restrict__ leaf_node,
                                               HmAcc& acc, int* __restrict__ leaf_out, long long N, long long i,
                                               bool valid, int first_tree) {
     int t = 0;
-#define HM_ROUND(K) hm_walk_round<APPLY, SMEM, K>(roots, nodes, t, xs_t, BD, leaf_tab, leaf_node, acc, leaf_out, N, i, valid, first_tree)
+#define HM_ROUND(K) hm_walk_round<APPLY, NEED_V, SMEM, K>(roots, nodes, t, xs_t, BD, leaf_tab, leaf_node, acc, leaf_out, N, i, valid, first_tree)
 #if HM_FOREST_MAXCH >= 5
     while (ntrees - t >= 5) { HM_ROUND(5); t += 5; }
 #endif
@@ -421,7 +457,7 @@ __device__ __forceinline__ void hm_walk_group(const uint32_t* __restrict__ roots
 #undef HM_ROUND
 }
 
-template <bool APPLY>
+template <bool APPLY, bool NEED_V>
 __global__ void __launch_bounds__(1024, 1) hm_forest_kernel(const __grid_constant__ HmEvalArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
@@ -481,7 +517,9 @@ __global__ void __launch_bounds__(1024, 1) hm_forest_kernel(const __grid_constan
         int step_in_tile = 0;
         for (int m = 0; m < a.M; ++m) {
             const HmForestDev& F = a.f[m];
-            HmAcc acc = {0.0, 0.0, 0.0, 0.0};
+            HmAcc acc;
+            acc.q = acc.s = acc.u = acc.v = 0.0;
+            acc.pn = 0;
             int* lo = APPLY ? a.leaf_out[m] : nullptr;
             if (F.staged) {
                 for (int g = 0; g < F.n_groups; ++g) {
@@ -492,7 +530,7 @@ __global__ void __launch_bounds__(1024, 1) hm_forest_kernel(const __grid_constan
                     const unsigned ntr = __ldg(&F.groups[g].n_trees);
                     const unsigned noff = __ldg(&F.groups[g].nodes_off);
                     const unsigned ft = __ldg(&F.groups[g].first_tree);
-                    hm_walk_group<APPLY, true>(reinterpret_cast<const uint32_t*>(gb),
+                    hm_walk_group<APPLY, NEED_V, true>(reinterpret_cast<const uint32_t*>(gb),
                                          reinterpret_cast<const uint2*>(gb + noff), (int)ntr, xs_t, BD, F.leaf_tab,
                                          F.leaf_node, acc, lo, a.N, i, valid, (int)ft);
                     if (!resident) {
@@ -506,11 +544,12 @@ __global__ void __launch_bounds__(1024, 1) hm_forest_kernel(const __grid_constan
                 for (int g = 0; g < F.n_groups; ++g) {
                     const HmGroupDesc gd = F.groups[g];
                     const unsigned char* gb = F.blob + gd.blob_off;
-                    hm_walk_group<APPLY, false>(reinterpret_cast<const uint32_t*>(gb),
+                    hm_walk_group<APPLY, NEED_V, false>(reinterpret_cast<const uint32_t*>(gb),
                                          reinterpret_cast<const uint2*>(gb + gd.nodes_off), (int)gd.n_trees, xs_t, BD,
                                          F.leaf_tab, F.leaf_node, acc, lo, a.N, i, valid, (int)gd.first_tree);
                 }
             }
+            hm_acc_flush<NEED_V>(acc);
             // models.py:266-273
             const double mean = acc.q;
             double vom = fabs(hm_sub(acc.s, hm_mul(mean, mean)));
@@ -756,13 +795,20 @@ extern "C" int hm_rf_eval(const hm_forest_t* const* forests, int M, const float*
     const long long n_tiles = (N + block - 1) / block;
     const int grid = (int)std::min<long long>(n_tiles, hm_num_sms());
     cudaStream_t st = (cudaStream_t)stream;
+    // the plain-predict column of the leaf records is only read for pred_out and Thompson sampling
+    const bool need_v = pred_out != nullptr || (acq && a.acq.kind == HM_ACQ_TS);
+#define HM_LAUNCH(AP, NV)                                                                                              \
+    do {                                                                                                               \
+        HM_CUDA_TRY(cudaFuncSetAttribute(hm_forest_kernel<AP, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                                         (int)smem));                                                                  \
+        hm_forest_kernel<AP, NV><<<grid, block, smem, st>>>(a);                                                        \
+    } while (0)
     if (any_leaf) {
-        HM_CUDA_TRY(cudaFuncSetAttribute(hm_forest_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        hm_forest_kernel<true><<<grid, block, smem, st>>>(a);
+        if (need_v) HM_LAUNCH(true, true); else HM_LAUNCH(true, false);
     } else {
-        HM_CUDA_TRY(cudaFuncSetAttribute(hm_forest_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        hm_forest_kernel<false><<<grid, block, smem, st>>>(a);
+        if (need_v) HM_LAUNCH(false, true); else HM_LAUNCH(false, false);
     }
+#undef HM_LAUNCH
     HM_CUDA_TRY(cudaGetLastError());
     if (scratch) HM_CUDA_TRY(cudaFreeAsync(scratch, st));
     return 0;
