@@ -457,15 +457,15 @@ __device__ __forceinline__ void hm_walk_group(const uint32_t* __restrict__ roots
 #undef HM_ROUND
 }
 
-template <bool APPLY, bool NEED_V>
-__global__ void __launch_bounds__(1024, 1) hm_forest_kernel(const __grid_constant__ HmEvalArgs a) {
+template <bool APPLY, bool NEED_V, int BDT>
+__global__ void __launch_bounds__(BDT, 1) hm_forest_kernel(const __grid_constant__ HmEvalArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
     unsigned char* nbuf0 = smem + HM_SMEM_HEADER;
     float* xs = reinterpret_cast<float*>(smem + HM_SMEM_HEADER + 2 * (size_t)a.nodebuf);
 
     const int tid = threadIdx.x;
-    const int BD = blockDim.x;
+    constexpr int BD = BDT;      // compile-time block size: the x-tile stride folds into the address arithmetic
     const long long n_tiles = (a.N + BD - 1) / BD;
     if ((long long)blockIdx.x >= n_tiles) return;
     const long long my_tiles = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
@@ -797,11 +797,18 @@ extern "C" int hm_rf_eval(const hm_forest_t* const* forests, int M, const float*
     cudaStream_t st = (cudaStream_t)stream;
     // the plain-predict column of the leaf records is only read for pred_out and Thompson sampling
     const bool need_v = pred_out != nullptr || (acq && a.acq.kind == HM_ACQ_TS);
+#define HM_LAUNCH_B(AP, NV, B)                                                                                         \
+    do {                                                                                                               \
+        HM_CUDA_TRY(cudaFuncSetAttribute(hm_forest_kernel<AP, NV, B>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                         (int)smem));                                                                  \
+        hm_forest_kernel<AP, NV, B><<<grid, B, smem, st>>>(a);                                                         \
+    } while (0)
 #define HM_LAUNCH(AP, NV)                                                                                              \
     do {                                                                                                               \
-        HM_CUDA_TRY(cudaFuncSetAttribute(hm_forest_kernel<AP, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
-                                         (int)smem));                                                                  \
-        hm_forest_kernel<AP, NV><<<grid, block, smem, st>>>(a);                                                        \
+        if (block == 1024) HM_LAUNCH_B(AP, NV, 1024);                                                                  \
+        else if (block == 512) HM_LAUNCH_B(AP, NV, 512);                                                               \
+        else if (block == 256) HM_LAUNCH_B(AP, NV, 256);                                                               \
+        else HM_LAUNCH_B(AP, NV, 128);                                                                                 \
     } while (0)
     if (any_leaf) {
         if (need_v) HM_LAUNCH(true, true); else HM_LAUNCH(true, false);
@@ -809,6 +816,7 @@ extern "C" int hm_rf_eval(const hm_forest_t* const* forests, int M, const float*
         if (need_v) HM_LAUNCH(false, true); else HM_LAUNCH(false, false);
     }
 #undef HM_LAUNCH
+#undef HM_LAUNCH_B
     HM_CUDA_TRY(cudaGetLastError());
     if (scratch) HM_CUDA_TRY(cudaFreeAsync(scratch, st));
     return 0;
