@@ -191,7 +191,7 @@ class RFBench:
         self.scores_host = torch.empty((N,), dtype=torch.float64).pin_memory()
         self.scorer = HostScorer(wl.D_enc, chunk=1 << 21)
         # hm_forest_kernel + hm_topk_stage1/2; forests that stream through shared memory add the coherence pre-pass
-        # (hm_forest_sortkey, hm_forest_scan, hm_forest_perm) for pools of >= 2^17 candidates
+        # (hm_forest_sortkey, hm_forest_scan, hm_forest_scatter_rows) for pools of >= 2^17 candidates
         self.prepass = sum(f.n_groups for f in self.forests if f.staged) > 2 and N >= (1 << 17)
         self.launches_per_step = 3 + (3 if self.prepass else 0)
 
@@ -221,7 +221,7 @@ class RFBench:
         b = 4 * self.wl.D_enc + 8
         ach = b * N / (kernel_ms / 1e3) / 1e9
         return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                "kernel": "hm_forest_kernel<false>" + (" (+ coherence pre-pass hm_forest_sortkey/scan/perm, inside "
+                "kernel": "hm_forest_kernel<false>" + (" (+ coherence pre-pass hm_forest_sortkey/scan/scatter_rows, inside "
                                                        "kernel_ms)" if getattr(self, "prepass", False) else ""),
                 "kernel_ms": kernel_ms, "algorithmic_bytes_per_eval": b, "peak_source": src,
                 "note": "forests with thousands of node visits per evaluation are bound by shared-memory load latency "

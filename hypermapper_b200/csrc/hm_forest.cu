@@ -29,8 +29,8 @@
 // visit (2.5-way bank conflicts) and 30 % of the lanes idle behind the deepest path.  The forest itself is a spatial
 // index: candidates that land in the same leaves of two "key" trees follow nearly the same path in every other tree.
 // So the pool is bucketed by (leaf of key tree A, leaf of key tree B) -- key kernel + histogram, scan, scatter: a
-// counting sort on <= 2^22 bins -- and the traversal kernel visits candidates through that permutation (gather on
-// load, scatter on store; every candidate's arithmetic is untouched, so results stay bit-identical).  Measured on
+// counting sort on <= 2^22 bins that also leaves the candidates as contiguous rows in bucket order -- and the
+// traversal kernel walks that copy (plain coalesced tile loads; results scattered back through the permutation; every candidate's arithmetic is untouched, so results stay bit-identical).  Measured on
 // the C3 shape this cuts distinct nodes per warp visit 12.5 -> 2.3 and raises lane utilisation 0.70 -> 0.86.
 #include <math.h>
 #include <stdlib.h>
@@ -100,6 +100,8 @@ struct HmEvalArgs {
     double* score_out;
     const double* feas;
     const unsigned* perm;     // coherence order (nullptr: arrival order)
+    const float* Xrows;       // with perm: the candidates physically in coherence order, row-major [N][Dp]
+    int Dp;                   // row stride of Xrows (D rounded up to a multiple of 4)
     HmAcqDev acq;
     int has_acq;
 };
@@ -511,7 +513,19 @@ __global__ void __launch_bounds__(BDT, 1) hm_forest_kernel(const __grid_constant
         const long long sl = valid ? slot : a.N - 1;
         // i = the candidate this thread evaluates: arrival order, or the coherence order of the pre-pass
         const long long i = a.perm ? (long long)__ldg(a.perm + sl) : sl;
-        for (int f = 0; f < a.D; ++f) xs_t[f * BD] = __ldg(a.X + (size_t)f * (size_t)a.ldx + (size_t)i);
+        if (a.Xrows) {
+            // the pre-pass left this slot's candidate as one contiguous row: Dp/4 128-bit loads
+            const float4* row = reinterpret_cast<const float4*>(a.Xrows + (size_t)sl * (size_t)a.Dp);
+            for (int q = 0; 4 * q < a.D; ++q) {
+                const float4 v = __ldg(row + q);
+                xs_t[(4 * q) * BD] = v.x;
+                if (4 * q + 1 < a.D) xs_t[(4 * q + 1) * BD] = v.y;
+                if (4 * q + 2 < a.D) xs_t[(4 * q + 2) * BD] = v.z;
+                if (4 * q + 3 < a.D) xs_t[(4 * q + 3) * BD] = v.w;
+            }
+        } else {
+            for (int f = 0; f < a.D; ++f) xs_t[f * BD] = __ldg(a.X + (size_t)f * (size_t)a.ldx + (size_t)i);
+        }
 
         double mean_l[HM_MAX_OBJECTIVES], var_l[HM_MAX_OBJECTIVES];
         int step_in_tile = 0;
@@ -656,12 +670,26 @@ __global__ void __launch_bounds__(1024, 1) hm_forest_scan(unsigned* __restrict__
     }
 }
 
-// perm[offset[key[i]]++] = i   (order inside a bucket is arbitrary: it cannot influence any result)
-__global__ void __launch_bounds__(256) hm_forest_perm(const unsigned* __restrict__ key, unsigned* __restrict__ offs,
-                                                      long long N, unsigned* __restrict__ perm) {
+// pos = offset[key[i]]++;  perm[pos] = i;  rows[pos] = candidate i   (order inside a bucket is arbitrary: it cannot
+// influence any result).  The column-major pool is read coalesced; each candidate leaves as Dp/4 128-bit stores into
+// its own row, so the traversal kernel's tile load is a plain coalesced row read.
+__global__ void __launch_bounds__(256) hm_forest_scatter_rows(const unsigned* __restrict__ key, unsigned* __restrict__ offs,
+                                                              const float* __restrict__ X, long long ldx, long long N,
+                                                              int D, int Dp, unsigned* __restrict__ perm,
+                                                              float* __restrict__ rows) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
-    perm[atomicAdd(offs + key[i], 1u)] = (unsigned)i;
+    const unsigned pos = atomicAdd(offs + key[i], 1u);
+    perm[pos] = (unsigned)i;
+    float4* row = reinterpret_cast<float4*>(rows + (size_t)pos * (size_t)Dp);
+    for (int q = 0; 4 * q < D; ++q) {
+        float4 v;
+        v.x = __ldg(X + (size_t)(4 * q) * (size_t)ldx + (size_t)i);
+        v.y = (4 * q + 1 < D) ? __ldg(X + (size_t)(4 * q + 1) * (size_t)ldx + (size_t)i) : 0.0f;
+        v.z = (4 * q + 2 < D) ? __ldg(X + (size_t)(4 * q + 2) * (size_t)ldx + (size_t)i) : 0.0f;
+        v.w = (4 * q + 3 < D) ? __ldg(X + (size_t)(4 * q + 3) * (size_t)ldx + (size_t)i) : 0.0f;
+        row[q] = v;
+    }
 }
 
 static int g_forest_sort_mode = -2;       // -1 auto, 0 off, 1 on; -2 = not read yet (env HM_B200_FOREST_SORT)
@@ -680,7 +708,7 @@ extern "C" int hm_forest_set_coherence_mode(int mode) {
 
 // builds the coherence permutation of the N candidates in *perm_out (stream-ordered allocation, freed by the caller)
 static int hm_forest_build_perm(const hm_forest_t* const* forests, int M, const float* Xcm, int64_t ldx, int64_t N,
-                                cudaStream_t st, unsigned** perm_out, void** scratch_out) {
+                                cudaStream_t st, unsigned** perm_out, float** rows_out, int* Dp_out, void** scratch_out) {
     HmKeyArgs ka;
     memset(&ka, 0, sizeof(ka));
     // key trees: one from each of the first two forests, or the first two trees of a single forest
@@ -718,18 +746,23 @@ static int hm_forest_build_perm(const hm_forest_t* const* forests, int M, const 
         pool_set = true;
     }
     unsigned* buf = nullptr;
-    const size_t words = (size_t)N * 2 + bins;
+    const int D = forests[0]->n_features, Dp = (D + 3) & ~3;
+    const size_t rows_words = (size_t)N * Dp;                       // 16-byte aligned rows at the front
+    const size_t words = rows_words + (size_t)N * 2 + bins;
     HM_CUDA_TRY(cudaMallocAsync((void**)&buf, words * sizeof(unsigned), st));
-    unsigned* key = buf;
-    unsigned* perm = buf + N;
-    unsigned* hist = buf + 2 * (size_t)N;
+    float* rows = reinterpret_cast<float*>(buf);
+    unsigned* key = buf + rows_words;
+    unsigned* perm = key + N;
+    unsigned* hist = perm + N;
     HM_CUDA_TRY(cudaMemsetAsync(hist, 0, bins * sizeof(unsigned), st));
     const unsigned grid = (unsigned)((N + 255) / 256);
     hm_forest_sortkey<<<grid, 256, 0, st>>>(ka, key, hist);
     hm_forest_scan<<<1, 1024, 0, st>>>(hist, (unsigned)bins);
-    hm_forest_perm<<<grid, 256, 0, st>>>(key, hist, N, perm);
+    hm_forest_scatter_rows<<<grid, 256, 0, st>>>(key, hist, Xcm, ldx, N, D, Dp, perm, rows);
     HM_CUDA_TRY(cudaGetLastError());
     *perm_out = perm;
+    *rows_out = rows;
+    *Dp_out = Dp;
     *scratch_out = buf;
     return 0;
 }
@@ -786,9 +819,11 @@ extern "C" int hm_rf_eval(const hm_forest_t* const* forests, int M, const float*
         const bool big = steps > 2 && N >= HM_SORT_MIN_N && N < 4294967295ll;
         if (!any_leaf && (mode == 1 || (mode == -1 && big))) {
             unsigned* perm = nullptr;
-            int rc = hm_forest_build_perm(forests, M, Xcm, ldx, N, (cudaStream_t)stream, &perm, &scratch);
+            float* rows = nullptr;
+            int rc = hm_forest_build_perm(forests, M, Xcm, ldx, N, (cudaStream_t)stream, &perm, &rows, &a.Dp, &scratch);
             if (rc) return rc;
             a.perm = perm;
+            a.Xrows = rows;
         }
     }
     const size_t smem = HM_SMEM_HEADER + 2 * (size_t)a.nodebuf + (size_t)block * a.D * 4;
