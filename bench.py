@@ -193,7 +193,31 @@ class RFBench:
         # hm_forest_kernel + hm_topk_stage1/2; forests that stream through shared memory add the coherence pre-pass
         # (hm_forest_sortkey, hm_forest_scan, hm_forest_scatter_rows) for pools of >= 2^17 candidates
         self.prepass = sum(f.n_groups for f in self.forests if f.staged) > 2 and N >= (1 << 17)
+        self.smem_bytes_per_eval = self._smem_bytes_per_eval()
         self.launches_per_step = 3 + (3 if self.prepass else 0)
+
+    def _smem_bytes_per_eval(self, sample=1 << 16):
+        """Bytes one evaluation moves through the shared-memory / L1 data pipe: per tree, 12 B per internal node on the
+        candidate's path (8 B node + 4 B feature value) + the 8 B leaf node.  Path lengths come from the leaves the
+        kernel itself reports (hm_rf_eval apply output) on a sample of the pool and the depth of every sklearn node."""
+        import torch
+        from hypermapper_b200 import forest
+        wl = self.wl
+        n = min(sample, self.N)
+        leaves = forest.rf_eval(self.forests, self.x_dev[:, :n].contiguous(), want_leaves=True)["leaves"]
+        total = 0.0
+        for m, o in enumerate(wl.objectives):
+            lv = leaves[m].cpu().numpy()
+            for t, est in enumerate(wl.models[o].estimators_):
+                tr = est.tree_
+                depth = np.zeros(tr.node_count, dtype=np.int64)
+                for node in range(tr.node_count):           # sklearn ids are pre-order: parents come first
+                    l, r = tr.children_left[node], tr.children_right[node]
+                    if l != r:
+                        depth[l] = depth[node] + 1
+                        depth[r] = depth[node] + 1
+                total += float(depth[lv[t]].mean()) * 12 + 8
+        return total
 
     def step(self, record):
         import torch
@@ -220,7 +244,17 @@ class RFBench:
         peak, src = measured_peaks()
         b = 4 * self.wl.D_enc + 8
         ach = b * N / (kernel_ms / 1e3) / 1e9
+        # secondary, physical roofline: the shared-memory / L1 data pipe moves 128 B per clock per SM
+        import torch
+        prop = torch.cuda.get_device_properties(0)
+        smem_peak = 128.0 * prop.multi_processor_count * 1.965e9 / 1e9      # GB/s at clocks.max.sm = 1965 MHz
+        smem_ach = self.smem_bytes_per_eval * N / (kernel_ms / 1e3) / 1e9
         return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "smem_pipe": {"achieved": smem_ach, "peak": smem_peak, "unit": "GB/s", "frac": smem_ach / smem_peak,
+                              "bytes_per_eval": self.smem_bytes_per_eval,
+                              "how": "per tree: 12 B per internal node on the path (8 B node + 4 B feature) + 8 B leaf "
+                                     "node, path lengths measured on 65536 pool candidates; peak = 128 B/clk/SM x SMs "
+                                     "x 1965 MHz"},
                 "kernel": "hm_forest_kernel<false>" + (" (+ coherence pre-pass hm_forest_sortkey/scan/scatter_rows, inside "
                                                        "kernel_ms)" if getattr(self, "prepass", False) else ""),
                 "kernel_ms": kernel_ms, "algorithmic_bytes_per_eval": b, "peak_source": src,
