@@ -28,7 +28,9 @@
 //             against the <= B pivots held in shared memory; survivors are compacted in index order (block
 //             counts -> scan -> scatter), so the next batch is again "the next B efficient points in index order".
 // The fast path raises a device flag when it meets a NaN and the call is redone on the exact path.
+#include <stdlib.h>
 #include <algorithm>
+#include <mutex>
 #include <vector>
 #include "hm_common.cuh"
 
@@ -836,6 +838,61 @@ static int hm_pareto_run_exact(const double* costs, int64_t N, uint8_t* mask, vo
     return 0;
 }
 
+// ---- tiny cache of instantiated launch-chain graphs -----------------------------------------------------------
+struct HmGraphKey {
+    const void* costs;
+    const void* mask;
+    const void* workspace;
+    int64_t N;
+    int M, pass2;
+};
+#define HM_GRAPH_SLOTS 8
+static struct {
+    HmGraphKey key;
+    cudaGraphExec_t exec;
+    int device;
+} g_graphs[HM_GRAPH_SLOTS];
+static int g_graph_next = 0, g_graph_off = -1;
+static cudaStream_t g_graph_stream = nullptr;
+static std::mutex g_graph_mutex;
+
+static bool hm_graph_enabled() {
+    if (g_graph_off < 0) {
+        const char* e = getenv("HM_B200_PARETO_GRAPH");
+        g_graph_off = (e && atoi(e) == 0) ? 1 : 0;
+    }
+    return g_graph_off == 0;
+}
+static void hm_graph_disable() { g_graph_off = 1; }
+static cudaStream_t hm_graph_capture_stream() {     // the caller's stream may be the legacy stream, which cannot capture
+    std::lock_guard<std::mutex> lk(g_graph_mutex);
+    if (!g_graph_stream && cudaStreamCreateWithFlags(&g_graph_stream, cudaStreamNonBlocking) != cudaSuccess)
+        g_graph_stream = nullptr;
+    return g_graph_stream;
+}
+static cudaGraphExec_t hm_graph_lookup(const HmGraphKey& k) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(g_graph_mutex);
+    for (int i = 0; i < HM_GRAPH_SLOTS; ++i)
+        if (g_graphs[i].exec && g_graphs[i].device == dev && g_graphs[i].key.costs == k.costs &&
+            g_graphs[i].key.mask == k.mask && g_graphs[i].key.workspace == k.workspace && g_graphs[i].key.N == k.N &&
+            g_graphs[i].key.M == k.M && g_graphs[i].key.pass2 == k.pass2)
+            return g_graphs[i].exec;
+    return nullptr;
+}
+static void hm_graph_store(const HmGraphKey& k, cudaGraphExec_t exec) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(g_graph_mutex);
+    const int i = g_graph_next;
+    g_graph_next = (g_graph_next + 1) % HM_GRAPH_SLOTS;
+    if (g_graphs[i].exec) cudaGraphExecDestroy(g_graphs[i].exec);
+    g_graphs[i].key = k;
+    g_graphs[i].exec = exec;
+    g_graphs[i].device = dev;
+}
+
 // NaN-free fast path; *saw_nan_out = 1 means the result is void and the exact path must run.
 template <int M>
 static int hm_pareto_run_fast(const double* costs, int64_t N, uint8_t* mask, void* workspace, int64_t* n_out, bool pass2,
@@ -860,43 +917,76 @@ static int hm_pareto_run_fast(const double* costs, int64_t N, uint8_t* mask, voi
     unsigned* list1 = ws.alive[0];
     unsigned* list2 = ws.alive[1];
 
-    hm_px_ctl_init<<<1, 32, 0, st>>>(ctl);
-    HM_CUDA_TRY(cudaMemsetAsync(mask, 0, (size_t)N, st));
+    // the whole launch chain (17 nodes, every size a device-side counter) as a function of the stream
+    auto enqueue = [&](cudaStream_t s) -> int {
+    hm_px_ctl_init<<<1, 32, 0, s>>>(ctl);
+    HM_CUDA_TRY(cudaMemsetAsync(mask, 0, (size_t)N, s));
     // ---- level 1: pivots from a strided sample of everything, stream the whole cost matrix ----
-    hm_px_gather_sample<M><<<(HM_SAMPLE1 + 255) / 256, 256, 0, st>>>(costs, nullptr, nullptr, n, HM_SAMPLE1, ws.sample, ctl);
-    hm_px_exact<M, false><<<(HM_SAMPLE1 + HM_PX_GROUP - 1) / HM_PX_GROUP, HM_PX_THREADS, exact_smem, st>>>(
+    hm_px_gather_sample<M><<<(HM_SAMPLE1 + 255) / 256, 256, 0, s>>>(costs, nullptr, nullptr, n, HM_SAMPLE1, ws.sample, ctl);
+    hm_px_exact<M, false><<<(HM_SAMPLE1 + HM_PX_GROUP - 1) / HM_PX_GROUP, HM_PX_THREADS, exact_smem, s>>>(
         ws.sample, nullptr, &ctl->n_sample, ws.piv_raw, nullptr, &ctl->n_piv_raw, &ctl->nan_flag);
-    hm_px_sort_pivots<M><<<1, 1024, sort_smem, st>>>(ws.piv_raw, ws.pivots, ctl);
+    hm_px_sort_pivots<M><<<1, 1024, sort_smem, s>>>(ws.piv_raw, ws.pivots, ctl);
     {
         const unsigned chunk = HM_PX_THREADS * IT1;
         const unsigned chunks = (n + chunk - 1) / chunk;
         const unsigned grid = std::min<unsigned>(chunks, (unsigned)sms * 4);
-        hm_px_stream<M, IT1><<<grid, HM_PX_THREADS, stream_smem1, st>>>(costs, nullptr, nullptr, n, ws.pivots, ctl,
+        hm_px_stream<M, IT1><<<grid, HM_PX_THREADS, stream_smem1, s>>>(costs, nullptr, nullptr, n, ws.pivots, ctl,
                                                                               list1, &ctl->n_list1);
     }
     // ---- level 2: pivots sampled from the survivors, re-filter the survivors ----
-    hm_px_gather_sample<M><<<(HM_SAMPLE2 + 255) / 256, 256, 0, st>>>(costs, list1, &ctl->n_list1, 0, HM_SAMPLE2, ws.sample, ctl);
-    hm_px_exact<M, false><<<(HM_SAMPLE2 + HM_PX_GROUP - 1) / HM_PX_GROUP, HM_PX_THREADS, exact_smem, st>>>(
+    hm_px_gather_sample<M><<<(HM_SAMPLE2 + 255) / 256, 256, 0, s>>>(costs, list1, &ctl->n_list1, 0, HM_SAMPLE2, ws.sample, ctl);
+    hm_px_exact<M, false><<<(HM_SAMPLE2 + HM_PX_GROUP - 1) / HM_PX_GROUP, HM_PX_THREADS, exact_smem, s>>>(
         ws.sample, nullptr, &ctl->n_sample, ws.piv_raw, nullptr, &ctl->n_piv_raw, &ctl->nan_flag);
-    hm_px_sort_pivots<M><<<1, 1024, sort_smem, st>>>(ws.piv_raw, ws.pivots, ctl);
-    hm_px_stream<M, HM_PS_ITEMS2><<<sms * 4, HM_PX_THREADS, stream_smem2, st>>>(costs, list1, &ctl->n_list1, 0, ws.pivots,
+    hm_px_sort_pivots<M><<<1, 1024, sort_smem, s>>>(ws.piv_raw, ws.pivots, ctl);
+    hm_px_stream<M, HM_PS_ITEMS2><<<sms * 4, HM_PX_THREADS, stream_smem2, s>>>(costs, list1, &ctl->n_list1, 0, ws.pivots,
                                                                              ctl, list2, &ctl->n_list2);
     // ---- exact all-pairs on what is left -> mask, and the front's indices into list1 ----
-    hm_px_exact<M, true><<<sms * 4, HM_PX_THREADS, exact_smem, st>>>(costs, list2, &ctl->n_list2, (double*)list1, mask,
+    hm_px_exact<M, true><<<sms * 4, HM_PX_THREADS, exact_smem, s>>>(costs, list2, &ctl->n_list2, (double*)list1, mask,
                                                                      &ctl->n_front1, &ctl->nan_flag);
     HM_CUDA_TRY(cudaGetLastError());
     if (pass2) {
         // survivors in index order (one-CTA sort of the front list; the ordered mask compaction only runs, device
         // side decision, when the front is too long for that), then the order-dependent clean-up pass
         const unsigned nblk = (n + HM_PF_CHUNK - 1) / HM_PF_CHUNK;
-        hm_px_sort_front<<<1, 1024, 0, st>>>(list1, ctl);
-        hm_px_count_flags<<<nblk, HM_PF_THREADS, 0, st>>>(mask, n, ws.block_counts, &ctl->need_scan);
-        hm_pareto_scan<<<1, 1024, 0, st>>>(ws.block_counts, nblk, ws.round, &ctl->need_scan);
-        hm_pareto_scatter<<<nblk, HM_PF_THREADS, 0, st>>>(nullptr, n, mask, ws.block_counts, list1, 0xffffffffu, ws.round,
+        hm_px_sort_front<<<1, 1024, 0, s>>>(list1, ctl);
+        hm_px_count_flags<<<nblk, HM_PF_THREADS, 0, s>>>(mask, n, ws.block_counts, &ctl->need_scan);
+        hm_pareto_scan<<<1, 1024, 0, s>>>(ws.block_counts, nblk, ws.round, &ctl->need_scan);
+        hm_pareto_scatter<<<nblk, HM_PF_THREADS, 0, s>>>(nullptr, n, mask, ws.block_counts, list1, 0xffffffffu, ws.round,
                                                           &ctl->need_scan);
-        hm_px_pass2_a<M><<<sms * 4, HM_PX_THREADS, 0, st>>>(costs, list1, &ctl->n_front1, ws.state, &ctl->nan_flag);
-        hm_px_pass2_b<M><<<1, 1024, 0, st>>>(costs, list1, &ctl->n_front1, ws.state, mask, ctl);
+        hm_px_pass2_a<M><<<sms * 4, HM_PX_THREADS, 0, s>>>(costs, list1, &ctl->n_front1, ws.state, &ctl->nan_flag);
+        hm_px_pass2_b<M><<<1, 1024, 0, s>>>(costs, list1, &ctl->n_front1, ws.state, mask, ctl);
         HM_CUDA_TRY(cudaGetLastError());
+    }
+        return 0;
+    };
+    // 16 back-to-back launches cost more CPU time than the GPU needs to run them (10^7 x 3: ~0.19 ms of work), so the
+    // chain is captured once per (buffers, N, pass 2) into a CUDA graph and replayed with one launch.
+    {
+        HmGraphKey key = {costs, mask, workspace, N, M, pass2 ? 1 : 0};
+        cudaGraphExec_t exec = hm_graph_lookup(key);
+        if (!exec && hm_graph_enabled()) {
+            cudaStream_t cap = hm_graph_capture_stream();
+            cudaGraph_t graph = nullptr;
+            if (cap && cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                const int rc = enqueue(cap);
+                const cudaError_t e = cudaStreamEndCapture(cap, &graph);
+                if (rc == 0 && e == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess)
+                    hm_graph_store(key, exec);
+                else
+                    exec = nullptr;
+                if (graph) cudaGraphDestroy(graph);
+            }
+            if (!exec) {
+                cudaGetLastError();
+                hm_graph_disable();
+            }
+        }
+        if (exec) {
+            HM_CUDA_TRY(cudaGraphLaunch(exec, st));
+        } else {
+            const int rc = enqueue(st);
+            if (rc) return rc;
+        }
     }
     HmParetoCtl h;
     HM_CUDA_TRY(cudaMemcpyAsync(&h, ctl, sizeof(h), cudaMemcpyDeviceToHost, st));
