@@ -24,6 +24,9 @@ EXPORTED_SYMBOLS = [
     "hm_topk_workspace_bytes", "hm_topk", "hm_topk_merge",
     "hm_gp_create", "hm_gp_destroy", "hm_gp_mean_var",
     "hm_pareto_workspace_bytes", "hm_pareto_filter", "hm_pareto_pass1",
+    "hm_space_create", "hm_space_destroy", "hm_space_n_params", "hm_space_n_encoded",
+    "hm_encode", "hm_sample_pool", "hm_sample_rows", "hm_prior_prob", "hm_prior_weight",
+    "hm_minmax", "hm_bopro_ratio", "hm_bopro_finish",
     "hm_host_ctx_create", "hm_host_ctx_destroy", "hm_rf_score_host",
 ]
 
@@ -41,6 +44,23 @@ class AcqParams(ctypes.Structure):
         ("weight", ctypes.c_double * HM_MAX_OBJECTIVES),
         ("f_min", ctypes.c_double * HM_MAX_OBJECTIVES),
         ("beta", ctypes.c_double),
+    ]
+
+
+class BoproParams(ctypes.Structure):
+    """hm_bopro_params_t"""
+    _fields_ = [
+        ("n_objectives", ctypes.c_int32),
+        ("prior_mode", ctypes.c_int32),
+        ("discrete_space", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+        ("weight", ctypes.c_double * HM_MAX_OBJECTIVES),
+        ("threshold", ctypes.c_double * HM_MAX_OBJECTIVES),
+        ("prior_lo", ctypes.c_double),
+        ("prior_hi", ctypes.c_double),
+        ("posterior_floor", ctypes.c_double),
+        ("discrete_divisor", ctypes.c_double),
+        ("model_exponent", ctypes.c_double),
     ]
 
 
@@ -92,6 +112,20 @@ def lib():
     L.hm_pareto_workspace_bytes.restype = i64
     L.hm_pareto_filter.argtypes = [vp, i64, i32, vp, vp, ctypes.POINTER(i64), vp]
     L.hm_pareto_pass1.argtypes = [vp, i64, i32, vp, vp, ctypes.POINTER(i64), vp]
+    u64 = ctypes.c_uint64
+    L.hm_space_create.argtypes = [i32, vp, vp, i64, ctypes.POINTER(vp)]
+    L.hm_space_destroy.argtypes = [vp]
+    L.hm_space_destroy.restype = None
+    L.hm_space_n_params.argtypes = [vp]
+    L.hm_space_n_encoded.argtypes = [vp]
+    L.hm_encode.argtypes = [vp, vp, i32, i64, i64, vp, i64, vp, i64, vp, vp]
+    L.hm_sample_pool.argtypes = [vp, u64, i64, i64, i32, vp, i64, vp, i64, vp, i64, vp, i32, vp, vp]
+    L.hm_sample_rows.argtypes = [vp, u64, i32, vp, i64, vp, vp]
+    L.hm_prior_prob.argtypes = [vp, vp, i32, i64, i64, vp, i32, vp, vp, vp]
+    L.hm_prior_weight.argtypes = [vp, vp, i64, dbl, dbl, i32, vp, vp, vp]
+    L.hm_minmax.argtypes = [vp, i64, i32, vp, vp, vp]
+    L.hm_bopro_ratio.argtypes = [ctypes.POINTER(BoproParams), vp, vp, vp, i64, i64, vp, vp]
+    L.hm_bopro_finish.argtypes = [vp, i64, i32, dbl, dbl, dbl, vp, vp, vp, vp]
     L.hm_host_ctx_create.argtypes = [i64, i32, ctypes.POINTER(vp)]
     L.hm_host_ctx_destroy.argtypes = [vp]
     L.hm_host_ctx_destroy.restype = None

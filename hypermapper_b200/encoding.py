@@ -102,6 +102,21 @@ class Encoder:
         return self.encode_columns(cols, dtype=dtype)
 
 
+def raw_matrix(bufferx, param_space):
+    """list of dicts / list of tuples / [N][D] array -> [N][D] float64 of raw values in input-parameter order
+    (categoricals as integer indices, space.py:669-673)."""
+    inputs = list(param_space.get_input_parameters())
+    if isinstance(bufferx, np.ndarray):
+        arr = bufferx
+    elif len(bufferx) > 0 and isinstance(bufferx[0], dict):
+        arr = np.array([[c[p] for p in inputs] for c in bufferx])
+    else:
+        arr = np.asarray(bufferx)
+    if arr.dtype != np.float64:
+        arr = arr.astype(np.float64)
+    return arr.reshape(-1, len(inputs))
+
+
 _encoders = {}
 
 

@@ -92,22 +92,19 @@ def get_neighbors(configuration, param_space):
     return neighbors
 
 
-def _is_device_scorer(optimization_function):
-    from . import random_scalarizations as rs
-    return optimization_function is rs.run_acquisition_function
+def _device_scorer(optimization_function):
+    """Acquisition plug-ins of this package carry `device_scores(candidates, **params) -> CUDA tensor`
+    (run_acquisition_function, pibo.prior_weighted_acquisition_function,
+    prior_optimization.compute_EI_from_posteriors): pools are scored as arrays and stay on the GPU."""
+    return getattr(optimization_function, "device_scores", None)
 
 
 def _score_pool(pool, inputs, optimization_function, params, device_scorer):
     """pool: object/float array [N][D] (or list of dicts when the whole space was enumerated).
     Returns (values, n_evaluated) where values is a CUDA tensor (device scorer) or a host list."""
-    if device_scorer:
-        from .random_scalarizations import acquisition_scores_device
-        p = {k: v for k, v in params.items() if k != "number_of_cpus"}
+    if device_scorer is not None:
         cand = pool if isinstance(pool, list) else np.asarray(pool, dtype=np.float64)
-        scores = acquisition_scores_device(p["acquisition_function"], cand, p["objective_weights"],
-                                           p["regression_models"], p["param_space"], p["scalarization_method"],
-                                           p["objective_limits"], p["iteration_number"], p["data_array"],
-                                           p["model_type"], p.get("classification_model"))
+        scores = device_scorer(cand, **params)
         return scores, scores.numel()
     configs = pool if isinstance(pool, list) else _rows_to_dicts(pool, inputs, range(len(pool)))
     values, _ = optimization_function(configurations=configs, **params)
@@ -168,7 +165,7 @@ def local_search(local_search_starting_points, local_search_random_points, param
     inputs = param_space.get_input_parameters()
     feasible_parameter = param_space.get_feasible_parameter()[0]
     params = optimization_function_parameters
-    device_scorer = _is_device_scorer(optimization_function) and not enable_feasible_predictor
+    device_scorer = None if enable_feasible_predictor else _device_scorer(optimization_function)
     oversampling_factor = 2
 
     # (kept for RNG / side-effect parity with local_search.py:429-432; the hash table copy is not used afterwards)

@@ -18,7 +18,7 @@ import sys
 import numpy as np
 
 from . import _lib
-from .encoding import encoder_for
+from .encoding import encoder_for, raw_matrix
 
 
 class EncodedCandidates:
@@ -48,14 +48,39 @@ def encode_host(bufferx, param_space, dtype=np.float64):
 
 
 def encode_to_device(bufferx, param_space, dtype):
-    torch = _lib.require_cuda()
+    """models.preprocess_data_array (models.py:941-984) on the device (K5 hm_encode): the raw [N][D] values are copied
+    to the GPU and encoded there, column-major.  float64 -> float32 is the round-to-nearest cast sklearn's
+    check_array(dtype=float32) applies."""
+    _lib.require_cuda()
     if isinstance(bufferx, EncodedCandidates):
         return bufferx.get(dtype)
-    # float64 -> float32 is the same round-to-nearest cast sklearn's check_array(dtype=float32) applies
-    host = encode_host(bufferx, param_space, dtype=np.float64)
-    if dtype == "float32":
-        host = host.astype(np.float32)
-    return torch.from_numpy(np.ascontiguousarray(host)).cuda()
+    from .space_device import device_space_for
+    x32, x64 = device_space_for(param_space).encode(raw_matrix(bufferx, param_space), want32=(dtype == "float32"),
+                                                    want64=(dtype != "float32"))
+    return x32 if dtype == "float32" else x64
+
+
+def mean_and_variance_device(candidates, regression_models, model_type, param_space):
+    """Per-objective posterior mean / variance left on the GPU: CUDA fp64 tensors [M][N] (objectives in
+    regression_models order).  NaN means are NOT yet patched to sys.maxsize (models.py:762-763); consumers do it."""
+    torch = _lib.require_cuda()
+    objectives = list(regression_models.keys())
+    if model_type == "random_forest":
+        from .forest import device_forest, rf_eval
+        X32 = encode_to_device(candidates, param_space, "float32")
+        out = rf_eval([device_forest(regression_models[o]) for o in objectives], X32, want_mean=True, want_var=True)
+        return out["mean"], out["var"]
+    if model_type == "gaussian_process":
+        from .gp import device_gp, gp_mean_var
+        X64 = encode_to_device(candidates, param_space, "float64")
+        N = X64.shape[1]
+        mean = torch.empty((len(objectives), N), dtype=torch.float64, device=X64.device)
+        var = torch.empty_like(mean)
+        for m, o in enumerate(objectives):
+            gp_mean_var(device_gp(regression_models[o]), X64, mean[m], var[m])
+        return mean, var
+    print("Unrecognized model type:", model_type)
+    raise SystemExit
 
 
 def preprocess_data_buffer(bufferx, param_space):

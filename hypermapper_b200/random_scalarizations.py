@@ -100,6 +100,16 @@ def run_acquisition_function(acquisition_function, configurations, objective_wei
     return scalarized_values, [1] * len(scalarized_values)
 
 
+def _device_scores(candidates, **p):
+    return acquisition_scores_device(p["acquisition_function"], candidates, p["objective_weights"],
+                                     p["regression_models"], p["param_space"], p["scalarization_method"],
+                                     p["objective_limits"], p["iteration_number"], p["data_array"], p["model_type"],
+                                     p.get("classification_model"))
+
+
+run_acquisition_function.device_scores = _device_scores
+
+
 def _acq_from_bufferx(kind, bufferx, data_array, objective_weights, regression_models, param_space,
                       scalarization_method, objective_limits, iteration_number, model_type, classification_model):
     scores = acquisition_scores_device(kind, bufferx, objective_weights, regression_models, param_space,

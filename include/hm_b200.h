@@ -171,6 +171,106 @@ int hm_pareto_pass1(const double* costs, int64_t N, int M, uint8_t* mask, void* 
                     int64_t* n_alive_out_host, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * K5 / K6 / K7  search-space side of the path on the device
+ * A space is the list of input parameters in input-parameter order (space.py Real/Integer/Ordinal/
+ * CategoricalParameter) plus one fp64 table blob the descriptors point into.
+ * ------------------------------------------------------------------------------------------ */
+#define HM_P_REAL 0
+#define HM_P_INTEGER 1
+#define HM_P_ORDINAL 2
+#define HM_P_CATEGORICAL 3
+/* how get_x_probability / randomly_select of the parameter work */
+#define HM_PRIOR_BETA 0      /* real, integer: stats.beta.pdf((x-lo)/(hi-lo), a, b) (space.py:279-286, 405-410); the
+                                 "uniform" prior is a = b = 1 */
+#define HM_PRIOR_TABLE 1     /* probability per value index: categorical, "distribution" priors, and ordinals with a
+                                 named density (cdf differences, space.py:524-533, precomputed by the host) */
+#define HM_PRIOR_GAUSSIAN 2  /* real "custom_gaussian": norm.pdf(x, a = mean, b = std) (space.py:272-277) */
+#define HM_PRIOR_INTERP 3    /* real list prior: np.interp on the normalised list (space.py:222-229) */
+typedef struct hm_param_desc {
+    int32_t kind;        /* HM_P_* */
+    int32_t n_values;    /* ordinal: number of values; categorical: number of categories */
+    int32_t out_col;     /* first encoded column (models.py:957-984: non-categoricals in input order, then the
+                            one-hot blocks) */
+    int32_t normalize;   /* real/integer: z-score with mean/std (models.py:966-971) */
+    int32_t prior_kind;  /* HM_PRIOR_* */
+    int32_t n_prior;     /* TABLE: entries; INTERP: length of the prior list */
+    int32_t ordinal_beta;/* ordinal / integer with a named density: sampled as Beta(a, b) -> rounded index
+                            (space.py:383-387, 496-499) even though its probability is a TABLE */
+    int32_t n_cdf;       /* INTERP: length of the sampling tables (10000 in the reference, space.py:127-130) */
+    int64_t values_off;  /* ordinal: tables[values_off ..] = n_values ascending values, then n_values encoded
+                            values index/size (models.py:962-965, host arithmetic) */
+    int64_t prior_off;   /* TABLE: n_prior probabilities, then n_prior cumulative sums (np.random.choice);
+                            INTERP: n_prior abscissae linspace(lo, hi, n_prior), then the n_prior densities */
+    int64_t cdf_off;     /* INTERP: n_cdf cumulative values, then the n_cdf abscissae (space.py:151-153) */
+    double lo, hi;       /* get_min() / get_max() */
+    double mean, std;    /* z-score statistics */
+    double a, b;         /* Beta alpha/beta, or Gaussian mean/std */
+    double lbeta;        /* log B(a, b) */
+} hm_param_desc_t;
+typedef struct hm_space hm_space_t;
+int hm_space_create(int n_params, const hm_param_desc_t* params_host, const double* tables_host, int64_t n_tables,
+                    hm_space_t** out);
+void hm_space_destroy(hm_space_t* s);
+int hm_space_n_params(const hm_space_t* s);
+int hm_space_n_encoded(const hm_space_t* s);
+
+/* K5  replaces models.preprocess_data_array (models.py:941-984), bit-exact.
+ *   raw: fp64 raw parameter values, row-major [N][ldr >= D] (raw_col_major = 0, the layout of the reference's
+ *        sample arrays) or column-major [D][ldr >= N]; categoricals as integer indices, ordinals as values.
+ *   X32cm / X64cm (either may be NULL): encoded column-major [D_enc][ld].
+ *   n_invalid_dev (nullable, caller zeroes it): incremented when an ordinal value is not in its list or a
+ *        categorical index is out of range (the reference raises ValueError there); such entries encode as NaN. */
+int hm_encode(const hm_space_t* s, const double* raw, int raw_col_major, int64_t ldr, int64_t N, float* X32cm,
+              int64_t ld32, double* X64cm, int64_t ld64, int32_t* n_invalid_dev, void* stream);
+
+/* K6  replaces space.get_random_configuration(size=N, use_priors, return_as_array=True) (space.py:1263-1311) followed
+ * by the encoding: candidate i of the pool = f(seed, index_base + i, use_priors) (Philox4x32-10; same distributions as
+ * the reference's per-parameter randomly_select / randomly_select_uniform, NOT numpy's Mersenne-Twister stream).
+ * Any output may be NULL.  prob_out: the prior probability of each candidate (K7) in the same pass.
+ * hm_sample_rows re-generates the raw rows [n][D] of the given pool indices (the top-k winners). */
+int hm_sample_pool(const hm_space_t* s, uint64_t seed, int64_t index_base, int64_t N, int use_priors,
+                   double* raw_cm_out, int64_t ldr, float* X32cm, int64_t ld32, double* X64cm, int64_t ld64,
+                   const double* objective_weights_host, int n_objectives, double* prob_out, void* stream);
+int hm_sample_rows(const hm_space_t* s, uint64_t seed, int use_priors, const int64_t* index_dev, int64_t n,
+                   double* raw_rows_out, void* stream);
+
+/* K7  replaces prior_optimization.compute_probability_from_prior (prior_optimization.py:65-95, the
+ * non-estimated branch): prob = prod_params prod_objectives get_x_probability(x) ** w_objective. */
+int hm_prior_prob(const hm_space_t* s, const double* raw, int raw_col_major, int64_t ldr, int64_t N,
+                  const double* objective_weights_host, int n_objectives, double* prob_out, int32_t* n_invalid_dev,
+                  void* stream);
+/* piBO weighting (pibo.py:101-113): out = acq * (prob + prior_floor) ** exponent with exponent = prior_beta /
+ * iteration_number; collapse_to_min = 1 reproduces the reference's np.min(acq, 0) for TS/UCB (pibo.py:103-104;
+ * workspace8 = 8 bytes of device memory). */
+int hm_prior_weight(const double* acq, const double* prob, int64_t N, double prior_floor, double exponent,
+                    int collapse_to_min, double* out, void* workspace8, void* stream);
+
+/* BOPrO acquisition (prior_optimization.compute_EI_from_posteriors, prior_optimization.py:161-374):
+ *   hm_minmax        min / max of a device vector (NaNs skipped; ignore_inf skips +-inf as :318-327 does);
+ *                    out2_dev = {min, max} (+inf / -inf when nothing qualifies); workspace16 = 16 device bytes
+ *   hm_bopro_ratio   log posterior(good) - log posterior(bad) per candidate from the prior probability (K7) and the
+ *                    per-objective model mean / VARIANCE [M][ldm] (the kernel applies models.py:762-763 and the sqrt)
+ *   hm_bopro_finish  optional rescale to [floor, 1] with the running limits, + feasibility indicator, negate,
+ *                    +-inf -> +-sys.maxsize; feas_prob = P(feasible) per candidate or NULL */
+typedef struct hm_bopro_params {
+    int32_t n_objectives;
+    int32_t prior_mode;        /* 0 = prior as is, 1 = rescale with [prior_lo, prior_hi] (:184-192), 2 = all ones (:181) */
+    int32_t discrete_space;    /* prior_bad /= discrete_divisor (:199-205) */
+    int32_t reserved;
+    double weight[HM_MAX_OBJECTIVES];
+    double threshold[HM_MAX_OBJECTIVES];
+    double prior_lo, prior_hi;
+    double posterior_floor;
+    double discrete_divisor;   /* get_discrete_space_size() - 1 */
+    double model_exponent;     /* iteration_number / model_weight */
+} hm_bopro_params_t;
+int hm_minmax(const double* v, int64_t N, int ignore_inf, double* out2_dev, void* workspace16, void* stream);
+int hm_bopro_ratio(const hm_bopro_params_t* p, const double* prior_prob, const double* mean, const double* var,
+                   int64_t ldm, int64_t N, double* ratio_out, void* stream);
+int hm_bopro_finish(const double* ratio, int64_t N, int normalize_mode, double lo, double hi, double posterior_floor,
+                    const double* feas_prob, double* out, double* feas_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Host-buffer convenience entry points (what a reference-side ctypes/cffi binding calls when its
  * data lives in numpy arrays): pinned staging + H2D/D2H copies happen inside.  Used for `e2e`.
  * ------------------------------------------------------------------------------------------ */

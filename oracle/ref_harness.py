@@ -64,7 +64,7 @@ _loaded = None
 
 def load():
     """Returns a namespace with the reference modules: models, random_scalarizations, local_search,
-    compute_pareto, utility_functions, space."""
+    compute_pareto, utility_functions, space, prior_optimization, pibo."""
     global _loaded
     if _loaded is not None:
         return _loaded
@@ -84,7 +84,8 @@ def load():
     import importlib
 
     ns = types.SimpleNamespace()
-    for mod in ("utility_functions", "space", "models", "local_search", "random_scalarizations", "compute_pareto"):
+    for mod in ("utility_functions", "space", "models", "local_search", "random_scalarizations", "compute_pareto",
+                "prior_optimization", "pibo"):
         setattr(ns, mod, importlib.import_module("hypermapper." + mod))
     import sklearn.preprocessing as skp
 

@@ -11,6 +11,9 @@ The reference cannot travel to the GPU box, so its outputs are frozen here:
   pareto.npz      sequential_is_pareto_efficient masks on random / tie-heavy / duplicated / NaN inputs and the
                   three known-answer cases of the reference's tests (tests/data/*pareto*.csv)
   local_search.npz  local_search() trajectory end points under fixed seeds (discrete space)
+  priors.npz      a space with every prior form (named Beta densities, probability lists, interpolated list prior,
+                  custom Gaussian): compute_probability_from_prior, pibo.prior_weighted_acquisition_function and
+                  prior_optimization.compute_EI_from_posteriors outputs of the reference
 """
 import copy
 import json
@@ -309,6 +312,124 @@ def local_search_case():
     print("local_search.npz", {k: v.tolist() for k, v in out.items() if k.startswith("best_")})
 
 
+
+PRIORS = {
+    "application_name": "golden_priors",
+    "optimization_objectives": ["obj_a"],
+    "optimization_iterations": 20,
+    "models": {"model": "random_forest", "number_of_trees": 8},
+    "custom_gaussian_prior_means": [0.3],
+    "custom_gaussian_prior_stds": [0.15],
+    "input_parameters": {
+        "r_gauss": {"parameter_type": "real", "values": [-5, 10], "parameter_default": 0, "prior": "gaussian"},
+        "r_decay": {"parameter_type": "real", "values": [0, 1], "parameter_default": 0.5, "prior": "decay"},
+        "r_list": {"parameter_type": "real", "values": [2, 6], "parameter_default": 3,
+                   "prior": [1, 2, 4, 8, 4, 2, 1, 1, 3, 1]},
+        "r_cg": {"parameter_type": "real", "values": [0, 1], "parameter_default": 0.5, "prior": "custom_gaussian"},
+        "i_exp": {"parameter_type": "integer", "values": [0, 20], "parameter_default": 3, "prior": "exponential"},
+        "i_list": {"parameter_type": "integer", "values": [1, 4], "parameter_default": 2, "prior": [0.1, 0.2, 0.3, 0.4]},
+        "o_gauss": {"parameter_type": "ordinal", "values": [1, 2, 4, 8, 16, 32, 64, 128], "parameter_default": 4,
+                    "prior": "gaussian"},
+        "o_list": {"parameter_type": "ordinal", "values": [0.5, 1.5, 2.5], "parameter_default": 1.5,
+                   "prior": [0.5, 0.25, 0.25]},
+        "c_list": {"parameter_type": "categorical", "values": ["a", "b", "c"], "parameter_default": "a",
+                   "prior": [0.2, 0.5, 0.3]},
+        "c_uni": {"parameter_type": "categorical", "values": ["p", "q"], "parameter_default": "q"},
+    },
+}
+
+
+def objective_priors(cfg):
+    return float((cfg["r_gauss"] - 2.0) ** 2 + 3 * cfg["r_decay"] + cfg["r_list"] + 5 * (cfg["r_cg"] - 0.3) ** 2 +
+                 0.3 * cfg["i_exp"] + cfg["i_list"] + np.log2(cfg["o_gauss"]) * (1 + cfg["c_list"]) +
+                 2 * cfg["o_list"] - 3 * cfg["c_uni"])
+
+
+def priors_case():
+    """Every prior form of space.py through the reference's prior-guided acquisition functions."""
+    from oracle import oracle
+    config = validated(PRIORS)
+    np.random.seed(31)
+    random.seed(31)
+    space = ns.space.Space(config)
+    objectives = config["optimization_objectives"]
+    inputs = space.get_input_parameters()
+    data = sample_data_array(space, 80, objective_priors, objectives)
+    models = fit(config, space, data, objectives)
+    uni = space.get_random_configuration(size=300, use_priors=False, return_as_array=True)
+    pri = space.get_random_configuration(size=300, use_priors=True, return_as_array=True)
+    cand = np.concatenate([uni, pri], axis=0)
+    # boundary values: pdf = inf for the decay / exponential densities (capped at 1242 for reals only)
+    cand[0, inputs.index("r_decay")] = 0.0
+    cand[1, inputs.index("i_exp")] = 20
+    cand[2, inputs.index("r_gauss")] = -5.0
+    cand[3, inputs.index("r_list")] = 6.0
+    configurations = [{k: to_native(c[k]) for k in inputs} for c in ns.utility_functions.array_to_list_of_dicts(cand, inputs)]
+    out = {}
+    out["config_json"] = np.array(json.dumps(config))
+    out["candidates"] = np.array([[float(c[k]) for k in inputs] for c in configurations], dtype=np.float64)
+    out["data_inputs"] = np.array([[float(data[k][r]) for k in inputs] for r in range(80)], dtype=np.float64)
+    out["data_obj_a"] = np.array(data["obj_a"], dtype=np.float64)
+    out.update(oracle.forest_arrays_from_model(models["obj_a"]).to_npz_dict("forest_obj_a_"))
+    with ref_harness.logger_stdout():
+        out["prior_w1"] = np.array(ns.prior_optimization.compute_probability_from_prior(
+            configurations, space, {"obj_a": 1.0}), dtype=np.float64)
+        out["prior_w07"] = np.array(ns.prior_optimization.compute_probability_from_prior(
+            configurations, space, {"obj_a": 0.7}), dtype=np.float64)
+        weights = {"obj_a": 1.0}
+        limits = {"obj_a": [min(data["obj_a"]), max(data["obj_a"])]}
+        for acq in ("EI", "UCB", "TS"):
+            for it in (1, 7):
+                vals, feas = ns.pibo.prior_weighted_acquisition_function(
+                    copy.deepcopy(configurations), space, ns.random_scalarizations.run_acquisition_function, acq,
+                    weights, copy.deepcopy(limits), it, 2.0, models, None, data, "random_forest", "linear")
+                out["pibo_%s_it%d" % (acq, it)] = np.array(vals, dtype=np.float64)
+    # BOPrO: compute_EI_from_posteriors calls get_min()/get_max() on every parameter (prior_optimization.py:189-197),
+    # which CategoricalParameter does not have -> the reference only runs it on spaces without categoricals
+    cfg_nc = copy.deepcopy(PRIORS)
+    for k in ("c_list", "c_uni"):
+        del cfg_nc["input_parameters"][k]
+    # Beta(1, 0.8) has an infinite density at the upper end, which an integer parameter reaches: the prior limits
+    # become [.., inf] and every normalised value NaN.  Use the bell-shaped density here (zero at both ends).
+    cfg_nc["input_parameters"]["i_exp"]["prior"] = "gaussian"
+    cfg_nc = validated(cfg_nc)
+    np.random.seed(32)
+    random.seed(32)
+    space_nc = ns.space.Space(cfg_nc)
+    inputs_nc = space_nc.get_input_parameters()
+    fn_nc = lambda c: objective_priors(dict(c, c_list=1, c_uni=0))
+    data_nc = sample_data_array(space_nc, 80, fn_nc, objectives)
+    models_nc = fit(cfg_nc, space_nc, data_nc, objectives)
+    cand_nc = np.concatenate([space_nc.get_random_configuration(size=300, use_priors=False, return_as_array=True),
+                              space_nc.get_random_configuration(size=300, use_priors=True, return_as_array=True)], axis=0)
+    conf_nc = [{k: to_native(c[k]) for k in inputs_nc}
+               for c in ns.utility_functions.array_to_list_of_dicts(cand_nc, inputs_nc)]
+    out["nc_config_json"] = np.array(json.dumps(cfg_nc))
+    out["nc_candidates"] = np.array([[float(c[k]) for k in inputs_nc] for c in conf_nc], dtype=np.float64)
+    out["nc_data_obj_a"] = np.array(data_nc["obj_a"], dtype=np.float64)
+    out.update(oracle.forest_arrays_from_model(models_nc["obj_a"]).to_npz_dict("nc_forest_obj_a_"))
+    with ref_harness.logger_stdout():
+        weights = {"obj_a": 1.0}
+        limits = {"obj_a": [min(data_nc["obj_a"]), max(data_nc["obj_a"])]}
+        thr = {"obj_a": float(np.quantile(data_nc["obj_a"], 0.05))}
+        out["bopro_threshold"] = np.array([thr["obj_a"]])
+        # (a) raw prior, no normalisation limits
+        vals, feas = ns.prior_optimization.compute_EI_from_posteriors(
+            copy.deepcopy(conf_nc), space_nc, weights, copy.deepcopy(limits), thr, 5, 10, models_nc, None,
+            "random_forest", None)
+        out["bopro_plain"] = np.array(vals, dtype=np.float64)
+        # (b) prior normalised with running limits, posterior normalised too (the constrained-run code path)
+        gl, pl = [0.5, 0.6], [float("inf"), float("-inf")]
+        vals, feas = ns.prior_optimization.compute_EI_from_posteriors(
+            copy.deepcopy(conf_nc), space_nc, weights, copy.deepcopy(limits), thr, 5, 10, models_nc, None,
+            "random_forest", gl, posterior_normalization_limits=pl)
+        out["bopro_norm"] = np.array(vals, dtype=np.float64)
+        out["bopro_norm_prior_limits"] = np.array(gl, dtype=np.float64)
+        out["bopro_norm_posterior_limits"] = np.array(pl, dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, "priors.npz"), **out)
+    print("priors.npz", {k: (v.shape, float(np.nanmin(v)), float(np.nanmax(v))) for k, v in out.items()
+                         if k.startswith(("prior_", "pibo_", "bopro_"))})
+
 def neighbors_case():
     """get_neighbors (local_search.py:83-161) on the discrete and the mixed scenario, RNG seeded per call."""
     out = {}
@@ -334,8 +455,12 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "neighbors":
         neighbors_case()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "priors":
+        priors_case()
+        sys.exit(0)
     rf_case(MIXED, objective_mixed, 90, 700, 1, "rf_mixed.npz")
     rf_case(BRANIN, branin, 40, 1500, 2, "rf_branin.npz")
     pareto_case()
     local_search_case()
     neighbors_case()
+    priors_case()

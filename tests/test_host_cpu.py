@@ -278,3 +278,70 @@ def test_install_rebinds_reference_entry_points():
     finally:
         for (tgt, n), fn in saved.items():
             setattr(tgt, n, fn)
+
+
+# ---- search-space descriptors (space_device.describe_space) -----------------------------------------------------
+def test_space_lite_priors_match_reference_golden():
+    """SpaceLite's per-parameter get_x_probability (the tables the device uses are built by calling it) against
+    compute_probability_from_prior of the unmodified reference (tests/golden/priors.npz)."""
+    z = load("priors.npz")
+    space = space_of(z)
+    inputs = space.get_input_parameters()
+    objs = space.get_input_parameters_objects()
+    kinds = [space.get_type(p) for p in inputs]
+    got = []
+    for row in z["candidates"]:
+        prob = 1
+        for p, k, v in zip(inputs, kinds, row):
+            x = float(v) if k == "real" else (int(v) if k != "ordinal" else
+                                             objs[p].get_values()[[float(t) for t in objs[p].get_values()].index(v)])
+            prob *= objs[p].get_x_probability(x) ** 1.0
+        got.append(prob)
+    assert np.array_equal(np.array(got, dtype=np.float64), z["prior_w1"])
+
+
+def test_describe_space_layout_and_tables():
+    from hypermapper_b200 import space_device as sd
+    z = load("priors.npz")
+    space = space_of(z)
+    descs, tables, n_enc = sd.describe_space(space)
+    inputs = space.get_input_parameters()
+    objs = space.get_input_parameters_objects()
+    assert n_enc == 8 + 3 + 2 and len(descs) == len(inputs) == 10
+    by = {p: descs[j] for j, p in enumerate(inputs)}
+    # encoded column order: non-categoricals in input order, then the one-hot blocks (models.py:957-984)
+    assert [by[p].out_col for p in inputs] == [0, 1, 2, 3, 4, 5, 6, 7, 8, 11]
+    assert by["r_gauss"].prior_kind == sd.PRIOR_BETA and (by["r_gauss"].a, by["r_gauss"].b) == (3.0, 3.0)
+    assert by["r_cg"].prior_kind == sd.PRIOR_GAUSSIAN and (by["r_cg"].a, by["r_cg"].b) == (0.3, 0.15)
+    d = by["r_list"]
+    assert d.prior_kind == sd.PRIOR_INTERP and d.n_prior == 10 and d.n_cdf == 10000
+    assert np.array_equal(tables[d.prior_off + 10: d.prior_off + 20], np.asarray(objs["r_list"].prior))
+    assert tables[d.cdf_off + d.n_cdf - 1] == 1.0
+    for p in ("i_exp", "i_list", "o_gauss", "o_list", "c_list", "c_uni"):
+        d, o = by[p], objs[p]
+        assert d.prior_kind == sd.PRIOR_TABLE
+        vals = (range(o.get_min(), o.get_max() + 1) if space.get_type(p) == "integer" else
+                (o.get_values() if space.get_type(p) == "ordinal" else range(o.get_size())))
+        assert np.array_equal(tables[d.prior_off: d.prior_off + d.n_prior],
+                              np.array([o.get_x_probability(v) for v in vals], dtype=np.float64))
+        assert d.ordinal_beta == (1 if p in ("i_exp", "o_gauss") else 0)
+    d = by["o_gauss"]
+    assert np.array_equal(tables[d.values_off: d.values_off + 8], [1, 2, 4, 8, 16, 32, 64, 128])
+    assert np.array_equal(tables[d.values_off + 8: d.values_off + 16], [k / 8 for k in range(8)])
+    assert ctypes.sizeof(sd.ParamDesc) == 8 * 4 + 3 * 8 + 7 * 8
+
+
+def test_describe_space_same_for_reference_space():
+    """The descriptors built from the real reference Space equal those built from SpaceLite."""
+    from oracle import ref_harness
+    if not ref_harness.available():
+        pytest.skip("reference tree not present")
+    from hypermapper_b200 import space_device as sd
+    ns = ref_harness.load()
+    z = load("priors.npz")
+    cfg = json.loads(str(z["config_json"]))
+    ref_space = ns.space.Space(cfg)
+    d0, t0, n0 = sd.describe_space(ref_space)
+    d1, t1, n1 = sd.describe_space(space_of(z))
+    assert n0 == n1 and np.array_equal(t0, t1)
+    assert bytes(d0) == bytes(d1)

@@ -1,0 +1,288 @@
+"""GPU parity of the search-space kernels (csrc/hm_space.cu) through the reference-facing API:
+K5 hm_encode (models.preprocess_data_array), K7 hm_prior_prob (compute_probability_from_prior), the piBO weighting
+(pibo.prior_weighted_acquisition_function), BOPrO (prior_optimization.compute_EI_from_posteriors) against golden
+vectors produced by the unmodified reference (tests/golden/make_golden.py), and K6 hm_sample_pool against the analytic
+distributions of space.py's randomly_select / randomly_select_uniform (the reference draws from numpy's global
+Mersenne-Twister stream, which a counter-based device generator cannot and need not reproduce)."""
+import copy
+import json
+import os
+
+import numpy as np
+import pytest
+from scipy import stats
+
+from conftest import GOLDEN
+from test_api_gpu import FrozenForest
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-5
+
+
+def load(name):
+    return np.load(os.path.join(GOLDEN, name), allow_pickle=False)
+
+
+def space_of(z, key="config_json"):
+    from hypermapper_b200.space_lite import SpaceLite
+    return SpaceLite(json.loads(str(z[key])))
+
+
+def close(got, want, rel=REL):
+    """allclose with infinities / NaNs required to coincide exactly"""
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    fin = np.isfinite(want)
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    assert np.array_equal(got[~fin & ~np.isnan(want)], want[~fin & ~np.isnan(want)])
+    assert np.allclose(got[fin], want[fin], rtol=rel, atol=0), np.max(np.abs(got[fin] - want[fin]) / np.abs(want[fin]).clip(1e-300))
+    return True
+
+
+# ---- K5 ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["rf_mixed.npz", "rf_branin.npz"])
+def test_device_encode_matches_reference_preprocess(name):
+    from hypermapper_b200.space_device import DeviceSpace
+    z = load(name)
+    ds = DeviceSpace(space_of(z))
+    x32, x64 = ds.encode(z["candidates"], want32=True, want64=True)
+    assert np.array_equal(x64.cpu().numpy().T, z["encoded"])                                   # bit-exact
+    assert np.array_equal(x32.cpu().numpy().T, z["encoded"].astype(np.float32))                # sklearn's cast
+    assert ds.n_encoded == z["encoded"].shape[1]
+
+
+def test_device_encode_api_forms_and_errors():
+    from hypermapper_b200 import models
+    z = load("rf_mixed.npz")
+    space = space_of(z)
+    inputs = space.get_input_parameters()
+    cand = z["candidates"][:50]
+    as_tuples = [tuple(r) for r in cand]
+    as_dicts = [dict(zip(inputs, r)) for r in cand]
+    want = z["encoded"][:50]
+    for form in (cand, as_tuples, as_dicts):
+        assert np.array_equal(models.encode_to_device(form, space, "float64").cpu().numpy().T, want)
+    assert models.preprocess_data_buffer(as_tuples, space) == [tuple(r) for r in want]
+    bad = cand.copy()
+    bad[1, 2] = 3.0                  # not one of the ordinal's values: list.index raises in the reference
+    with pytest.raises(ValueError):
+        models.encode_to_device(bad, space, "float32")
+    bad = cand.copy()
+    bad[4, 3] = 7.0                  # unknown category: OneHotEncoder raises in the reference
+    with pytest.raises(ValueError):
+        models.encode_to_device(bad, space, "float32")
+    assert models.encode_to_device(cand[:0], space, "float32").shape == (want.shape[1], 0)
+
+
+def test_device_encode_zscore_matches_host_encoder():
+    """normalize_inputs: (x - mean) / std in fp64 (models.py:966-971); the statistics are read at encode time."""
+    from hypermapper_b200.encoding import Encoder
+    from hypermapper_b200.space_device import device_space_for
+    z = load("rf_mixed.npz")
+    cfg = json.loads(str(z["config_json"]))
+    cfg["normalize_inputs"] = True
+    from hypermapper_b200.space_lite import SpaceLite
+    space = SpaceLite(cfg)
+    for rep, (m, s) in enumerate(((1.25, 3.5), (-0.3, 0.07))):
+        for p in ("x_real", "x_int"):
+            space.set_parameter_mean(p, m + rep)
+            space.set_parameter_std(p, s)
+        want = Encoder(space).encode(z["candidates"])
+        _, x64 = device_space_for(space).encode(z["candidates"], want32=False, want64=True)
+        assert np.array_equal(x64.cpu().numpy(), want)
+
+
+# ---- K7 / piBO / BOPrO ---------------------------------------------------------------------------------------------
+def test_prior_probability_matches_reference():
+    from hypermapper_b200 import prior_optimization as po
+    z = load("priors.npz")
+    space = space_of(z)
+    inputs = space.get_input_parameters()
+    confs = [dict(zip(inputs, r)) for r in z["candidates"]]
+    for key, w in (("prior_w1", 1.0), ("prior_w07", 0.7)):
+        got = po.compute_probability_from_prior(confs, space, {"obj_a": w})
+        assert isinstance(got, list) and len(got) == len(confs)
+        close(got, z[key], rel=1e-9)
+    assert np.isinf(z["prior_w1"]).any() and (z["prior_w1"] == 0).any()       # the fixture covers the edge values
+
+
+def _priors_models(z, prefix=""):
+    return {"obj_a": FrozenForest(z, prefix + "forest_obj_a_")}
+
+
+@pytest.mark.parametrize("acq", ["EI", "UCB", "TS"])
+@pytest.mark.parametrize("it", [1, 7])
+def test_pibo_prior_weighted_acquisition_matches_reference(acq, it):
+    from hypermapper_b200 import pibo, random_scalarizations as rs
+    z = load("priors.npz")
+    space = space_of(z)
+    inputs = space.get_input_parameters()
+    confs = [dict(zip(inputs, r)) for r in z["candidates"]]
+    data = {p: z["data_inputs"][:, j].tolist() for j, p in enumerate(inputs)}
+    data["obj_a"] = z["data_obj_a"].tolist()
+    limits = {"obj_a": [min(data["obj_a"]), max(data["obj_a"])]}
+    vals, feas = pibo.prior_weighted_acquisition_function(
+        confs, space, rs.run_acquisition_function, acq, {"obj_a": 1.0}, copy.deepcopy(limits), it, 2.0,
+        _priors_models(z), None, data, "random_forest", "linear")
+    assert feas == [1] * len(confs)
+    close(vals, z["pibo_%s_it%d" % (acq, it)])
+
+
+def test_bopro_posterior_scores_match_reference():
+    from hypermapper_b200 import prior_optimization as po
+    z = load("priors.npz")
+    space = space_of(z, "nc_config_json")
+    inputs = space.get_input_parameters()
+    confs = [dict(zip(inputs, r)) for r in z["nc_candidates"]]
+    models = _priors_models(z, "nc_")
+    thr = {"obj_a": float(z["bopro_threshold"][0])}
+    lim = {"obj_a": [float(z["nc_data_obj_a"].min()), float(z["nc_data_obj_a"].max())]}
+    vals, feas = po.compute_EI_from_posteriors(copy.deepcopy(confs), space, {"obj_a": 1.0}, lim, thr, 5, 10, models,
+                                               None, "random_forest", None)
+    assert list(feas) == [1] * len(confs)
+    close(vals, z["bopro_plain"])
+    gl, pl = [0.5, 0.6], [float("inf"), float("-inf")]
+    vals, _ = po.compute_EI_from_posteriors(copy.deepcopy(confs), space, {"obj_a": 1.0}, lim, thr, 5, 10, models,
+                                            None, "random_forest", gl, posterior_normalization_limits=pl)
+    close(vals, z["bopro_norm"])
+    close(gl, z["bopro_norm_prior_limits"], rel=1e-9)          # the running limits are updated in place (:173-178)
+    close(pl, z["bopro_norm_posterior_limits"])
+
+
+def test_local_search_runs_with_prior_weighted_plugins():
+    """The two prior-guided plug-ins drive local_search on the device path and return an unseen configuration."""
+    from hypermapper_b200 import pibo, prior_optimization as po
+    from hypermapper_b200.utility_functions import compute_data_array_scalarization
+    z = load("priors.npz")
+    for key, prefix, runner in (("config_json", "", pibo.run_pibo), ("nc_config_json", "nc_", po.prior_guided_optimization)):
+        cfg = json.loads(str(z[key]))
+        cfg.update({"local_search_random_points": 2000, "local_search_starting_points": 3, "number_of_cpus": 1,
+                    "scalarization_key": "scalarization", "scalarization_method": "linear",
+                    "acquisition_function": "EI", "prior_beta": -1, "prior_floor": 1e-6,
+                    "model_posterior_weight": 10, "posterior_computation_lower_limit": 1e-8,
+                    "model_good_quantile": 0.05, "prior_limit_estimation_points": 200})
+        cfg.setdefault("models", {})["model"] = "random_forest"
+        # get_neighbors maps 0 -> round(0 * size - 0.5 + min) (space.py:437-453): with min = 1 that is 0, outside the
+        # range, and the reference's list.index raises for a "distribution" prior.  [0, 4] has no such boundary case.
+        cfg["input_parameters"]["i_list"].update({"values": [0, 4], "prior": [0.1, 0.2, 0.3, 0.2, 0.2]})
+        from hypermapper_b200.space_lite import SpaceLite
+        space = SpaceLite(cfg)
+        inputs = space.get_input_parameters()
+        np.random.seed(5)
+        rows = z[prefix + "candidates"][:40]
+        data = {p: [space.get_input_parameters_objects()[p].get_values()[int(np.searchsorted(
+            np.asarray(space.get_input_parameters_objects()[p].get_values(), dtype=float), v))]
+            if space.get_type(p) == "ordinal" else (float(v) if space.get_type(p) == "real" else int(v))
+            for v in rows[:, j]] for j, p in enumerate(inputs)}
+        data["obj_a"] = np.random.rand(40).tolist()
+        weights = {"obj_a": 1.0}
+        limits = {"obj_a": [0.0, 1.0]}
+        scal, _ = compute_data_array_scalarization(data, weights, copy.deepcopy(limits), "linear")
+        data["scalarization"] = list(scal)
+        fast = {space.get_unique_hash_string_from_values({p: data[p][r] for p in inputs}): r for r in range(40)}
+        best = runner(cfg, data, space, fast, _priors_models(z, prefix), 3, weights, limits)
+        assert set(best.keys()) >= set(inputs)
+        assert space.get_unique_hash_string_from_values(best) not in fast
+
+
+# ---- K6 ---------------------------------------------------------------------------------------------------------
+def _ks_discrete(sample, values, probs, n):
+    """chi-square goodness of fit p-value of a discrete sample"""
+    counts = np.array([(sample == v).sum() for v in values], dtype=np.float64)
+    assert counts.sum() == n, "values outside the parameter's support"
+    keep = np.asarray(probs) > 0
+    assert counts[~keep].sum() == 0
+    return stats.chisquare(counts[keep], np.asarray(probs)[keep] * n).pvalue
+
+
+def test_sample_pool_distributions_and_regeneration():
+    from hypermapper_b200.space_device import DeviceSpace
+    z = load("priors.npz")
+    space = space_of(z)
+    inputs = space.get_input_parameters()
+    objs = space.get_input_parameters_objects()
+    ds = DeviceSpace(space)
+    N = 200_000
+    for use_priors in (False, True):
+        out = ds.sample_pool(seed=1234, N=N, use_priors=use_priors, want_raw=True, want32=True, want64=True,
+                             prob_weights=[1.0])
+        raw = out["raw"].cpu().numpy()                      # [D][N]
+        # the encoded matrices of the same pass == encoding the raw values; prob == prior of the raw values
+        x32, x64 = ds.encode(np.ascontiguousarray(raw.T), want32=True, want64=True)
+        assert np.array_equal(out["x64"].cpu().numpy(), x64.cpu().numpy())
+        assert np.array_equal(out["x32"].cpu().numpy(), x32.cpu().numpy())
+        assert np.array_equal(out["prob"].cpu().numpy(), ds.prior_prob(np.ascontiguousarray(raw.T), [1.0]).cpu().numpy(),
+                              equal_nan=True)
+        # any candidate can be regenerated from (seed, index); a pool is the same whether drawn whole or in pieces
+        idx = np.array([0, 1, 77, N - 1, 12345], dtype=np.int64)
+        assert np.array_equal(ds.sample_rows(1234, use_priors, idx), raw[:, idx].T)
+        part = ds.sample_pool(seed=1234, N=1000, use_priors=use_priors, index_base=5000, want_raw=True, want32=False)
+        assert np.array_equal(part["raw"].cpu().numpy(), raw[:, 5000:6000])
+        other = ds.sample_pool(seed=1235, N=1000, use_priors=use_priors, want_raw=True, want32=False)
+        assert not np.array_equal(other["raw"].cpu().numpy(), raw[:, :1000])
+        pvals = {}
+        for j, p in enumerate(inputs):
+            x, o, kind = raw[j], objs[p], space.get_type(p)
+            prior = o.prior if use_priors else "uniform"
+            if kind == "real":
+                lo, hi = o.get_min(), o.get_max()
+                assert x.min() >= lo and x.max() <= hi
+                if isinstance(prior, list):
+                    # np.interp(u, cdf_distribution, param_xs) (space.py:151-153): the cdf is the table itself
+                    pvals[p] = stats.kstest(x, lambda v: np.interp(v, o.param_xs, o.cdf_distribution)).pvalue
+                elif prior == "custom_gaussian":
+                    m, s = o.custom_gaussian_prior_mean, o.custom_gaussian_prior_std
+                    a, b = (lo - m) / s, (hi - m) / s
+                    pvals[p] = stats.kstest(x, stats.truncnorm(a, b, loc=m, scale=s).cdf).pvalue
+                else:
+                    al, be = (o.alpha, o.beta) if use_priors else (1.0, 1.0)
+                    pvals[p] = stats.kstest((x - lo) / (hi - lo), stats.beta(al, be).cdf).pvalue
+            elif kind == "integer":
+                vals = list(range(o.get_min(), o.get_max() + 1))
+                if prior == "distribution":
+                    probs = o.distribution
+                elif prior == "uniform" or not use_priors:
+                    probs = [1.0 / len(vals)] * len(vals)
+                else:   # round(x * size - 0.5 + min) of a Beta draw (space.py:437-453)
+                    edges = np.arange(len(vals) + 1) / len(vals)
+                    probs = np.diff(stats.beta(o.alpha, o.beta).cdf(edges))
+                pvals[p] = _ks_discrete(x, vals, probs, N)
+            else:
+                vals = list(o.get_values()) if kind == "ordinal" else list(range(o.get_size()))
+                if not use_priors:
+                    probs = [1.0 / len(vals)] * len(vals)
+                else:
+                    probs = [o.get_x_probability(v) for v in vals]
+                pvals[p] = _ks_discrete(x, np.asarray(vals, dtype=np.float64), probs, N)
+        assert min(pvals.values()) > 1e-4, pvals
+        # parameters are drawn independently
+        c = np.corrcoef(raw)
+        assert np.abs(c - np.eye(len(inputs))).max() < 0.02
+
+
+def test_device_pools_in_local_search_score_like_host_pools():
+    """The fused sample+encode pass feeds the same scoring kernels: scores of a device pool == scores of its raw rows
+    taken through the host API."""
+    from hypermapper_b200 import models, random_scalarizations as rs
+    from hypermapper_b200.space_device import device_space_for
+    z = load("rf_mixed.npz")
+    space = space_of(z)
+    objectives = json.loads(str(z["objectives_json"]))
+    forests = {o: FrozenForest(z, "forest_%s_" % o) for o in objectives}
+    inputs = space.get_input_parameters()
+    data = {p: z["data_inputs"][:, j].tolist() for j, p in enumerate(inputs)}
+    for o in objectives:
+        data[o] = z["data_" + o].tolist()
+    weights = {o: float(w) for o, w in zip(objectives, z["weights"])}
+    limits = {o: [float(a), float(b)] for o, (a, b) in zip(objectives, z["stored_limits"])}
+    ds = device_space_for(space)
+    pool = ds.sample_pool(seed=9, N=5000, use_priors=False, want_raw=True, want32=True)
+    enc = models.EncodedCandidates(x32=pool["x32"])
+    got = rs.acquisition_scores_device("EI", enc, weights, forests, space, "tchebyshev", copy.deepcopy(limits), 7, data,
+                                       "random_forest")
+    raw_rows = np.ascontiguousarray(pool["raw"].cpu().numpy().T)
+    want = rs.acquisition_scores_device("EI", raw_rows, weights, forests, space, "tchebyshev", copy.deepcopy(limits), 7,
+                                        data, "random_forest")
+    assert np.array_equal(got.cpu().numpy(), want.cpu().numpy())
+    confs = ds.rows_to_configurations(raw_rows[:5])
+    assert all(isinstance(c["x_cat"], int) and c["x_ord"] in (1, 2, 4, 8, 16, 32, 64, 128) for c in confs)
