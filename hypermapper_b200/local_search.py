@@ -18,6 +18,7 @@ local_search.py:666-675), which changes with the interpreter's hash seed; input-
 """
 import copy
 import datetime
+import os
 import sys
 
 import numpy as np
@@ -36,6 +37,18 @@ from .utility_functions import (
 
 # pools larger than this are not materialised as Python lists in the returned data_array
 MATERIALISE_LIMIT = 262144
+
+# Device pools: when enabled and the acquisition plug-in is one of this package's device
+# scorers, the two random pools are generated AND encoded on the GPU (hm_sample_pool: same per-parameter distributions
+# as space.get_random_configuration, Philox stream instead of numpy's) and never exist on the host; the few rows the
+# optimiser needs as configurations are re-generated from (seed, index).  Off by default: with it off the pools are
+# drawn by param_space.get_random_configuration from numpy's global stream exactly as the reference does.
+_device_pools = os.environ.get("HM_B200_DEVICE_POOLS", "0") not in ("", "0")
+
+
+def set_device_pools(enabled):
+    global _device_pools
+    _device_pools = bool(enabled)
 
 
 def _log(msg, verbose=False):
@@ -103,7 +116,10 @@ def _score_pool(pool, inputs, optimization_function, params, device_scorer):
     """pool: object/float array [N][D] (or list of dicts when the whole space was enumerated).
     Returns (values, n_evaluated) where values is a CUDA tensor (device scorer) or a host list."""
     if device_scorer is not None:
-        cand = pool if isinstance(pool, list) else np.asarray(pool, dtype=np.float64)
+        if hasattr(pool, "candidates"):
+            cand = pool.candidates
+        else:
+            cand = pool if isinstance(pool, list) else np.asarray(pool, dtype=np.float64)
         scores = device_scorer(cand, **params)
         return scores, scores.numel()
     configs = pool if isinstance(pool, list) else _rows_to_dicts(pool, inputs, range(len(pool)))
@@ -112,6 +128,8 @@ def _score_pool(pool, inputs, optimization_function, params, device_scorer):
 
 
 def _rows_to_dicts(pool, inputs, rows):
+    if hasattr(pool, "candidates"):
+        return pool.rows(rows)
     if isinstance(pool, list):
         return [pool[r] for r in rows]
     return [{k: pool[r, j] for j, k in enumerate(inputs)} for r in rows]
@@ -176,6 +194,13 @@ def local_search(local_search_starting_points, local_search_random_points, param
         everything = dict_of_lists_to_list_of_dicts(param_space.get_space())
         half = int(len(everything) / 2)
         pool_u, pool_p = everything[0:half], everything[half::]
+    elif _device_pools and device_scorer is not None:
+        from .space_device import DevicePool, device_space_for
+        seed = int(np.random.randint(0, 2 ** 62))            # reproducible under np.random.seed
+        want64 = params.get("model_type") == "gaussian_process"
+        ds = device_space_for(param_space)
+        pool_u = DevicePool(ds, seed, False, local_search_random_points, want64=want64)
+        pool_p = DevicePool(ds, seed, True, local_search_random_points, want64=want64)
     else:
         pool_u = param_space.get_random_configuration(size=local_search_random_points, use_priors=False, return_as_array=True)
         pool_p = param_space.get_random_configuration(size=local_search_random_points, use_priors=True, return_as_array=True)

@@ -22,11 +22,17 @@ from .encoding import encoder_for, raw_matrix
 
 
 class EncodedCandidates:
-    """Candidates that are already encoded and resident on the GPU (column-major [D_enc][N])."""
+    """Candidates that are already encoded and resident on the GPU (column-major [D_enc][N]); `raw_cm` optionally
+    holds their raw parameter values (column-major [D][N] fp64) for the prior-weighted acquisitions."""
 
-    def __init__(self, x32=None, x64=None):
+    def __init__(self, x32=None, x64=None, raw_cm=None):
         self.x32 = x32
         self.x64 = x64
+        self.raw_cm = raw_cm
+
+    def __len__(self):
+        t = self.x32 if self.x32 is not None else self.x64
+        return int(t.shape[1])
 
     def get(self, dtype):
         torch = _lib.require_cuda()

@@ -16,8 +16,10 @@ def prior_weighted_scores_device(configurations, param_space, acquisition_functi
     acquisition values to their minimum before weighting (pibo.py:103-104); both are reproduced."""
     torch = _lib.require_cuda()
     from . import random_scalarizations as rs
-    raw = _raw_matrix(configurations, param_space)
-    if acquisition_function_wrapper is rs.run_acquisition_function or acquisition_function_wrapper is None:
+    from .models import EncodedCandidates
+    raw = configurations if isinstance(configurations, EncodedCandidates) else _raw_matrix(configurations, param_space)
+    if (acquisition_function_wrapper is rs.run_acquisition_function or acquisition_function_wrapper is None or
+            isinstance(raw, EncodedCandidates)):
         acq = rs.acquisition_scores_device(acquisition_function, raw, objective_weights, regression_models,
                                            param_space, scalarization_method, objective_limits, iteration_number,
                                            data_array, model_type, None)

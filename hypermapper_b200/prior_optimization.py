@@ -28,6 +28,10 @@ def prior_probability_device(configurations, param_space, objective_weights):
     """compute_probability_from_prior, result left on the GPU (CUDA fp64 tensor [N])."""
     objectives = param_space.get_optimization_parameters()
     w = [objective_weights[o] for o in objectives]
+    if isinstance(configurations, models.EncodedCandidates):
+        if configurations.raw_cm is None:
+            raise _lib.HmError("prior-weighted acquisitions need the raw parameter values of the candidates")
+        return device_space_for(param_space).prior_prob(configurations.raw_cm, w, col_major=True)
     return device_space_for(param_space).prior_prob(_raw_matrix(configurations, param_space), w)
 
 
@@ -83,15 +87,22 @@ def posterior_scores_device(configurations, param_space, objective_weights, obje
     torch = _lib.require_cuda()
     L = _lib.lib()
     objectives = list(param_space.get_optimization_parameters())
-    raw = _raw_matrix(configurations, param_space)
-    # :180-188 clip every configuration to the parameter range (in place in the reference)
-    objs = param_space.get_input_parameters_objects()
-    for j, p in enumerate(param_space.get_input_parameters()):
-        raw[:, j] = np.maximum(np.minimum(raw[:, j], objs[p].get_max()), objs[p].get_min())
     ds = device_space_for(param_space)
-    raw_d = ds.raw_to_device(raw)
-    N = raw_d.shape[0]
-    prior = ds.prior_prob(raw_d, [objective_weights[o] for o in objectives])
+    if isinstance(configurations, models.EncodedCandidates):
+        # a device pool: generated inside the parameter ranges, the clipping of :189-197 is the identity
+        enc = configurations
+        N = len(enc)
+        prior = prior_probability_device(enc, param_space, objective_weights)
+    else:
+        raw = _raw_matrix(configurations, param_space)
+        # :189-197 clip every configuration to the parameter range
+        objs = param_space.get_input_parameters_objects()
+        for j, p in enumerate(param_space.get_input_parameters()):
+            raw[:, j] = np.maximum(np.minimum(raw[:, j], objs[p].get_max()), objs[p].get_min())
+        raw_d = ds.raw_to_device(raw)
+        N = raw_d.shape[0]
+        prior = ds.prior_prob(raw_d, [objective_weights[o] for o in objectives])
+        enc = models.EncodedCandidates(*ds.encode(raw_d, want32=True, want64=(model_type == "gaussian_process")))
 
     bp = _lib.BoproParams()
     bp.n_objectives = len(objectives)
@@ -114,7 +125,6 @@ def posterior_scores_device(configurations, param_space, objective_weights, obje
     bp.discrete_divisor = float(param_space.get_discrete_space_size() - 1) if discrete else 1.0
     bp.model_exponent = iteration_number / model_weight
 
-    enc = models.EncodedCandidates(*ds.encode(raw_d, want32=True, want64=(model_type == "gaussian_process")))
     mean, var = models.mean_and_variance_device(enc, regression_models, model_type, param_space)
     feas_prob = None
     if classification_model is not None:
@@ -147,7 +157,7 @@ def compute_EI_from_posteriors(configurations, param_space, objective_weights, o
     """prior_optimization.py:161-374 -> (list of values, feasibility indicator).  Like the reference it clips the
     passed configurations to the parameter ranges in place and updates the two limit lists in place."""
     objs = param_space.get_input_parameters_objects()
-    if len(configurations) > 0 and isinstance(configurations[0], dict):
+    if isinstance(configurations, list) and len(configurations) > 0 and isinstance(configurations[0], dict):
         for p in param_space.get_input_parameters():
             lo, hi = objs[p].get_min(), objs[p].get_max()
             for c in configurations:

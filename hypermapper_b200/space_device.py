@@ -214,18 +214,19 @@ class DeviceSpace:
         return x32, x64
 
     # -- K7 -------------------------------------------------------------------------------------------
-    def prior_prob(self, raw, objective_weights):
-        """compute_probability_from_prior on the device -> CUDA fp64 tensor [N]."""
+    def prior_prob(self, raw, objective_weights, col_major=False):
+        """compute_probability_from_prior on the device -> CUDA fp64 tensor [N].
+        raw: [N][D] values (host or device), or with col_major a CUDA fp64 tensor [D][N]."""
         torch = _lib.require_cuda()
-        rd = self.raw_to_device(raw)
-        N = rd.shape[0]
+        rd = raw if col_major else self.raw_to_device(raw)
+        N = rd.shape[1] if col_major else rd.shape[0]
         out = torch.empty((N,), dtype=torch.float64, device="cuda")
         if N == 0:
             return out
         w = (ctypes.c_double * len(objective_weights))(*[float(x) for x in objective_weights])
         bad = self._invalid_counter()
-        rc = _lib.lib().hm_prior_prob(self.handle, _lib.dptr(rd), 0, self.D, N, w, len(objective_weights),
-                                      _lib.dptr(out), _lib.dptr(bad), _lib.stream_ptr())
+        rc = _lib.lib().hm_prior_prob(self.handle, _lib.dptr(rd), 1 if col_major else 0, N if col_major else self.D, N,
+                                      w, len(objective_weights), _lib.dptr(out), _lib.dptr(bad), _lib.stream_ptr())
         _lib.check(rc, "hm_prior_prob")
         if int(bad.item()) != 0:
             raise ValueError("a discrete parameter value is not in its list of values")
@@ -280,6 +281,27 @@ class DeviceSpace:
                     c[name] = int(v)
             out.append(c)
         return out
+
+
+class DevicePool:
+    """One random pool of local_search that lives on the GPU only: generated and encoded by hm_sample_pool, scored in
+    place; single rows are re-generated from (seed, index) when the optimiser needs them as configurations."""
+
+    def __init__(self, device_space, seed, use_priors, n, want64=False):
+        from .models import EncodedCandidates
+        self.ds, self.seed, self.use_priors, self.n = device_space, int(seed), bool(use_priors), int(n)
+        out = device_space.sample_pool(seed, n, use_priors, want_raw=True, want32=True, want64=want64)
+        self.candidates = EncodedCandidates(x32=out["x32"], x64=out["x64"], raw_cm=out["raw"])
+
+    def __len__(self):
+        return self.n
+
+    def rows(self, indices):
+        """-> list of configuration dicts of the given pool rows"""
+        idx = np.asarray(list(indices), dtype=np.int64)
+        if idx.size == 0:
+            return []
+        return self.ds.rows_to_configurations(self.ds.sample_rows(self.seed, self.use_priors, idx))
 
 
 def _stats_key(param_space):

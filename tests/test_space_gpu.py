@@ -286,3 +286,71 @@ def test_device_pools_in_local_search_score_like_host_pools():
     assert np.array_equal(got.cpu().numpy(), want.cpu().numpy())
     confs = ds.rows_to_configurations(raw_rows[:5])
     assert all(isinstance(c["x_cat"], int) and c["x_ord"] in (1, 2, 4, 8, 16, 32, 64, 128) for c in confs)
+
+
+def test_local_search_with_device_pools():
+    """HM_B200_DEVICE_POOLS: the pools are drawn and encoded on the GPU; the optimiser returns an unseen configuration
+    whose acquisition value is the minimum over everything it evaluated, and the run is reproducible under
+    np.random.seed."""
+    import random
+    from hypermapper_b200 import local_search as ls, random_scalarizations as rs, utility_functions as uf
+    from hypermapper_b200.space_lite import SpaceLite
+    z = load("local_search.npz")
+    config = json.loads(str(z["config_json"]))
+    config["local_search_random_points"] = 20000
+    space = SpaceLite(config)
+    inputs = space.get_input_parameters()
+    models = {"Value": FrozenForest(z, "forest_Value_")}
+    data = {k: [int(v) for v in z["data_inputs"][:, j]] for j, k in enumerate(inputs)}
+    data["Value"] = z["data_Value"].tolist()
+    fast = {space.get_unique_hash_string_from_values({k: data[k][r] for k in inputs}): r for r in range(60)}
+    weights = {"Value": 1.0}
+    limits = {"Value": [min(data["Value"]), max(data["Value"])]}
+    scal, _ = uf.compute_data_array_scalarization(data, weights, copy.deepcopy(limits), "tchebyshev")
+    data[config["scalarization_key"]] = scal.tolist()
+    p = {"regression_models": models, "iteration_number": 3, "data_array": data, "classification_model": None,
+         "param_space": space, "objective_weights": weights, "model_type": "random_forest",
+         "objective_limits": limits, "acquisition_function": "EI", "scalarization_method": "tchebyshev",
+         "number_of_cpus": 1}
+    ls.set_device_pools(True)
+    try:
+        picks = []
+        for rep in range(2):
+            np.random.seed(3)
+            random.seed(3)
+            data_array, best = ls.local_search(4, 20000, space, fast, False, rs.run_acquisition_function, p,
+                                               config["scalarization_key"], 1, previous_points=data)
+            picks.append(best)
+            assert space.get_unique_hash_string_from_values(best) not in fast
+            vals, _ = rs.run_acquisition_function(configurations=[best], **p)
+            unseen = [v for i, v in enumerate(data_array[config["scalarization_key"]])
+                      if space.get_unique_hash_string_from_values({k: data_array[k][i] for k in inputs}) not in fast]
+            assert vals[0] == min(unseen)
+            # 20000 draws of a 32*7*4*3 = 2688-point space cover it: the pick is the global optimum among unseen points
+            everything = [dict(zip(inputs, c)) for c in __import__("itertools").product(
+                *[space.get_input_parameters_objects()[k].get_discrete_values() for k in inputs])]
+            allv, _ = rs.run_acquisition_function(configurations=everything, **p)
+            best_unseen = min(v for c, v in zip(everything, allv)
+                              if space.get_unique_hash_string_from_values(c) not in fast)
+            assert vals[0] == best_unseen
+        assert picks[0] == picks[1]
+    finally:
+        ls.set_device_pools(False)
+
+
+def test_pibo_on_a_device_pool_equals_pibo_on_its_rows():
+    from hypermapper_b200 import pibo, random_scalarizations as rs
+    from hypermapper_b200.space_device import DevicePool, device_space_for
+    z = load("priors.npz")
+    space = space_of(z)
+    inputs = space.get_input_parameters()
+    data = {p: z["data_inputs"][:, j].tolist() for j, p in enumerate(inputs)}
+    data["obj_a"] = z["data_obj_a"].tolist()
+    limits = {"obj_a": [min(data["obj_a"]), max(data["obj_a"])]}
+    pool = DevicePool(device_space_for(space), 77, True, 3000)
+    args = (space, rs.run_acquisition_function, "EI", {"obj_a": 1.0}, limits, 4, 2.0, _priors_models(z), None, data,
+            "random_forest", "linear")
+    got = pibo.prior_weighted_scores_device(pool.candidates, *args).cpu().numpy()
+    rows = pool.rows(range(3000))
+    want, _ = pibo.prior_weighted_acquisition_function(rows, *args)
+    assert np.array_equal(got, np.asarray(want), equal_nan=True)
