@@ -2,7 +2,7 @@
 """bench.py -- acquisition evaluations / second on the surrogate-prediction + acquisition hot path.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
-                    [--workload c3|c1|c5rf|c2|c5gp|c4] [--candidates n]
+                    [--workload c3|c1|c5rf|c2|c5gp|c4|c3raw|c3pool] [--candidates n]
 
 Default workload = BASELINE.json configs[2] ("C3"), the configuration the north-star's RF+EI target is quoted on:
 2-objective mixed ordinal/categorical space (D_enc = 23), two 256-tree Hutter forests, random_scalarizations
@@ -11,6 +11,8 @@ One "step" = one pass of the hot path over the whole pool:
   RF : fused forest traversal + Hutter reduction + EI scalarisation (hm_rf_eval) -> stable top-k (hm_topk)
   GP : hm_gp_mean_var -> hm_acq_score -> hm_topk                      (c2: Hartmann-6, n=256; c5gp: 20-D, n=512)
   c4 : hm_pareto_filter on 10^7 x 3 points (metric: points/s)
+  c3raw : C3 with the candidates as RAW parameter values, the form the reference API takes: hm_encode -> RF step
+  c3pool: C3 with the pool drawn on the device: hm_sample_pool (generate + encode) -> RF step
 [-> all-gather + merge of the per-rank top-k when N > 1].  Weak scaling: every rank owns its own shard (seed + rank),
 model replicated, the only collective is the k-pair all-gather.
 
@@ -35,7 +37,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOADS = ["c3", "c1", "c5rf", "c2", "c5gp", "c4"]
+WORKLOADS = ["c3", "c1", "c5rf", "c2", "c5gp", "c4", "c3raw", "c3pool"]
 
 
 def parse():
@@ -120,7 +122,8 @@ class RFBench:
     def __init__(self, name):
         from hypermapper_b200 import workloads
         self.name = name
-        cache = os.path.join(os.environ.get("HM_BENCH_CACHE", "/tmp"), "hm_bench_wl_%s.pkl" % name)
+        cache = os.path.join(os.environ.get("HM_BENCH_CACHE", "/tmp"),
+                             "hm_bench_wl_%s.pkl" % ("c3" if name.startswith("c3") else name))
         cached = None
         if os.path.exists(cache):
             import pickle
@@ -131,7 +134,7 @@ class RFBench:
                 cached = None
         if cached is not None:
             self.wl = cached
-        if name == "c3":
+        if name in ("c3", "c3raw", "c3pool"):
             self.wl = cached or workloads.RFWorkload(workloads.scenario_c3(), n_train=2000, seed=5)
             self.n_default = 1 << 24
             self.desc = "C3: 2-objective mixed ordinal/categorical (D_enc=23), 256-tree RF x2, EI+tchebyshev, top-20"
@@ -260,6 +263,143 @@ class RFBench:
                 "kernel_ms": kernel_ms, "algorithmic_bytes_per_eval": b, "peak_source": src,
                 "note": "forests with thousands of node visits per evaluation are bound by shared-memory load latency "
                         "and the L1/shared-memory data pipe, not HBM (profiles/, DESIGN.md section 3)"}
+
+
+class SpaceRFBench(RFBench):
+    """C3 with the search-space kernels in front of the forest kernel (csrc/hm_space.cu):
+      c3raw  : inputs are the RAW parameter values [N][D] fp64 (what the reference API takes); step = hm_encode ->
+               hm_rf_eval -> hm_topk; e2e = pinned raw host array -> H2D -> the same -> D2H scores + top-k
+      c3pool : the pool is drawn on the device; step = hm_sample_pool (generate + encode) -> hm_rf_eval -> hm_topk;
+               nothing but the top-k crosses PCIe, so e2e == the device path + the D2H of the top-k and their rows
+    roofline.space_kernel reports hm_space_kernel alone against the HBM peak (it is the HBM-bound part of the step)."""
+    cpu_desc = ("numpy restatement of models.py:941-984 (encode) + OpenMP C port of models.py:174-275 + numpy/scipy EI "
+                "+ top-20")
+
+    def __init__(self, name):
+        RFBench.__init__(self, name)
+        self.desc = {"c3raw": "C3 from raw parameter values: device encode (D=10 -> D_enc=23) + 256-tree RF x2, "
+                              "EI+tchebyshev, top-20",
+                     "c3pool": "C3 with device-generated pools: Philox sample+encode (D=10 -> D_enc=23) + 256-tree RF "
+                               "x2, EI+tchebyshev, top-20"}[name]
+        self.e2e_api = {"c3raw": "acquisition_scores_device(raw ndarray): pinned raw host values -> H2D -> hm_encode -> "
+                                 "hm_rf_eval -> hm_topk -> D2H scores + top-k",
+                        "c3pool": "DevicePool + acquisition_scores_device: hm_sample_pool -> hm_rf_eval -> hm_topk -> "
+                                  "D2H top-k + hm_sample_rows of the winners (no candidate crosses PCIe)"}[name]
+
+    def raw_rows(self, n, seed):
+        from hypermapper_b200 import workloads
+        wl = self.wl
+        rng = np.random.default_rng(seed)
+        inputs = wl.space.get_input_parameters()
+        out = np.empty((n, len(inputs)), dtype=np.float64)
+        chunk = 1 << 21
+        for lo in range(0, n, chunk):
+            hi = min(n, lo + chunk)
+            cols = workloads.raw_uniform_columns(wl.space, hi - lo, rng)
+            for j, p in enumerate(inputs):
+                out[lo:hi, j] = cols[p]
+        return out
+
+    def cpu_port(self, sample):
+        from oracle import oracle
+        wl = self.wl
+        if not hasattr(self, "_fas"):
+            self._fas = {o: oracle.forest_arrays_from_model(m) for o, m in wl.models.items()}
+            self._raw_cpu = {}
+        if sample not in self._raw_cpu:
+            self._raw_cpu = {sample: self.raw_rows(sample, 1234)}
+        raw = self._raw_cpu[sample]
+        t0 = time.perf_counter()
+        X = np.ascontiguousarray(wl.encoder.encode(raw).T)
+        means, variances = {}, {}
+        for o, fa in self._fas.items():
+            means[o], variances[o], _ = oracle.rf_mean_var_omp(fa, X)
+        vals = oracle.EI(means, variances, wl.data_array, wl.objective_weights, wl.scalarization, wl.objective_limits)
+        oracle.get_min_indices_fast(vals, self.k)
+        return time.perf_counter() - t0
+
+    def setup_device(self, N, rank):
+        import torch
+        from hypermapper_b200 import forest
+        from hypermapper_b200.space_device import device_space_for
+        wl = self.wl
+        self.N, self.rank = N, rank
+        self.forests = [forest.device_forest(wl.models[o]) for o in wl.objectives]
+        self.acq = wl.acq_params()
+        self.ds = device_space_for(wl.space)
+        self.D = self.ds.D
+        self.seed = 6 + rank
+        if self.name == "c3raw":
+            self.raw_host = torch.from_numpy(self.raw_rows(N, 6 + rank)).pin_memory()
+            self.raw_dev = self.raw_host.cuda()
+            self.raw_stage = torch.empty_like(self.raw_dev)
+            self.x_dev = self.ds.encode(self.raw_dev)[0]
+        else:
+            self.x_dev = self.ds.sample_pool(self.seed, N, False)["x32"]
+        self.scores_host = torch.empty((N,), dtype=torch.float64).pin_memory()
+        self.prepass = sum(f.n_groups for f in self.forests if f.staged) > 2 and N >= (1 << 17)
+        self.smem_bytes_per_eval = self._smem_bytes_per_eval()
+        self.launches_per_step = 4 + (3 if self.prepass else 0)
+        self.space_ms = []
+
+    def _front(self, raw_dev):
+        if self.name == "c3raw":
+            return self.ds.encode(raw_dev)[0]
+        return self.ds.sample_pool(self.seed, self.N, False)["x32"]
+
+    def step(self, record):
+        import torch
+        from hypermapper_b200 import forest
+        ev = None
+        e0 = e1 = None
+        if record:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            e0.record()
+        x32 = self._front(getattr(self, "raw_dev", None))
+        if record:
+            e1.record()
+            self.space_ms.append((e0, e1))
+            ev[0].record()
+        out = forest.rf_eval(self.forests, x32, acq=self.acq)
+        if record:
+            ev[1].record()
+        tv, ti = forest.topk(out["score"], self.k, index_base=self.rank * self.N)
+        return (tv, ti), ev
+
+    def e2e_step(self):
+        import torch
+        from hypermapper_b200 import forest
+        if self.name == "c3raw":
+            self.raw_stage.copy_(self.raw_host, non_blocking=True)
+            x32 = self._front(self.raw_stage)
+        else:
+            x32 = self._front(None)
+        out = forest.rf_eval(self.forests, x32, acq=self.acq)
+        tv, ti = forest.topk(out["score"], self.k, index_base=self.rank * self.N)
+        if self.name == "c3raw":
+            self.scores_host.copy_(out["score"], non_blocking=True)
+        else:
+            self.winner_rows = self.ds.sample_rows(self.seed, False, ti - self.rank * self.N)
+        return tv, ti
+
+    def e2e_bytes(self, N):
+        if self.name == "c3raw":
+            return 8 * self.D * N, 8 * N + 16 * self.k
+        return 0, 16 * self.k + 8 * self.D * self.k
+
+    def roofline(self, N, kernel_ms):
+        roof = RFBench.roofline(self, N, kernel_ms)
+        peak, src = measured_peaks()
+        ms = statistics.mean(a.elapsed_time(b) for a, b in self.space_ms)
+        wl = self.wl
+        b = (8 * self.D if self.name == "c3raw" else 0) + 4 * wl.D_enc
+        roof["space_kernel"] = {"kernel": "hm_space_kernel<%s>" % ("false" if self.name == "c3raw" else "true"),
+                                "bound": "hbm", "kernel_ms": ms, "algorithmic_bytes_per_candidate": b,
+                                "achieved": b * N / (ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                                "frac": b * N / (ms / 1e3) / 1e9 / peak,
+                                "how": "raw fp64 values read (c3raw) + fp32 encoded columns written, per candidate"}
+        return roof
 
 
 class GPBench:
@@ -446,6 +586,8 @@ class ParetoBench:
 
 
 def make_bench(name):
+    if name in ("c3raw", "c3pool"):
+        return SpaceRFBench(name)
     if name in ("c3", "c1", "c5rf"):
         return RFBench(name)
     if name in ("c2", "c5gp"):

@@ -52,7 +52,7 @@ extern "C" int hm_space_create(int n_params, const hm_param_desc_t* params_host,
                                int64_t n_tables, hm_space_t** out) {
     HM_REQUIRE(out != nullptr && params_host != nullptr, "out/params");
     HM_REQUIRE(n_params >= 1 && n_params <= HM_SPACE_MAX_PARAMS, "1 <= n_params <= 256");
-    HM_REQUIRE(n_tables >= 0 && (n_tables == 0 || tables_host != nullptr), "tables");
+    HM_REQUIRE(n_tables >= 0 && n_tables < (1ll << 30) && (n_tables == 0 || tables_host != nullptr), "tables");
     int d_enc = 0;
     for (int j = 0; j < n_params; ++j) {
         int rc = hm_check_desc(params_host[j], n_tables, j);
@@ -96,7 +96,7 @@ extern "C" void hm_space_destroy(hm_space_t* S) {
 extern "C" int hm_space_n_params(const hm_space_t* s) { return s ? s->D : 0; }
 extern "C" int hm_space_n_encoded(const hm_space_t* s) { return s ? s->D_enc : 0; }
 
-// ---- Philox4x32-10 ---------------------------------------------------------------------------------------------
+// ---- Philox4x32-10: one stream per (seed, candidate index, pool kind), consumed sequentially over the parameters ------
 struct HmPhilox {
     uint32_t c0, c1, c2, c3, k0, k1, o0, o1, o2, o3;
     int have;
@@ -122,13 +122,19 @@ struct HmPhilox {
         }
         o0 = x0; o1 = x1; o2 = x2; o3 = x3;
         ++c3;
-        have = 2;
+        have = 4;
     }
+    __device__ __forceinline__ uint32_t u32() {
+        if (have == 0) block();
+        const uint32_t v = have == 4 ? o0 : (have == 3 ? o1 : (have == 2 ? o2 : o3));
+        --have;
+        return v;
+    }
+    // uniform index in [0, n): np.random.choice(n) without probabilities
+    __device__ __forceinline__ int below(int n) { return (int)__umulhi(u32(), (uint32_t)n); }
     // uniform in [0, 1) with 53 random bits
     __device__ __forceinline__ double u53() {
-        if (have == 0) block();
-        const uint32_t hi = have == 2 ? o0 : o2, lo = have == 2 ? o1 : o3;
-        --have;
+        const uint32_t hi = u32(), lo = u32();
         return ((double)(hi >> 5) * 67108864.0 + (double)(lo >> 6)) * (1.0 / 9007199254740992.0);
     }
     __device__ __forceinline__ double normal() {
@@ -164,58 +170,53 @@ struct HmPhilox {
 };
 
 // ---- per-parameter device functions ----------------------------------------------------------------------------
-struct HmSpaceCtx {
-    const hm_param_desc_t* params;     // shared memory
-    const double* tab_s;               // first tab_s_n doubles of the tables, in shared memory
-    const double* tab_g;               // all tables, global
-    long long tab_s_n;
-    __device__ __forceinline__ double tab(long long o) const { return o < tab_s_n ? tab_s[o] : __ldg(tab_g + o); }
+// compact copy of hm_param_desc_t in shared memory (32-bit table offsets)
+struct HmP {
+    int kind, n_values, out_col, flags;          // flags: 1 = z-score, 2 = discrete parameter sampled as Beta(a, b)
+    int prior_kind, n_prior, n_cdf, values_off;
+    int prior_off, cdf_off, pad0, pad1;
+    double lo, hi, mean, std, a, b, lbeta, pad2;
 };
+#define HM_PF_NORMALIZE 1
+#define HM_PF_BETA_SAMPLED 2
 
-// index of x in the ascending table [off, off+n): -1 when x is not one of the values (list.index raises in the reference)
-__device__ __forceinline__ int hm_find_value(const HmSpaceCtx& c, long long off, int n, double x) {
+// index of x in the ascending table tab[0..n): -1 when x is not one of the values (list.index raises in the reference).
+// Branch-free lower bound: ceil(log2 n) dependent shared-memory loads.
+__device__ __forceinline__ int hm_find_value(const double* __restrict__ tab, int n, double x) {
     int lo = 0, len = n;
-    while (len > 0) {
+    while (len > 1) {
         const int half = len >> 1;
-        if (c.tab(off + lo + half) < x) {
-            lo += half + 1;
-            len -= half + 1;
-        } else {
-            len = half;
-        }
+        lo += (tab[lo + half - 1] < x) ? half : 0;
+        len -= half;
     }
-    return (lo < n && c.tab(off + lo) == x) ? lo : -1;
+    return tab[lo] == x ? lo : -1;
 }
 // np.random.choice(n, p=...): first index whose cumulative probability exceeds u
-__device__ __forceinline__ int hm_choice(const HmSpaceCtx& c, long long cum_off, int n, double u) {
+__device__ __forceinline__ int hm_choice(const double* __restrict__ cum, int n, double u) {
     int lo = 0, len = n;
-    while (len > 0) {
+    while (len > 1) {
         const int half = len >> 1;
-        if (c.tab(cum_off + lo + half) <= u) {
-            lo += half + 1;
-            len -= half + 1;
-        } else {
-            len = half;
-        }
+        lo += (cum[lo + half - 1] <= u) ? half : 0;
+        len -= half;
     }
-    return lo < n ? lo : n - 1;
+    return lo;
 }
 // np.interp(x, xp, fp) with xp ascending (numpy/core/src/multiarray/compiled_base.c arr_interp)
-__device__ __forceinline__ double hm_interp(const HmSpaceCtx& c, long long xp, long long fp, int n, double x) {
+__device__ __forceinline__ double hm_interp(const double* __restrict__ xp, const double* __restrict__ fp, int n, double x) {
     if (x != x) return x;
-    if (x < c.tab(xp)) return c.tab(fp);
-    if (x > c.tab(xp + n - 1)) return c.tab(fp + n - 1);
+    if (x < xp[0]) return fp[0];
+    if (x > xp[n - 1]) return fp[n - 1];
     // largest j with xp[j] <= x
     int lo = 0, hi = n - 1;
     while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
-        if (c.tab(xp + mid) <= x) lo = mid; else hi = mid;
+        if (xp[mid] <= x) lo = mid; else hi = mid;
     }
-    if (c.tab(xp + hi) <= x) lo = hi;
-    if (lo == n - 1) return c.tab(fp + lo);
-    const double x0 = c.tab(xp + lo), y0 = c.tab(fp + lo);
+    if (xp[hi] <= x) lo = hi;
+    if (lo == n - 1) return fp[lo];
+    const double x0 = xp[lo], y0 = fp[lo];
     if (x0 == x) return y0;
-    const double slope = hm_sub(c.tab(fp + lo + 1), y0) / hm_sub(c.tab(xp + lo + 1), x0);
+    const double slope = hm_sub(fp[lo + 1], y0) / hm_sub(xp[lo + 1], x0);
     return hm_add(hm_mul(slope, hm_sub(x, x0)), y0);
 }
 // scipy.stats.beta.pdf on [0, 1]
@@ -228,13 +229,13 @@ __device__ __forceinline__ double hm_beta_pdf(double x, double a, double b, doub
     return exp((a - 1.0) * log(x) + (b - 1.0) * log1p(-x) - lbeta);
 }
 
-// one parameter value drawn as space.py's randomly_select (use_priors) / randomly_select_uniform would
-__device__ double hm_draw(const HmSpaceCtx& c, const hm_param_desc_t& p, HmPhilox& g, bool use_priors) {
-    const bool prior = use_priors;
+// One parameter value drawn as space.py's randomly_select (use_priors) / randomly_select_uniform would; *idx_out = its
+// value index for ordinal / categorical parameters (so that the encoder does not search for it again).
+__device__ double hm_draw(const double* __restrict__ tab, const HmP& p, HmPhilox& g, bool prior, int* idx_out) {
     if (p.kind == HM_P_REAL) {
         if (!prior) return hm_add(hm_mul(g.u53(), hm_sub(p.hi, p.lo)), p.lo);                   // space.py:201-209
         if (p.prior_kind == HM_PRIOR_INTERP)                                                     // space.py:151-153
-            return hm_interp(c, p.cdf_off, p.cdf_off + p.n_cdf, p.n_cdf, g.u53());
+            return hm_interp(tab + p.cdf_off, tab + p.cdf_off + p.n_cdf, p.n_cdf, g.u53());
         if (p.prior_kind == HM_PRIOR_GAUSSIAN) {                                                 // space.py:167-193
             double x = p.a;
             for (int it = 0; it < 256; ++it) {
@@ -247,38 +248,40 @@ __device__ double hm_draw(const HmSpaceCtx& c, const hm_param_desc_t& p, HmPhilo
     }
     if (p.kind == HM_P_INTEGER) {
         const double size = p.hi - p.lo + 1.0;
-        if (!prior) return p.lo + floor(g.u53() * size);                                         // space.py:389-395
-        if (p.prior_kind == HM_PRIOR_TABLE && !p.ordinal_beta)                                   // space.py:379-382
-            return p.lo + (double)hm_choice(c, p.prior_off + p.n_prior, p.n_prior, g.u53());
+        if (!prior) return p.lo + (double)g.below((int)size);                                    // space.py:389-395
+        if (p.prior_kind == HM_PRIOR_TABLE && !(p.flags & HM_PF_BETA_SAMPLED))                   // space.py:379-382
+            return p.lo + (double)hm_choice(tab + p.prior_off + p.n_prior, p.n_prior, g.u53());
         const double v = rint(g.beta(p.a, p.b) * size - 0.5 + p.lo);                             // space.py:437-453
         return fmin(fmax(v, p.lo), p.hi);
     }
     int idx;
     if (!prior) {
-        idx = (int)floor(g.u53() * (double)p.n_values);                                          // space.py:505-511, 639-645
-    } else if (p.prior_kind == HM_PRIOR_TABLE && !p.ordinal_beta) {
-        idx = hm_choice(c, p.prior_off + p.n_prior, p.n_prior, g.u53());                         // space.py:493-494, 634-637
+        idx = g.below(p.n_values);                                                               // space.py:505-511, 639-645
+    } else if (p.prior_kind == HM_PRIOR_TABLE && !(p.flags & HM_PF_BETA_SAMPLED)) {
+        idx = hm_choice(tab + p.prior_off + p.n_prior, p.n_prior, g.u53());                      // space.py:493-494, 634-637
     } else {
         idx = (int)rint(g.beta(p.a, p.b) * (double)p.n_values - 0.5);                            // space.py:578-595
     }
     idx = min(max(idx, 0), p.n_values - 1);
-    return p.kind == HM_P_ORDINAL ? c.tab(p.values_off + idx) : (double)idx;
+    *idx_out = idx;
+    return p.kind == HM_P_ORDINAL ? tab[p.values_off + idx] : (double)idx;
 }
 
-// get_x_probability of one parameter (space.py:264-286, 412-417, 513-540, 647-660)
-__device__ double hm_x_probability(const HmSpaceCtx& c, const hm_param_desc_t& p, double x, int* bad) {
+// get_x_probability of one parameter (space.py:264-286, 412-417, 513-540, 647-660); idx = value index if known (>= 0)
+__device__ double hm_x_probability(const double* __restrict__ tab, const HmP& p, double x, int idx, int* bad) {
     if (p.prior_kind == HM_PRIOR_TABLE) {
-        int idx;
-        if (p.kind == HM_P_ORDINAL) idx = hm_find_value(c, p.values_off, p.n_values, x);
-        else if (p.kind == HM_P_INTEGER) idx = (x >= p.lo && x <= p.hi && x == rint(x)) ? (int)(x - p.lo) : -1;
-        else idx = (x >= 0.0 && x < (double)p.n_values && x == rint(x)) ? (int)x : -1;
+        if (idx < 0) {
+            if (p.kind == HM_P_ORDINAL) idx = hm_find_value(tab + p.values_off, p.n_values, x);
+            else if (p.kind == HM_P_INTEGER) idx = (x >= p.lo && x <= p.hi && x == rint(x)) ? (int)(x - p.lo) : -1;
+            else idx = (x >= 0.0 && x < (double)p.n_values && x == rint(x)) ? (int)x : -1;
+        }
         if (idx < 0) {
             *bad = 1;
             return __longlong_as_double(0x7ff8000000000000ll);
         }
-        return c.tab(p.prior_off + idx);
+        return tab[p.prior_off + idx];
     }
-    if (p.prior_kind == HM_PRIOR_INTERP) return hm_interp(c, p.prior_off, p.prior_off + p.n_prior, p.n_prior, x);
+    if (p.prior_kind == HM_PRIOR_INTERP) return hm_interp(tab + p.prior_off, tab + p.prior_off + p.n_prior, p.n_prior, x);
     if (p.prior_kind == HM_PRIOR_GAUSSIAN) {
         const double y = hm_sub(x, p.a) / p.b;
         return hm_norm_pdf(y) / p.b;
@@ -318,39 +321,78 @@ struct HmSpaceArgs {
     int* n_invalid;
 };
 
-template <bool GENERATE>
-__global__ void __launch_bounds__(256) hm_space_kernel(const HmSpaceArgs a) {
+#define HM_SPACE_BLOCK 256
+// GENERATE: draw the raw values (K6) instead of reading them.  STAGED: the raw matrix is row-major and contiguous
+// (ldr == D): a tile of 256 candidates x D values is copied into shared memory with coalesced loads and each thread
+// then reads its own row (row stride D|1 doubles: conflict-free).
+template <bool GENERATE, bool STAGED>
+__global__ void __launch_bounds__(HM_SPACE_BLOCK) hm_space_kernel(const HmSpaceArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
-    hm_param_desc_t* sp = reinterpret_cast<hm_param_desc_t*>(smem);
-    double* st = reinterpret_cast<double*>(smem + sizeof(hm_param_desc_t) * a.D);
-    const long long tab_s_n = a.n_tables < HM_SPACE_SMEM_TABLES ? a.n_tables : HM_SPACE_SMEM_TABLES;
-    {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(a.params);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(sp);
-        const int nw = (int)(sizeof(hm_param_desc_t) / 4) * a.D;
-        for (int q = threadIdx.x; q < nw; q += blockDim.x) dst[q] = __ldg(src + q);
-        for (int q = threadIdx.x; q < (int)tab_s_n; q += blockDim.x) st[q] = __ldg(a.tables + q);
+    HmP* sp = reinterpret_cast<HmP*>(smem);
+    double* st = reinterpret_cast<double*>(smem + sizeof(HmP) * a.D);
+    const int tab_s_n = (int)(a.n_tables <= HM_SPACE_SMEM_TABLES ? a.n_tables : 0);   // all tables or none
+    double* tile = st + tab_s_n;
+    const int Dp = a.D | 1;
+    for (int j = threadIdx.x; j < a.D; j += blockDim.x) {
+        const hm_param_desc_t& d = a.params[j];
+        HmP p;
+        p.kind = d.kind;
+        p.n_values = d.n_values;
+        p.out_col = d.out_col;
+        p.flags = (d.normalize ? HM_PF_NORMALIZE : 0) | (d.ordinal_beta ? HM_PF_BETA_SAMPLED : 0);
+        p.prior_kind = d.prior_kind;
+        p.n_prior = d.n_prior;
+        p.n_cdf = d.n_cdf;
+        p.values_off = (int)d.values_off;
+        p.prior_off = (int)d.prior_off;
+        p.cdf_off = (int)d.cdf_off;
+        p.pad0 = p.pad1 = 0;
+        p.lo = d.lo; p.hi = d.hi; p.mean = d.mean; p.std = d.std; p.a = d.a; p.b = d.b; p.lbeta = d.lbeta; p.pad2 = 0.0;
+        sp[j] = p;
     }
+    for (int q = threadIdx.x; q < tab_s_n; q += blockDim.x) st[q] = __ldg(a.tables + q);
     __syncthreads();
-    HmSpaceCtx c;
-    c.params = sp;
-    c.tab_s = st;
-    c.tab_g = a.tables;
-    c.tab_s_n = tab_s_n;
+    // the tables: shared memory when they fit, else global (generic addressing serves both)
+    const double* tab = tab_s_n ? st : a.tables;
 
     const bool want_enc = a.x32 != nullptr || a.x64 != nullptr;
+    const double nan = __longlong_as_double(0x7ff8000000000000ll);
     int bad_any = 0;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.N; i += (long long)gridDim.x * blockDim.x) {
+    for (long long base = (long long)blockIdx.x * HM_SPACE_BLOCK; base < a.N; base += (long long)gridDim.x * HM_SPACE_BLOCK) {
+        if (STAGED) {
+            __syncthreads();
+            const long long rows = a.N - base < HM_SPACE_BLOCK ? a.N - base : HM_SPACE_BLOCK;
+            const int total = (int)rows * a.D;
+            const double* src = a.raw + (size_t)base * (size_t)a.D;
+            int r = threadIdx.x / a.D, c = threadIdx.x - r * a.D;
+            const int dr = HM_SPACE_BLOCK / a.D, dc = HM_SPACE_BLOCK - dr * a.D;
+            for (int q = threadIdx.x; q < total; q += HM_SPACE_BLOCK) {
+                tile[r * Dp + c] = __ldg(src + q);
+                r += dr;
+                c += dc;
+                if (c >= a.D) {
+                    c -= a.D;
+                    ++r;
+                }
+            }
+            __syncthreads();
+        }
+        const long long i = base + threadIdx.x;
+        if (i >= a.N) continue;
         double prob = 1.0;
-        const unsigned long long gi =
-            GENERATE ? (unsigned long long)(a.gather ? __ldg(a.gather + i) : a.index_base + i) : 0ull;
+        HmPhilox g;
+        if (GENERATE) {
+            const unsigned long long gi = (unsigned long long)(a.gather ? __ldg(a.gather + i) : a.index_base + i);
+            g.init(a.seed, gi, a.use_priors ? 1u : 0u);
+        }
         for (int j = 0; j < a.D; ++j) {
-            const hm_param_desc_t& p = sp[j];
+            const HmP& p = sp[j];
             double x;
+            int idx = -1;
             if (GENERATE) {
-                HmPhilox g;
-                g.init(a.seed, gi, (uint32_t)j * 2u + (a.use_priors ? 1u : 0u));
-                x = hm_draw(c, p, g, a.use_priors != 0);
+                x = hm_draw(tab, p, g, a.use_priors != 0, &idx);
+            } else if (STAGED) {
+                x = tile[threadIdx.x * Dp + j];
             } else {
                 x = a.raw_col_major ? __ldg(a.raw + (size_t)j * (size_t)a.ldr + (size_t)i)
                                     : __ldg(a.raw + (size_t)i * (size_t)a.ldr + (size_t)j);
@@ -359,38 +401,35 @@ __global__ void __launch_bounds__(256) hm_space_kernel(const HmSpaceArgs a) {
                 if (a.raw_out_rows) a.raw_out[(size_t)i * (size_t)a.D + j] = x;
                 else a.raw_out[(size_t)j * (size_t)a.ldro + (size_t)i] = x;
             }
+            if (!GENERATE && p.kind >= HM_P_ORDINAL && (want_enc || a.prob)) {
+                // value index of a discrete parameter: ordinal -> position in its value list, categorical -> the value
+                if (p.kind == HM_P_ORDINAL) idx = hm_find_value(tab + p.values_off, p.n_values, x);
+                else idx = (x >= 0.0 && x < (double)p.n_values && x == rint(x)) ? (int)x : -1;
+                bad_any |= idx < 0;
+            }
             if (want_enc) {
                 // models.py:957-984
-                int bad = 0;
                 if (p.kind == HM_P_CATEGORICAL) {
-                    const bool ok = x >= 0.0 && x < (double)p.n_values && x == rint(x);
-                    const int idx = ok ? (int)x : -1;
-                    bad = !ok;
+                    float* o32 = a.x32 ? a.x32 + (size_t)p.out_col * (size_t)a.ld32 + (size_t)i : nullptr;
+                    double* o64 = a.x64 ? a.x64 + (size_t)p.out_col * (size_t)a.ld64 + (size_t)i : nullptr;
                     for (int k = 0; k < p.n_values; ++k) {
-                        const double v = ok ? (k == idx ? 1.0 : 0.0) : __longlong_as_double(0x7ff8000000000000ll);
-                        if (a.x32) a.x32[(size_t)(p.out_col + k) * (size_t)a.ld32 + (size_t)i] = (float)v;
-                        if (a.x64) a.x64[(size_t)(p.out_col + k) * (size_t)a.ld64 + (size_t)i] = v;
+                        const double v = idx < 0 ? nan : (k == idx ? 1.0 : 0.0);
+                        if (o32) o32[(size_t)k * (size_t)a.ld32] = (float)v;
+                        if (o64) o64[(size_t)k * (size_t)a.ld64] = v;
                     }
                 } else {
                     double v;
-                    if (p.kind == HM_P_ORDINAL) {
-                        const int idx = hm_find_value(c, p.values_off, p.n_values, x);
-                        bad = idx < 0;
-                        v = bad ? __longlong_as_double(0x7ff8000000000000ll) : c.tab(p.values_off + p.n_values + idx);
-                    } else if (p.normalize) {
-                        v = hm_sub(x, p.mean) / p.std;
-                    } else {
-                        v = x;
-                    }
+                    if (p.kind == HM_P_ORDINAL) v = idx < 0 ? nan : tab[p.values_off + p.n_values + idx];
+                    else if (p.flags & HM_PF_NORMALIZE) v = hm_sub(x, p.mean) / p.std;
+                    else v = x;
                     if (a.x32) a.x32[(size_t)p.out_col * (size_t)a.ld32 + (size_t)i] = (float)v;
                     if (a.x64) a.x64[(size_t)p.out_col * (size_t)a.ld64 + (size_t)i] = v;
                 }
-                bad_any |= bad;
             }
             if (a.prob) {
                 // prior_optimization.py:85-93: for every parameter, for every objective: probability *= p ** w
                 int bad = 0;
-                const double px = hm_x_probability(c, p, x, &bad);
+                const double px = hm_x_probability(tab, p, x, idx, &bad);
                 bad_any |= bad;
                 for (int o = 0; o < a.n_obj; ++o) prob = hm_mul(prob, a.w[o] == 1.0 ? px : pow(px, a.w[o]));
             }
@@ -406,19 +445,22 @@ static int hm_space_launch(const hm_space_t* s, HmSpaceArgs& a, bool generate, v
     a.n_tables = s->n_tables;
     a.D = s->D;
     if (a.N == 0) return 0;
-    const int block = 256;
-    const long long blocks = (a.N + block - 1) / block;
+    const long long blocks = (a.N + HM_SPACE_BLOCK - 1) / HM_SPACE_BLOCK;
     const int grid = (int)std::min<long long>(blocks, (long long)hm_num_sms() * 8);
-    const size_t smem = sizeof(hm_param_desc_t) * s->D +
-                        sizeof(double) * (size_t)std::min<long long>(s->n_tables, HM_SPACE_SMEM_TABLES);
+    const bool staged = !generate && !a.raw_col_major && a.ldr == a.D && a.D <= 32;
+    const size_t smem = sizeof(HmP) * s->D +
+                        sizeof(double) * (size_t)(s->n_tables <= HM_SPACE_SMEM_TABLES ? s->n_tables : 0) +
+                        (staged ? sizeof(double) * (size_t)HM_SPACE_BLOCK * (size_t)(s->D | 1) : 0);
     cudaStream_t st = (cudaStream_t)stream;
-    if (generate) {
-        HM_CUDA_TRY(cudaFuncSetAttribute(hm_space_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        hm_space_kernel<true><<<grid, block, smem, st>>>(a);
-    } else {
-        HM_CUDA_TRY(cudaFuncSetAttribute(hm_space_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        hm_space_kernel<false><<<grid, block, smem, st>>>(a);
-    }
+#define HM_SPACE_GO(G, S)                                                                                              \
+    do {                                                                                                               \
+        HM_CUDA_TRY(cudaFuncSetAttribute(hm_space_kernel<G, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        hm_space_kernel<G, S><<<grid, HM_SPACE_BLOCK, smem, st>>>(a);                                                  \
+    } while (0)
+    if (generate) HM_SPACE_GO(true, false);
+    else if (staged) HM_SPACE_GO(false, true);
+    else HM_SPACE_GO(false, false);
+#undef HM_SPACE_GO
     HM_CUDA_TRY(cudaGetLastError());
     return 0;
 }

@@ -173,6 +173,57 @@ def _hill_climb(start, param_space, inputs, optimization_function, params, enabl
     return iteration_data, log
 
 
+def _neighbors_use_rng(param_space):
+    """get_neighbors draws truncated normals only for real / integer parameters (local_search.py:138-157)."""
+    return any(param_space.get_type(p) in ("real", "integer") for p in param_space.get_input_parameters())
+
+
+# Lock-step hill climb (SURVEY section 8 row N4): every start advances one step per round and the neighbour batches of
+# all live starts are scored in ONE launch.  The climbs are independent, so the trajectories -- and the returned
+# data_array, which is assembled per start afterwards -- are identical to running the starts one after the other,
+# PROVIDED get_neighbors consumes no random numbers (discrete spaces).  With real / integer parameters the order of the
+# truncnorm draws would change, so those spaces keep the sequential order unless set_lockstep(True) is called.
+_lockstep = os.environ.get("HM_B200_LOCKSTEP", "auto")
+
+
+def set_lockstep(mode):
+    """True / False / "auto" (default: lock-step only when it is exactly equivalent)."""
+    global _lockstep
+    _lockstep = mode
+
+
+def _hill_climb_lockstep(start_list, param_space, inputs, device_scorer, params, scalarization_key):
+    """All starts in lock-step; returns [(iteration_data, log)] in start order."""
+    n = len(start_list)
+    current = list(start_list)
+    data = [{} for _ in range(n)]
+    logs = ["Starting local search on configuration: " + str(c) + "\n" for c in current]
+    live = list(range(n))
+    while live:
+        batches = [get_neighbors(current[s], param_space) for s in live]
+        flat = np.asarray([row for b in batches for row in b], dtype=np.float64)
+        scores = device_scorer(flat, **params).cpu().tolist()
+        nxt = []
+        pos = 0
+        for s, b in zip(live, batches):
+            neighbors = data_tuples_to_dict_list(b, inputs)
+            values = scores[pos:pos + len(b)]
+            pos += len(b)
+            batch = concatenate_list_of_dictionaries(neighbors)
+            batch[scalarization_key] = values
+            data[s] = concatenate_data_dictionaries(data[s], batch)
+            best = get_min_configurations(batch, 1, scalarization_key)
+            here = {k: [v] for k, v in current[s].items()}
+            if are_configurations_equal(best, here, inputs):
+                logs[s] += "Local minimum found: " + str(dict(best)) + "\n"
+            else:
+                logs[s] += "Replacing configuration by best neighbor: " + str(dict(best)) + "\n"
+                current[s] = {k: v[0] for k, v in best.items()}
+                nxt.append(s)
+        live = nxt
+    return list(zip(data, logs))
+
+
 def local_search(local_search_starting_points, local_search_random_points, param_space,
                  fast_addressing_of_data_array, enable_feasible_predictor, optimization_function,
                  optimization_function_parameters, scalarization_key, number_of_cpus, previous_points=None,
@@ -265,10 +316,18 @@ def local_search(local_search_starting_points, local_search_random_points, param
 
     # ---- hot loop B: multi-start hill climb, starts in order (keeps the RNG order of get_neighbors) ----------
     result_array = {}
-    for s in range(n_starts):
-        start = {key: starts[key][s] for key in keys}
-        it_data, log = _hill_climb(start, param_space, inputs, optimization_function, params, enable_feasible_predictor,
-                                   scalarization_key, feasible_parameter)
+    start_list = [{key: starts[key][s] for key in keys} for s in range(n_starts)]
+    # "auto": only when it is exactly equivalent -- no RNG in get_neighbors, and a scorer whose value for a candidate
+    # does not depend on what else is in the batch (piBO's TS/UCB branch and BOPrO's running limits do)
+    lockstep = device_scorer is not None and (_lockstep is True or _lockstep in ("1", "on") or
+                                              (_lockstep == "auto" and not _neighbors_use_rng(param_space) and
+                                               getattr(device_scorer, "batch_invariant", False)))
+    if lockstep:
+        climbs = _hill_climb_lockstep(start_list, param_space, inputs, device_scorer, params, scalarization_key)
+    else:
+        climbs = (_hill_climb(start, param_space, inputs, optimization_function, params, enable_feasible_predictor,
+                              scalarization_key, feasible_parameter) for start in start_list)
+    for it_data, log in climbs:
         _log(log, verbose=True)
         result_array = concatenate_data_dictionaries(result_array, it_data)
     local_search_time = datetime.datetime.now()

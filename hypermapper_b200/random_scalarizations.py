@@ -107,6 +107,7 @@ def _device_scores(candidates, **p):
                                      p.get("classification_model"))
 
 
+_device_scores.batch_invariant = True        # a candidate's score does not depend on the rest of the batch
 run_acquisition_function.device_scores = _device_scores
 
 

@@ -234,3 +234,41 @@ def test_local_search_generic_callable_and_return_shape():
     i = int(np.argmin(data_array["scalarization"]))
     assert [data_array[k][i] for k in ("a", "b", "c")] == [best[k] for k in ("a", "b", "c")]
     assert best["a"] == 17 and best["b"] == 4
+
+
+def test_lockstep_hill_climb_equals_sequential():
+    """The lock-step hill climb (all starts advance together, one scoring launch per round) returns exactly what the
+    start-after-start climb returns on a discrete space: same data_array (order included), same pick."""
+    from hypermapper_b200 import local_search as ls, random_scalarizations as rs, utility_functions as uf
+    from hypermapper_b200.space_lite import SpaceLite
+    z = load("local_search.npz")
+    config = json.loads(str(z["config_json"]))
+    space = SpaceLite(config)
+    inputs = space.get_input_parameters()
+    models = {"Value": FrozenForest(z, "forest_Value_")}
+    data = {k: [int(v) for v in z["data_inputs"][:, j]] for j, k in enumerate(inputs)}
+    data["Value"] = z["data_Value"].tolist()
+    fast = {space.get_unique_hash_string_from_values({k: data[k][r] for k in inputs}): r for r in range(60)}
+    weights = {"Value": 1.0}
+    limits = {"Value": [min(data["Value"]), max(data["Value"])]}
+    scal, _ = uf.compute_data_array_scalarization(data, weights, copy.deepcopy(limits), "tchebyshev")
+    data[config["scalarization_key"]] = scal.tolist()
+    p = {"regression_models": models, "iteration_number": 3, "data_array": data, "classification_model": None,
+         "param_space": space, "objective_weights": weights, "model_type": "random_forest",
+         "objective_limits": limits, "acquisition_function": "EI", "scalarization_method": "tchebyshev",
+         "number_of_cpus": 1}
+    assert not ls._neighbors_use_rng(space)
+    results = []
+    try:
+        for mode in (False, True, "auto"):
+            ls.set_lockstep(mode)
+            np.random.seed(4)
+            random.seed(4)
+            results.append(ls.local_search(6, 400, space, fast, False, rs.run_acquisition_function, p,
+                                           config["scalarization_key"], 1, previous_points=data))
+    finally:
+        ls.set_lockstep("auto")
+    for data_array, best in results[1:]:
+        assert best == results[0][1]
+        assert data_array == results[0][0]
+    assert len(results[0][0][config["scalarization_key"]]) > 800 + 60      # the climbs did evaluate neighbours
