@@ -255,7 +255,12 @@ def test_install_rebinds_reference_entry_points():
                (ns.random_scalarizations, ["run_acquisition_function", "EI", "ucb", "thompson_sampling", "random_scalarizations"]),
                (ns.local_search, ["local_search", "get_neighbors"]),
                (ns.compute_pareto, ["sequential_is_pareto_efficient", "sequential_is_pareto_efficient_dumb",
-                                    "parallel_is_pareto_efficient", "compute_pareto"])]
+                                    "parallel_is_pareto_efficient", "compute_pareto"]),
+               (ns.prior_optimization, ["compute_probability_from_prior", "estimate_prior_limits",
+                                        "compute_probability_from_model", "compute_EI_from_posteriors",
+                                        "prior_guided_optimization", "local_search"]),
+               (ns.pibo, ["prior_weighted_acquisition_function", "run_pibo", "compute_probability_from_prior",
+                          "run_acquisition_function", "local_search"])]
     for tgt, names in targets:
         for n in names:
             saved[(tgt, n)] = getattr(tgt, n)
@@ -267,6 +272,9 @@ def test_install_rebinds_reference_entry_points():
         assert ns.local_search.local_search is b_ls.local_search
         assert ns.compute_pareto.sequential_is_pareto_efficient is b_cp.sequential_is_pareto_efficient
         assert ns.models.RFModel.get_leaves_per_sample is b_models.rf_get_leaves_per_sample
+        from hypermapper_b200 import pibo as b_pibo, prior_optimization as b_po
+        assert ns.pibo.prior_weighted_acquisition_function is b_pibo.prior_weighted_acquisition_function
+        assert ns.prior_optimization.compute_EI_from_posteriors is b_po.compute_EI_from_posteriors
         # signatures keep the reference's positional parameter names
         import inspect
         for (tgt, n), ref_fn in saved.items():
