@@ -531,7 +531,9 @@ class ParetoBench:
 
     def config(self, N, world):
         return {"workload": self.desc, "points_per_gpu": N, "objectives": self.M,
-                "parallelism": "replicas x%d (each rank filters its own chunk)" % world,
+                "parallelism": ("single GPU" if world == 1 else
+                                "row blocks x%d: local pass 1, all-gather of the survivors, full filter on the union "
+                                "(distributed.pareto_mask_sharded)" % world),
                 "l2": "inputs (%.2f GB) larger than L2" % (8 * self.M * N / 1e9)}
 
     def cpu_port(self, sample):
@@ -543,7 +545,9 @@ class ParetoBench:
 
     def setup_device(self, N, rank):
         import torch
+        import torch.distributed as dist
         self.N, self.rank = N, rank
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
         c = np.random.default_rng(7 + rank).random((N, self.M))
         self.c_host = torch.from_numpy(c).pin_memory()
         self.c_dev = self.c_host.cuda()
@@ -551,7 +555,8 @@ class ParetoBench:
         self.mask_host = torch.empty((N,), dtype=torch.uint8).pin_memory()
         # fast path: ctl_init, 2 x (gather_sample, exact, sort_pivots, stream), exact, sort_front, count_flags, scan,
         # scatter, pass2_a, pass2_b
-        self.launches_per_step = 16
+        # sharded: pass 1 on the block (fast path up to hm_px_exact = 9 launches) + full filter on the union (16)
+        self.launches_per_step = 16 if self.world == 1 else 25
 
     def step(self, record):
         import torch
@@ -560,7 +565,11 @@ class ParetoBench:
         if record:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record()
-        mask = compute_pareto.pareto_mask_device(self.c_dev)
+        if self.world > 1:
+            from hypermapper_b200.distributed import pareto_mask_sharded
+            mask = pareto_mask_sharded(self.c_dev)
+        else:
+            mask = compute_pareto.pareto_mask_device(self.c_dev)
         if record:
             ev[1].record()
         return (mask, None), ev
@@ -568,7 +577,11 @@ class ParetoBench:
     def e2e_step(self):
         from hypermapper_b200 import compute_pareto
         self.c_stage.copy_(self.c_host, non_blocking=True)
-        mask = compute_pareto.pareto_mask_device(self.c_stage)
+        if self.world > 1:
+            from hypermapper_b200.distributed import pareto_mask_sharded
+            mask = pareto_mask_sharded(self.c_stage)
+        else:
+            mask = compute_pareto.pareto_mask_device(self.c_stage)
         self.mask_host.copy_(mask, non_blocking=True)
         return mask, None
 

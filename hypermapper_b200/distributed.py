@@ -50,3 +50,70 @@ def allgather_topk(local_vals, local_idx, k, group=None):
     out_v[: len(mv)] = torch.from_numpy(mv)
     out_i[: len(mi)] = torch.from_numpy(mi)
     return out_v, out_i
+
+
+# rows per rank in the first exchange round of pareto_mask_sharded (10^7 uniform 3-objective points leave ~10^3)
+_PARETO_EXCHANGE_ROWS = 4096
+
+
+def pareto_mask_sharded(costs_local, filter_fn=None, group=None):
+    """Pareto mask of a cost matrix whose rows are sharded over the ranks in contiguous, ascending blocks
+    (rank r owns global rows [sum of the sizes of ranks < r, ...)).  Returns this rank's slice of the mask that
+    compute_pareto.sequential_is_pareto_efficient (compute_pareto.py:89-117) gives on the whole matrix.
+
+    One exchange step, the scheme of the reference's own parallel_is_pareto_efficient (compute_pareto.py:180-200) made
+    exact: (1) every rank runs pass 1 on its block -- "not strictly dominated in every coordinate", order independent
+    and transitive, so a global pass-1 survivor survives locally; (2) the local survivors (typically 10^2-10^3 rows)
+    are all-gathered in rank order = global index order; (3) every rank runs the full filter on that union: pass 1
+    removes the points dominated from another block, pass 2 -- sequential and index-order dependent -- then sees
+    exactly the rows and the order it sees in the single-process run; (4) every rank keeps the verdicts of its own rows.
+    NaN costs break the transitivity argument: they are detected and rejected.
+
+    costs_local: CUDA (nccl, or gloo with the collectives staged through the host) or CPU tensor [n_local][M] fp64.
+    filter_fn(costs, pass2) -> uint8/bool mask tensor on the same device; default: the K4 kernels."""
+    import torch
+    import torch.distributed as dist
+    if filter_fn is None:
+        from .compute_pareto import pareto_mask_device as filter_fn
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    dev = costs_local.device
+    n_local, M = costs_local.shape
+    has_nan = torch.isnan(costs_local).any().to(torch.float64)             # stays on the device until the exchange
+    alive = filter_fn(costs_local, False).to(torch.bool) if n_local else torch.zeros((0,), dtype=torch.bool, device=dev)
+    rows = torch.nonzero(alive).view(-1)
+    mine = costs_local[rows].contiguous()
+    out = torch.zeros((n_local,), dtype=torch.uint8, device=dev)
+    nan_msg = ("pareto_mask_sharded: NaN costs (the dominance relation is not transitive with NaNs; filter them on one "
+               "rank with sequential_is_pareto_efficient)")
+    if world == 1:
+        if float(has_nan.item()):
+            raise ValueError(nan_msg)
+        keep = filter_fn(mine, True).to(torch.bool) if len(rows) else alive[:0]
+        out[rows[keep]] = 1
+        return out
+    # ONE collective in the common case: every rank contributes a fixed-capacity block [1 + cap][M] whose header row
+    # carries its survivor count (+0.5 if it saw a NaN); a second round with the exact capacity only if a rank overflows.
+    # On the tensors' device with nccl, through the host otherwise (gloo).
+    cdev = dev if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    rank = dist.get_rank(group)
+    cap = _PARETO_EXCHANGE_ROWS
+    while True:
+        block = torch.zeros((1 + cap, M), dtype=torch.float64, device=dev)
+        block[0, 0] = has_nan * 0.5 + float(len(rows))
+        block[1: 1 + min(len(rows), cap)] = mine[:cap]
+        block = block.to(cdev)
+        gathered = torch.empty((world * (1 + cap), M), dtype=torch.float64, device=cdev)
+        dist.all_gather_into_tensor(gathered, block, group=group)
+        gathered = gathered.view(world, 1 + cap, M)
+        heads = gathered[:, 0, 0].cpu().tolist()
+        if any(h != int(h) for h in heads):
+            raise ValueError(nan_msg)                    # every rank sees the same headers and raises together
+        counts = [int(h) for h in heads]
+        if max(counts) <= cap:
+            break
+        cap = max(counts)
+    union = torch.cat([gathered[r, 1: 1 + counts[r]] for r in range(world)], dim=0).to(dev).contiguous()
+    keep = filter_fn(union, True).to(torch.bool) if union.shape[0] else torch.zeros((0,), dtype=torch.bool, device=dev)
+    start = sum(counts[:rank])
+    out[rows[keep[start: start + counts[rank]]]] = 1
+    return out

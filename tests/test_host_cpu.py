@@ -239,6 +239,62 @@ def test_two_rank_topk_merge_over_gloo(tmp_path):
         assert p.returncode == 0, o
 
 
+GLOO_PARETO_WORKER = r"""
+import os, sys
+import numpy as np
+import torch
+import torch.distributed as dist
+sys.path.insert(0, %r)
+from hypermapper_b200.distributed import pareto_mask_sharded, shard_bounds
+from oracle import oracle
+rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+
+def cpu_filter(costs, pass2):           # the oracle stands in for the K4 kernels on this GPU-less box
+    c = costs.numpy()
+    if len(c) == 0:
+        return torch.zeros((0,), dtype=torch.uint8)
+    return torch.from_numpy((oracle.pareto(c) if pass2 else oracle.pareto_pass1(c)).astype(np.uint8))
+
+rng = np.random.default_rng(3)
+cases = {"uniform3": rng.random((6001, 3)), "ties3": np.floor(rng.random((5000, 3)) * 12) / 12,
+         "ties2": np.floor(rng.random((4000, 2)) * 40) / 40, "quirk": np.array([[1., 5., 9.], [1., 4., 10.], [2., 2., 2.]]),
+         "dups": np.repeat(rng.random((300, 3)), 3, axis=0)}
+for name, c in cases.items():
+    lo, hi = shard_bounds(len(c), rank, world)
+    got = pareto_mask_sharded(torch.from_numpy(np.ascontiguousarray(c[lo:hi])), filter_fn=cpu_filter).numpy().astype(bool)
+    want = oracle.pareto(c)[lo:hi]
+    assert np.array_equal(got, want), (name, rank, got.sum(), want.sum())
+import hypermapper_b200.distributed as D
+D._PARETO_EXCHANGE_ROWS = 16            # force the overflow round: an anti-correlated front keeps every point
+x = rng.random(3000); front = np.stack([x, 1 - x], 1)
+lo, hi = shard_bounds(len(front), rank, world)
+got = pareto_mask_sharded(torch.from_numpy(np.ascontiguousarray(front[lo:hi])), filter_fn=cpu_filter).numpy().astype(bool)
+assert np.array_equal(got, oracle.pareto(front)[lo:hi]) and got.sum() > 1000
+bad = rng.random((100, 3)); bad[5 + 50 * rank, 1] = np.nan
+try:
+    pareto_mask_sharded(torch.from_numpy(bad), filter_fn=cpu_filter)
+    raise SystemExit("NaN input was accepted")
+except ValueError:
+    pass
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_two_rank_sharded_pareto_over_gloo(tmp_path):
+    """SURVEY 8(e) row 2 on CPU: contiguous row blocks, local pass 1, all-gather of the survivors, full filter on the
+    union -> every rank holds its slice of the single-process mask (pass 2's index-order dependence included)."""
+    script = tmp_path / "worker_pareto.py"
+    script.write_text(GLOO_PARETO_WORKER % ROOT)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+
+
 def test_install_rebinds_reference_entry_points():
     """with the real reference importable (build container only): install() rebinds every hot-path name"""
     from oracle import ref_harness

@@ -100,3 +100,42 @@ def test_parallel_is_pareto_efficient_two_stage():
     keep = np.concatenate([oracle.pareto(c[lo:hi]) for lo, hi in bounds])
     assert np.array_equal(preds["a"], c[keep, 0])
     assert np.array_equal(keep2, oracle.pareto(c[keep]))
+
+
+SHARDED_WORKER = r"""
+import os, sys
+import numpy as np
+import torch
+import torch.distributed as dist
+sys.path.insert(0, %r)
+from hypermapper_b200.distributed import pareto_mask_sharded, shard_bounds
+from hypermapper_b200.compute_pareto import pareto_mask_device
+rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)      # both ranks share cuda:0; collectives via the host
+rng = np.random.default_rng(5)
+cases = {"uniform3": rng.random((400_000, 3)), "ties3": np.floor(rng.random((200_000, 3)) * 64) / 64,
+         "uniform2": rng.random((300_001, 2))}
+for name, c in cases.items():
+    whole = pareto_mask_device(torch.from_numpy(c).cuda()).cpu().numpy()
+    lo, hi = shard_bounds(len(c), rank, world)
+    got = pareto_mask_sharded(torch.from_numpy(np.ascontiguousarray(c[lo:hi])).cuda()).cpu().numpy()
+    assert np.array_equal(got, whole[lo:hi]), (name, rank, int(got.sum()), int(whole[lo:hi].sum()))
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_sharded_pareto_two_ranks_equals_single_gpu(tmp_path):
+    """row blocks on two ranks (sharing this GPU; gloo carries the survivor exchange), K4 kernels on both
+    -> each rank's slice equals the single-GPU mask."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    script = tmp_path / "worker_pareto_gpu.py"
+    script.write_text(SHARDED_WORKER % ROOT)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29535", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
