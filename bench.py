@@ -39,6 +39,13 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = ["c3", "c1", "c5rf", "c2", "c5gp", "c4", "c3raw", "c3pool"]
 
+# roofline.traffic: dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel from an
+# `ncu --set full` capture of the same command at the same size (profiles/<file>); None where no capture at that size exists
+NCU_TRAFFIC = {
+    ("c3", 1 << 24): (2.235832e9 + 0.561338e9, "profiles/r01_forest_c3_default_ncu_raw.csv"),
+    ("c1", 1 << 26): (0.537153e9 + 0.501310e9, "profiles/r01_forest_c1_ncu_raw.csv"),
+}
+
 
 def parse():
     ap = argparse.ArgumentParser()
@@ -252,7 +259,9 @@ class RFBench:
         prop = torch.cuda.get_device_properties(0)
         smem_peak = 128.0 * prop.multi_processor_count * 1.965e9 / 1e9      # GB/s at clocks.max.sm = 1965 MHz
         smem_ach = self.smem_bytes_per_eval * N / (kernel_ms / 1e3) / 1e9
-        return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+        traffic, traffic_src = NCU_TRAFFIC.get((self.name, N), (None, None))
+        return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                "traffic_source": traffic_src,
                 "smem_pipe": {"achieved": smem_ach, "peak": smem_peak, "unit": "GB/s", "frac": smem_ach / smem_peak,
                               "bytes_per_eval": self.smem_bytes_per_eval,
                               "how": "per tree: 12 B per internal node on the path (8 B node + 4 B feature) + 8 B leaf "
