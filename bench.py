@@ -156,8 +156,10 @@ class RFBench:
         if cached is None:
             try:
                 import pickle
-                with open(cache, "wb") as f:
+                tmp = "%s.%d.tmp" % (cache, os.getpid())        # atomic: concurrent ranks never read a partial file
+                with open(tmp, "wb") as f:
                     pickle.dump(self.wl, f)
+                os.replace(tmp, cache)
             except Exception:
                 pass
         self.k = 20
