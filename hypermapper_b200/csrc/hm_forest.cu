@@ -42,6 +42,13 @@
 
 #define HM_LEFT_BITS 22
 #define HM_LEFT_MASK ((1u << HM_LEFT_BITS) - 1u)
+// Forests that stream through shared memory use a second layout of a node's word 1 (word 0 = threshold bits / leaf
+// ordinal in both):   (feature * block) << 16 | left      -- "packed"
+// i.e. the upper half is the float index of the feature's column inside the [feature][thread] tile, so that the tile
+// address is  tile + (word1 >> 14)  (left < 2^14 keeps bits 14-15 clear) and the child address  nodes + left * 8:
+// one instruction each, where  feature << 22 | left  costs a shift and a multiply-add for the tile address.
+// A group holds < 2^14 nodes (HM_NODEBUF_MAX / 8) and feature * block <= HM_XTILE_MAX / 4 < 2^16.
+#define HM_PK_LEFT_MASK 0xffffu
 #define HM_MAX_FEATURES 1023
 #define HM_SMEM_TOTAL (227 * 1024)
 #define HM_SMEM_HEADER 128
@@ -73,6 +80,8 @@ struct HmKeyTree {
     const unsigned* leaf_rank;   // forest-wide: DFS rank of a leaf among the leaves of its own tree
     unsigned root;               // group-relative index of the root
     unsigned n_leaves;
+    unsigned feat_shift;         // feature = word1 >> feat_shift      (22, or 16 + log2(block) for the packed layout)
+    unsigned left_mask;          // left    = word1 & left_mask
 };
 
 struct hm_forest {
@@ -203,6 +212,7 @@ extern "C" int hm_forest_create(int n_trees, int n_features, const int64_t* off,
         const size_t hdr = (((size_t)ng * 4) + 15) & ~(size_t)15;
         size_t bytes = (hdr + nodes * 8 + 15) & ~(size_t)15;
         HM_REQUIRE(nodes <= HM_LEFT_MASK, "group too large");
+        HM_REQUIRE(!staged || nodes < (1u << 14), "shared-memory group too large for the packed node layout");
         HmGroupDesc g;
         g.blob_off = blob.size();
         g.bytes = (unsigned)bytes;
@@ -230,7 +240,8 @@ extern "C" int hm_forest_create(int n_trees, int n_features, const int64_t* off,
                     uint32_t tb;
                     memcpy(&tb, &thr, 4);
                     slot[0] = tb;
-                    slot[1] = ((uint32_t)feature[b + nd] << HM_LEFT_BITS) | (base + (uint32_t)L.newidx[l]);
+                    slot[1] = staged ? (((uint32_t)feature[b + nd] * (uint32_t)block) << 16) | (base + (uint32_t)L.newidx[l])
+                                     : ((uint32_t)feature[b + nd] << HM_LEFT_BITS) | (base + (uint32_t)L.newidx[l]);
                 } else {
                     slot[0] = (uint32_t)leaf_ord;
                     slot[1] = 0u;
@@ -299,6 +310,10 @@ extern "C" int hm_forest_create(int n_trees, int n_features, const int64_t* off,
         F->key[kk].leaf_rank = (const unsigned*)F->d_leaf_rank;
         F->key[kk].root = tree_root[kk];
         F->key[kk].n_leaves = (unsigned)(tree_leaf_base[kk + 1] - tree_leaf_base[kk]);
+        unsigned lg = 0;
+        while ((1 << lg) < block) ++lg;
+        F->key[kk].feat_shift = staged ? 16u + lg : (unsigned)HM_LEFT_BITS;
+        F->key[kk].left_mask = staged ? HM_PK_LEFT_MASK : HM_LEFT_MASK;
     }
     *out = F;
     return 0;
@@ -360,26 +375,26 @@ __device__ __forceinline__ void hm_walk_round(const uint32_t* __restrict__ roots
         // shared-memory forest.  One visit = one PTX block per chain (ptxas interleaves the chains): both loads are
         // predicated on "this chain is still at an internal node", so a finished chain issues no load and no branch;
         // the node lives in one 64-bit register {threshold bits | leaf ordinal, feature << 22 | left}.
-        const uint32_t xs_a = hm_smem_u32(xs_t), nodes_a = hm_smem_u32(nodes), xstride = (uint32_t)BD * 4u;
+        const uint32_t xs_a = hm_smem_u32(xs_t), nodes_a = hm_smem_u32(nodes);
         unsigned long long nq[NCH];
 #pragma unroll
         for (int c = 0; c < NCH; ++c) nq[c] = reinterpret_cast<const unsigned long long*>(nodes)[roots[t0 + c]];
         bool any = false;
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) any = any || ((uint32_t)(nq[c] >> 32) & HM_LEFT_MASK);
+        for (int c = 0; c < NCH; ++c) any = any || ((uint32_t)(nq[c] >> 32) & HM_PK_LEFT_MASK);
         while (any) {
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
+                // packed word 1: tile byte offset = y >> 14 (as the high half of y * 2^18, one IMAD.HI), child = y & 0xffff
                 asm volatile(
                     "{\n\t"
                     ".reg .pred p, q;\n\t"
-                    ".reg .b32 th, y, left, f, xa, na;\n\t"
+                    ".reg .b32 th, y, left, xa, na;\n\t"
                     ".reg .f32 xv, thf;\n\t"
                     "mov.b64 {th, y}, %0;\n\t"
-                    "and.b32 left, y, 0x3fffff;\n\t"
+                    "and.b32 left, y, 0xffff;\n\t"
                     "setp.ne.u32 p, left, 0;\n\t"
-                    "shr.u32 f, y, 22;\n\t"
-                    "mad.lo.u32 xa, f, %3, %1;\n\t"
+                    "mad.hi.u32 xa, y, 0x40000, %1;\n\t"
                     "@p ld.shared.f32 xv, [xa];\n\t"
                     "mov.b32 thf, th;\n\t"
                     "mad.lo.u32 na, left, 8, %2;\n\t"
@@ -388,11 +403,11 @@ __device__ __forceinline__ void hm_walk_round(const uint32_t* __restrict__ roots
                     "@p ld.shared.b64 %0, [na];\n\t"
                     "}"
                     : "+l"(nq[c])
-                    : "r"(xs_a), "r"(nodes_a), "r"(xstride));
+                    : "r"(xs_a), "r"(nodes_a));
             }
             any = false;
 #pragma unroll
-            for (int c = 0; c < NCH; ++c) any = any || ((uint32_t)(nq[c] >> 32) & HM_LEFT_MASK);
+            for (int c = 0; c < NCH; ++c) any = any || ((uint32_t)(nq[c] >> 32) & HM_PK_LEFT_MASK);
         }
 #pragma unroll
         for (int c = 0; c < NCH; ++c) nd[c] = make_uint2((uint32_t)nq[c], (uint32_t)(nq[c] >> 32));
@@ -616,9 +631,10 @@ __global__ void __launch_bounds__(256) hm_forest_sortkey(const HmKeyArgs a, unsi
         if (q < a.n_key) {
             const uint2* __restrict__ nodes = a.t[q].nodes;
             uint2 nd = __ldg(nodes + a.t[q].root);
-            while (nd.y & HM_LEFT_MASK) {
-                const float xv = __ldg(a.X + (size_t)(nd.y >> HM_LEFT_BITS) * (size_t)a.ldx + (size_t)i);
-                nd = __ldg(nodes + (nd.y & HM_LEFT_MASK) + ((xv <= __uint_as_float(nd.x)) ? 0u : 1u));
+            const unsigned fs = a.t[q].feat_shift, lm = a.t[q].left_mask;
+            while (nd.y & lm) {
+                const float xv = __ldg(a.X + (size_t)(nd.y >> fs) * (size_t)a.ldx + (size_t)i);
+                nd = __ldg(nodes + (nd.y & lm) + ((xv <= __uint_as_float(nd.x)) ? 0u : 1u));
             }
             const unsigned r = __ldg(a.t[q].leaf_rank + nd.x) >> a.shift[q];
             k = (q == 0) ? r : k * a.nB + r;
