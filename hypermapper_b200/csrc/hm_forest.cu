@@ -341,20 +341,23 @@ extern "C" int hm_forest_n_groups(const hm_forest_t* f) { return f ? f->dev.n_gr
 struct HmAcc {
     double q, s, u, v;
     double pq[HM_MAX_CHAINS], ps[HM_MAX_CHAINS], pu[HM_MAX_CHAINS], pv[HM_MAX_CHAINS];
-    int pn;
 };
+// All HM_MAX_CHAINS pending slots are added on every flush, in slot (= tree) order; a slot that holds no record holds
+// +0.0, and x + 0.0 == x bit for bit (only -0.0 becomes +0.0, which compares equal), so the sums are those of the
+// reference's tree-order loop without a data-dependent slot count in the instruction stream.
 template <bool NEED_V>
 __device__ __forceinline__ void hm_acc_flush(HmAcc& acc) {
 #pragma unroll
     for (int c = 0; c < HM_MAX_CHAINS; ++c) {
-        if (c < acc.pn) {
-            acc.q = hm_add(acc.q, acc.pq[c]);
-            acc.s = hm_add(acc.s, acc.ps[c]);
-            acc.u = hm_add(acc.u, acc.pu[c]);
-            if (NEED_V) acc.v = hm_add(acc.v, acc.pv[c]);
-        }
+        acc.q = hm_add(acc.q, acc.pq[c]);
+        acc.s = hm_add(acc.s, acc.ps[c]);
+        acc.u = hm_add(acc.u, acc.pu[c]);
+        if (NEED_V) acc.v = hm_add(acc.v, acc.pv[c]);
     }
-    acc.pn = 0;
+}
+__device__ __forceinline__ void hm_acc_clear_pending(HmAcc& acc) {
+#pragma unroll
+    for (int c = 0; c < HM_MAX_CHAINS; ++c) acc.pq[c] = acc.ps[c] = acc.pu[c] = acc.pv[c] = 0.0;
 }
 
 #ifndef HM_FOREST_MAXCH
@@ -435,7 +438,8 @@ __device__ __forceinline__ void hm_walk_round(const uint32_t* __restrict__ roots
     hm_acc_flush<NEED_V>(acc);
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
-        const double* rec = leaf_tab + 4 * (size_t)nd[c].x;
+        const double* rec = reinterpret_cast<const double*>(reinterpret_cast<const unsigned char*>(leaf_tab) +
+                                                            (unsigned long long)nd[c].x * 32ull);
         if (NEED_V) {
             asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
                          : "=d"(acc.pq[c]), "=d"(acc.ps[c]), "=d"(acc.pu[c]), "=d"(acc.pv[c])
@@ -449,7 +453,9 @@ __device__ __forceinline__ void hm_walk_round(const uint32_t* __restrict__ roots
                 leaf_out[(size_t)(first_tree + t0 + c) * (size_t)N + (size_t)i] = __ldg(leaf_node + nd[c].x);
         }
     }
-    acc.pn = NCH;
+    // slots of chains this round does not have go back to +0.0
+#pragma unroll
+    for (int c = NCH; c < HM_MAX_CHAINS; ++c) acc.pq[c] = acc.ps[c] = acc.pu[c] = acc.pv[c] = 0.0;
 }
 
 // Walk `ntrees` trees whose roots/nodes are at the given pointers (shared or global), in tree order: rounds of 3,
@@ -548,7 +554,7 @@ __global__ void __launch_bounds__(BDT, 1) hm_forest_kernel(const __grid_constant
             const HmForestDev& F = a.f[m];
             HmAcc acc;
             acc.q = acc.s = acc.u = acc.v = 0.0;
-            acc.pn = 0;
+            hm_acc_clear_pending(acc);
             int* lo = APPLY ? a.leaf_out[m] : nullptr;
             if (F.staged) {
                 for (int g = 0; g < F.n_groups; ++g) {

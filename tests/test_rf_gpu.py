@@ -269,3 +269,43 @@ def test_threshold_rounding_edge_cases():
     Xd = torch.from_numpy(np.ascontiguousarray(Xn.astype(np.float32).T)).cuda()
     out = forest.rf_eval([df], Xd, want_leaves=True)
     assert np.array_equal(out["leaves"][0].cpu().numpy().astype(np.int64), oracle.rf_apply(fa, Xn))
+
+
+def test_forest_edge_cases_empty_single_leaf_mixed_layouts_eight_objectives():
+    """Edge cases in one go: N = 0 and N = 1 pools; trees that are a single leaf; eight objectives in one launch; a
+    call that mixes a shared-memory forest with one whose trees only fit in global memory (the two node layouts)."""
+    from hypermapper_b200 import forest, _lib
+    from oracle import oracle
+    torch = _torch()
+    rng = np.random.default_rng(77)
+    D = 6
+    small = [_synthetic_forest(rng, 5, D, 0, 4) for _ in range(7)]          # depth_lo = 0: some trees are one leaf
+    assert any(np.any(np.diff(f["tree_off"]) == 1) for f in small)
+    deep = _synthetic_forest(rng, 3, D, 14, 15)                               # > 16 k nodes per tree: not staged
+    fs = small + [deep]
+    dfs = [forest.DeviceForest(forest.tables_from_arrays(**f)) for f in fs]
+    assert [int(_lib.lib().hm_forest_staged(d.handle)) for d in dfs] == [1] * 7 + [0]
+    fas = [oracle.ForestArrays(f["tree_off"], f["left"], f["right"], f["feature"], f["threshold"], f["leaf_mean"],
+                               f["leaf_var"], f["value"], D) for f in fs]
+    acq = _lib.make_acq_params("UCB", "linear", [1.0 / 8] * 8, None, 0.7)
+    for N in (0, 1, 2500):
+        X = rng.random((N, D))
+        Xd = torch.from_numpy(np.ascontiguousarray(X.astype(np.float32).T)).cuda().reshape(D, N)
+        out = forest.rf_eval(dfs, Xd, want_leaves=True, want_mean=True, want_var=True, acq=acq)
+        assert out["score"].shape == (N,) and out["mean"].shape == (8, N)
+        for m, fa in enumerate(fas):
+            leaf = oracle.rf_apply(fa, X.astype(np.float32).astype(np.float64)) if N else np.zeros((len(fa.tree_off) - 1, 0), dtype=np.int64)
+            assert np.array_equal(out["leaves"][m].cpu().numpy().astype(np.int64), leaf)
+            if N:
+                assert np.array_equal(out["mean"][m].cpu().numpy(), oracle.rf_prediction(fa, leaf))
+        if N:
+            mean = out["mean"].cpu().numpy()
+            var = out["var"].cpu().numpy()
+            want = (mean / 8).sum(0) * 0          # UCB linear: sum w*mu - beta*sqrt(sum w*var)
+            s = np.zeros(N)
+            b = np.zeros(N)
+            for m in range(8):
+                s = s + (1.0 / 8) * mean[m]
+                b = b + (1.0 / 8) * var[m]
+            want = s - 0.7 * np.sqrt(b)
+            assert_rel(out["score"].cpu().numpy(), want, 1e-12)
