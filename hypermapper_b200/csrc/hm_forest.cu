@@ -52,7 +52,9 @@
 #define HM_MAX_FEATURES 1023
 #define HM_SMEM_TOTAL (227 * 1024)
 #define HM_SMEM_HEADER 128
-#define HM_XTILE_MAX (100 * 1024)
+// tile budget: 1024 candidates per CTA up to 33 encoded features (32 warps hide the shared-memory latency better than
+// larger tree groups do: C5-RF, D_enc = 32, 43.9 -> 40.3 ms when the block went from 512 to 1024 threads)
+#define HM_XTILE_MAX (132 * 1024)
 #define HM_NODEBUF_MAX (96 * 1024)
 
 struct HmGroupDesc {
@@ -118,7 +120,12 @@ struct HmEvalArgs {
 // block size / node-buffer size as a function of the encoded feature count (shared by create and launch)
 static void hm_forest_geometry(int D, int* block, int* nodebuf) {
     int b = 1024;
-    while (b > 128 && (size_t)b * D * 4 > HM_XTILE_MAX) b >>= 1;
+    static long long xtile_max = -1;          // experiments: HM_B200_XTILE_MAX overrides the tile budget (bytes)
+    if (xtile_max < 0) {
+        const char* e = getenv("HM_B200_XTILE_MAX");
+        xtile_max = e ? atoll(e) : (long long)HM_XTILE_MAX;
+    }
+    while (b > 128 && (long long)b * D * 4 > xtile_max) b >>= 1;
     size_t xt = (size_t)b * D * 4;
     long long nb = ((long long)HM_SMEM_TOTAL - HM_SMEM_HEADER - (long long)xt) / 2;
     nb &= ~15ll;
@@ -146,7 +153,7 @@ extern "C" int hm_forest_create(int n_trees, int n_features, const int64_t* off,
     HM_REQUIRE(off && feature && threshold && left && right, "tree arrays");
     int block, nodebuf;
     hm_forest_geometry(n_features, &block, &nodebuf);
-    HM_REQUIRE((size_t)block * n_features * 4 <= HM_XTILE_MAX, "n_features too large for the shared-memory tile");
+    HM_REQUIRE((size_t)block * n_features * 4 <= 160 * 1024, "n_features too large for the shared-memory tile");
 
     // pass 1: per-tree BFS relayout (children adjacent), sizes
     struct TreeLay { std::vector<int> order; std::vector<int> newidx; };
