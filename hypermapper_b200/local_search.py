@@ -38,17 +38,31 @@ from .utility_functions import (
 # pools larger than this are not materialised as Python lists in the returned data_array
 MATERIALISE_LIMIT = 262144
 
-# Device pools: when enabled and the acquisition plug-in is one of this package's device
-# scorers, the two random pools are generated AND encoded on the GPU (hm_sample_pool: same per-parameter distributions
-# as space.get_random_configuration, Philox stream instead of numpy's) and never exist on the host; the few rows the
-# optimiser needs as configurations are re-generated from (seed, index).  Off by default: with it off the pools are
-# drawn by param_space.get_random_configuration from numpy's global stream exactly as the reference does.
-_device_pools = os.environ.get("HM_B200_DEVICE_POOLS", "0") not in ("", "0")
+# Device pools: when the acquisition plug-in is one of this package's device scorers, the two
+# random pools can be generated AND encoded on the GPU (hm_sample_pool: same per-parameter distributions as
+# space.get_random_configuration, Philox stream instead of numpy's) and never exist on the host; the few rows the
+# optimiser needs as configurations are re-generated from (seed, index).
+#   "auto" (default): host pools -- drawn by param_space.get_random_configuration from numpy's global stream exactly as
+#                     the reference does, so seeded runs pick the reference's configurations -- up to
+#                     DEVICE_POOL_AUTO_POINTS candidates per pool; device pools above (the reference's list-of-dicts
+#                     path cannot run there, and building the numpy object array alone takes seconds: 2.4 s per
+#                     iteration at 2 x 10^6 candidates against 0.03 s)
+#   True / False    : always / never       (also HM_B200_DEVICE_POOLS=1 / 0)
+DEVICE_POOL_AUTO_POINTS = 1 << 20
+_env = os.environ.get("HM_B200_DEVICE_POOLS", "auto")
+_device_pools = "auto" if _env == "auto" else (_env not in ("", "0"))
 
 
-def set_device_pools(enabled):
+def set_device_pools(mode):
+    """True / False / "auto" """
     global _device_pools
-    _device_pools = bool(enabled)
+    _device_pools = mode if mode == "auto" else bool(mode)
+
+
+def _use_device_pools(n_points):
+    if _device_pools == "auto":
+        return n_points >= DEVICE_POOL_AUTO_POINTS
+    return bool(_device_pools)
 
 
 def _log(msg, verbose=False):
@@ -245,7 +259,7 @@ def local_search(local_search_starting_points, local_search_random_points, param
         everything = dict_of_lists_to_list_of_dicts(param_space.get_space())
         half = int(len(everything) / 2)
         pool_u, pool_p = everything[0:half], everything[half::]
-    elif _device_pools and device_scorer is not None:
+    elif device_scorer is not None and _use_device_pools(local_search_random_points):
         from .space_device import DevicePool, device_space_for
         seed = int(np.random.randint(0, 2 ** 62))            # reproducible under np.random.seed
         want64 = params.get("model_type") == "gaussian_process"

@@ -309,3 +309,41 @@ def test_forest_edge_cases_empty_single_leaf_mixed_layouts_eight_objectives():
                 b = b + (1.0 / 8) * var[m]
             want = s - 0.7 * np.sqrt(b)
             assert_rel(out["score"].cpu().numpy(), want, 1e-12)
+
+
+def test_full_size_pool_properties():
+    """BASELINE size (2^24 candidates, D_enc = 23, two streamed forests): size-independent properties.
+    (1) the score of a candidate does not depend on where it sits in the pool (a pool built from a 2^20 base block
+        repeated 16 times under different shuffles scores every copy identically -- exercises the coherence pre-pass and
+        the scatter back through its permutation at full size);
+    (2) the stable top-k of that pool is the base block's best candidate, all 16 copies of it, lowest index first;
+    (3) a sample agrees with the C oracle."""
+    from hypermapper_b200 import forest, _lib
+    from oracle import oracle
+    torch = _torch()
+    rng = np.random.default_rng(2024)
+    D, T, base_n, reps = 23, 48, 1 << 20, 16
+    fs = [_synthetic_forest(rng, T, D, 7, 11) for _ in range(2)]
+    dfs = [forest.DeviceForest(forest.tables_from_arrays(**f)) for f in fs]
+    assert all(int(_lib.lib().hm_forest_n_groups(d.handle)) > 1 for d in dfs)          # streamed, pre-pass active
+    base = torch.from_numpy(np.round(rng.random((D, base_n)) * 16) / 16).to(torch.float32).cuda()
+    perms = [torch.randperm(base_n, device="cuda") for _ in range(reps)]
+    pool = torch.cat([base[:, p] for p in perms], dim=1).contiguous()                  # [D][2^24]
+    acq = _lib.make_acq_params("EI", "tchebyshev", [0.4, 0.6], [0.3, 0.1], 0.0)
+    score = forest.rf_eval(dfs, pool, acq=acq)["score"]
+    ref = forest.rf_eval(dfs, base.contiguous(), acq=acq)["score"]
+    for r, p in enumerate(perms):
+        assert torch.equal(score[r * base_n:(r + 1) * base_n], ref[p]), r
+    k = 16
+    tv, ti = forest.topk(score, k)
+    best = ref.min()
+    n_best = int((ref == best).sum())
+    where = torch.nonzero(score == best).view(-1)[:k]
+    assert torch.equal(ti, where) and bool((tv == best).all()) and n_best * reps >= k
+    sub = rng.choice(base_n, 3000, replace=False)
+    Xs = base[:, torch.from_numpy(sub).cuda()].T.cpu().numpy().astype(np.float64)
+    out = forest.rf_eval(dfs, base.contiguous(), want_mean=True)
+    for m, f in enumerate(fs):
+        fa = oracle.ForestArrays(f["tree_off"], f["left"], f["right"], f["feature"], f["threshold"], f["leaf_mean"],
+                                 f["leaf_var"], f["value"], D)
+        assert np.array_equal(out["mean"][m].cpu().numpy()[sub], oracle.rf_prediction(fa, oracle.rf_apply(fa, Xs)))

@@ -335,7 +335,8 @@ def test_local_search_with_device_pools():
             assert vals[0] == best_unseen
         assert picks[0] == picks[1]
     finally:
-        ls.set_device_pools(False)
+        ls.set_device_pools("auto")
+    assert not ls._use_device_pools(10000) and ls._use_device_pools(1 << 20)
 
 
 def test_pibo_on_a_device_pool_equals_pibo_on_its_rows():
