@@ -292,8 +292,8 @@ class SpaceRFBench(RFBench):
                               "EI+tchebyshev, top-20",
                      "c3pool": "C3 with device-generated pools: Philox sample+encode (D=10 -> D_enc=23) + 256-tree RF "
                                "x2, EI+tchebyshev, top-20"}[name]
-        self.e2e_api = {"c3raw": "acquisition_scores_device(raw ndarray): pinned raw host values -> H2D -> hm_encode -> "
-                                 "hm_rf_eval -> hm_topk -> D2H scores + top-k",
+        self.e2e_api = {"c3raw": "hm_rf_score_raw_host (C-ABI, pinned raw host values, 2M-candidate double-buffered chunks: "
+                                 "H2D -> hm_encode -> hm_rf_eval -> D2H scores; hm_topk -> D2H top-k)",
                         "c3pool": "DevicePool + acquisition_scores_device: hm_sample_pool -> hm_rf_eval -> hm_topk -> "
                                   "D2H top-k + hm_sample_rows of the winners (no candidate crosses PCIe)"}[name]
 
@@ -343,7 +343,8 @@ class SpaceRFBench(RFBench):
         if self.name == "c3raw":
             self.raw_host = torch.from_numpy(self.raw_rows(N, 6 + rank)).pin_memory()
             self.raw_dev = self.raw_host.cuda()
-            self.raw_stage = torch.empty_like(self.raw_dev)
+            from hypermapper_b200.scoring import HostScorer
+            self.scorer = HostScorer(wl.D_enc, chunk=1 << 21)
             self.x_dev = self.ds.encode(self.raw_dev)[0]
         else:
             self.x_dev = self.ds.sample_pool(self.seed, N, False)["x32"]
@@ -382,16 +383,13 @@ class SpaceRFBench(RFBench):
         import torch
         from hypermapper_b200 import forest
         if self.name == "c3raw":
-            self.raw_stage.copy_(self.raw_host, non_blocking=True)
-            x32 = self._front(self.raw_stage)
-        else:
-            x32 = self._front(None)
+            _, tv, ti = self.scorer.score_raw(self.ds, self.forests, self.raw_host, self.acq, k=self.k,
+                                              scores_out=self.scores_host)
+            return torch.from_numpy(tv).cuda(), torch.from_numpy(ti + self.rank * self.N).cuda()
+        x32 = self._front(None)
         out = forest.rf_eval(self.forests, x32, acq=self.acq)
         tv, ti = forest.topk(out["score"], self.k, index_base=self.rank * self.N)
-        if self.name == "c3raw":
-            self.scores_host.copy_(out["score"], non_blocking=True)
-        else:
-            self.winner_rows = self.ds.sample_rows(self.seed, False, ti - self.rank * self.N)
+        self.winner_rows = self.ds.sample_rows(self.seed, False, ti - self.rank * self.N)
         return tv, ti
 
     def e2e_bytes(self, N):

@@ -18,6 +18,9 @@ struct hm_host_ctx {
     int64_t topk_ws_bytes;
     double* d_topk_vals;
     int64_t* d_topk_idx;
+    double* d_raw[2];       // [chunk][raw_params] staging of raw parameter values (hm_rf_score_raw_host), lazily sized
+    int raw_params;
+    int32_t* d_invalid;
 };
 
 extern "C" int hm_host_ctx_create(int64_t max_candidates_per_chunk, int max_features, hm_host_ctx_t** out) {
@@ -55,6 +58,9 @@ extern "C" void hm_host_ctx_destroy(hm_host_ctx_t* c) {
         if (c->ev[i]) cudaEventDestroy(c->ev[i]);
         if (c->st[i]) cudaStreamDestroy(c->st[i]);
     }
+    for (int i = 0; i < 2; ++i)
+        if (c->d_raw[i]) cudaFree(c->d_raw[i]);
+    if (c->d_invalid) cudaFree(c->d_invalid);
     if (c->d_scores) cudaFree(c->d_scores);
     if (c->d_topk_ws) cudaFree(c->d_topk_ws);
     if (c->d_topk_vals) cudaFree(c->d_topk_vals);
@@ -108,5 +114,76 @@ extern "C" int hm_rf_score_host(hm_host_ctx_t* c, const hm_forest_t* const* fore
     }
     HM_CUDA_TRY(cudaStreamSynchronize(c->st[0]));
     HM_CUDA_TRY(cudaStreamSynchronize(c->st[1]));
+    return 0;
+}
+
+
+// The same from RAW parameter values (what the reference API is handed): per chunk  H2D of the raw rows -> hm_encode
+// (K5) -> fused forest/acquisition kernel -> D2H of the scores, double-buffered across the two streams.
+extern "C" int hm_rf_score_raw_host(hm_host_ctx_t* c, const hm_space_t* space, const hm_forest_t* const* forests, int M,
+                                    const double* raw_host, int64_t N, const hm_acq_params_t* acq,
+                                    double* score_out_host, int k, double* topk_vals_host, int64_t* topk_idx_host,
+                                    int32_t* n_invalid_out_host) {
+    HM_REQUIRE(c != nullptr && space != nullptr && forests != nullptr && acq != nullptr, "ctx/space/forests/acq");
+    HM_REQUIRE(N >= 0 && (N == 0 || raw_host != nullptr), "raw_host");
+    HM_REQUIRE(k >= 0 && k <= 1024, "0 <= k <= 1024");
+    HM_REQUIRE(k == 0 || (topk_vals_host && topk_idx_host), "top-k outputs");
+    const int D = hm_forest_n_features(forests[0]);
+    const int Dr = hm_space_n_params(space);
+    HM_REQUIRE(D > 0 && D <= c->max_features && D == hm_space_n_encoded(space),
+               "encoded width of the space must equal the forests' n_features (and fit the context)");
+    if (Dr > c->raw_params) {
+        for (int i = 0; i < 2; ++i) {
+            if (c->d_raw[i]) cudaFree(c->d_raw[i]);
+            c->d_raw[i] = nullptr;
+        }
+        c->raw_params = 0;
+        for (int i = 0; i < 2; ++i) HM_CUDA_TRY(cudaMalloc((void**)&c->d_raw[i], (size_t)c->chunk * Dr * sizeof(double)));
+        c->raw_params = Dr;
+    }
+    if (!c->d_invalid) HM_CUDA_TRY(cudaMalloc((void**)&c->d_invalid, sizeof(int32_t)));
+    if (N > c->cap_scores) {
+        if (c->d_scores) cudaFree(c->d_scores);
+        c->d_scores = nullptr;
+        c->cap_scores = 0;
+        HM_CUDA_TRY(cudaMalloc((void**)&c->d_scores, (size_t)N * sizeof(double)));
+        c->cap_scores = N;
+    }
+    HM_CUDA_TRY(cudaMemsetAsync(c->d_invalid, 0, sizeof(int32_t), c->st[0]));
+    HM_CUDA_TRY(cudaEventRecord(c->ev[0], c->st[0]));
+    HM_CUDA_TRY(cudaStreamWaitEvent(c->st[1], c->ev[0], 0));
+    int n_chunks = 0;
+    for (int64_t lo = 0; lo < N; lo += c->chunk, ++n_chunks) {
+        const int b = n_chunks & 1;
+        const int64_t n = std::min<int64_t>(c->chunk, N - lo);
+        cudaStream_t st = c->st[b];
+        HM_CUDA_TRY(cudaMemcpyAsync(c->d_raw[b], raw_host + (size_t)lo * Dr, (size_t)n * Dr * sizeof(double),
+                                    cudaMemcpyHostToDevice, st));
+        int rc = hm_encode(space, c->d_raw[b], 0, Dr, n, c->d_x[b], n, nullptr, 0, c->d_invalid, (void*)st);
+        if (rc) return rc;
+        rc = hm_rf_eval(forests, M, c->d_x[b], n, n, nullptr, nullptr, nullptr, nullptr, acq, nullptr,
+                        c->d_scores + lo, (void*)st);
+        if (rc) return rc;
+        if (score_out_host)
+            HM_CUDA_TRY(cudaMemcpyAsync(score_out_host + lo, c->d_scores + lo, (size_t)n * sizeof(double),
+                                        cudaMemcpyDeviceToHost, st));
+    }
+    if (n_chunks > 1) {
+        HM_CUDA_TRY(cudaEventRecord(c->ev[1], c->st[1]));
+        HM_CUDA_TRY(cudaStreamWaitEvent(c->st[0], c->ev[1], 0));
+    }
+    if (k > 0) {
+        int rc = hm_topk(c->d_scores, N, 0, k, c->d_topk_vals, c->d_topk_idx, c->d_topk_ws, (void*)c->st[0]);
+        if (rc) return rc;
+        HM_CUDA_TRY(cudaMemcpyAsync(topk_vals_host, c->d_topk_vals, (size_t)k * sizeof(double), cudaMemcpyDeviceToHost,
+                                    c->st[0]));
+        HM_CUDA_TRY(cudaMemcpyAsync(topk_idx_host, c->d_topk_idx, (size_t)k * sizeof(int64_t), cudaMemcpyDeviceToHost,
+                                    c->st[0]));
+    }
+    int32_t bad = 0;
+    HM_CUDA_TRY(cudaMemcpyAsync(&bad, c->d_invalid, sizeof(int32_t), cudaMemcpyDeviceToHost, c->st[0]));
+    HM_CUDA_TRY(cudaStreamSynchronize(c->st[0]));
+    HM_CUDA_TRY(cudaStreamSynchronize(c->st[1]));
+    if (n_invalid_out_host) *n_invalid_out_host = bad;
     return 0;
 }

@@ -47,3 +47,31 @@ class HostScorer:
                                          _lib.hptr(tv), _lib.hptr(ti))
         _lib.check(rc, "hm_rf_score_host")
         return scores_out, tv[:k], ti[:k]
+
+    def score_raw(self, device_space, forests, raw_host, acq, k=0, scores_out=None):
+        """Like score(), from RAW parameter values: raw_host is a float64 row-major [N][D] host array (numpy, or a pinned
+        torch CPU tensor) in input-parameter order, categoricals as indices.  Raises ValueError like the reference when
+        a discrete value is not one of its parameter's values."""
+        if hasattr(raw_host, "data_ptr"):
+            N, D = raw_host.shape
+            assert raw_host.is_contiguous() and not raw_host.is_cuda and str(raw_host.dtype) == "torch.float64"
+            rp = ctypes.c_void_p(raw_host.data_ptr())
+        else:
+            assert raw_host.dtype == np.float64 and raw_host.flags.c_contiguous
+            N, D = raw_host.shape
+            rp = _lib.hptr(raw_host)
+        assert D == device_space.D
+        sp = None
+        if scores_out is not None:
+            sp = ctypes.c_void_p(scores_out.data_ptr()) if hasattr(scores_out, "data_ptr") else _lib.hptr(scores_out)
+        tv = np.empty(max(k, 1), dtype=np.float64)
+        ti = np.empty(max(k, 1), dtype=np.int64)
+        M = len(forests)
+        handles = (ctypes.c_void_p * M)(*[f.handle for f in forests])
+        bad = ctypes.c_int32(0)
+        rc = _lib.lib().hm_rf_score_raw_host(self.handle, device_space.handle, handles, M, rp, N, ctypes.byref(acq), sp,
+                                             int(k), _lib.hptr(tv), _lib.hptr(ti), ctypes.byref(bad))
+        _lib.check(rc, "hm_rf_score_raw_host")
+        if bad.value:
+            raise ValueError("a discrete parameter value is not in its list of values (models.py:962-983)")
+        return scores_out, tv[:k], ti[:k]

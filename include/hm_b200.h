@@ -284,6 +284,14 @@ int hm_rf_score_host(hm_host_ctx_t* c, const hm_forest_t* const* forests, int M,
                      int64_t ldx, int64_t N, const hm_acq_params_t* acq, double* score_out_host, int k,
                      double* topk_vals_host, int64_t* topk_idx_host);
 
+/* The same from RAW parameter values, row-major fp64 [N][n_params] in host memory -- the form the reference's API is
+ * handed (run_acquisition_function's configurations, random_scalarizations.py:75-157): per chunk H2D -> hm_encode ->
+ * fused forest + acquisition kernel -> D2H, double-buffered.  *n_invalid_out_host (nullable) receives the number of
+ * CTAs that met a discrete value outside its parameter's value list (the reference raises ValueError there). */
+int hm_rf_score_raw_host(hm_host_ctx_t* c, const hm_space_t* space, const hm_forest_t* const* forests, int M,
+                         const double* raw_host, int64_t N, const hm_acq_params_t* acq, double* score_out_host, int k,
+                         double* topk_vals_host, int64_t* topk_idx_host, int32_t* n_invalid_out_host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -355,3 +355,31 @@ def test_pibo_on_a_device_pool_equals_pibo_on_its_rows():
     rows = pool.rows(range(3000))
     want, _ = pibo.prior_weighted_acquisition_function(rows, *args)
     assert np.array_equal(got, np.asarray(want), equal_nan=True)
+
+
+def test_raw_host_scoring_entry_matches_device_path():
+    """hm_rf_score_raw_host (raw host rows -> chunked H2D -> hm_encode -> fused forest + acquisition -> D2H) equals the
+    device-resident path bit for bit, top-k included, across a chunk boundary; unknown discrete values raise."""
+    from hypermapper_b200 import models, random_scalarizations as rs, _lib, forest
+    from hypermapper_b200.scoring import HostScorer
+    from hypermapper_b200.space_device import device_space_for
+    z = load("rf_mixed.npz")
+    space = space_of(z)
+    objectives = json.loads(str(z["objectives_json"]))
+    forests = {o: FrozenForest(z, "forest_%s_" % o) for o in objectives}
+    ds = device_space_for(space)
+    pool = ds.sample_pool(seed=3, N=5000, use_priors=False, want_raw=True, want32=True)
+    raw_rows = np.ascontiguousarray(pool["raw"].cpu().numpy().T)
+    dfs = [forest.device_forest(forests[o]) for o in objectives]
+    acq = _lib.make_acq_params("EI", "tchebyshev", [0.37, 0.63], [0.4, 0.2], 0.0)
+    want = forest.rf_eval(dfs, pool["x32"], acq=acq)["score"]
+    wv, wi = forest.topk(want, 20)
+    scorer = HostScorer(ds.n_encoded, chunk=2048)             # 3 chunks
+    scores = np.empty(5000)
+    _, tv, ti = scorer.score_raw(ds, dfs, raw_rows, acq, k=20, scores_out=scores)
+    assert np.array_equal(scores, want.cpu().numpy())
+    assert np.array_equal(ti, wi.cpu().numpy()) and np.array_equal(tv, wv.cpu().numpy())
+    bad = raw_rows.copy()
+    bad[4321, 2] = 3.0
+    with pytest.raises(ValueError):
+        scorer.score_raw(ds, dfs, bad, acq, k=0, scores_out=scores)
