@@ -439,22 +439,232 @@ __global__ void __launch_bounds__(HM_SPACE_BLOCK) hm_space_kernel(const HmSpaceA
     if (a.n_invalid && bad_any) atomicAdd(a.n_invalid, 1);
 }
 
+// ---- K5 fast path: parameter-major over a staged tile --------------------------------------------------------------
+// The generic kernel above interprets the descriptor once per (candidate, parameter): ~160 instructions per pair, issue
+// bound at 0.4 of HBM.  Here a CTA stages 256*KC rows of the contiguous row-major raw matrix in shared memory (coalesced
+// loads) and walks the PARAMETERS in the outer loop: the descriptor is decoded, the kind dispatched and the output
+// column addresses formed once per parameter and thread, then applied to the thread's KC candidates (rows tid + 256 c,
+// so every column store is still 32 consecutive candidates per warp); the KC value searches of an ordinal are
+// independent and overlap.  Tables live in shared memory (32-bit addressing).  Same arithmetic, same outputs.
+// MODE: 0 = fp32 columns, 1 = fp64 columns, 2 = both, 3 = prior probability only (hm_prior_prob)
+template <int KC, int MODE, bool FULL>
+__device__ __forceinline__ void hm_encode_tile_body(const HmSpaceArgs& a, const HmP* __restrict__ sp,
+                                                    const double* __restrict__ st, const double* __restrict__ tile, int Dp,
+                                                    long long base, int& bad_any) {
+    constexpr bool W32 = MODE == 0 || MODE == 2, W64 = MODE == 1 || MODE == 2, PROB = MODE == 3;
+    const double nan = __longlong_as_double(0x7ff8000000000000ll);
+    const long long i0 = base + threadIdx.x;
+    bool live[KC];
+    double prob[KC];
+#pragma unroll
+    for (int c = 0; c < KC; ++c) {
+        live[c] = FULL || i0 + c * HM_SPACE_BLOCK < a.N;
+        prob[c] = 1.0;
+    }
+    for (int j = 0; j < a.D; ++j) {
+        const HmP& p = sp[j];
+        const int kind = p.kind, nv = p.n_values;
+        double x[KC];
+        int idx[KC];
+#pragma unroll
+        for (int c = 0; c < KC; ++c) {
+            x[c] = tile[(threadIdx.x + c * HM_SPACE_BLOCK) * Dp + j];      // rows past N hold stale data; never stored
+            idx[c] = -1;
+        }
+        if (kind == HM_P_ORDINAL) {
+            const double* vt = st + p.values_off;
+            int lo[KC], len = nv;
+#pragma unroll
+            for (int c = 0; c < KC; ++c) lo[c] = 0;
+            while (len > 1) {                                               // KC independent lower-bound searches
+                const int half = len >> 1;
+#pragma unroll
+                for (int c = 0; c < KC; ++c) lo[c] += (vt[lo[c] + half - 1] < x[c]) ? half : 0;
+                len -= half;
+            }
+#pragma unroll
+            for (int c = 0; c < KC; ++c) {
+                idx[c] = vt[lo[c]] == x[c] ? lo[c] : -1;
+                bad_any |= (live[c] && idx[c] < 0);
+            }
+        } else if (kind == HM_P_CATEGORICAL) {
+#pragma unroll
+            for (int c = 0; c < KC; ++c) {
+                idx[c] = (x[c] >= 0.0 && x[c] < (double)nv && x[c] == rint(x[c])) ? (int)x[c] : -1;
+                bad_any |= (live[c] && idx[c] < 0);
+            }
+        }
+        if (!PROB) {
+            // models.py:957-984
+            float* o32 = W32 ? a.x32 + (size_t)p.out_col * (size_t)a.ld32 + (size_t)i0 : nullptr;
+            double* o64 = W64 ? a.x64 + (size_t)p.out_col * (size_t)a.ld64 + (size_t)i0 : nullptr;
+            if (kind == HM_P_CATEGORICAL) {
+                for (int k = 0; k < nv; ++k) {
+#pragma unroll
+                    for (int c = 0; c < KC; ++c) {
+                        const float v = idx[c] < 0 ? __int_as_float(0x7fc00000) : (k == idx[c] ? 1.0f : 0.0f);
+                        if (FULL || live[c]) {
+                            if (W32) o32[c * HM_SPACE_BLOCK] = v;
+                            if (W64) o64[c * HM_SPACE_BLOCK] = (double)v;
+                        }
+                    }
+                    if (W32) o32 += a.ld32;
+                    if (W64) o64 += a.ld64;
+                }
+            } else {
+                const double* enc = st + p.values_off + nv;
+                const bool norm = (p.flags & HM_PF_NORMALIZE) != 0;
+                const double mean = p.mean, sd = p.std;
+#pragma unroll
+                for (int c = 0; c < KC; ++c) {
+                    double v;
+                    if (kind == HM_P_ORDINAL) v = idx[c] < 0 ? nan : enc[idx[c] < 0 ? 0 : idx[c]];
+                    else if (norm) v = hm_sub(x[c], mean) / sd;
+                    else v = x[c];
+                    if (FULL || live[c]) {
+                        if (W32) o32[c * HM_SPACE_BLOCK] = (float)v;
+                        if (W64) o64[c * HM_SPACE_BLOCK] = v;
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < KC; ++c) {
+                int bad = 0;
+                const double px = hm_x_probability(st, p, x[c], idx[c], &bad);
+                bad_any |= (live[c] && bad);
+                for (int o = 0; o < a.n_obj; ++o) prob[c] = hm_mul(prob[c], a.w[o] == 1.0 ? px : pow(px, a.w[o]));
+            }
+        }
+    }
+    if (PROB) {
+#pragma unroll
+        for (int c = 0; c < KC; ++c)
+            if (live[c]) a.prob[i0 + c * HM_SPACE_BLOCK] = prob[c];
+    }
+}
+
+template <int KC, int MODE>
+__global__ void __launch_bounds__(HM_SPACE_BLOCK) hm_encode_tile_kernel(const HmSpaceArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    HmP* sp = reinterpret_cast<HmP*>(smem);
+    double* st = reinterpret_cast<double*>(smem + sizeof(HmP) * a.D);
+    const int tab_n = (int)a.n_tables;
+    double* tile = st + tab_n;
+    const int Dp = a.D | 1;
+    constexpr int TR = HM_SPACE_BLOCK * KC;
+    for (int j = threadIdx.x; j < a.D; j += HM_SPACE_BLOCK) {
+        const hm_param_desc_t& d = a.params[j];
+        HmP p;
+        p.kind = d.kind;
+        p.n_values = d.n_values;
+        p.out_col = d.out_col;
+        p.flags = (d.normalize ? HM_PF_NORMALIZE : 0) | (d.ordinal_beta ? HM_PF_BETA_SAMPLED : 0);
+        p.prior_kind = d.prior_kind;
+        p.n_prior = d.n_prior;
+        p.n_cdf = d.n_cdf;
+        p.values_off = (int)d.values_off;
+        p.prior_off = (int)d.prior_off;
+        p.cdf_off = (int)d.cdf_off;
+        p.pad0 = p.pad1 = 0;
+        p.lo = d.lo; p.hi = d.hi; p.mean = d.mean; p.std = d.std; p.a = d.a; p.b = d.b; p.lbeta = d.lbeta; p.pad2 = 0.0;
+        sp[j] = p;
+    }
+    for (int q = threadIdx.x; q < tab_n; q += HM_SPACE_BLOCK) st[q] = __ldg(a.tables + q);
+    int bad_any = 0;
+    for (long long base = (long long)blockIdx.x * TR; base < a.N; base += (long long)gridDim.x * TR) {
+        __syncthreads();
+        const long long rows = a.N - base < TR ? a.N - base : TR;
+        {
+            const int total = (int)rows * a.D;
+            const double* src = a.raw + (size_t)base * (size_t)a.D;
+            int r = threadIdx.x / a.D, c = threadIdx.x - r * a.D;
+            const int dr = HM_SPACE_BLOCK / a.D, dc = HM_SPACE_BLOCK - dr * a.D;
+#pragma unroll 4
+            for (int q = threadIdx.x; q < total; q += HM_SPACE_BLOCK) {
+                tile[r * Dp + c] = __ldg(src + q);
+                r += dr;
+                c += dc;
+                if (c >= a.D) {
+                    c -= a.D;
+                    ++r;
+                }
+            }
+        }
+        __syncthreads();
+        if (rows == TR) hm_encode_tile_body<KC, MODE, true>(a, sp, st, tile, Dp, base, bad_any);
+        else hm_encode_tile_body<KC, MODE, false>(a, sp, st, tile, Dp, base, bad_any);
+    }
+    if (a.n_invalid && bad_any) atomicAdd(a.n_invalid, 1);
+}
+
+// launches the tile kernel when its preconditions hold; *done = 0 otherwise
+static int hm_space_launch_tile(const hm_space_t* s, HmSpaceArgs& a, cudaStream_t st, int* done) {
+    *done = 0;
+    if (a.raw_col_major || a.ldr != s->D || s->n_tables > HM_SPACE_SMEM_TABLES || a.raw_out) return 0;
+    const bool w32 = a.x32 != nullptr, w64 = a.x64 != nullptr, wp = a.prob != nullptr;
+    if (wp == (w32 || w64)) return 0;             // exactly one of {encode, prior}: what hm_encode / hm_prior_prob ask for
+    const int mode = wp ? 3 : (w32 && w64 ? 2 : (w64 ? 1 : 0));
+    const size_t fixed = sizeof(HmP) * s->D + sizeof(double) * (size_t)s->n_tables;
+    const size_t row = sizeof(double) * (size_t)(s->D | 1) * HM_SPACE_BLOCK;
+    int kc = 0;
+    if (4 * row <= 48 * 1024) kc = 4;
+    else if (2 * row <= 48 * 1024) kc = 2;
+    else if (row <= 96 * 1024) kc = 1;
+    if (!kc) return 0;
+    const size_t smem = fixed + kc * row;
+    const long long tiles = (a.N + (long long)HM_SPACE_BLOCK * kc - 1) / ((long long)HM_SPACE_BLOCK * kc);
+#define HM_TILE_GO(K, MD)                                                                                              \
+    do {                                                                                                               \
+        HM_CUDA_TRY(cudaFuncSetAttribute(hm_encode_tile_kernel<K, MD>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                         (int)smem));                                                                  \
+        int occ = 0;                                                                                                   \
+        HM_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hm_encode_tile_kernel<K, MD>, HM_SPACE_BLOCK,  \
+                                                                  smem));                                              \
+        const int grid = (int)std::min<long long>(tiles, (long long)hm_num_sms() * (occ < 1 ? 1 : occ));               \
+        hm_encode_tile_kernel<K, MD><<<grid, HM_SPACE_BLOCK, smem, st>>>(a);                                           \
+    } while (0)
+#define HM_TILE_MODE(K)                                                                                                \
+    do {                                                                                                               \
+        if (mode == 0) HM_TILE_GO(K, 0);                                                                               \
+        else if (mode == 1) HM_TILE_GO(K, 1);                                                                          \
+        else if (mode == 2) HM_TILE_GO(K, 2);                                                                          \
+        else HM_TILE_GO(K, 3);                                                                                         \
+    } while (0)
+    if (kc == 4) HM_TILE_MODE(4);
+    else if (kc == 2) HM_TILE_MODE(2);
+    else HM_TILE_MODE(1);
+#undef HM_TILE_MODE
+#undef HM_TILE_GO
+    HM_CUDA_TRY(cudaGetLastError());
+    *done = 1;
+    return 0;
+}
+
 static int hm_space_launch(const hm_space_t* s, HmSpaceArgs& a, bool generate, void* stream) {
     a.params = s->d_params;
     a.tables = s->d_tables;
     a.n_tables = s->n_tables;
     a.D = s->D;
     if (a.N == 0) return 0;
+    if (!generate) {
+        int done = 0;
+        int rc = hm_space_launch_tile(s, a, (cudaStream_t)stream, &done);
+        if (rc || done) return rc;
+    }
     const long long blocks = (a.N + HM_SPACE_BLOCK - 1) / HM_SPACE_BLOCK;
-    const int grid = (int)std::min<long long>(blocks, (long long)hm_num_sms() * 8);
     const bool staged = !generate && !a.raw_col_major && a.ldr == a.D && a.D <= 32;
     const size_t smem = sizeof(HmP) * s->D +
                         sizeof(double) * (size_t)(s->n_tables <= HM_SPACE_SMEM_TABLES ? s->n_tables : 0) +
                         (staged ? sizeof(double) * (size_t)HM_SPACE_BLOCK * (size_t)(s->D | 1) : 0);
     cudaStream_t st = (cudaStream_t)stream;
+    // grid-stride over uniform work: exactly one resident wave (SMs x CTAs that fit), no low-occupancy tail
 #define HM_SPACE_GO(G, S)                                                                                              \
     do {                                                                                                               \
         HM_CUDA_TRY(cudaFuncSetAttribute(hm_space_kernel<G, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        int occ = 0;                                                                                                   \
+        HM_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hm_space_kernel<G, S>, HM_SPACE_BLOCK, smem));  \
+        const int grid = (int)std::min<long long>(blocks, (long long)hm_num_sms() * (occ < 1 ? 1 : occ));              \
         hm_space_kernel<G, S><<<grid, HM_SPACE_BLOCK, smem, st>>>(a);                                                  \
     } while (0)
     if (generate) HM_SPACE_GO(true, false);
