@@ -74,6 +74,21 @@ def _log(msg, verbose=False):
             w(msg)
 
 
+def _truncnorm_draws(means, n):
+    """[stats.truncnorm.rvs(0, 1, loc=m, scale=0.2, size=n).tolist() for m in means] (local_search.py:140-146) in one
+    vectorised step.  scipy's rvs is `ppf(random_state.uniform(size), a, b) * scale + loc` on numpy's global stream
+    (0.27 ms of distribution infrastructure per call, most of a hill-climb step on the host); the same three steps are
+    done here for all numeric parameters of a configuration at once: the uniforms are drawn in the same order
+    (row-major), ppf is elementwise, so values and stream position are identical (checked against the reference's
+    neighbour sets in tests/golden/neighbors.npz)."""
+    ppf = getattr(stats.truncnorm, "_ppf", None)
+    if ppf is None or len(means) == 0:
+        return [stats.truncnorm.rvs(0, 1, loc=m, scale=0.2, size=n).tolist() for m in means]
+    u = np.random.uniform(size=(len(means), n))
+    z = ppf(u.ravel(), 0.0, 1.0).reshape(len(means), n)
+    return [(z[r] * 0.2 + m).tolist() for r, m in enumerate(means)]
+
+
 def get_neighbors(configuration, param_space):
     """SMAC-style one-exchange neighbourhood (local_search.py:83-161), same enumeration order, same RNG draws."""
     neighbors = []
@@ -87,6 +102,14 @@ def get_neighbors(configuration, param_space):
         cand[pos] = value
         if cand not in neighbors:
             neighbors.append(cand)
+
+    # the truncated-normal draws of all real / integer parameters, in parameter order (= the reference's RNG order)
+    numeric = [name for name in inputs if param_space.get_type(name) in ("real", "integer")]
+    means = {}
+    for name in numeric:
+        lo, hi = objects[name].get_min(), objects[name].get_max()
+        means[name] = (configuration[name] - lo) / (hi - lo)
+    drawn = dict(zip(numeric, _truncnorm_draws([means[name] for name in numeric], numeric_neighbors)))
 
     for pos, name in enumerate(inputs):
         kind = param_space.get_type(name)
@@ -106,9 +129,8 @@ def get_neighbors(configuration, param_space):
             for value in window:
                 push(pos, value)
         elif kind in ("real", "integer"):
-            lo, hi = obj.get_min(), obj.get_max()
-            mean = (configuration[name] - lo) / (hi - lo)
-            draws = stats.truncnorm.rvs(0, 1, loc=mean, scale=0.2, size=numeric_neighbors).tolist()
+            mean = means[name]
+            draws = drawn[name]
             draws.append(mean)
             for value in draws:
                 value = 0 if value < 0 else (1 if value > 1 else value)

@@ -93,11 +93,47 @@ def run_acquisition_function(acquisition_function, configurations, objective_wei
     if acquisition_function not in _lib.ACQ_KINDS:
         print("Unrecognized acquisition function:", acquisition_function)
         raise SystemExit
-    scores = acquisition_scores_device(acquisition_function, configurations, objective_weights, regression_models,
-                                       param_space, scalarization_method, objective_limits, iteration_number, data_array,
-                                       model_type, classification_model)
-    scalarized_values = scores.cpu().tolist()
+    if model_type == "random_forest" and classification_model is None and not isinstance(configurations, models.EncodedCandidates):
+        scalarized_values = _rf_scores_host(acquisition_function, configurations, objective_weights, regression_models,
+                                            param_space, scalarization_method, objective_limits, iteration_number,
+                                            data_array).tolist()
+    else:
+        scores = acquisition_scores_device(acquisition_function, configurations, objective_weights, regression_models,
+                                           param_space, scalarization_method, objective_limits, iteration_number,
+                                           data_array, model_type, classification_model)
+        scalarized_values = scores.cpu().tolist()
     return scalarized_values, [1] * len(scalarized_values)
+
+
+_host_scorers = {}
+
+
+def _rf_scores_host(acquisition_function, configurations, objective_weights, regression_models, param_space,
+                    scalarization_method, objective_limits, iteration_number, data_array):
+    """Host in, host out through ONE C-ABI call (hm_rf_score_raw_host: H2D of the raw values -> hm_encode -> fused forest
+    + acquisition kernel -> D2H, chunked and double-buffered): the latency path of the hill climb's small neighbour
+    batches and the bandwidth path of large host-resident pools alike.  Returns a float64 numpy array [N]."""
+    import numpy as np
+    from .encoding import raw_matrix
+    from .forest import device_forest
+    from .scoring import HostScorer
+    from .space_device import device_space_for
+    _lib.require_cuda()
+    objectives = list(regression_models.keys())
+    weights, f_min, beta = acquisition_constants(acquisition_function, scalarization_method, objectives,
+                                                 objective_weights, objective_limits, data_array, iteration_number)
+    params = _lib.make_acq_params(acquisition_function, scalarization_method, weights, f_min, beta)
+    raw = np.ascontiguousarray(raw_matrix(configurations, param_space))
+    out = np.empty((raw.shape[0],), dtype=np.float64)
+    if raw.shape[0] == 0:
+        return out
+    ds = device_space_for(param_space)
+    scorer = _host_scorers.get(ds.n_encoded)
+    if scorer is None:
+        scorer = _host_scorers[ds.n_encoded] = HostScorer(ds.n_encoded, chunk=1 << 20)
+    forests = [device_forest(regression_models[o]) for o in objectives]
+    scorer.score_raw(ds, forests, raw, params, k=0, scores_out=out)
+    return out
 
 
 def _device_scores(candidates, **p):
