@@ -177,6 +177,8 @@ def _values_at(values, rows):
     if len(rows) == 0:
         return []
     import torch
+    if isinstance(rows, list) and len(rows) == values.numel() and rows[0] == 0 and rows[-1] == len(rows) - 1:
+        return values.cpu().tolist()                     # everything, in order
     return values[torch.as_tensor(np.asarray(rows, dtype=np.int64), device=values.device)].cpu().tolist()
 
 
@@ -422,9 +424,14 @@ def local_search(local_search_starting_points, local_search_random_points, param
     # ---- returned data_array: [LS results, pools, previous] as dict of lists (pools only when small) ---------
     data_array = {}
     if n_u + n_p <= MATERIALISE_LIMIT:
-        du = concatenate_list_of_dictionaries(_rows_to_dicts(pool_u, inputs, range(n_u))) if n_u else {p: [] for p in inputs}
+        def columns(pool, n):
+            if isinstance(pool, np.ndarray):           # column slices of the sample array: no per-row dicts
+                return {p: pool[:n, j].tolist() for j, p in enumerate(inputs)}
+            return concatenate_list_of_dictionaries(_rows_to_dicts(pool, inputs, range(n))) if n else {p: [] for p in inputs}
+
+        du = columns(pool_u, n_u)
         du[scalarization_key] = _values_at(val_u, list(range(n_u)))
-        dp = concatenate_list_of_dictionaries(_rows_to_dicts(pool_p, inputs, range(n_p))) if n_p else {p: [] for p in inputs}
+        dp = columns(pool_p, n_p)
         dp[scalarization_key] = _values_at(val_p, list(range(n_p)))
         data_array = {key: list(du[key]) + list(dp[key]) for key in keys}
     else:
