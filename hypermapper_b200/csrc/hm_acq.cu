@@ -94,6 +94,7 @@ struct HmSelState {
     HmPair* buf;      // [HM_TK_CAP] shared
     int* count;       // shared
     HmPair* tau;      // shared
+    double* tau_v;    // shared: the value tau's key stands for (+inf while fewer than k elements are held)
 };
 
 // keep the k smallest of buf[0..*count); tighten tau.  Called by all threads (uniformly).
@@ -108,7 +109,13 @@ __device__ void hm_sel_compact(HmSelState& s, int k) {
     if (threadIdx.x == 0) {
         const int nc = c < k ? c : k;
         *s.count = nc;
-        if (nc >= k) *s.tau = s.buf[k - 1];
+        if (nc >= k) {
+            *s.tau = s.buf[k - 1];
+            const unsigned long long key = s.buf[k - 1].key;
+            // inverse of hm_order_key (key 0 = NaN: then nothing is ever rejected by the value test)
+            const unsigned long long b = (key & 0x8000000000000000ull) ? (key ^ 0x8000000000000000ull) : ~key;
+            *s.tau_v = key == 0ull ? __longlong_as_double(0x7ff8000000000000ll) : __longlong_as_double((long long)b);
+        }
     }
     __syncthreads();
 }
@@ -120,20 +127,43 @@ __device__ const HmPair* hm_select_k(Load load, long long n, long long first_til
     __shared__ HmPair buf[HM_TK_CAP];
     __shared__ int count;
     __shared__ HmPair tau;
-    HmSelState s = {buf, &count, &tau};
+    __shared__ double tau_v;
+    HmSelState s = {buf, &count, &tau, &tau_v};
     if (threadIdx.x == 0) {
         count = 0;
         tau = hm_pad_pair();
+        tau_v = __longlong_as_double(0x7ff0000000000000ll);
     }
     __syncthreads();
     const long long n_tiles = (n + HM_TK_TILE - 1) / HM_TK_TILE;
-    for (long long tile = first_tile; tile < n_tiles; tile += tile_stride) {
-        const HmPair tl = tau;
+    constexpr int R = HM_TK_TILE / HM_TK_BLOCK;
+    // Software pipeline: the loads of the next tile are in flight while this tile is filtered and the CTA synchronises.
+    // Value streams are filtered on the raw double first: an element can only enter the buffer if NOT (v > tau_v)
+    // (NaN, -0.0 and ties fall through to the exact (key, index) comparison), so the common case is load + compare.
+    typename Load::Item cur[R], nxt[R];
+    bool cv[R], nv[R];
+    auto fetch = [&](long long tile, typename Load::Item* e, bool* valid) {
 #pragma unroll
-        for (int r = 0; r < HM_TK_TILE / HM_TK_BLOCK; ++r) {
+        for (int r = 0; r < R; ++r) {
             const long long p = tile * HM_TK_TILE + r * HM_TK_BLOCK + threadIdx.x;
-            if (p < n) {
-                HmPair e = load(p);
+            valid[r] = tile < n_tiles && p < n;
+            if (valid[r]) e[r] = load.item(p);
+        }
+    };
+    fetch(first_tile, nxt, nv);
+    for (long long tile = first_tile; tile < n_tiles; tile += tile_stride) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            cur[r] = nxt[r];
+            cv[r] = nv[r];
+        }
+        fetch(tile + tile_stride, nxt, nv);
+        const HmPair tl = tau;
+        const double tv = tau_v;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (cv[r] && Load::maybe(cur[r], tv)) {
+                const HmPair e = load.pair(cur[r], tile * HM_TK_TILE + r * HM_TK_BLOCK + threadIdx.x);
                 if (hm_pair_less(e, tl)) {
                     const int pos = atomicAdd(&count, 1);
                     buf[pos] = e;
@@ -150,29 +180,39 @@ __device__ const HmPair* hm_select_k(Load load, long long n, long long first_til
     return buf;
 }
 
+// loaders: item(p) = what is fetched early, maybe(item, tau_value) = cheap necessary condition, pair(item, p) = exact key
 struct HmLoadVals {
+    typedef double Item;
     const double* vals;
     long long base;
-    __device__ __forceinline__ HmPair operator()(long long p) const {
+    __device__ __forceinline__ double item(long long p) const { return __ldg(vals + p); }
+    static __device__ __forceinline__ bool maybe(double v, double tv) { return !(v > tv); }
+    __device__ __forceinline__ HmPair pair(double v, long long p) const {
         HmPair e;
-        e.key = hm_order_key(__ldg(vals + p));
+        e.key = hm_order_key(v);
         e.idx = base + p;
         return e;
     }
 };
 struct HmLoadValIdx {
+    typedef double Item;
     const double* vals;
     const long long* idx;
-    __device__ __forceinline__ HmPair operator()(long long p) const {
+    __device__ __forceinline__ double item(long long p) const { return __ldg(vals + p); }
+    static __device__ __forceinline__ bool maybe(double v, double tv) { return !(v > tv); }
+    __device__ __forceinline__ HmPair pair(double v, long long p) const {
         HmPair e;
-        e.key = hm_order_key(__ldg(vals + p));
+        e.key = hm_order_key(v);
         e.idx = __ldg(idx + p);
         return e;
     }
 };
 struct HmLoadPairs {
+    typedef HmPair Item;
     const HmPair* pairs;
-    __device__ __forceinline__ HmPair operator()(long long p) const { return pairs[p]; }
+    __device__ __forceinline__ HmPair item(long long p) const { return pairs[p]; }
+    static __device__ __forceinline__ bool maybe(const HmPair&, double) { return true; }
+    __device__ __forceinline__ HmPair pair(const HmPair& e, long long) const { return e; }
 };
 
 template <typename Load>
@@ -215,7 +255,10 @@ static int hm_topk_run(Load load, int64_t n, int k, double* out_vals, int64_t* o
     HM_REQUIRE(n >= 0, "n >= 0");
     HmPair* ws = reinterpret_cast<HmPair*>(workspace);
     long long tiles = (n + HM_TK_TILE - 1) / HM_TK_TILE;
-    int grid = (int)std::max<long long>(1, std::min<long long>(tiles, std::min(HM_TK_MAXGRID, hm_num_sms() * 2)));
+    int occ = 0;
+    HM_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hm_topk_stage1<Load>, HM_TK_BLOCK, 0));
+    if (occ < 1) occ = 1;
+    int grid = (int)std::max<long long>(1, std::min<long long>(tiles, std::min(HM_TK_MAXGRID, hm_num_sms() * occ)));
     hm_topk_stage1<<<grid, HM_TK_BLOCK, 0, st>>>(load, (long long)n, k, ws);
     HM_CUDA_TRY(cudaGetLastError());
     hm_topk_stage2<<<1, HM_TK_BLOCK, 0, st>>>(ws, (long long)grid * k, k, out_vals, (long long*)out_idx);
