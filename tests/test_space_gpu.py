@@ -383,3 +383,100 @@ def test_raw_host_scoring_entry_matches_device_path():
     bad[4321, 2] = 3.0
     with pytest.raises(ValueError):
         scorer.score_raw(ds, dfs, bad, acq, k=0, scores_out=scores)
+
+
+def _random_space_config(rng, normalize):
+    """a random mix of parameter kinds / sizes / priors (every prior form the device supports)"""
+    ip = {}
+    n = int(rng.integers(1, 14))
+    for j in range(n):
+        kind = rng.choice(["real", "integer", "ordinal", "categorical"])
+        if kind == "real":
+            lo = float(np.round(rng.normal() * 5, 2))
+            hi = lo + float(np.round(rng.random() * 10 + 0.5, 2))
+            prior = rng.choice(["uniform", "gaussian", "decay", "exponential", "list"])
+            p = {"parameter_type": "real", "values": [lo, hi], "parameter_default": lo}
+            p["prior"] = [float(v) for v in rng.random(int(rng.integers(2, 12))) + 0.05] if prior == "list" else str(prior)
+        elif kind == "integer":
+            lo = int(rng.integers(-5, 5))
+            hi = lo + int(rng.integers(1, 40))
+            p = {"parameter_type": "integer", "values": [lo, hi], "parameter_default": lo}
+            if rng.random() < 0.4:
+                w = rng.random(hi - lo + 1) + 0.01
+                p["prior"] = [float(v) for v in w / w.sum()]
+            else:
+                p["prior"] = str(rng.choice(["uniform", "gaussian"]))
+        elif kind == "ordinal":
+            size = int(rng.integers(1, 70))
+            vals = np.unique(np.round(np.cumsum(rng.random(size) + 0.01) * (10 ** int(rng.integers(-2, 4))), 6)).tolist()
+            if rng.random() < 0.5:
+                vals = [int(v) for v in np.unique(np.asarray(vals).astype(np.int64))]
+            p = {"parameter_type": "ordinal", "values": vals, "parameter_default": vals[0]}
+            if rng.random() < 0.4:
+                w = rng.random(len(vals)) + 0.01
+                p["prior"] = [float(v) for v in w / w.sum()]
+            else:
+                p["prior"] = str(rng.choice(["uniform", "gaussian", "decay", "exponential"]))
+        else:
+            size = int(rng.integers(1, 12))
+            p = {"parameter_type": "categorical", "values": ["v%d" % i for i in range(size)], "parameter_default": "v0"}
+            if rng.random() < 0.5:
+                w = rng.random(size) + 0.01
+                p["prior"] = [float(v) for v in w / w.sum()]
+        ip["p%d" % j] = p
+    return {"optimization_objectives": ["y"], "input_parameters": ip, "normalize_inputs": bool(normalize)}
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_spaces_encode_and_prior_match_host(seed):
+    """Random spaces (1-13 parameters of every kind, random sizes, priors and z-score statistics), candidates drawn by
+    the host samplers: device encode == host Encoder bit for bit (both kernels: contiguous rows -> tile kernel,
+    column-major -> generic kernel); device prior == the product of the parameter objects' get_x_probability."""
+    from hypermapper_b200 import _lib
+    from hypermapper_b200.encoding import Encoder
+    from hypermapper_b200.space_device import DeviceSpace
+    from hypermapper_b200.space_lite import SpaceLite
+    torch = __import__("torch")
+    rng = np.random.default_rng(1000 + seed)
+    space = SpaceLite(_random_space_config(rng, normalize=seed % 2 == 0))
+    inputs = space.get_input_parameters()
+    objs = space.get_input_parameters_objects()
+    if seed % 2 == 0:
+        for p in inputs:
+            if space.get_type(p) in ("real", "integer"):
+                space.set_parameter_mean(p, float(rng.normal()))
+                space.set_parameter_std(p, float(rng.random() + 0.1))
+    np.random.seed(seed)
+    N = int(rng.integers(1, 3000))
+    pools = [space.get_random_configuration(size=N, use_priors=u, return_as_array=True) for u in (False, True)]
+    raw = np.concatenate([np.asarray(p, dtype=np.float64).reshape(N, len(inputs)) for p in pools], axis=0)
+    ds = DeviceSpace(space)
+    want = Encoder(space).encode(raw)
+    x32, x64 = ds.encode(raw, want32=True, want64=True)
+    assert np.array_equal(x64.cpu().numpy(), want) and np.array_equal(x32.cpu().numpy(), want.astype(np.float32))
+    # column-major raw input -> the generic kernel
+    rd = torch.from_numpy(np.ascontiguousarray(raw.T)).cuda()
+    g64 = torch.empty_like(x64)
+    bad = torch.zeros((1,), dtype=torch.int32, device="cuda")
+    rc = _lib.lib().hm_encode(ds.handle, _lib.dptr(rd), 1, raw.shape[0], raw.shape[0], None, 0, _lib.dptr(g64),
+                              raw.shape[0], _lib.dptr(bad), _lib.stream_ptr())
+    _lib.check(rc, "hm_encode")
+    assert int(bad.item()) == 0 and np.array_equal(g64.cpu().numpy(), want)
+    # priors
+    got = ds.prior_prob(raw, [1.0]).cpu().numpy()
+    host = np.ones(len(raw))
+    for j, p in enumerate(inputs):
+        kind = space.get_type(p)
+        col = raw[:, j]
+        if kind == "real":
+            px = np.array([objs[p].get_x_probability(float(v)) for v in col], dtype=np.float64)
+        elif kind == "ordinal":
+            vals = objs[p].get_values()
+            lut = {float(v): v for v in vals}
+            px = np.array([objs[p].get_x_probability(lut[float(v)]) for v in col], dtype=np.float64)
+        else:
+            px = np.array([objs[p].get_x_probability(int(v)) for v in col], dtype=np.float64)
+        host = host * px
+    close(got, host, rel=1e-9)
+    gp = ds.prior_prob(rd, [1.0], col_major=True).cpu().numpy()
+    assert np.array_equal(gp, got, equal_nan=True)
