@@ -40,6 +40,7 @@
 struct hm_gp {
     int n, n_pad, D, kind;
     int G, stage_k, n_stages, aliased;
+    int warps;         // warps per CTA: 4 (two CTAs per SM, see hm_gp_plan) or 8
     size_t smem_bytes;
     double sf2, noise, y_mean, y_std, y_std2;
     double* d_XsF;     // [n_pad/8][Dp/4][32]  training inputs / lengthscale in B-fragment order (zero padded)
@@ -65,14 +66,14 @@ struct HmGpArgs {
 };
 
 // shared-memory plan: candidate groups per CTA (G), ring geometry.  Returns 0 if nothing fits.
-static int hm_gp_plan(int n_pad, int D, int* G_out, int* stage_k_out, int* n_stages_out, int* aliased_out,
-                      size_t* smem_out) {
+static int hm_gp_plan_w(int n_pad, int D, int warps, size_t limit, int* G_out, int* stage_k_out, int* n_stages_out,
+                        int* aliased_out, size_t* smem_out) {
     const int Dp = (D + 3) & ~3;
-    for (int G = 8; G >= 1; G >>= 1) {
+    for (int G = warps; G >= 1; G >>= 1) {
         const size_t BM = 32 * (size_t)G;
         const size_t fixed = HM_GP_SMEM_HEADER + 8 * ((size_t)n_pad * BM      // Kt
                                                        + BM                     // a2s
-                                                       + HM_GP_WARPS * 32       // red
+                                                       + (size_t)warps * 32     // red
                                                        + (size_t)(n_pad / HM_GP_BLK) * BM);   // mur
         const size_t xs = 8 * (size_t)Dp * BM;
         // ring geometries in order of preference: (k-steps per stage, stages); 16-step stages halve the per-chunk
@@ -83,9 +84,9 @@ static int hm_gp_plan(int n_pad, int D, int* G_out, int* stage_k_out, int* n_sta
             for (const auto& gm : geom) {
                 const int stage_k = gm[0], ns = gm[1];
                 if (!aliased && ns < 3 && stage_k < 16) continue;
-                const size_t ring = (size_t)HM_GP_WARPS * stage_k * 32 * 8 * ns;
+                const size_t ring = (size_t)warps * stage_k * 32 * 8 * ns;
                 const size_t total = fixed + (aliased ? std::max(xs, ring) : xs + ring);
-                if (total <= HM_GP_SMEM_LIMIT) {
+                if (total <= limit) {
                     *G_out = G;
                     *stage_k_out = stage_k;
                     *n_stages_out = ns;
@@ -97,6 +98,24 @@ static int hm_gp_plan(int n_pad, int D, int* G_out, int* stage_k_out, int* n_sta
         }
     }
     return 0;
+}
+
+// Two 4-warp CTAs per SM when the plan fits half of the shared memory (n up to ~300 training points): the two CTAs run
+// their phases independently, so one CTA's phase A (sqrt/exp transform: DFMA chains that leave FP64-unit slots idle) can
+// run against the other's phase B (DMMA); the phases of ONE CTA cannot overlap because phase B needs the whole Kx tile.
+// C2: 4.13 -> 3.94 ms.  (Delaying the second CTA by half a tile to force the interleave changes nothing: DFMA and DMMA
+// share one unit, which both phases together keep ~90 % busy once phase A's real DFMA count is included.)  Larger
+// models keep one 8-warp CTA per SM.  HM_B200_GP_WARPS=8 forces the latter (measurements).
+static int hm_gp_plan(int n_pad, int D, int* warps_out, int* G_out, int* stage_k_out, int* n_stages_out, int* aliased_out,
+                      size_t* smem_out) {
+    const char* e = getenv("HM_B200_GP_WARPS");
+    const int forced = e ? atoi(e) : 0;
+    if (forced != 8 && hm_gp_plan_w(n_pad, D, 4, (size_t)113 * 1024, G_out, stage_k_out, n_stages_out, aliased_out, smem_out)) {
+        *warps_out = 4;
+        return 1;
+    }
+    *warps_out = 8;
+    return hm_gp_plan_w(n_pad, D, 8, HM_GP_SMEM_LIMIT, G_out, stage_k_out, n_stages_out, aliased_out, smem_out);
 }
 
 extern "C" int hm_gp_create(int n, int D, const double* Xs, const double* ls, const double* alpha, const double* Linv,
@@ -123,7 +142,7 @@ extern "C" int hm_gp_create(int n, int D, const double* Xs, const double* ls, co
     g->y_mean = y_mean;
     g->y_std = y_std;
     g->y_std2 = pow(y_std, 2.0);      // normaliser: var * std**2
-    if (!hm_gp_plan(n_pad, D, &g->G, &g->stage_k, &g->n_stages, &g->aliased, &g->smem_bytes)) {
+    if (!hm_gp_plan(n_pad, D, &g->warps, &g->G, &g->stage_k, &g->n_stages, &g->aliased, &g->smem_bytes)) {
         hm_set_error("hm_gp_create: n = %d, D = %d does not fit the shared-memory plan", n, D);
         delete g;
         return HM_E_UNSUPPORTED;
@@ -259,16 +278,16 @@ __device__ __forceinline__ int hm_gp_panel(int j, int slot, int S, int R) {
     return R - 1 - idx;      // < 0: no panel in this round
 }
 
-template <int KIND>
-__global__ void __launch_bounds__(HM_GP_THREADS, 1) hm_gp_kernel(const __grid_constant__ HmGpArgs a) {
+template <int KIND, int NW>
+__global__ void __launch_bounds__(NW * 32, NW == 4 ? 2 : 1) hm_gp_kernel(const __grid_constant__ HmGpArgs a) {
     extern __shared__ __align__(128) unsigned char gp_smem[];
-    const int G = a.G, BM = 32 * G, NBt = 4 * G, S = HM_GP_WARPS / G, R = a.n_pad / HM_GP_BLK;
+    const int G = a.G, BM = 32 * G, NBt = 4 * G, S = NW / G, R = a.n_pad / HM_GP_BLK;
     const int D4 = (a.D + 3) >> 2;
     uint64_t* bars = reinterpret_cast<uint64_t*>(gp_smem);
     double* KtF = reinterpret_cast<double*>(gp_smem + HM_GP_SMEM_HEADER);  // [n_pad/4][NBt][32]  A fragments of Kx
     double* a2s = KtF + (size_t)a.n_pad * BM;                                // [BM]
     double* red = a2s + BM;                                                  // [S][BM] == [8][32] partial ||T||^2
-    double* mur = red + HM_GP_WARPS * 32;                                    // [R][BM] partial mu
+    double* mur = red + NW * 32;                                    // [R][BM] partial mu
     double* xsF = mur + (size_t)R * BM;                                      // [D4][NBt][32]  A fragments of x / ls
     const int stage_shift = (a.stage_k == 16) ? 4 : (a.stage_k == 8) ? 3 : 2;
     const size_t stage_dbl = (size_t)a.stage_k * 32;
@@ -321,7 +340,7 @@ __global__ void __launch_bounds__(HM_GP_THREADS, 1) hm_gp_kernel(const __grid_co
         }
 
         // ---- scaled candidates (A-fragment order) + squared norms ------------------------------------------
-        for (int e = tid; e < D4 * 4 * BM; e += HM_GP_THREADS) {
+        for (int e = tid; e < D4 * 4 * BM; e += NW * 32) {
             const int d = e / BM, i = e - d * BM;
             double v = 0.0;
             if (d < a.D) {
@@ -344,7 +363,7 @@ __global__ void __launch_bounds__(HM_GP_THREADS, 1) hm_gp_kernel(const __grid_co
 
         // ---- phase A: Kx[i][k] = k(x_i, X_k) into KtF, partial mu ------------------------------------------
         // item = (8 candidates, 32 training points): 4 accumulator tiles, the transform runs in registers
-        for (int item = warp; item < NBt * R; item += HM_GP_WARPS) {
+        for (int item = warp; item < NBt * R; item += NW) {
             const int iblk = item % NBt, kb = item / NBt;
             double c[4][2];
 #pragma unroll
@@ -509,14 +528,20 @@ extern "C" int hm_gp_mean_var(const hm_gp_t* g, const double* Xcm, int64_t ldx, 
     cudaStream_t st = (cudaStream_t)stream;
     const int BM = 32 * g->G;
     const long long n_tiles = (N + BM - 1) / BM;
-    const int grid = (int)std::min<long long>(n_tiles, hm_num_sms());
+    const int ctas_per_sm = g->warps == 4 ? 2 : 1;
+    const int grid = (int)std::min<long long>(n_tiles, (long long)hm_num_sms() * ctas_per_sm);
+#define HM_GP_GO(K, W)                                                                                                 \
+    do {                                                                                                               \
+        HM_CUDA_TRY(cudaFuncSetAttribute(hm_gp_kernel<K, W>, cudaFuncAttributeMaxDynamicSharedMemorySize,              \
+                                         (int)g->smem_bytes));                                                         \
+        hm_gp_kernel<K, W><<<grid, W * 32, g->smem_bytes, st>>>(a);                                                    \
+    } while (0)
     if (g->kind == 0) {
-        HM_CUDA_TRY(cudaFuncSetAttribute(hm_gp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem_bytes));
-        hm_gp_kernel<0><<<grid, HM_GP_THREADS, g->smem_bytes, st>>>(a);
+        if (g->warps == 4) HM_GP_GO(0, 4); else HM_GP_GO(0, 8);
     } else {
-        HM_CUDA_TRY(cudaFuncSetAttribute(hm_gp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem_bytes));
-        hm_gp_kernel<1><<<grid, HM_GP_THREADS, g->smem_bytes, st>>>(a);
+        if (g->warps == 4) HM_GP_GO(1, 4); else HM_GP_GO(1, 8);
     }
+#undef HM_GP_GO
     HM_CUDA_TRY(cudaGetLastError());
     return 0;
 }
