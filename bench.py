@@ -414,7 +414,8 @@ class SpaceRFBench(RFBench):
 class GPBench:
     metric, unit, dtype = "acquisition_evals_per_sec", "evals/s", "f64"
     cpu_desc = "numpy/scipy (BLAS) restatement of GPy predict, not GPy itself + EI + top-20"
-    e2e_api = "GP path: pinned host candidates -> H2D -> hm_gp_mean_var + hm_acq_score + hm_topk -> D2H scores + top-k"
+    e2e_api = ("hm_gp_score_host (C-ABI, pinned host candidates, 512k-candidate double-buffered chunks: H2D -> "
+               "hm_gp_mean_var -> hm_acq_score -> D2H scores; hm_topk -> D2H top-k)")
 
     def __init__(self, name):
         from hypermapper_b200 import gp, workloads
@@ -499,14 +500,12 @@ class GPBench:
         return (tv, ti), ev
 
     def e2e_step(self):
-        from hypermapper_b200 import forest, gp, models
-        self.x_stage.copy_(self.x_host, non_blocking=True)
-        gp.gp_mean_var(self.dgp, self.x_stage, self.mean[0], self.var[0])
-        scores = models.acq_score_device(self.acq, self.mean, self.var)
-        self.scores_host.copy_(scores, non_blocking=True)
-        tv, ti = forest.topk(scores, self.k, index_base=self.rank * self.N)
-        ti.cpu()
-        return tv, ti
+        import torch
+        if not hasattr(self, "scorer"):
+            from hypermapper_b200.scoring import HostScorer
+            self.scorer = HostScorer(self.D, chunk=1 << 19)
+        _, tv, ti = self.scorer.score_gp([self.dgp], self.x_host, self.acq, k=self.k, scores_out=self.scores_host)
+        return torch.from_numpy(tv).cuda(), torch.from_numpy(ti + self.rank * self.N).cuda()
 
     def e2e_bytes(self, N):
         return 8 * self.D * N, 8 * N + 16 * self.k

@@ -27,7 +27,7 @@ EXPORTED_SYMBOLS = [
     "hm_space_create", "hm_space_destroy", "hm_space_n_params", "hm_space_n_encoded",
     "hm_encode", "hm_sample_pool", "hm_sample_rows", "hm_prior_prob", "hm_prior_weight",
     "hm_minmax", "hm_bopro_ratio", "hm_bopro_finish",
-    "hm_host_ctx_create", "hm_host_ctx_destroy", "hm_rf_score_host", "hm_rf_score_raw_host",
+    "hm_host_ctx_create", "hm_host_ctx_destroy", "hm_rf_score_host", "hm_rf_score_raw_host", "hm_gp_score_host",
 ]
 
 
@@ -132,6 +132,8 @@ def lib():
     L.hm_rf_score_host.argtypes = [vp, ctypes.POINTER(vp), i32, vp, i64, i64, ctypes.POINTER(AcqParams), vp, i32, vp, vp]
     L.hm_rf_score_raw_host.argtypes = [vp, vp, ctypes.POINTER(vp), i32, vp, i64, ctypes.POINTER(AcqParams), vp, i32, vp,
                                        vp, ctypes.POINTER(ctypes.c_int32)]
+    L.hm_gp_score_host.argtypes = [vp, ctypes.POINTER(vp), i32, i32, vp, i64, i64, ctypes.POINTER(AcqParams), vp, i32, vp,
+                                   vp]
     _lib = L
     return L
 

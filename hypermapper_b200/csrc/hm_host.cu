@@ -21,6 +21,8 @@ struct hm_host_ctx {
     double* d_raw[2];       // [chunk][raw_params] staging of raw parameter values (hm_rf_score_raw_host), lazily sized
     int raw_params;
     int32_t* d_invalid;
+    double* d_mv[2];        // [2 M][chunk] posterior mean / variance of a chunk (hm_gp_score_host), lazily sized
+    int mv_objectives;
 };
 
 extern "C" int hm_host_ctx_create(int64_t max_candidates_per_chunk, int max_features, hm_host_ctx_t** out) {
@@ -60,6 +62,8 @@ extern "C" void hm_host_ctx_destroy(hm_host_ctx_t* c) {
     }
     for (int i = 0; i < 2; ++i)
         if (c->d_raw[i]) cudaFree(c->d_raw[i]);
+    for (int i = 0; i < 2; ++i)
+        if (c->d_mv[i]) cudaFree(c->d_mv[i]);
     if (c->d_invalid) cudaFree(c->d_invalid);
     if (c->d_scores) cudaFree(c->d_scores);
     if (c->d_topk_ws) cudaFree(c->d_topk_ws);
@@ -185,5 +189,79 @@ extern "C" int hm_rf_score_raw_host(hm_host_ctx_t* c, const hm_space_t* space, c
     HM_CUDA_TRY(cudaStreamSynchronize(c->st[0]));
     HM_CUDA_TRY(cudaStreamSynchronize(c->st[1]));
     if (n_invalid_out_host) *n_invalid_out_host = bad;
+    return 0;
+}
+
+
+// GP path from host buffers: per chunk  H2D of the fp64 column-major candidates -> hm_gp_mean_var per objective ->
+// hm_acq_score -> D2H of the scores, double-buffered across the two streams; stable top-k at the end.
+extern "C" int hm_gp_score_host(hm_host_ctx_t* c, const hm_gp_t* const* gps, int M, int n_features, const double* X_host,
+                                int64_t ldx, int64_t N, const hm_acq_params_t* acq, double* score_out_host, int k,
+                                double* topk_vals_host, int64_t* topk_idx_host) {
+    HM_REQUIRE(c != nullptr && gps != nullptr && acq != nullptr, "ctx/gps/acq");
+    HM_REQUIRE(M >= 1 && M <= HM_MAX_OBJECTIVES && n_features >= 1, "1 <= M <= 8, n_features >= 1");
+    HM_REQUIRE(N >= 0 && ldx >= N && (N == 0 || X_host != nullptr), "ldx >= N >= 0");
+    HM_REQUIRE(k >= 0 && k <= 1024, "0 <= k <= 1024");
+    HM_REQUIRE(k == 0 || (topk_vals_host && topk_idx_host), "top-k outputs");
+    const int D = n_features;
+    if (D > c->raw_params) {
+        for (int i = 0; i < 2; ++i) {
+            if (c->d_raw[i]) cudaFree(c->d_raw[i]);
+            c->d_raw[i] = nullptr;
+        }
+        c->raw_params = 0;
+        for (int i = 0; i < 2; ++i) HM_CUDA_TRY(cudaMalloc((void**)&c->d_raw[i], (size_t)c->chunk * D * sizeof(double)));
+        c->raw_params = D;
+    }
+    if (M > c->mv_objectives) {
+        for (int i = 0; i < 2; ++i) {
+            if (c->d_mv[i]) cudaFree(c->d_mv[i]);
+            c->d_mv[i] = nullptr;
+        }
+        c->mv_objectives = 0;
+        for (int i = 0; i < 2; ++i) HM_CUDA_TRY(cudaMalloc((void**)&c->d_mv[i], (size_t)2 * M * c->chunk * sizeof(double)));
+        c->mv_objectives = M;
+    }
+    if (N > c->cap_scores) {
+        if (c->d_scores) cudaFree(c->d_scores);
+        c->d_scores = nullptr;
+        c->cap_scores = 0;
+        HM_CUDA_TRY(cudaMalloc((void**)&c->d_scores, (size_t)N * sizeof(double)));
+        c->cap_scores = N;
+    }
+    int n_chunks = 0;
+    for (int64_t lo = 0; lo < N; lo += c->chunk, ++n_chunks) {
+        const int b = n_chunks & 1;
+        const int64_t n = std::min<int64_t>(c->chunk, N - lo);
+        cudaStream_t st = c->st[b];
+        HM_CUDA_TRY(cudaMemcpy2DAsync(c->d_raw[b], (size_t)n * sizeof(double), X_host + lo, (size_t)ldx * sizeof(double),
+                                      (size_t)n * sizeof(double), (size_t)D, cudaMemcpyHostToDevice, st));
+        double* mean = c->d_mv[b];
+        double* var = c->d_mv[b] + (size_t)M * c->chunk;
+        for (int m = 0; m < M; ++m) {
+            int rc = hm_gp_mean_var(gps[m], c->d_raw[b], n, n, mean + (size_t)m * c->chunk, var + (size_t)m * c->chunk,
+                                    (void*)st);
+            if (rc) return rc;
+        }
+        int rc = hm_acq_score(acq, mean, var, c->chunk, nullptr, n, c->d_scores + lo, (void*)st);
+        if (rc) return rc;
+        if (score_out_host)
+            HM_CUDA_TRY(cudaMemcpyAsync(score_out_host + lo, c->d_scores + lo, (size_t)n * sizeof(double),
+                                        cudaMemcpyDeviceToHost, st));
+    }
+    if (k > 0) {
+        if (n_chunks > 1) {
+            HM_CUDA_TRY(cudaEventRecord(c->ev[1], c->st[1]));
+            HM_CUDA_TRY(cudaStreamWaitEvent(c->st[0], c->ev[1], 0));
+        }
+        int rc = hm_topk(c->d_scores, N, 0, k, c->d_topk_vals, c->d_topk_idx, c->d_topk_ws, (void*)c->st[0]);
+        if (rc) return rc;
+        HM_CUDA_TRY(cudaMemcpyAsync(topk_vals_host, c->d_topk_vals, (size_t)k * sizeof(double), cudaMemcpyDeviceToHost,
+                                    c->st[0]));
+        HM_CUDA_TRY(cudaMemcpyAsync(topk_idx_host, c->d_topk_idx, (size_t)k * sizeof(int64_t), cudaMemcpyDeviceToHost,
+                                    c->st[0]));
+    }
+    HM_CUDA_TRY(cudaStreamSynchronize(c->st[0]));
+    HM_CUDA_TRY(cudaStreamSynchronize(c->st[1]));
     return 0;
 }

@@ -75,3 +75,26 @@ class HostScorer:
         if bad.value:
             raise ValueError("a discrete parameter value is not in its list of values (models.py:962-983)")
         return scores_out, tv[:k], ti[:k]
+
+    def score_gp(self, device_gps, x_host, acq, k=0, scores_out=None):
+        """GP models: x_host is a float64 column-major [D_enc][N] host array (numpy or pinned torch CPU tensor) of encoded
+        candidates; device_gps: list of DeviceGP, one per objective.  Returns (scores_out, topk_values, topk_indices)."""
+        if hasattr(x_host, "data_ptr"):
+            D, N = x_host.shape
+            assert x_host.is_contiguous() and not x_host.is_cuda and str(x_host.dtype) == "torch.float64"
+            xp = ctypes.c_void_p(x_host.data_ptr())
+        else:
+            assert x_host.dtype == np.float64 and x_host.flags.c_contiguous
+            D, N = x_host.shape
+            xp = _lib.hptr(x_host)
+        sp = None
+        if scores_out is not None:
+            sp = ctypes.c_void_p(scores_out.data_ptr()) if hasattr(scores_out, "data_ptr") else _lib.hptr(scores_out)
+        tv = np.empty(max(k, 1), dtype=np.float64)
+        ti = np.empty(max(k, 1), dtype=np.int64)
+        M = len(device_gps)
+        handles = (ctypes.c_void_p * M)(*[g.handle for g in device_gps])
+        rc = _lib.lib().hm_gp_score_host(self.handle, handles, M, D, xp, N, N, ctypes.byref(acq), sp, int(k),
+                                         _lib.hptr(tv), _lib.hptr(ti))
+        _lib.check(rc, "hm_gp_score_host")
+        return scores_out, tv[:k], ti[:k]

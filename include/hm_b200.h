@@ -292,6 +292,13 @@ int hm_rf_score_raw_host(hm_host_ctx_t* c, const hm_space_t* space, const hm_for
                          const double* raw_host, int64_t N, const hm_acq_params_t* acq, double* score_out_host, int k,
                          double* topk_vals_host, int64_t* topk_idx_host, int32_t* n_invalid_out_host);
 
+/* GP path from host buffers (compute_gp_prediction_mean_and_uncertainty + EI/UCB, models.py:997-1024 +
+ * random_scalarizations.py:160-506): X_host = fp64 column-major [n_features][N] (ld = ldx) encoded candidates; per chunk
+ * H2D -> hm_gp_mean_var per objective -> hm_acq_score -> D2H, double-buffered; stable top-k if k > 0. */
+int hm_gp_score_host(hm_host_ctx_t* c, const hm_gp_t* const* gps, int M, int n_features, const double* X_host,
+                     int64_t ldx, int64_t N, const hm_acq_params_t* acq, double* score_out_host, int k,
+                     double* topk_vals_host, int64_t* topk_idx_host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -73,3 +73,30 @@ def test_gp_ei_matches_oracle_c2_shape():
     p = _lib.make_acq_params("EI", "tchebyshev", [1.0], [oracle.ei_f_min(data, "Value", lim2)], 0.0)
     got = models.acq_score_device(p, mean, var).cpu().numpy()
     assert rel_err(got, want) <= REL
+
+
+def test_gp_host_scoring_entry_matches_device_path():
+    """hm_gp_score_host (host candidates -> chunked H2D -> hm_gp_mean_var -> hm_acq_score -> D2H) equals the
+    device-resident path bit for bit, top-k included, across chunk boundaries."""
+    import torch
+    from hypermapper_b200 import gp, models, forest, _lib
+    from hypermapper_b200.scoring import HostScorer
+    rng = np.random.default_rng(5)
+    n, D, N = 96, 5, 7000
+    X = rng.random((n, D))
+    y = np.sin(X.sum(1) * 3) + 0.1 * rng.standard_normal(n)
+    state = gp.GPState.from_hyperparameters(X, y, rng.uniform(0.3, 1.0, D), 1.3, 1e-4, "matern52")
+    dgp = gp.DeviceGP(state)
+    Xc = np.ascontiguousarray(rng.random((D, N)))
+    acq = _lib.make_acq_params("EI", "tchebyshev", [1.0], [0.4], 0.0)
+    xd = torch.from_numpy(Xc).cuda()
+    mean = torch.empty((1, N), dtype=torch.float64, device="cuda")
+    var = torch.empty_like(mean)
+    gp.gp_mean_var(dgp, xd, mean[0], var[0])
+    want = models.acq_score_device(acq, mean, var)
+    wv, wi = forest.topk(want, 20)
+    scorer = HostScorer(D, chunk=2048)
+    scores = np.empty(N)
+    _, tv, ti = scorer.score_gp([dgp], Xc, acq, k=20, scores_out=scores)
+    assert np.array_equal(scores, want.cpu().numpy())
+    assert np.array_equal(ti, wi.cpu().numpy()) and np.array_equal(tv, wv.cpu().numpy())
