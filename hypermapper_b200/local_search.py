@@ -231,35 +231,44 @@ def set_lockstep(mode):
 
 
 def _hill_climb_lockstep(start_list, param_space, inputs, device_scorer, params, scalarization_key):
-    """All starts in lock-step; returns [(iteration_data, log)] in start order."""
+    """All starts in lock-step; returns [(iteration_data, log)] in start order.  Rows and scores are kept as plain
+    lists per start and turned into the reference's dict-of-lists once, at the end (the per-round dict concatenations
+    of the sequential version are most of its host time)."""
     n = len(start_list)
-    current = list(start_list)
-    data = [{} for _ in range(n)]
-    logs = ["Starting local search on configuration: " + str(c) + "\n" for c in current]
+    current = [[c[p] for p in inputs] for c in start_list]
+    rows_of = [[] for _ in range(n)]
+    vals_of = [[] for _ in range(n)]
+    logs = ["Starting local search on configuration: " + str(c) + "\n" for c in start_list]
     live = list(range(n))
     while live:
-        batches = [get_neighbors(current[s], param_space) for s in live]
+        batches = [get_neighbors(dict(zip(inputs, current[s])), param_space) for s in live]
         flat = np.asarray([row for b in batches for row in b], dtype=np.float64)
         scores = device_scorer(flat, **params).cpu().tolist()
         nxt = []
         pos = 0
         for s, b in zip(live, batches):
-            neighbors = data_tuples_to_dict_list(b, inputs)
             values = scores[pos:pos + len(b)]
             pos += len(b)
-            batch = concatenate_list_of_dictionaries(neighbors)
-            batch[scalarization_key] = values
-            data[s] = concatenate_data_dictionaries(data[s], batch)
-            best = get_min_configurations(batch, 1, scalarization_key)
-            here = {k: [v] for k, v in current[s].items()}
-            if are_configurations_equal(best, here, inputs):
-                logs[s] += "Local minimum found: " + str(dict(best)) + "\n"
+            rows_of[s].extend(b)
+            vals_of[s].extend(values)
+            # get_min_configurations(batch, 1): first index of the minimum, NaN first, -0.0 == +0.0
+            k = min(range(len(values)), key=lambda i: (0, 0.0) if values[i] != values[i] else (1, values[i] + 0.0))
+            best = dict(zip(inputs, b[k]))
+            best[scalarization_key] = values[k]
+            shown = {key: [v] for key, v in best.items()}
+            if b[k] == current[s]:
+                logs[s] += "Local minimum found: " + str(shown) + "\n"
             else:
-                logs[s] += "Replacing configuration by best neighbor: " + str(dict(best)) + "\n"
-                current[s] = {k: v[0] for k, v in best.items()}
+                logs[s] += "Replacing configuration by best neighbor: " + str(shown) + "\n"
+                current[s] = list(b[k])
                 nxt.append(s)
         live = nxt
-    return list(zip(data, logs))
+    out = []
+    for s in range(n):
+        data = {p: [row[j] for row in rows_of[s]] for j, p in enumerate(inputs)}
+        data[scalarization_key] = vals_of[s]
+        out.append((data, logs[s]))
+    return out
 
 
 def local_search(local_search_starting_points, local_search_random_points, param_space,
