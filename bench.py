@@ -130,7 +130,7 @@ class RFBench:
         from hypermapper_b200 import workloads
         self.name = name
         cache = os.path.join(os.environ.get("HM_BENCH_CACHE", "/tmp"),
-                             "hm_bench_wl_%s.pkl" % ("c3" if name.startswith("c3") else name))
+                             "hm_bench_wl_v3_%s.pkl" % ("c3" if name.startswith("c3") else name))
         cached = None
         if os.path.exists(cache):
             import pickle
