@@ -42,7 +42,7 @@ WORKLOADS = ["c3", "c1", "c5rf", "c2", "c5gp", "c4", "c3raw", "c3pool"]
 # roofline.traffic: dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel from an
 # `ncu --set full` capture of the same command at the same size (profiles/<file>); None where no capture at that size exists
 NCU_TRAFFIC = {
-    ("c3", 1 << 24): (2.235832e9 + 0.561338e9, "profiles/r01_forest_c3_default_ncu_raw.csv"),
+    ("c3", 1 << 24): (2.234378e9 + 0.545148e9, "profiles/r01_forest_c3_default_ncu_raw.csv"),
     ("c1", 1 << 26): (0.537153e9 + 0.501310e9, "profiles/r01_forest_c1_ncu_raw.csv"),
 }
 
