@@ -41,6 +41,13 @@ WORKLOADS = ["c3", "c1", "c5rf", "c2", "c5gp", "c4", "c3raw", "c3pool"]
 
 # roofline.traffic: dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel from an
 # `ncu --set full` capture of the same command at the same size (profiles/<file>); None where no capture at that size exists
+# on-chip utilisation of the same launch in the same capture (per cent of peak): what actually bounds the kernel
+NCU_ONCHIP = {
+    ("c3", 1 << 24): {"l1tex_data_pipe_pct": 87.9, "issue_slots_pct": 63.5, "dram_pct": 0.7,
+                      "source": "profiles/r01_forest_c3_default_ncu_raw.csv"},
+    ("c1", 1 << 26): {"l1tex_data_pipe_pct": 71.0, "issue_slots_pct": 83.9, "dram_pct": 4.8,
+                      "source": "profiles/r01_forest_c1_ncu_raw.csv"},
+}
 NCU_TRAFFIC = {
     ("c3", 1 << 24): (2.234378e9 + 0.545148e9, "profiles/r01_forest_c3_default_ncu_raw.csv"),
     ("c1", 1 << 26): (0.537153e9 + 0.501310e9, "profiles/r01_forest_c1_ncu_raw.csv"),
@@ -263,7 +270,7 @@ class RFBench:
         smem_ach = self.smem_bytes_per_eval * N / (kernel_ms / 1e3) / 1e9
         traffic, traffic_src = NCU_TRAFFIC.get((self.name, N), (None, None))
         return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-                "traffic_source": traffic_src,
+                "traffic_source": traffic_src, "ncu_onchip": NCU_ONCHIP.get((self.name, N)),
                 "smem_pipe": {"achieved": smem_ach, "peak": smem_peak, "unit": "GB/s", "frac": smem_ach / smem_peak,
                               "bytes_per_eval": self.smem_bytes_per_eval,
                               "how": "per tree: 12 B per internal node on the path (8 B node + 4 B feature) + 8 B leaf "
