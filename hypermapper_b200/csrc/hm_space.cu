@@ -321,18 +321,8 @@ struct HmSpaceArgs {
     int* n_invalid;
 };
 
-#define HM_SPACE_BLOCK 256
-// GENERATE: draw the raw values (K6) instead of reading them.  STAGED: the raw matrix is row-major and contiguous
-// (ldr == D): a tile of 256 candidates x D values is copied into shared memory with coalesced loads and each thread
-// then reads its own row (row stride D|1 doubles: conflict-free).
-template <bool GENERATE, bool STAGED>
-__global__ void __launch_bounds__(HM_SPACE_BLOCK) hm_space_kernel(const HmSpaceArgs a) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    HmP* sp = reinterpret_cast<HmP*>(smem);
-    double* st = reinterpret_cast<double*>(smem + sizeof(HmP) * a.D);
-    const int tab_s_n = (int)(a.n_tables <= HM_SPACE_SMEM_TABLES ? a.n_tables : 0);   // all tables or none
-    double* tile = st + tab_s_n;
-    const int Dp = a.D | 1;
+// descriptors (compact form) and the first n_tab table entries into shared memory; ends with a CTA barrier
+__device__ __forceinline__ void hm_space_load_shared(const HmSpaceArgs& a, HmP* sp, double* st, int n_tab) {
     for (int j = threadIdx.x; j < a.D; j += blockDim.x) {
         const hm_param_desc_t& d = a.params[j];
         HmP p;
@@ -350,8 +340,23 @@ __global__ void __launch_bounds__(HM_SPACE_BLOCK) hm_space_kernel(const HmSpaceA
         p.lo = d.lo; p.hi = d.hi; p.mean = d.mean; p.std = d.std; p.a = d.a; p.b = d.b; p.lbeta = d.lbeta; p.pad2 = 0.0;
         sp[j] = p;
     }
-    for (int q = threadIdx.x; q < tab_s_n; q += blockDim.x) st[q] = __ldg(a.tables + q);
+    for (int q = threadIdx.x; q < n_tab; q += blockDim.x) st[q] = __ldg(a.tables + q);
     __syncthreads();
+}
+
+#define HM_SPACE_BLOCK 256
+// GENERATE: draw the raw values (K6) instead of reading them.  STAGED: the raw matrix is row-major and contiguous
+// (ldr == D): a tile of 256 candidates x D values is copied into shared memory with coalesced loads and each thread
+// then reads its own row (row stride D|1 doubles: conflict-free).
+template <bool GENERATE, bool STAGED>
+__global__ void __launch_bounds__(HM_SPACE_BLOCK) hm_space_kernel(const HmSpaceArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    HmP* sp = reinterpret_cast<HmP*>(smem);
+    double* st = reinterpret_cast<double*>(smem + sizeof(HmP) * a.D);
+    const int tab_s_n = (int)(a.n_tables <= HM_SPACE_SMEM_TABLES ? a.n_tables : 0);   // all tables or none
+    double* tile = st + tab_s_n;
+    const int Dp = a.D | 1;
+    hm_space_load_shared(a, sp, st, tab_s_n);
     // the tables: shared memory when they fit, else global (generic addressing serves both)
     const double* tab = tab_s_n ? st : a.tables;
 
@@ -553,24 +558,7 @@ __global__ void __launch_bounds__(HM_SPACE_BLOCK) hm_encode_tile_kernel(const Hm
     double* tile = st + tab_n;
     const int Dp = a.D | 1;
     constexpr int TR = HM_SPACE_BLOCK * KC;
-    for (int j = threadIdx.x; j < a.D; j += HM_SPACE_BLOCK) {
-        const hm_param_desc_t& d = a.params[j];
-        HmP p;
-        p.kind = d.kind;
-        p.n_values = d.n_values;
-        p.out_col = d.out_col;
-        p.flags = (d.normalize ? HM_PF_NORMALIZE : 0) | (d.ordinal_beta ? HM_PF_BETA_SAMPLED : 0);
-        p.prior_kind = d.prior_kind;
-        p.n_prior = d.n_prior;
-        p.n_cdf = d.n_cdf;
-        p.values_off = (int)d.values_off;
-        p.prior_off = (int)d.prior_off;
-        p.cdf_off = (int)d.cdf_off;
-        p.pad0 = p.pad1 = 0;
-        p.lo = d.lo; p.hi = d.hi; p.mean = d.mean; p.std = d.std; p.a = d.a; p.b = d.b; p.lbeta = d.lbeta; p.pad2 = 0.0;
-        sp[j] = p;
-    }
-    for (int q = threadIdx.x; q < tab_n; q += HM_SPACE_BLOCK) st[q] = __ldg(a.tables + q);
+    hm_space_load_shared(a, sp, st, tab_n);
     int bad_any = 0;
     for (long long base = (long long)blockIdx.x * TR; base < a.N; base += (long long)gridDim.x * TR) {
         __syncthreads();
