@@ -409,3 +409,27 @@ def test_describe_space_same_for_reference_space():
     d1, t1, n1 = sd.describe_space(space_of(z))
     assert n0 == n1 and np.array_equal(t0, t1)
     assert bytes(d0) == bytes(d1)
+
+
+def test_bench_reference_arm_contract(tmp_path):
+    """`bench.py --impl reference` runs without a GPU (it times the CPU port) and prints ONE JSON line with the keys the
+    driver reads; the default arm refuses to run without a CUDA device instead of falling back."""
+    env = dict(os.environ, HM_BENCH_CACHE=str(tmp_path))
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c1",
+                          "--steps", "2", "--warmup", "1", "--cpu-sample", "20000"], env=env, capture_output=True,
+                         text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "impl", "config", "cpu_baseline", "e2e", "gpu_launches"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["steps"] == 2 and d["warmup"] == 1 and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["gpu_launches"] == 0
+    import torch
+    if not torch.cuda.is_available():
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", "c1", "--steps", "1",
+                              "--warmup", "0"], env=env, capture_output=True, text=True, timeout=300)
+        assert out.returncode != 0 and "CUDA" in (out.stderr + out.stdout)
