@@ -100,3 +100,44 @@ def test_gp_host_scoring_entry_matches_device_path():
     _, tv, ti = scorer.score_gp([dgp], Xc, acq, k=20, scores_out=scores)
     assert np.array_equal(scores, want.cpu().numpy())
     assert np.array_equal(ti, wi.cpu().numpy()) and np.array_equal(tv, wv.cpu().numpy())
+
+
+def test_gp_full_size_properties_c2():
+    """BASELINE C2 size (Hartmann-6, n = 256, 2^20 candidates): size-independent properties.
+    (1) a candidate's mean / variance do not depend on its position in the pool or on its tile mates (a pool built from
+        a 2^16 block repeated 16 times under different shuffles gives every copy bit-identical results);
+    (2) the stable top-k of the EI scores is the block's best candidate, lowest index first;
+    (3) a sample agrees with the oracle within 1e-5."""
+    import torch
+    from hypermapper_b200 import gp, models, forest, _lib
+    from oracle import oracle
+    st_o, st = _setup(256, 6, 1e-4, seed=2)
+    dgp = gp.device_gp(st)
+    rng = np.random.default_rng(4)
+    base_n, reps = 1 << 16, 16
+    base = torch.from_numpy(np.ascontiguousarray(rng.random((6, base_n)))).cuda()
+    perms = [torch.randperm(base_n, device="cuda") for _ in range(reps)]
+    pool = torch.cat([base[:, p] for p in perms], dim=1).contiguous()
+    N = pool.shape[1]
+    mean = torch.empty((1, N), dtype=torch.float64, device="cuda")
+    var = torch.empty_like(mean)
+    gp.gp_mean_var(dgp, pool, mean[0], var[0])
+    bm = torch.empty((1, base_n), dtype=torch.float64, device="cuda")
+    bv = torch.empty_like(bm)
+    gp.gp_mean_var(dgp, base, bm[0], bv[0])
+    for r, p in enumerate(perms):
+        assert torch.equal(mean[0, r * base_n:(r + 1) * base_n], bm[0, p]), r
+        assert torch.equal(var[0, r * base_n:(r + 1) * base_n], bv[0, p]), r
+    acq = _lib.make_acq_params("EI", "tchebyshev", [1.0], [0.6], 0.0)
+    score = models.acq_score_device(acq, mean, var)
+    bscore = models.acq_score_device(acq, bm, bv)
+    tv, ti = forest.topk(score, 16)
+    best = bscore.min()
+    where = torch.nonzero(score == best).view(-1)[:16]
+    assert torch.equal(ti[: len(where)], where) and bool((tv[: len(where)] == best).all())
+    sub = rng.choice(base_n, 2000, replace=False)
+    mo, vo = oracle.gp_predict(st_o, base[:, torch.from_numpy(sub).cuda()].T.cpu().numpy())
+    m, v = bm[0].cpu().numpy()[sub], bv[0].cpu().numpy()[sub]
+    assert np.max(np.abs(m - mo)) <= REL * max(1.0, np.max(np.abs(mo)))
+    floor = 64 * 256 * np.finfo(np.float64).eps * st.variance * st.y_std ** 2
+    assert np.all(np.abs(v - vo) <= REL * vo + floor)
