@@ -26,7 +26,7 @@ EXPORTED_SYMBOLS = [
     "hm_pareto_workspace_bytes", "hm_pareto_filter", "hm_pareto_pass1",
     "hm_space_create", "hm_space_destroy", "hm_space_n_params", "hm_space_n_encoded",
     "hm_encode", "hm_sample_pool", "hm_sample_rows", "hm_prior_prob", "hm_prior_weight",
-    "hm_minmax", "hm_bopro_ratio", "hm_bopro_finish",
+    "hm_minmax", "hm_bopro_ratio", "hm_bopro_finish", "hm_ls_neighbors", "hm_ls_move",
     "hm_host_ctx_create", "hm_host_ctx_destroy", "hm_rf_score_host", "hm_rf_score_raw_host", "hm_gp_score_host",
 ]
 
@@ -126,6 +126,8 @@ def lib():
     L.hm_minmax.argtypes = [vp, i64, i32, vp, vp, vp]
     L.hm_bopro_ratio.argtypes = [ctypes.POINTER(BoproParams), vp, vp, vp, i64, i64, vp, vp]
     L.hm_bopro_finish.argtypes = [vp, i64, i32, dbl, dbl, dbl, vp, vp, vp, vp]
+    L.hm_ls_neighbors.argtypes = [vp, vp, i32, vp, vp, i32, vp, vp]
+    L.hm_ls_move.argtypes = [vp, vp, i32, i32, vp, i32, vp, vp, vp, vp]
     L.hm_host_ctx_create.argtypes = [i64, i32, ctypes.POINTER(vp)]
     L.hm_host_ctx_destroy.argtypes = [vp]
     L.hm_host_ctx_destroy.restype = None

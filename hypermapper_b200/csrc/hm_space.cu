@@ -938,3 +938,108 @@ extern "C" int hm_bopro_finish(const double* ratio, int64_t N, int normalize_mod
     HM_CUDA_TRY(cudaGetLastError());
     return 0;
 }
+
+// ---- N4: neighbourhoods and moves of the multi-start hill climb on the device (discrete spaces) -----------------------
+// get_neighbors (local_search.py:83-161) for spaces without real / integer parameters draws no random numbers, and its
+// `cand not in neighbors` filter only ever removes repetitions of the unchanged configuration, so a configuration has a
+// FIXED number K of neighbours, enumerated parameter by parameter:
+//   categorical, or ordinal with <= 5 values : every value in order                    (local_search.py:103-109)
+//   ordinal                                   : the window of 5 values around the current index (:110-137)
+//   and for every parameter but the first the entry equal to the current value is skipped (it repeats the unchanged
+//   configuration, which parameter 0 already emitted).
+// plan[q] = {parameter, rank inside that parameter's emitted list} for q < K, built by the host.
+__global__ void __launch_bounds__(256) hm_ls_neighbors_kernel(const hm_param_desc_t* __restrict__ params,
+                                                              const double* __restrict__ tables, int D,
+                                                              const int2* __restrict__ plan, int K,
+                                                              const double* __restrict__ current,     // [S][D] raw
+                                                              const int* __restrict__ live, int n_live,
+                                                              double* __restrict__ rows) {           // [n_live*K][D]
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)n_live * K) return;
+    const int ls = (int)(t / K), q = (int)(t - (long long)ls * K);
+    const int s = live[ls];
+    const int j = plan[q].x, e = plan[q].y;
+    const hm_param_desc_t& p = params[j];
+    const double cur = current[(size_t)s * D + j];
+    // index of the current value
+    int idx;
+    if (p.kind == HM_P_ORDINAL) {
+        idx = 0;
+        for (int v = 0; v < p.n_values; ++v)
+            if (tables[p.values_off + v] == cur) idx = v;
+    } else {
+        idx = (int)cur;
+    }
+    int pick;                                     // value index of this neighbour
+    if (p.kind == HM_P_CATEGORICAL || p.n_values <= 5) {
+        pick = (j > 0 && e >= idx) ? e + 1 : e;
+    } else {
+        const int n = p.n_values;
+        const int w0 = idx < 2 ? 0 : ((n - idx) <= 2 ? n - 5 : idx - 2);
+        const int rel = idx - w0;                 // position of the current value inside the window
+        pick = w0 + ((j > 0 && e >= rel) ? e + 1 : e);
+    }
+    double* out = rows + (size_t)t * D;
+    for (int d = 0; d < D; ++d) out[d] = current[(size_t)s * D + d];
+    out[j] = p.kind == HM_P_ORDINAL ? tables[p.values_off + pick] : (double)pick;
+}
+
+// One warp per live start: argmin of its K scores with get_min_configurations' order (NaN first, -0.0 == +0.0, first
+// index among equals); the start has converged iff the best neighbour is the unchanged configuration, else it moves.
+__global__ void __launch_bounds__(32) hm_ls_move_kernel(const double* __restrict__ scores, const double* __restrict__ rows,
+                                                        int K, int D, const int* __restrict__ live,
+                                                        double* __restrict__ current, int* __restrict__ converged,
+                                                        int* __restrict__ best_q) {
+    const int ls = blockIdx.x, lane = threadIdx.x;
+    const int s = live[ls];
+    HmPair best = {~0ull, 0x7fffffffffffffffll};
+    for (int q = lane; q < K; q += 32) {
+        HmPair e;
+        e.key = hm_order_key(scores[(size_t)ls * K + q]);
+        e.idx = q;
+        if (hm_pair_less(e, best)) best = e;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        HmPair other;
+        other.key = __shfl_xor_sync(0xffffffffu, best.key, o);
+        other.idx = __shfl_xor_sync(0xffffffffu, best.idx, o);
+        if (hm_pair_less(other, best)) best = other;
+    }
+    const int q = (int)best.idx;
+    const double* row = rows + ((size_t)ls * K + q) * D;
+    bool same = true;
+    for (int d = lane; d < D; d += 32) same = same && (row[d] == current[(size_t)s * D + d]);
+    same = __all_sync(0xffffffffu, same);
+    if (!same)
+        for (int d = lane; d < D; d += 32) current[(size_t)s * D + d] = row[d];
+    if (lane == 0) {
+        converged[s] = same ? 1 : 0;
+        best_q[s] = q;
+    }
+}
+
+extern "C" int hm_ls_neighbors(const hm_space_t* s, const int32_t* plan_dev, int K, const double* current_dev,
+                               const int32_t* live_dev, int n_live, double* rows_out, void* stream) {
+    HM_REQUIRE(s != nullptr && plan_dev != nullptr && current_dev != nullptr && live_dev != nullptr && rows_out != nullptr,
+               "arguments");
+    HM_REQUIRE(K >= 1 && n_live >= 0, "K >= 1, n_live >= 0");
+    for (int j = 0; j < s->D; ++j)
+        HM_REQUIRE(s->params[j].kind >= HM_P_ORDINAL, "hm_ls_neighbors: discrete spaces only (ordinal / categorical)");
+    if (n_live == 0) return 0;
+    const long long total = (long long)n_live * K;
+    hm_ls_neighbors_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        s->d_params, s->d_tables, s->D, reinterpret_cast<const int2*>(plan_dev), K, current_dev, live_dev, n_live, rows_out);
+    HM_CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int hm_ls_move(const double* scores, const double* rows, int K, int D, const int32_t* live_dev, int n_live,
+                          double* current_dev, int32_t* converged_dev, int32_t* best_q_dev, void* stream) {
+    HM_REQUIRE(scores && rows && live_dev && current_dev && converged_dev && best_q_dev, "arguments");
+    HM_REQUIRE(K >= 1 && D >= 1 && n_live >= 0, "K, D >= 1, n_live >= 0");
+    if (n_live == 0) return 0;
+    hm_ls_move_kernel<<<n_live, 32, 0, (cudaStream_t)stream>>>(scores, rows, K, D, live_dev, current_dev, converged_dev,
+                                                             best_q_dev);
+    HM_CUDA_TRY(cudaGetLastError());
+    return 0;
+}

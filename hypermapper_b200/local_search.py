@@ -224,6 +224,19 @@ def _neighbors_use_rng(param_space):
 _lockstep = os.environ.get("HM_B200_LOCKSTEP", "auto")
 
 
+# Neighbourhoods and moves on the GPU (hm_ls_neighbors / hm_ls_move) when the lock-step climb runs on a discrete space
+_device_climb = os.environ.get("HM_B200_DEVICE_CLIMB", "1") not in ("", "0")
+
+
+def set_device_climb(enabled):
+    global _device_climb
+    _device_climb = bool(enabled)
+
+
+def _all_discrete(param_space):
+    return all(param_space.get_type(p) in ("ordinal", "categorical") for p in param_space.get_input_parameters())
+
+
 def set_lockstep(mode):
     """True / False / "auto" (default: lock-step only when it is exactly equivalent)."""
     global _lockstep
@@ -266,6 +279,97 @@ def _hill_climb_lockstep(start_list, param_space, inputs, device_scorer, params,
     out = []
     for s in range(n):
         data = {p: [row[j] for row in rows_of[s]] for j, p in enumerate(inputs)}
+        data[scalarization_key] = vals_of[s]
+        out.append((data, logs[s]))
+    return out
+
+
+def neighbor_plan(param_space):
+    """For a space without real / integer parameters: the enumeration get_neighbors follows, as K x (parameter,
+    rank inside that parameter's emitted list).  Every configuration has exactly K neighbours there: all values of a
+    categorical / small ordinal, the 5-window of a larger ordinal, minus -- for every parameter but the first -- the
+    entry that repeats the unchanged configuration (local_search.py:96-137)."""
+    inputs = param_space.get_input_parameters()
+    objs = param_space.get_input_parameters_objects()
+    plan = []
+    for j, name in enumerate(inputs):
+        kind = param_space.get_type(name)
+        n = len(objs[name].get_discrete_values())
+        count = n if (kind == "categorical" or n <= 5) else 5
+        if j > 0:
+            count -= 1
+        plan += [(j, e) for e in range(count)]
+    return np.asarray(plan, dtype=np.int32).reshape(-1, 2)
+
+
+def _hill_climb_device(start_list, param_space, inputs, device_scorer, params, scalarization_key):
+    """The lock-step hill climb with the neighbourhoods generated and the moves decided on the GPU (hm_ls_neighbors /
+    hm_ls_move); per round: one neighbour launch, the scoring launches, one move launch and one 4-byte-per-start
+    read-back of the convergence flags.  Same trajectories, same returned data as _hill_climb_lockstep."""
+    import ctypes
+    from . import _lib
+    from .space_device import device_space_for, P_ORDINAL
+    torch = _lib.require_cuda()
+    L = _lib.lib()
+    ds = device_space_for(param_space)
+    D = ds.D
+    n = len(start_list)
+    plan = neighbor_plan(param_space)
+    K = len(plan)
+    plan_d = torch.from_numpy(plan).cuda()
+    current = torch.from_numpy(np.array([[float(c[p]) for p in inputs] for c in start_list], dtype=np.float64)
+                               .reshape(n, D)).cuda()
+    converged = torch.zeros((n,), dtype=torch.int32, device="cuda")
+    best_q = torch.zeros((n,), dtype=torch.int32, device="cuda")
+    live = list(range(n))
+    rounds = []                      # (live list, rows [n_live*K][D], scores [n_live*K], best_q snapshot, converged snapshot)
+    while live:
+        live_d = torch.tensor(live, dtype=torch.int32, device="cuda")
+        rows = torch.empty((len(live) * K, D), dtype=torch.float64, device="cuda")
+        _lib.check(L.hm_ls_neighbors(ds.handle, _lib.dptr(plan_d), K, _lib.dptr(current), _lib.dptr(live_d), len(live),
+                                     _lib.dptr(rows), _lib.stream_ptr()), "hm_ls_neighbors")
+        scores = device_scorer(rows, **params).contiguous()
+        _lib.check(L.hm_ls_move(_lib.dptr(scores), _lib.dptr(rows), K, D, _lib.dptr(live_d), len(live),
+                                _lib.dptr(current), _lib.dptr(converged), _lib.dptr(best_q), _lib.stream_ptr()),
+                   "hm_ls_move")
+        flags = converged.cpu().numpy()
+        rounds.append((live, rows, scores, best_q.cpu().numpy().copy(), flags.copy()))
+        live = [s for s in live if not flags[s]]
+    # ---- back to the reference's dict-of-lists, with the parameter objects' own value types ----------------------
+    objs = param_space.get_input_parameters_objects()
+    ordinal_values = {}
+    for j, p in enumerate(inputs):
+        if ds.descs[j].kind == P_ORDINAL:
+            vals = objs[p].get_values()
+            ordinal_values[j] = (np.asarray(vals, dtype=np.float64), vals)
+    cols_of = [[[] for _ in range(D)] for _ in range(n)]
+    vals_of = [[] for _ in range(n)]
+    logs = ["Starting local search on configuration: " + str(c) + "\n" for c in start_list]
+    for live_r, rows, scores, bq, flags in rounds:
+        rows_h = rows.cpu().numpy().reshape(len(live_r), K, D)
+        scores_h = scores.cpu().numpy().reshape(len(live_r), K)
+        typed = []
+        for j in range(D):
+            col = rows_h[:, :, j]
+            if j in ordinal_values:
+                sv, vals = ordinal_values[j]
+                idx = np.searchsorted(sv, col)
+                typed.append([[vals[i] for i in r] for r in idx])
+            else:
+                typed.append(col.astype(np.int64).tolist())
+        for l, s in enumerate(live_r):
+            for j in range(D):
+                cols_of[s][j].extend(typed[j][l])
+            v = scores_h[l].tolist()
+            vals_of[s].extend(v)
+            q = int(bq[s])
+            shown = {p: [typed[j][l][q]] for j, p in enumerate(inputs)}
+            shown[scalarization_key] = [v[q]]
+            logs[s] += ("Local minimum found: " if flags[s] else "Replacing configuration by best neighbor: ") + \
+                str(shown) + "\n"
+    out = []
+    for s in range(n):
+        data = {p: cols_of[s][j] for j, p in enumerate(inputs)}
         data[scalarization_key] = vals_of[s]
         out.append((data, logs[s]))
     return out
@@ -369,7 +473,9 @@ def local_search(local_search_starting_points, local_search_random_points, param
     lockstep = device_scorer is not None and (_lockstep is True or _lockstep in ("1", "on") or
                                               (_lockstep == "auto" and not _neighbors_use_rng(param_space) and
                                                getattr(device_scorer, "batch_invariant", False)))
-    if lockstep:
+    if lockstep and _device_climb and _all_discrete(param_space) and n_starts > 0:
+        climbs = _hill_climb_device(start_list, param_space, inputs, device_scorer, params, scalarization_key)
+    elif lockstep:
         climbs = _hill_climb_lockstep(start_list, param_space, inputs, device_scorer, params, scalarization_key)
     else:
         climbs = (_hill_climb(start, param_space, inputs, optimization_function, params, enable_feasible_predictor,

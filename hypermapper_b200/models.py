@@ -61,8 +61,8 @@ def encode_to_device(bufferx, param_space, dtype):
     if isinstance(bufferx, EncodedCandidates):
         return bufferx.get(dtype)
     from .space_device import device_space_for
-    x32, x64 = device_space_for(param_space).encode(raw_matrix(bufferx, param_space), want32=(dtype == "float32"),
-                                                    want64=(dtype != "float32"))
+    raw = bufferx if (hasattr(bufferx, "is_cuda") and bufferx.is_cuda) else raw_matrix(bufferx, param_space)
+    x32, x64 = device_space_for(param_space).encode(raw, want32=(dtype == "float32"), want64=(dtype != "float32"))
     return x32 if dtype == "float32" else x64
 
 

@@ -245,6 +245,19 @@ int hm_prior_prob(const hm_space_t* s, const double* raw, int raw_col_major, int
 int hm_prior_weight(const double* acq, const double* prob, int64_t N, double prior_floor, double exponent,
                     int collapse_to_min, double* out, void* workspace8, void* stream);
 
+/* N4  multi-start hill climb on the device, discrete spaces (get_neighbors, local_search.py:83-161, draws no random
+ * numbers there and every configuration has the same number K of neighbours):
+ *   hm_ls_neighbors  rows_out[(l*K + q)][D] = neighbour q of live start l (raw values, row-major), enumerated in the
+ *                    reference's order; plan_dev = K x {parameter, rank inside that parameter's emitted list} (int32
+ *                    pairs, built by the host: local_search.neighbor_plan); current_dev = [S][D] raw configurations;
+ *                    live_dev = indices of the starts still climbing
+ *   hm_ls_move       per live start: argmin of its K scores in get_min_configurations' order; converged[s] = 1 if the
+ *                    best neighbour is the unchanged configuration, else current[s] <- that neighbour; best_q[s] = q */
+int hm_ls_neighbors(const hm_space_t* s, const int32_t* plan_dev, int K, const double* current_dev,
+                    const int32_t* live_dev, int n_live, double* rows_out, void* stream);
+int hm_ls_move(const double* scores, const double* rows, int K, int D, const int32_t* live_dev, int n_live,
+               double* current_dev, int32_t* converged_dev, int32_t* best_q_dev, void* stream);
+
 /* BOPrO acquisition (prior_optimization.compute_EI_from_posteriors, prior_optimization.py:161-374):
  *   hm_minmax        min / max of a device vector (NaNs skipped; ignore_inf skips +-inf as :318-327 does);
  *                    out2_dev = {min, max} (+inf / -inf when nothing qualifies); workspace16 = 16 device bytes

@@ -260,15 +260,21 @@ def test_lockstep_hill_climb_equals_sequential():
     assert not ls._neighbors_use_rng(space)
     results = []
     try:
-        for mode in (False, True, "auto"):
+        # sequential / lock-step with host neighbourhoods / lock-step with device neighbourhoods and moves / default
+        for mode, device in ((False, False), (True, False), (True, True), ("auto", True)):
             ls.set_lockstep(mode)
+            ls.set_device_climb(device)
             np.random.seed(4)
             random.seed(4)
             results.append(ls.local_search(6, 400, space, fast, False, rs.run_acquisition_function, p,
                                            config["scalarization_key"], 1, previous_points=data))
     finally:
         ls.set_lockstep("auto")
+        ls.set_device_climb(True)
     for data_array, best in results[1:]:
         assert best == results[0][1]
         assert data_array == results[0][0]
+        # same python types as the reference's neighbour lists (they end up in hash strings): ints stay ints
+        for k in inputs:
+            assert [type(v) for v in data_array[k]] == [type(v) for v in results[0][0][k]], k
     assert len(results[0][0][config["scalarization_key"]]) > 800 + 60      # the climbs did evaluate neighbours

@@ -433,3 +433,33 @@ def test_bench_reference_arm_contract(tmp_path):
         out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", "c1", "--steps", "1",
                               "--warmup", "0"], env=env, capture_output=True, text=True, timeout=300)
         assert out.returncode != 0 and "CUDA" in (out.stderr + out.stdout)
+
+
+def test_neighbor_plan_enumerates_like_get_neighbors():
+    """local_search.neighbor_plan (what hm_ls_neighbors follows on the device) against get_neighbors on the discrete
+    golden space: same number of neighbours for every configuration, same order, same rows."""
+    from hypermapper_b200.local_search import get_neighbors, neighbor_plan
+    z = load("local_search.npz")
+    space = space_of(z)
+    plan = neighbor_plan(space)
+    inputs = space.get_input_parameters()
+    objs = space.get_input_parameters_objects()
+    np.random.seed(0)
+    for _ in range(200):
+        conf = space.get_random_configuration(use_priors=False)
+        nb = get_neighbors(conf, space)
+        rows = []
+        for j, e in plan:
+            name = inputs[j]
+            vals = list(objs[name].get_discrete_values())
+            n = len(vals)
+            idx = vals.index(conf[name])
+            if space.get_type(name) == "categorical" or n <= 5:
+                pick = e + 1 if (j > 0 and e >= idx) else e
+            else:
+                w0 = 0 if idx < 2 else (n - 5 if (n - idx) <= 2 else idx - 2)
+                pick = w0 + (e + 1 if (j > 0 and e >= idx - w0) else e)
+            row = [conf[p] for p in inputs]
+            row[j] = vals[pick]
+            rows.append(row)
+        assert rows == nb
