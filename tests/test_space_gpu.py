@@ -480,3 +480,62 @@ def test_random_spaces_encode_and_prior_match_host(seed):
     close(got, host, rel=1e-9)
     gp = ds.prior_prob(rd, [1.0], col_major=True).cpu().numpy()
     assert np.array_equal(gp, got, equal_nan=True)
+
+
+def test_device_neighbourhoods_equal_get_neighbors():
+    """hm_ls_neighbors against get_neighbors row for row (order included) on every window position of every ordinal,
+    and hm_ls_move against a host argmin with the reference's tie-break."""
+    import ctypes
+    import torch
+    from hypermapper_b200 import _lib
+    from hypermapper_b200.local_search import get_neighbors, neighbor_plan
+    from hypermapper_b200.space_device import device_space_for
+    from hypermapper_b200.space_lite import SpaceLite
+    cfg = {"optimization_objectives": ["y"], "input_parameters": {
+        "big": {"parameter_type": "ordinal", "values": [1, 2, 4, 8, 16, 32, 64, 128, 256], "parameter_default": 1},
+        "cat": {"parameter_type": "categorical", "values": ["a", "b", "c"], "parameter_default": "a"},
+        "five": {"parameter_type": "ordinal", "values": [0.5, 1.5, 2.5, 3.5, 4.5], "parameter_default": 0.5},
+        "six": {"parameter_type": "ordinal", "values": [10, 20, 30, 40, 50, 60], "parameter_default": 10},
+        "one": {"parameter_type": "categorical", "values": ["z"], "parameter_default": "z"}}}
+    space = SpaceLite(cfg)
+    inputs = space.get_input_parameters()
+    objs = space.get_input_parameters_objects()
+    plan = neighbor_plan(space)
+    K = len(plan)
+    ds = device_space_for(space)
+    rng = np.random.default_rng(0)
+    starts = []
+    for i in range(9):                                     # every index of the 9-value ordinal, others random
+        starts.append({"big": objs["big"].get_values()[i], "cat": int(rng.integers(0, 3)),
+                       "five": objs["five"].get_values()[int(rng.integers(0, 5))],
+                       "six": objs["six"].get_values()[i % 6], "one": 0})
+    S = len(starts)
+    cur = torch.from_numpy(np.array([[float(c[p]) for p in inputs] for c in starts])).cuda()
+    live = torch.arange(S, dtype=torch.int32, device="cuda")
+    rows = torch.empty((S * K, len(inputs)), dtype=torch.float64, device="cuda")
+    L = _lib.lib()
+    _lib.check(L.hm_ls_neighbors(ds.handle, _lib.dptr(torch.from_numpy(plan).cuda()), K, _lib.dptr(cur), _lib.dptr(live), S,
+                                 _lib.dptr(rows), _lib.stream_ptr()), "hm_ls_neighbors")
+    got = rows.cpu().numpy().reshape(S, K, len(inputs))
+    for s, c in enumerate(starts):
+        want = np.array([[float(v) for v in r] for r in get_neighbors(c, space)])
+        assert want.shape == (K, len(inputs)) and np.array_equal(got[s], want), s
+    # moves: ties -> first index, NaN first, -0.0 == +0.0
+    scores = rng.integers(0, 3, (S, K)).astype(np.float64)
+    scores[1, 5] = np.nan
+    scores[2, 3] = -0.0
+    scores[2, 1] = 0.0
+    scores[2][scores[2] > 0] += 1
+    sd = torch.from_numpy(scores.reshape(-1)).cuda()
+    conv = torch.zeros((S,), dtype=torch.int32, device="cuda")
+    bq = torch.zeros((S,), dtype=torch.int32, device="cuda")
+    before = cur.clone()
+    _lib.check(L.hm_ls_move(_lib.dptr(sd), _lib.dptr(rows), K, len(inputs), _lib.dptr(live), S, _lib.dptr(cur),
+                            _lib.dptr(conv), _lib.dptr(bq), _lib.stream_ptr()), "hm_ls_move")
+    for s in range(S):
+        v = scores[s]
+        q = min(range(K), key=lambda i: (0, 0.0) if v[i] != v[i] else (1, v[i] + 0.0))
+        assert int(bq[s]) == q, (s, int(bq[s]), q)
+        same = np.array_equal(got[s, q], before[s].cpu().numpy())
+        assert int(conv[s]) == int(same)
+        assert np.array_equal(cur[s].cpu().numpy(), got[s, q])
