@@ -120,60 +120,90 @@ __device__ void hm_sel_compact(HmSelState& s, int k) {
     __syncthreads();
 }
 
-// returns the shared buffer whose first min(k, #elements) entries are the selection, ascending
+// returns the shared buffer whose first min(k, #elements) entries are the selection, ascending.
+// The CTA owns the contiguous element range [lo, hi).  It walks it in super-tiles of HM_TK_SUPER elements: every thread
+// issues all its loads of the super-tile first (8 independent 8-byte loads: enough bytes in flight for HBM speed), then
+// filters them on the raw value -- an element can only enter the buffer if NOT (v > tau_v); NaN, -0.0 and ties fall
+// through to the exact (key, index) comparison -- and the CTA synchronises ONCE per super-tile.  A super-tile that
+// would overflow the buffer (only while tau is still loose, i.e. the first one or two of a CTA, or adversarial input) is
+// rolled back and redone in tiles of HM_TK_TILE elements with a compaction whenever the buffer is more than half full.
+#define HM_TK_RS 8
+#define HM_TK_SUPER (HM_TK_BLOCK * HM_TK_RS)
 template <typename Load>
-__device__ const HmPair* hm_select_k(Load load, long long n, long long first_tile, long long tile_stride, int k,
-                                     int* n_selected) {
+__device__ const HmPair* hm_select_k(Load load, long long lo, long long hi, int k, int* n_selected) {
     __shared__ HmPair buf[HM_TK_CAP];
     __shared__ int count;
+    __shared__ int overflow;
     __shared__ HmPair tau;
     __shared__ double tau_v;
     HmSelState s = {buf, &count, &tau, &tau_v};
     if (threadIdx.x == 0) {
         count = 0;
+        overflow = 0;
         tau = hm_pad_pair();
         tau_v = __longlong_as_double(0x7ff0000000000000ll);
     }
     __syncthreads();
-    const long long n_tiles = (n + HM_TK_TILE - 1) / HM_TK_TILE;
-    constexpr int R = HM_TK_TILE / HM_TK_BLOCK;
-    // Software pipeline: the loads of the next tile are in flight while this tile is filtered and the CTA synchronises.
-    // Value streams are filtered on the raw double first: an element can only enter the buffer if NOT (v > tau_v)
-    // (NaN, -0.0 and ties fall through to the exact (key, index) comparison), so the common case is load + compare.
-    typename Load::Item cur[R], nxt[R];
-    bool cv[R], nv[R];
-    auto fetch = [&](long long tile, typename Load::Item* e, bool* valid) {
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const long long p = tile * HM_TK_TILE + r * HM_TK_BLOCK + threadIdx.x;
-            valid[r] = tile < n_tiles && p < n;
-            if (valid[r]) e[r] = load.item(p);
-        }
-    };
-    fetch(first_tile, nxt, nv);
-    for (long long tile = first_tile; tile < n_tiles; tile += tile_stride) {
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            cur[r] = nxt[r];
-            cv[r] = nv[r];
-        }
-        fetch(tile + tile_stride, nxt, nv);
+    // warm-up: the first HM_TK_BLOCK elements go straight into the buffer and give the first threshold (one small sort),
+    // so that the first super-tile does not overflow; later compactions are triggered early (a few hundred entries)
+    // so that they sort 512 entries, not 2048 -- the sorts, not the stream, were most of the kernel
+    {
+        const long long p = lo + threadIdx.x;
+        if (p < hi) buf[atomicAdd(&count, 1)] = load.pair(load.item(p), p);
+        __syncthreads();
+        if (hi - lo > HM_TK_BLOCK) hm_sel_compact(s, k);
+    }
+    const int compact_at = min(HM_TK_CAP / 2, max(256, 2 * k));
+    for (long long e0 = lo + HM_TK_BLOCK; e0 < hi; e0 += HM_TK_SUPER) {
+        const long long e1 = e0 + HM_TK_SUPER < hi ? e0 + HM_TK_SUPER : hi;
+        const int c0 = count;                       // the roll-back point of this super-tile ...
         const HmPair tl = tau;
         const double tv = tau_v;
+        __syncthreads();                            // ... which every thread must have read before anybody appends
+        typename Load::Item it[HM_TK_RS];
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            if (cv[r] && Load::maybe(cur[r], tv)) {
-                const HmPair e = load.pair(cur[r], tile * HM_TK_TILE + r * HM_TK_BLOCK + threadIdx.x);
+        for (int r = 0; r < HM_TK_RS; ++r) {
+            const long long p = e0 + r * HM_TK_BLOCK + threadIdx.x;
+            if (p < e1) it[r] = load.item(p);
+        }
+#pragma unroll
+        for (int r = 0; r < HM_TK_RS; ++r) {
+            const long long p = e0 + r * HM_TK_BLOCK + threadIdx.x;
+            if (p < e1 && load.maybe(it[r], tv, p, tl.idx)) {
+                const HmPair e = load.pair(it[r], p);
                 if (hm_pair_less(e, tl)) {
                     const int pos = atomicAdd(&count, 1);
-                    buf[pos] = e;
+                    if (pos < HM_TK_CAP) buf[pos] = e;
+                    else overflow = 1;
                 }
             }
         }
         __syncthreads();
+        const bool redo = overflow != 0;
         const int c = count;
-        __syncthreads();   // nobody appends for the next tile before everyone has read the same count
-        if (c > HM_TK_CAP - HM_TK_TILE) hm_sel_compact(s, k);
+        __syncthreads();
+        if (redo) {
+            if (threadIdx.x == 0) {
+                count = c0;
+                overflow = 0;
+            }
+            __syncthreads();
+            for (long long t0 = e0; t0 < e1; t0 += HM_TK_TILE) {
+                if (count > HM_TK_CAP - HM_TK_TILE) hm_sel_compact(s, k);      // uniform; leaves room for a whole tile
+                const HmPair tl2 = tau;
+#pragma unroll
+                for (int r = 0; r < HM_TK_TILE / HM_TK_BLOCK; ++r) {
+                    const long long p = t0 + r * HM_TK_BLOCK + threadIdx.x;
+                    if (p < e1 && p < t0 + HM_TK_TILE) {
+                        const HmPair e = load.pair(load.item(p), p);
+                        if (hm_pair_less(e, tl2)) buf[atomicAdd(&count, 1)] = e;
+                    }
+                }
+                __syncthreads();
+            }
+        } else if (c > compact_at) {
+            hm_sel_compact(s, k);
+        }
     }
     hm_sel_compact(s, k);
     *n_selected = count;
@@ -186,7 +216,10 @@ struct HmLoadVals {
     const double* vals;
     long long base;
     __device__ __forceinline__ double item(long long p) const { return __ldg(vals + p); }
-    static __device__ __forceinline__ bool maybe(double v, double tv) { return !(v > tv); }
+    // exact for non-NaN values: smaller value, or equal value (-0.0 == +0.0) with a smaller global index
+    __device__ __forceinline__ bool maybe(double v, double tv, long long p, long long tau_idx) const {
+        return v < tv || (v == tv && base + p < tau_idx) || v != v;
+    }
     __device__ __forceinline__ HmPair pair(double v, long long p) const {
         HmPair e;
         e.key = hm_order_key(v);
@@ -199,7 +232,7 @@ struct HmLoadValIdx {
     const double* vals;
     const long long* idx;
     __device__ __forceinline__ double item(long long p) const { return __ldg(vals + p); }
-    static __device__ __forceinline__ bool maybe(double v, double tv) { return !(v > tv); }
+    __device__ __forceinline__ bool maybe(double v, double tv, long long, long long) const { return !(v > tv); }
     __device__ __forceinline__ HmPair pair(double v, long long p) const {
         HmPair e;
         e.key = hm_order_key(v);
@@ -211,14 +244,20 @@ struct HmLoadPairs {
     typedef HmPair Item;
     const HmPair* pairs;
     __device__ __forceinline__ HmPair item(long long p) const { return pairs[p]; }
-    static __device__ __forceinline__ bool maybe(const HmPair&, double) { return true; }
+    __device__ __forceinline__ bool maybe(const HmPair&, double, long long, long long) const { return true; }
     __device__ __forceinline__ HmPair pair(const HmPair& e, long long) const { return e; }
 };
 
 template <typename Load>
 __global__ void __launch_bounds__(HM_TK_BLOCK) hm_topk_stage1(Load load, long long n, int k, HmPair* ws) {
     int c;
-    const HmPair* sel = hm_select_k(load, n, blockIdx.x, gridDim.x, k, &c);
+    // contiguous share of this CTA, a multiple of the super-tile
+    const long long supers = (n + HM_TK_SUPER - 1) / HM_TK_SUPER;
+    const long long per = (supers + gridDim.x - 1) / gridDim.x;
+    const long long lo = (long long)blockIdx.x * per * HM_TK_SUPER;
+    long long hi = lo + per * HM_TK_SUPER;
+    if (hi > n) hi = n;
+    const HmPair* sel = hm_select_k(load, lo < n ? lo : n, hi, k, &c);
     HmPair* out = ws + (size_t)blockIdx.x * k;
     for (int t = threadIdx.x; t < k; t += blockDim.x) out[t] = (t < c) ? sel[t] : hm_pad_pair();
 }
@@ -233,7 +272,7 @@ __global__ void __launch_bounds__(HM_TK_BLOCK) hm_topk_stage2(const HmPair* ws, 
                                                               long long* out_idx) {
     HmLoadPairs load = {ws};
     int c;
-    const HmPair* sel = hm_select_k(load, n, 0, 1, k, &c);
+    const HmPair* sel = hm_select_k(load, 0, n, k, &c);
     for (int t = threadIdx.x; t < k; t += blockDim.x) {
         const HmPair e = (t < c) ? sel[t] : hm_pad_pair();
         const bool pad = (e.key == ~0ull && e.idx == 0x7fffffffffffffffll);
