@@ -208,7 +208,7 @@ class RFBench:
         wl.candidates_encoded(N, seed=6 + rank, out=self.x_host.numpy())
         self.x_dev = self.x_host.cuda()
         self.scores_host = torch.empty((N,), dtype=torch.float64).pin_memory()
-        self.scorer = HostScorer(wl.D_enc, chunk=1 << 21)
+        self.scorer = HostScorer(wl.D_enc, chunk=int(os.environ.get("HM_BENCH_CHUNK", 1 << 21)))
         # hm_forest_kernel + hm_topk_stage1/2; forests that stream through shared memory add the coherence pre-pass
         # (hm_forest_sortkey, hm_forest_scan, hm_forest_scatter_rows) for pools of >= 2^17 candidates
         self.prepass = sum(f.n_groups for f in self.forests if f.staged) > 2 and N >= (1 << 17)
