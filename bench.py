@@ -193,8 +193,48 @@ class RFBench:
         for o, fa in self._fas.items():
             means[o], variances[o], _ = oracle.rf_mean_var_omp(fa, X)
         vals = oracle.EI(means, variances, wl.data_array, wl.objective_weights, wl.scalarization, wl.objective_limits)
-        oracle.get_min_indices_fast(vals, self.k)
-        return time.perf_counter() - t0
+        top = oracle.get_min_indices_fast(vals, self.k)
+        dt = time.perf_counter() - t0
+        self._cpu_out = (sample, means, vals, top)
+        return dt
+
+    def parity(self):
+        """BASELINE.md section 3.6 gate: the GPU path on the very sample the CPU leg just scored with the oracle --
+        leaf ids and means bit-exact, acquisition values within 1e-5 relative, top-k indices identical (near ties
+        re-scored with the reference's arithmetic, hypermapper_b200/exact.py).  The oracle is the checker here."""
+        import torch
+        from oracle import oracle
+        from hypermapper_b200 import exact, forest
+        wl = self.wl
+        sample, means, vals, top = self._cpu_out
+        X = self._Xcpu[sample]                                       # [sample][D_enc] float32 rows
+        X32 = torch.from_numpy(np.ascontiguousarray(X.T)).cuda()
+        out = forest.rf_eval(self.forests, X32, want_mean=True, acq=self.acq)
+        mean_exact = all(np.array_equal(out["mean"][m].cpu().numpy(), means[o]) for m, o in enumerate(wl.objectives))
+        sc = out["score"].cpu().numpy()
+        with np.errstate(all="ignore"):
+            err = np.abs(sc - vals) / np.maximum(np.abs(vals), 1e-300)
+        err[sc == vals] = 0
+        n_leaf = min(4096, sample)
+        lv = forest.rf_eval(self.forests, X32[:, :n_leaf].contiguous(), want_leaves=True)["leaves"]
+        leaf_exact = all(np.array_equal(lv[m].cpu().numpy().astype(np.int64),
+                                        oracle.rf_apply(self._fas[o], np.ascontiguousarray(X[:n_leaf])))
+                         for m, o in enumerate(wl.objectives))
+
+        def exact_rows(idx):
+            sub = X32[:, torch.as_tensor(np.asarray(idx, dtype=np.int64), device="cuda")].contiguous()
+            leaves = [t.cpu().numpy() for t in forest.rf_eval(self.forests, sub, want_leaves=True)["leaves"]]
+            return exact.reference_rf_scores_from_leaves(wl.acquisition, wl.scalarization, wl.models, leaves,
+                                                         wl.objective_weights, wl.objective_limits,
+                                                         wl.iteration_number, wl.data_array)
+        got = exact.exact_min_indices(out["score"], self.k, exact_rows)
+        raw = forest.topk(out["score"], self.k)[1].cpu().numpy()
+        res = {"sample": sample, "leaves_bit_exact": bool(leaf_exact), "leaves_checked": n_leaf * wl.n_trees * len(wl.objectives),
+               "mean_bit_exact": bool(mean_exact), "score_max_rel_err": float(err.max()), "score_tol": 1e-5,
+               "topk_identical": bool(np.array_equal(got, top)), "topk_identical_without_rescore": bool(np.array_equal(raw, top)),
+               "near_tie_rescores": dict(exact.stats_counters)}
+        res["ok"] = bool(leaf_exact and mean_exact and err.max() <= 1e-5 and res["topk_identical"])
+        return res
 
     def setup_device(self, N, rank):
         import torch
@@ -333,8 +373,11 @@ class SpaceRFBench(RFBench):
         for o, fa in self._fas.items():
             means[o], variances[o], _ = oracle.rf_mean_var_omp(fa, X)
         vals = oracle.EI(means, variances, wl.data_array, wl.objective_weights, wl.scalarization, wl.objective_limits)
-        oracle.get_min_indices_fast(vals, self.k)
-        return time.perf_counter() - t0
+        top = oracle.get_min_indices_fast(vals, self.k)
+        dt = time.perf_counter() - t0
+        self._Xcpu = {sample: X.astype(np.float32)}
+        self._cpu_out = (sample, means, vals, top)
+        return dt
 
     def setup_device(self, N, rank):
         import torch
@@ -469,8 +512,36 @@ class GPBench:
         t0 = time.perf_counter()
         mean, var = oracle.gp_predict(self._st, self._Xs)
         vals = oracle.EI({"Value": mean}, {"Value": var}, self.data, self.weights, "tchebyshev", self.limits)
-        oracle.get_min_indices_fast(vals, self.k)
-        return time.perf_counter() - t0
+        top = oracle.get_min_indices_fast(vals, self.k)
+        dt = time.perf_counter() - t0
+        self._cpu_out = (sample, mean, var, vals, top)
+        return dt
+
+    def parity(self):
+        """GPU posterior mean / variance / EI on the CPU leg's sample against the oracle (pinned to scikit-learn's GPR,
+        tests/golden/gp_sklearn.npz): 1e-5 relative (mean: relative to max(|mean|, 1e-3 std(y)); variance: plus the
+        rounding floor of the cancellation sf2 - |L^-1 k|^2), top-k identical."""
+        import torch
+        from hypermapper_b200 import forest, gp, models
+        sample, mean_o, var_o, vals, top = self._cpu_out
+        X64 = torch.from_numpy(np.ascontiguousarray(self._Xs.T)).cuda()
+        mean = torch.empty((1, sample), dtype=torch.float64, device="cuda")
+        var = torch.empty_like(mean)
+        gp.gp_mean_var(self.dgp, X64, mean[0], var[0])
+        sc = models.acq_score_device(self.acq, mean, var)
+        m, v, s = mean[0].cpu().numpy(), var[0].cpu().numpy(), sc.cpu().numpy()
+        ystd = float(np.std(self.y))
+        em = float(np.max(np.abs(m - mean_o) / np.maximum(np.abs(mean_o), 1e-3 * ystd)))
+        floor = 64 * self.n * np.finfo(np.float64).eps * self.state.variance * self.state.y_std ** 2
+        ev = float(np.max(np.maximum(np.abs(v - var_o) - floor, 0) / var_o))
+        with np.errstate(all="ignore"):
+            es = np.abs(s - vals) / np.maximum(np.abs(vals), 1e-300)
+        es[s == vals] = 0
+        got = forest.topk(sc, self.k)[1].cpu().numpy()
+        res = {"sample": sample, "mean_max_rel_err": em, "var_max_rel_err": ev, "score_max_rel_err": float(es.max()),
+               "tol": 1e-5, "topk_identical": bool(np.array_equal(got, top))}
+        res["ok"] = bool(em <= 1e-5 and ev <= 1e-5 and es.max() <= 1e-5 and res["topk_identical"])
+        return res
 
     def setup_device(self, N, rank):
         import torch
@@ -555,8 +626,19 @@ class ParetoBench:
         from oracle import oracle
         c = np.random.default_rng(7).random((sample, self.M))
         t0 = time.perf_counter()
-        oracle.pareto(c)
-        return time.perf_counter() - t0
+        mask = oracle.pareto(c)
+        dt = time.perf_counter() - t0
+        self._cpu_out = (sample, c, mask)
+        return dt
+
+    def parity(self):
+        """the GPU mask on the CPU leg's points == the oracle's mask, bit for bit"""
+        import torch
+        from hypermapper_b200 import compute_pareto
+        sample, c, mask = self._cpu_out
+        got = compute_pareto.pareto_mask_device(torch.from_numpy(c).cuda()).cpu().numpy().astype(bool)
+        same = bool(np.array_equal(got, np.asarray(mask).astype(bool)))
+        return {"sample": sample, "mask_bit_exact": same, "front_size": int(got.sum()), "ok": same}
 
     def setup_device(self, N, rank):
         import torch
@@ -737,6 +819,7 @@ def main():
         if world == 1 and ti is not None:
             assert torch.equal(ti.cpu(), res[1].cpu()), "e2e and device-resident top-k differ"
 
+    parity_failed = False
     if rank == 0:
         roof = b.roofline(N, kernel_ms)
         roof["share_of_step"] = kernel_ms / ms_per_step
@@ -754,9 +837,16 @@ def main():
             dt = b.cpu_port(sample)
             line["cpu_baseline"] = {"value": sample / dt, "unit": b.unit, "cores": threads, "kind": "port",
                                     "sample": "%d units of the same workload (%.1f s); %s" % (sample, dt, b.cpu_desc)}
+            # parity gate: no throughput number counts unless the GPU path reproduces the oracle
+            # on the sample the CPU leg just scored
+            line["parity"] = b.parity()
+            parity_failed = not line["parity"]["ok"]
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if parity_failed:
+        sys.stderr.write("bench.py: PARITY GATE FAILED: %s\n" % json.dumps(line["parity"]))
+        sys.exit(1)
 
 
 if __name__ == "__main__":

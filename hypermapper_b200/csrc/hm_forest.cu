@@ -302,6 +302,9 @@ extern "C" int hm_forest_create(int n_trees, int n_features, const int64_t* off,
     HM_F_TRY(cudaMemcpy(F->d_leaf_tab, leaf_tab.data(), leaf_tab.size() * sizeof(double), cudaMemcpyHostToDevice));
     HM_F_TRY(cudaMemcpy(F->d_leaf_node, leaf_node.data(), leaf_node.size() * sizeof(int), cudaMemcpyHostToDevice));
     HM_F_TRY(cudaMemcpy(F->d_leaf_rank, leaf_rank.data(), leaf_rank.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+    // the handle is consumed on caller streams (often cudaStreamNonBlocking) that do not order against the legacy
+    // stream these pageable-memory uploads went through
+    HM_F_TRY(cudaDeviceSynchronize());
 #undef HM_F_TRY
     F->dev.blob = (const unsigned char*)F->d_blob;
     F->dev.groups = (const HmGroupDesc*)F->d_groups;
@@ -881,7 +884,8 @@ extern "C" int hm_rf_eval(const hm_forest_t* const* forests, int M, const float*
     }
 #undef HM_LAUNCH
 #undef HM_LAUNCH_B
-    HM_CUDA_TRY(cudaGetLastError());
-    if (scratch) HM_CUDA_TRY(cudaFreeAsync(scratch, st));
+    const cudaError_t launch_err = cudaGetLastError();
+    if (scratch) cudaFreeAsync(scratch, st);          // also on a failed launch: the scratch must not leak
+    HM_CUDA_TRY(launch_err);
     return 0;
 }

@@ -184,6 +184,7 @@ extern "C" int hm_gp_create(int n, int D, const double* Xs, const double* ls, co
     HM_G_TRY(cudaMemcpy(g->d_alpha, ha.data(), ha.size() * 8, cudaMemcpyHostToDevice));
     HM_G_TRY(cudaMemcpy(g->d_LpF, hLp.data(), hLp.size() * 8, cudaMemcpyHostToDevice));
     HM_G_TRY(cudaMemcpy(g->d_ls, ls, (size_t)D * 8, cudaMemcpyHostToDevice));
+    HM_G_TRY(cudaDeviceSynchronize());      // consumed on non-blocking caller streams (see hm_forest_create)
 #undef HM_G_TRY
     *out = g;
     return 0;

@@ -6,6 +6,24 @@
 #include <new>
 #include "hm_common.cuh"
 
+// Error paths: the two non-blocking streams may still have asynchronous D2H copies in flight into CALLER-owned host
+// buffers (a numpy array that can be freed as soon as the binding raises), so both streams are drained before any
+// error code is returned.
+#define HM_HOST_FAIL(c, code)                  \
+    do {                                       \
+        cudaStreamSynchronize((c)->st[0]);     \
+        cudaStreamSynchronize((c)->st[1]);     \
+        return (code);                         \
+    } while (0)
+#define HM_HOST_TRY(c, x)                                               \
+    do {                                                                \
+        cudaError_t e__ = (x);                                          \
+        if (e__ != cudaSuccess) {                                       \
+            hm_set_error("%s: %s", #x, cudaGetErrorString(e__));        \
+            HM_HOST_FAIL(c, (int)e__);                                  \
+        }                                                               \
+    } while (0)
+
 struct hm_host_ctx {
     int64_t chunk;          // candidates per chunk
     int max_features;
@@ -94,30 +112,30 @@ extern "C" int hm_rf_score_host(hm_host_ctx_t* c, const hm_forest_t* const* fore
         const int64_t n = std::min<int64_t>(c->chunk, N - lo);
         cudaStream_t st = c->st[b];
         // [D][n] slab of the column-major host matrix -> dense [D][n] device buffer
-        HM_CUDA_TRY(cudaMemcpy2DAsync(c->d_x[b], (size_t)n * sizeof(float), X_host + lo, (size_t)ldx * sizeof(float),
+        HM_HOST_TRY(c, cudaMemcpy2DAsync(c->d_x[b], (size_t)n * sizeof(float), X_host + lo, (size_t)ldx * sizeof(float),
                                       (size_t)n * sizeof(float), (size_t)D, cudaMemcpyHostToDevice, st));
         int rc = hm_rf_eval(forests, M, c->d_x[b], n, n, nullptr, nullptr, nullptr, nullptr, acq, nullptr,
                             c->d_scores + lo, (void*)st);
-        if (rc) return rc;
+        if (rc) HM_HOST_FAIL(c, rc);
         if (score_out_host)
-            HM_CUDA_TRY(cudaMemcpyAsync(score_out_host + lo, c->d_scores + lo, (size_t)n * sizeof(double),
+            HM_HOST_TRY(c, cudaMemcpyAsync(score_out_host + lo, c->d_scores + lo, (size_t)n * sizeof(double),
                                         cudaMemcpyDeviceToHost, st));
     }
     if (k > 0) {
         // stream 0 waits for stream 1's kernels, then selects over the whole score vector
         if (n_chunks > 1) {
-            HM_CUDA_TRY(cudaEventRecord(c->ev[1], c->st[1]));
-            HM_CUDA_TRY(cudaStreamWaitEvent(c->st[0], c->ev[1], 0));
+            HM_HOST_TRY(c, cudaEventRecord(c->ev[1], c->st[1]));
+            HM_HOST_TRY(c, cudaStreamWaitEvent(c->st[0], c->ev[1], 0));
         }
         int rc = hm_topk(c->d_scores, N, 0, k, c->d_topk_vals, c->d_topk_idx, c->d_topk_ws, (void*)c->st[0]);
-        if (rc) return rc;
-        HM_CUDA_TRY(cudaMemcpyAsync(topk_vals_host, c->d_topk_vals, (size_t)k * sizeof(double), cudaMemcpyDeviceToHost,
+        if (rc) HM_HOST_FAIL(c, rc);
+        HM_HOST_TRY(c, cudaMemcpyAsync(topk_vals_host, c->d_topk_vals, (size_t)k * sizeof(double), cudaMemcpyDeviceToHost,
                                     c->st[0]));
-        HM_CUDA_TRY(cudaMemcpyAsync(topk_idx_host, c->d_topk_idx, (size_t)k * sizeof(int64_t), cudaMemcpyDeviceToHost,
+        HM_HOST_TRY(c, cudaMemcpyAsync(topk_idx_host, c->d_topk_idx, (size_t)k * sizeof(int64_t), cudaMemcpyDeviceToHost,
                                     c->st[0]));
     }
-    HM_CUDA_TRY(cudaStreamSynchronize(c->st[0]));
-    HM_CUDA_TRY(cudaStreamSynchronize(c->st[1]));
+    HM_HOST_TRY(c, cudaStreamSynchronize(c->st[0]));
+    HM_HOST_TRY(c, cudaStreamSynchronize(c->st[1]));
     return 0;
 }
 
@@ -161,33 +179,33 @@ extern "C" int hm_rf_score_raw_host(hm_host_ctx_t* c, const hm_space_t* space, c
         const int b = n_chunks & 1;
         const int64_t n = std::min<int64_t>(c->chunk, N - lo);
         cudaStream_t st = c->st[b];
-        HM_CUDA_TRY(cudaMemcpyAsync(c->d_raw[b], raw_host + (size_t)lo * Dr, (size_t)n * Dr * sizeof(double),
+        HM_HOST_TRY(c, cudaMemcpyAsync(c->d_raw[b], raw_host + (size_t)lo * Dr, (size_t)n * Dr * sizeof(double),
                                     cudaMemcpyHostToDevice, st));
         int rc = hm_encode(space, c->d_raw[b], 0, Dr, n, c->d_x[b], n, nullptr, 0, c->d_invalid, (void*)st);
-        if (rc) return rc;
+        if (rc) HM_HOST_FAIL(c, rc);
         rc = hm_rf_eval(forests, M, c->d_x[b], n, n, nullptr, nullptr, nullptr, nullptr, acq, nullptr,
                         c->d_scores + lo, (void*)st);
-        if (rc) return rc;
+        if (rc) HM_HOST_FAIL(c, rc);
         if (score_out_host)
-            HM_CUDA_TRY(cudaMemcpyAsync(score_out_host + lo, c->d_scores + lo, (size_t)n * sizeof(double),
+            HM_HOST_TRY(c, cudaMemcpyAsync(score_out_host + lo, c->d_scores + lo, (size_t)n * sizeof(double),
                                         cudaMemcpyDeviceToHost, st));
     }
     if (n_chunks > 1) {
-        HM_CUDA_TRY(cudaEventRecord(c->ev[1], c->st[1]));
-        HM_CUDA_TRY(cudaStreamWaitEvent(c->st[0], c->ev[1], 0));
+        HM_HOST_TRY(c, cudaEventRecord(c->ev[1], c->st[1]));
+        HM_HOST_TRY(c, cudaStreamWaitEvent(c->st[0], c->ev[1], 0));
     }
     if (k > 0) {
         int rc = hm_topk(c->d_scores, N, 0, k, c->d_topk_vals, c->d_topk_idx, c->d_topk_ws, (void*)c->st[0]);
-        if (rc) return rc;
-        HM_CUDA_TRY(cudaMemcpyAsync(topk_vals_host, c->d_topk_vals, (size_t)k * sizeof(double), cudaMemcpyDeviceToHost,
+        if (rc) HM_HOST_FAIL(c, rc);
+        HM_HOST_TRY(c, cudaMemcpyAsync(topk_vals_host, c->d_topk_vals, (size_t)k * sizeof(double), cudaMemcpyDeviceToHost,
                                     c->st[0]));
-        HM_CUDA_TRY(cudaMemcpyAsync(topk_idx_host, c->d_topk_idx, (size_t)k * sizeof(int64_t), cudaMemcpyDeviceToHost,
+        HM_HOST_TRY(c, cudaMemcpyAsync(topk_idx_host, c->d_topk_idx, (size_t)k * sizeof(int64_t), cudaMemcpyDeviceToHost,
                                     c->st[0]));
     }
     int32_t bad = 0;
-    HM_CUDA_TRY(cudaMemcpyAsync(&bad, c->d_invalid, sizeof(int32_t), cudaMemcpyDeviceToHost, c->st[0]));
-    HM_CUDA_TRY(cudaStreamSynchronize(c->st[0]));
-    HM_CUDA_TRY(cudaStreamSynchronize(c->st[1]));
+    HM_HOST_TRY(c, cudaMemcpyAsync(&bad, c->d_invalid, sizeof(int32_t), cudaMemcpyDeviceToHost, c->st[0]));
+    HM_HOST_TRY(c, cudaStreamSynchronize(c->st[0]));
+    HM_HOST_TRY(c, cudaStreamSynchronize(c->st[1]));
     if (n_invalid_out_host) *n_invalid_out_host = bad;
     return 0;
 }
@@ -234,34 +252,34 @@ extern "C" int hm_gp_score_host(hm_host_ctx_t* c, const hm_gp_t* const* gps, int
         const int b = n_chunks & 1;
         const int64_t n = std::min<int64_t>(c->chunk, N - lo);
         cudaStream_t st = c->st[b];
-        HM_CUDA_TRY(cudaMemcpy2DAsync(c->d_raw[b], (size_t)n * sizeof(double), X_host + lo, (size_t)ldx * sizeof(double),
+        HM_HOST_TRY(c, cudaMemcpy2DAsync(c->d_raw[b], (size_t)n * sizeof(double), X_host + lo, (size_t)ldx * sizeof(double),
                                       (size_t)n * sizeof(double), (size_t)D, cudaMemcpyHostToDevice, st));
         double* mean = c->d_mv[b];
         double* var = c->d_mv[b] + (size_t)M * c->chunk;
         for (int m = 0; m < M; ++m) {
             int rc = hm_gp_mean_var(gps[m], c->d_raw[b], n, n, mean + (size_t)m * c->chunk, var + (size_t)m * c->chunk,
                                     (void*)st);
-            if (rc) return rc;
+            if (rc) HM_HOST_FAIL(c, rc);
         }
         int rc = hm_acq_score(acq, mean, var, c->chunk, nullptr, n, c->d_scores + lo, (void*)st);
-        if (rc) return rc;
+        if (rc) HM_HOST_FAIL(c, rc);
         if (score_out_host)
-            HM_CUDA_TRY(cudaMemcpyAsync(score_out_host + lo, c->d_scores + lo, (size_t)n * sizeof(double),
+            HM_HOST_TRY(c, cudaMemcpyAsync(score_out_host + lo, c->d_scores + lo, (size_t)n * sizeof(double),
                                         cudaMemcpyDeviceToHost, st));
     }
     if (k > 0) {
         if (n_chunks > 1) {
-            HM_CUDA_TRY(cudaEventRecord(c->ev[1], c->st[1]));
-            HM_CUDA_TRY(cudaStreamWaitEvent(c->st[0], c->ev[1], 0));
+            HM_HOST_TRY(c, cudaEventRecord(c->ev[1], c->st[1]));
+            HM_HOST_TRY(c, cudaStreamWaitEvent(c->st[0], c->ev[1], 0));
         }
         int rc = hm_topk(c->d_scores, N, 0, k, c->d_topk_vals, c->d_topk_idx, c->d_topk_ws, (void*)c->st[0]);
-        if (rc) return rc;
-        HM_CUDA_TRY(cudaMemcpyAsync(topk_vals_host, c->d_topk_vals, (size_t)k * sizeof(double), cudaMemcpyDeviceToHost,
+        if (rc) HM_HOST_FAIL(c, rc);
+        HM_HOST_TRY(c, cudaMemcpyAsync(topk_vals_host, c->d_topk_vals, (size_t)k * sizeof(double), cudaMemcpyDeviceToHost,
                                     c->st[0]));
-        HM_CUDA_TRY(cudaMemcpyAsync(topk_idx_host, c->d_topk_idx, (size_t)k * sizeof(int64_t), cudaMemcpyDeviceToHost,
+        HM_HOST_TRY(c, cudaMemcpyAsync(topk_idx_host, c->d_topk_idx, (size_t)k * sizeof(int64_t), cudaMemcpyDeviceToHost,
                                     c->st[0]));
     }
-    HM_CUDA_TRY(cudaStreamSynchronize(c->st[0]));
-    HM_CUDA_TRY(cudaStreamSynchronize(c->st[1]));
+    HM_HOST_TRY(c, cudaStreamSynchronize(c->st[0]));
+    HM_HOST_TRY(c, cudaStreamSynchronize(c->st[1]));
     return 0;
 }

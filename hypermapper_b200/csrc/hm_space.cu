@@ -82,6 +82,7 @@ extern "C" int hm_space_create(int n_params, const hm_param_desc_t* params_host,
     HM_S_TRY(cudaMalloc((void**)&S->d_tables, sizeof(double) * std::max<long long>(n_tables, 1)));
     if (n_tables)
         HM_S_TRY(cudaMemcpy(S->d_tables, tables_host, sizeof(double) * n_tables, cudaMemcpyHostToDevice));
+    HM_S_TRY(cudaDeviceSynchronize());      // consumed on non-blocking caller streams (see hm_forest_create)
 #undef HM_S_TRY
     *out = S;
     return 0;

@@ -12,7 +12,7 @@ import numpy as np
 from . import _lib
 
 
-def forest_tables(model, value_column=0):
+def forest_tables(model, value_column=0, normalize_value=False):
     """Flatten `model` (reference RFModel, or any sklearn forest) into the host arrays hm_forest_create takes.
 
     The three per-leaf fp64 tables are computed here with the reference's own scalar arithmetic so that the
@@ -46,7 +46,15 @@ def forest_tables(model, value_column=0):
         right[b:e] = tr.children_right
         feature[b:e] = tr.feature
         threshold[b:e] = tr.threshold
-        value[b:e] = np.asarray(tr.value, dtype=np.float64).reshape(e - b, -1)[:, value_column]
+        val = np.asarray(tr.value, dtype=np.float64).reshape(e - b, -1)
+        if normalize_value:
+            # class fractions whatever the scikit-learn version: tree_.value holds weighted class COUNTS before 1.4
+            # and fractions from 1.4 on; predict_proba normalises per node (sklearn/tree/_classes.py), so do the same
+            tot = val.sum(axis=1)
+            tot[tot == 0.0] = 1.0
+            value[b:e] = val[:, value_column] / tot
+        else:
+            value[b:e] = val[:, value_column]
         if means is not None:
             for leaf, m in means[t].items():
                 q[b + int(leaf)] = m / T
@@ -112,13 +120,26 @@ class DeviceForest:
 _cache = weakref.WeakKeyDictionary()
 
 
+def _model_stamp(model):
+    """Identity of what a DeviceForest was flattened from.  A new fit creates new estimator objects; the reference's
+    fit_RF (models.py:184-223) additionally fills the Hutter tables and rewrites tree_.threshold IN PLACE after the
+    sklearn fit, so the stamp also covers the tables (identity + length) and the threshold bytes of the first, middle and
+    last tree (fit_RF re-draws the splits of every tree; three crc32s keep the check off the hill climb's latency path)."""
+    import zlib
+    ests = model.estimators_
+    means = getattr(model, "tree_means_per_leaf", None)
+    crc = 0
+    for t in sorted({0, len(ests) // 2, len(ests) - 1}):
+        crc = zlib.crc32(np.ascontiguousarray(ests[t].tree_.threshold).view(np.uint8), crc)
+    return (id(ests), len(ests), id(ests[0].tree_), id(ests[-1].tree_), id(means), len(means) if means else 0, crc)
+
+
 def device_forest(model):
-    """DeviceForest for a fitted model, cached on the model object (a new fit creates new estimator objects,
-    which invalidates the entry)."""
+    """DeviceForest for a fitted model, cached on the model object and rebuilt whenever the model's trees, thresholds or
+    Hutter tables changed (see _model_stamp)."""
     if isinstance(model, DeviceForest):
         return model
-    ests = model.estimators_
-    stamp = (id(ests), len(ests), id(ests[0].tree_), id(ests[-1].tree_))
+    stamp = _model_stamp(model)
     try:
         hit = _cache.get(model)
     except TypeError:
@@ -146,7 +167,7 @@ def classifier_forest(clf, cls):
     hit = _clf_cache.get(clf)
     if hit is not None and stamp in hit:
         return hit[stamp]
-    df = DeviceForest(forest_tables(_NoHutter(clf), value_column=col))
+    df = DeviceForest(forest_tables(_NoHutter(clf), value_column=col, normalize_value=True))
     _clf_cache.setdefault(clf, {})[stamp] = df
     return df
 

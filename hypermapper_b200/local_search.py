@@ -12,9 +12,14 @@
 pools bypass the list-of-dicts form.  The multi-process branches of the reference (number_of_cpus != 1) are not
 reproduced: a CUDA context must not be forked, and the GPU replaces the worker pool.
 
-Known non-determinism of the reference that cannot be matched bit for bit: the column order used by the
-duplicate filter comes from iterating a Python `set` of key strings (utility_functions.py:237-239 via
-local_search.py:666-675), which changes with the interpreter's hash seed; input-parameter order is used here.
+Known non-determinism of the reference: the column order used by the duplicate filter comes from iterating a Python
+`set` of key strings (utility_functions.py:237-239 via local_search.py:666-675), which changes with the interpreter's
+string-hash seed.  Input-parameter order (scalarization key last) is used here; `set_dedup_column_order` pins any other
+order, e.g. the one a recorded reference run used (tests/golden/local_search_traj.npz).
+
+Selection identity: the seeds, every hill-climb move and the final pick are argmins over acquisition values; where the
+scorer provides `exact_scores` (run_acquisition_function on random forests) the distinct device values that are closer
+than 1e-9 relative are re-scored on the host with the reference's own arithmetic before they are ordered (exact.py).
 """
 import copy
 import datetime
@@ -24,6 +29,7 @@ import sys
 import numpy as np
 from scipy import stats
 
+from .exact import NEAR_TIE_REL, exact_argmin_host, exact_min_indices
 from .utility_functions import (
     are_configurations_equal,
     concatenate_data_dictionaries,
@@ -63,6 +69,26 @@ def _use_device_pools(n_points):
     if _device_pools == "auto":
         return n_points >= DEVICE_POOL_AUTO_POINTS
     return bool(_device_pools)
+
+
+_dedup_column_order = None
+
+
+def set_dedup_column_order(keys):
+    """None (input-parameter order + scalarization key) or the explicit list of column keys the duplicate filter of
+    local_search.py:673-699 should see (what iterating the reference's key `set` gave in a recorded run)."""
+    global _dedup_column_order
+    _dedup_column_order = None if keys is None else list(keys)
+
+
+def _pool_rows_matrix(pool, inputs, rows):
+    """raw parameter values [n][D] fp64 of the given pool rows (categoricals as indices)"""
+    rows = [int(r) for r in rows]
+    if hasattr(pool, "candidates"):
+        return pool.ds.sample_rows(pool.seed, pool.use_priors, np.asarray(rows, dtype=np.int64))
+    if isinstance(pool, list):
+        return np.array([[float(pool[r][p]) for p in inputs] for r in rows], dtype=np.float64).reshape(len(rows), len(inputs))
+    return np.asarray(pool[rows], dtype=np.float64).reshape(len(rows), len(inputs))
 
 
 def _log(msg, verbose=False):
@@ -182,8 +208,18 @@ def _values_at(values, rows):
     return values[torch.as_tensor(np.asarray(rows, dtype=np.int64), device=values.device)].cpu().tolist()
 
 
+def _exact_rows_fn(exact_fn, params, rows_of_positions):
+    """positions -> exact reference values, or None when the scorer has no exact re-score"""
+    if exact_fn is None:
+        return None
+
+    def f(positions):
+        return exact_fn(np.asarray(rows_of_positions(positions), dtype=np.float64), **params)
+    return f
+
+
 def _hill_climb(start, param_space, inputs, optimization_function, params, enable_feasible_predictor,
-                scalarization_key, feasible_parameter):
+                scalarization_key, feasible_parameter, exact_fn=None):
     """One start of the multi-start local search (local_search.py:337-386)."""
     iteration_data = {}
     configuration = start
@@ -199,6 +235,10 @@ def _hill_climb(start, param_space, inputs, optimization_function, params, enabl
         iteration_data = concatenate_data_dictionaries(iteration_data, batch)
         if enable_feasible_predictor:
             best = get_min_feasible_configurations(batch, 1, scalarization_key, feasible_parameter)
+        elif exact_fn is not None and m > 0:
+            q = exact_argmin_host(list(values), _exact_rows_fn(
+                exact_fn, params, lambda pos: [[float(neighbors[i][p]) for p in inputs] for i in pos]))
+            best = {key: [col[q]] for key, col in batch.items()}
         else:
             best = get_min_configurations(batch, 1, scalarization_key)
         current = {k: [v] for k, v in configuration.items()}
@@ -243,7 +283,7 @@ def set_lockstep(mode):
     _lockstep = mode
 
 
-def _hill_climb_lockstep(start_list, param_space, inputs, device_scorer, params, scalarization_key):
+def _hill_climb_lockstep(start_list, param_space, inputs, device_scorer, params, scalarization_key, exact_fn=None):
     """All starts in lock-step; returns [(iteration_data, log)] in start order.  Rows and scores are kept as plain
     lists per start and turned into the reference's dict-of-lists once, at the end (the per-round dict concatenations
     of the sequential version are most of its host time)."""
@@ -264,8 +304,9 @@ def _hill_climb_lockstep(start_list, param_space, inputs, device_scorer, params,
             pos += len(b)
             rows_of[s].extend(b)
             vals_of[s].extend(values)
-            # get_min_configurations(batch, 1): first index of the minimum, NaN first, -0.0 == +0.0
-            k = min(range(len(values)), key=lambda i: (0, 0.0) if values[i] != values[i] else (1, values[i] + 0.0))
+            # get_min_configurations(batch, 1): first index of the minimum, NaN first, -0.0 == +0.0 (near ties between
+            # distinct values are settled with the reference's arithmetic)
+            k = exact_argmin_host(values, _exact_rows_fn(exact_fn, params, lambda pos, b=b: [b[i] for i in pos]))
             best = dict(zip(inputs, b[k]))
             best[scalarization_key] = values[k]
             shown = {key: [v] for key, v in best.items()}
@@ -302,7 +343,7 @@ def neighbor_plan(param_space):
     return np.asarray(plan, dtype=np.int32).reshape(-1, 2)
 
 
-def _hill_climb_device(start_list, param_space, inputs, device_scorer, params, scalarization_key):
+def _hill_climb_device(start_list, param_space, inputs, device_scorer, params, scalarization_key, exact_fn=None):
     """The lock-step hill climb with the neighbourhoods generated and the moves decided on the GPU (hm_ls_neighbors /
     hm_ls_move); per round: one neighbour launch, the scoring launches, one move launch and one 4-byte-per-start
     read-back of the convergence flags.  Same trajectories, same returned data as _hill_climb_lockstep."""
@@ -325,6 +366,7 @@ def _hill_climb_device(start_list, param_space, inputs, device_scorer, params, s
     rounds = []                      # (live list, rows [n_live*K][D], scores [n_live*K], best_q snapshot, converged snapshot)
     while live:
         live_d = torch.tensor(live, dtype=torch.int32, device="cuda")
+        start_of_round = current.clone() if exact_fn is not None else None
         rows = torch.empty((len(live) * K, D), dtype=torch.float64, device="cuda")
         _lib.check(L.hm_ls_neighbors(ds.handle, _lib.dptr(plan_d), K, _lib.dptr(current), _lib.dptr(live_d), len(live),
                                      _lib.dptr(rows), _lib.stream_ptr()), "hm_ls_neighbors")
@@ -332,6 +374,23 @@ def _hill_climb_device(start_list, param_space, inputs, device_scorer, params, s
         _lib.check(L.hm_ls_move(_lib.dptr(scores), _lib.dptr(rows), K, D, _lib.dptr(live_d), len(live),
                                 _lib.dptr(current), _lib.dptr(converged), _lib.dptr(best_q), _lib.stream_ptr()),
                    "hm_ls_move")
+        if exact_fn is not None:
+            # near ties between DISTINCT values inside a neighbourhood: the device move stands unless the reference's own
+            # arithmetic orders them differently (rare; the start's state is then rewritten from the host)
+            sh = scores.view(len(live), K).cpu().numpy()
+            with np.errstate(all="ignore"):
+                mn = sh.min(axis=1, keepdims=True)
+                suspicious = np.isfinite(mn[:, 0]) & ((sh <= mn + NEAR_TIE_REL * np.abs(mn)) & (sh != mn)).any(axis=1)
+            for l in np.nonzero(suspicious)[0]:
+                s_id = live[l]
+                rows_l = rows.view(len(live), K, D)[l]
+                q = exact_argmin_host(sh[l].tolist(), _exact_rows_fn(
+                    exact_fn, params, lambda pos, r=rows_l: r[torch.as_tensor(pos, device="cuda")].cpu().numpy()))
+                if q != int(best_q[s_id].item()):
+                    best_q[s_id] = q
+                    same = bool(torch.equal(rows_l[q], start_of_round[s_id]))
+                    converged[s_id] = 1 if same else 0
+                    current[s_id] = rows_l[q] if not same else start_of_round[s_id]
         flags = converged.cpu().numpy()
         rounds.append((live, rows, scores, best_q.cpu().numpy().copy(), flags.copy()))
         live = [s for s in live if not flags[s]]
@@ -386,6 +445,9 @@ def local_search(local_search_starting_points, local_search_random_points, param
     feasible_parameter = param_space.get_feasible_parameter()[0]
     params = optimization_function_parameters
     device_scorer = None if enable_feasible_predictor else _device_scorer(optimization_function)
+    exact_fn = None if enable_feasible_predictor else getattr(optimization_function, "exact_scores", None)
+    if exact_fn is not None and exact_fn(np.zeros((0, len(inputs))), **params) is None:
+        exact_fn = None                                       # e.g. GP models: no bit-exact host restatement
     oversampling_factor = 2
 
     # (kept for RNG / side-effect parity with local_search.py:429-432; the hash table copy is not used afterwards)
@@ -421,6 +483,12 @@ def local_search(local_search_starting_points, local_search_random_points, param
     # ---- seeds: 2*starting_points best of each pool, ranked separately (local_search.py:625-645) ------------
     k = local_search_starting_points * oversampling_factor
 
+    def _select(pool, vals, kk):
+        """indices of the kk smallest values in the reference's order (device top-k; near ties re-scored exactly)"""
+        if exact_fn is None or isinstance(vals, list):
+            return min_indices(vals, kk)
+        return exact_min_indices(vals, kk, lambda idx: exact_fn(_pool_rows_matrix(pool, inputs, idx), **params))
+
     def best_of(pool, values, n_eval):
         if enable_feasible_predictor:
             d = concatenate_list_of_dictionaries(_rows_to_dicts(pool, inputs, range(n_eval)))
@@ -429,7 +497,7 @@ def local_search(local_search_starting_points, local_search_random_points, param
             d[feasible_parameter] = [1] * n_eval
             return get_min_feasible_configurations(d, k, scalarization_key, feasible_parameter)
         vals = values if not isinstance(values, list) else values[:n_eval]
-        rows = [int(i) for i in min_indices(vals, k)]
+        rows = [int(i) for i in _select(pool, vals, k)]
         d = concatenate_list_of_dictionaries(_rows_to_dicts(pool, inputs, rows)) if rows else {p: [] for p in inputs}
         d[scalarization_key] = _values_at(values, rows)
         return d
@@ -451,16 +519,22 @@ def local_search(local_search_starting_points, local_search_random_points, param
 
     # duplicate filter (local_search.py:673-699 -> space.remove_duplicate_configs): first occurrence wins in the order
     # previous > prior > uniform; every group comes back sorted lexicographically by parameter values.
-    table = np.zeros((len(seeds[scalarization_key]), len(keys)), dtype=np.dtype(object))
-    for j, key in enumerate(keys):
+    table_keys = keys
+    if _dedup_column_order is not None:
+        if sorted(_dedup_column_order) != sorted(keys):
+            raise ValueError("set_dedup_column_order: keys must be a permutation of %r" % (keys,))
+        table_keys = list(_dedup_column_order)
+    table = np.zeros((len(seeds[scalarization_key]), len(table_keys)), dtype=np.dtype(object))
+    for j, key in enumerate(table_keys):
         table[:, j] = seeds[key]
     grp_u = table[0:n_seed_u]
     grp_p = table[n_seed_u:n_seed_u + n_seed_p]
     grp_prev = table[n_seed_u + n_seed_p:]
-    grp_prev, grp_p, grp_u = param_space.remove_duplicate_configs(grp_prev, grp_p, grp_u, ignore_columns=len(inputs))
+    grp_prev, grp_p, grp_u = param_space.remove_duplicate_configs(grp_prev, grp_p, grp_u,
+                                                                  ignore_columns=table_keys.index(scalarization_key))
     chosen = np.concatenate((grp_u[0:local_search_starting_points], grp_p[0:local_search_starting_points],
                              grp_prev[0:local_search_starting_points]), axis=0)
-    starts = {key: chosen[:, j].tolist() for j, key in enumerate(keys)}
+    starts = {key: chosen[:, j].tolist() for j, key in enumerate(table_keys)}
     data_collection_time = datetime.datetime.now()
     n_starts = len(starts[scalarization_key])
     _log("Starting local search iteration: " + ", #configs:" + str(n_starts) + "\n")
@@ -474,12 +548,12 @@ def local_search(local_search_starting_points, local_search_random_points, param
                                               (_lockstep == "auto" and not _neighbors_use_rng(param_space) and
                                                getattr(device_scorer, "batch_invariant", False)))
     if lockstep and _device_climb and _all_discrete(param_space) and n_starts > 0:
-        climbs = _hill_climb_device(start_list, param_space, inputs, device_scorer, params, scalarization_key)
+        climbs = _hill_climb_device(start_list, param_space, inputs, device_scorer, params, scalarization_key, exact_fn)
     elif lockstep:
-        climbs = _hill_climb_lockstep(start_list, param_space, inputs, device_scorer, params, scalarization_key)
+        climbs = _hill_climb_lockstep(start_list, param_space, inputs, device_scorer, params, scalarization_key, exact_fn)
     else:
         climbs = (_hill_climb(start, param_space, inputs, optimization_function, params, enable_feasible_predictor,
-                              scalarization_key, feasible_parameter) for start in start_list)
+                              scalarization_key, feasible_parameter, exact_fn) for start in start_list)
     for it_data, log in climbs:
         _log(log, verbose=True)
         result_array = concatenate_data_dictionaries(result_array, it_data)
@@ -511,9 +585,9 @@ def local_search(local_search_starting_points, local_search_random_points, param
     while best_configuration is None:
         cand = [(v, i) for i, v in enumerate(ls_vals)]
         horizons = []
-        for values, n_eval, off in ((val_u, n_u, off_u), (val_p, n_p, off_p)):
+        for pool, values, n_eval, off in ((pool_u, val_u, n_u, off_u), (pool_p, val_p, n_p, off_p)):
             vals = values if not isinstance(values, list) else values[:n_eval]
-            rows = [int(i) for i in min_indices(vals, min(want, n_eval))]
+            rows = [int(i) for i in _select(pool, vals, min(want, n_eval))]
             fetched = [(v, off + r) for v, r in zip(_values_at(values, rows), rows)]
             cand += fetched
             if n_eval > want and fetched:
@@ -521,18 +595,32 @@ def local_search(local_search_starting_points, local_search_random_points, param
         cand += [(v, off_prev + i) for i, v in enumerate(prev_vals)]
         cand.sort(key=lambda c: rank_key(*c))
         need_more = False
+        eligible = []          # the first configuration not evaluated yet + the ones whose value is a near tie with it
+        limit = None
         for v, pos in cand:
+            if limit is not None and not (v <= limit):
+                break
             if any(rank_key(v, pos) > h for h in horizons):
                 need_more = True
                 break
             conf = config_at(pos)
             if param_space.get_unique_hash_string_from_values(conf) not in fast_addressing_of_data_array:
-                best_configuration = conf
-                break
-        if best_configuration is None:
-            if not need_more:
-                raise ValueError("attempt to get argmin of an empty sequence")   # what np.argmin raises in the reference
-            want *= 8
+                eligible.append((v, pos, conf))
+                if limit is None:
+                    if exact_fn is None or v != v or v in (float("inf"), float("-inf")):
+                        break
+                    limit = v + NEAR_TIE_REL * abs(v)
+        if need_more:
+            want *= 8                                       # the answer (or its near-tie window) lies beyond what was fetched
+            continue
+        if not eligible:
+            raise ValueError("attempt to get argmin of an empty sequence")   # what np.argmin raises in the reference
+        pick = 0
+        if len({v + 0.0 for v, _, _ in eligible}) > 1:
+            # distinct values closer than 1e-9 relative: order them with the reference's own arithmetic
+            exact = exact_fn(np.array([[float(c[p]) for p in inputs] for _, _, c in eligible], dtype=np.float64), **params)
+            pick = min(range(len(eligible)), key=lambda i: rank_key(float(exact[i]), eligible[i][1]))
+        best_configuration = eligible[pick][2]
     post_time = datetime.datetime.now()
     _log("MSLS time %10.4f sec\n" % (post_time - acquisition_time).total_seconds())
 

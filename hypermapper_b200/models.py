@@ -127,11 +127,13 @@ def compute_rf_prediction_mean_and_uncertainty(bufferx, model, param_space, var=
 def rf_get_leaves_per_sample(model, bufferx, param_space=None):
     """RFModel.get_leaves_per_sample (models.py:174-182): bufferx is ALREADY encoded (list of tuples or [N][D_enc]
     array); returns int64 [T][N]."""
-    from .forest import device_forest, rf_eval
+    from .forest import DeviceForest, _NoHutter, forest_tables, rf_eval
     torch = _lib.require_cuda()
     X = np.asarray(bufferx, dtype=np.float64)
     X32 = torch.from_numpy(np.ascontiguousarray(X.astype(np.float32).T)).cuda()
-    out = rf_eval([device_forest(model)], X32, want_leaves=True)
+    # an UNCACHED, table-less forest: the reference's fit_RF calls this in the middle of the fit (models.py:200),
+    # before the Hutter tables exist and before the split thresholds are re-drawn in place
+    out = rf_eval([DeviceForest(forest_tables(_NoHutter(model)))], X32, want_leaves=True)
     return out["leaves"][0].cpu().numpy().astype(np.int64)
 
 

@@ -147,6 +147,32 @@ _device_scores.batch_invariant = True        # a candidate's score does not depe
 run_acquisition_function.device_scores = _device_scores
 
 
+def _exact_scores(rows, **p):
+    """The reference's own value of run_acquisition_function for a HANDFUL of candidates (rows: [n][D] raw values, or
+    an EncodedCandidates), used to order near-tied finalists exactly as the reference would (exact.py): the GPU
+    reports their leaf ids (integers, bit-exact) and -- with a feasibility classifier -- P(feasible) (bit-exact with
+    predict_proba); the Hutter tables, the variance with its libm pow and scipy's norm.cdf / pdf are evaluated on the
+    host.  Random forests only (returns None otherwise: GPy's arithmetic cannot be reproduced bit for bit)."""
+    if p["model_type"] != "random_forest":
+        return None
+    from . import exact
+    from .forest import device_forest, rf_eval
+    models_ = p["regression_models"]
+    objectives = list(models_.keys())
+    X32 = models.encode_to_device(rows, p["param_space"], "float32")
+    out = rf_eval([device_forest(models_[o]) for o in objectives], X32, want_leaves=True)
+    leaves = [lv.cpu().numpy() for lv in out["leaves"]]
+    feas = None
+    if p.get("classification_model") is not None:
+        feas = _feasibility_tensor(X32, p["classification_model"], p["param_space"]).cpu().numpy()
+    return exact.reference_rf_scores_from_leaves(p["acquisition_function"], p["scalarization_method"], models_, leaves,
+                                                 p["objective_weights"], p["objective_limits"], p["iteration_number"],
+                                                 p["data_array"], feas)
+
+
+run_acquisition_function.exact_scores = _exact_scores
+
+
 def _acq_from_bufferx(kind, bufferx, data_array, objective_weights, regression_models, param_space,
                       scalarization_method, objective_limits, iteration_number, model_type, classification_model):
     scores = acquisition_scores_device(kind, bufferx, objective_weights, regression_models, param_space,

@@ -111,6 +111,10 @@ def describe_space(param_space):
                 d.a, d.b = float(obj.alpha), float(obj.beta)
         elif kind == P_INTEGER:
             size = int(obj.get_max()) - int(obj.get_min()) + 1
+            if size > 2 ** 31 - 1:
+                # hm_sample_pool draws integer values with one 32-bit Philox word (csrc/hm_space.cu)
+                raise _lib.HmError("integer parameter %r spans %d values; the device sampler supports at most 2^31 - 1"
+                                   % (name, size))
             if prior == "distribution":
                 d.prior_kind = PRIOR_TABLE
                 d.n_prior = size

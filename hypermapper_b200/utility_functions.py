@@ -129,8 +129,16 @@ def min_indices(values, k):
             k = min(int(k), values.numel())
             if k == 0:
                 return np.zeros(0, dtype=np.int64)
-            _, idx = topk(values.contiguous().view(-1).to(torch.float64), k)
-            return idx.cpu().numpy()
+            v = values.contiguous().view(-1).to(torch.float64)
+            if k <= 1024:
+                _, idx = topk(v, k)
+                return idx.cpu().numpy()
+            # beyond the k <= 1024 limit of hm_topk (a pool whose best 256+ entries were all evaluated already, or
+            # local_search_starting_points > 512): full stable device sort on the same key
+            nan = torch.isnan(v)
+            order = torch.sort(torch.where(nan, torch.full_like(v, float("-inf")), v + 0.0), stable=True).indices
+            isn = nan[order]
+            return torch.cat([order[isn], order[~isn]])[:k].cpu().numpy()
     except ImportError:
         pass
     v = np.asarray(values, dtype=np.float64)

@@ -27,6 +27,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 
+# The reference iterates Python `set`s of key strings (utility_functions.py:237-239), so some of its results (the column
+# order of the duplicate filter in local_search.py:673-699, hence which seeds survive and in which order the hill climbs
+# consume numpy's RNG stream) depend on the interpreter's string-hash seed.  Pin it so that this script is reproducible.
+if os.environ.get("PYTHONHASHSEED") != "0":
+    os.environ["PYTHONHASHSEED"] = "0"
+    os.execv(sys.executable, [sys.executable] + sys.argv)
+
 from oracle import ref_harness  # noqa: E402
 
 ns = ref_harness.load()
@@ -430,6 +437,172 @@ def priors_case():
     print("priors.npz", {k: (v.shape, float(np.nanmin(v)), float(np.nanmax(v))) for k, v in out.items()
                          if k.startswith(("prior_", "pibo_", "bopro_"))})
 
+# ---------------------------------------------------------------------------------------------------------------------
+# local_search() trajectories on spaces WITH real / integer parameters (C1 = the bundled Branin scenario shape, and the
+# mixed space) and on the discrete space with a different training set per seed.  The neighbourhoods of real / integer
+# parameters draw truncated normals from numpy's global stream (local_search.py:138-157), so the RNG state right after
+# the two pools were drawn is frozen next to the pools: a replay that restores it consumes the very same numbers.
+# ---------------------------------------------------------------------------------------------------------------------
+def _traj_one(out, tag, config, space, models, data, objectives, weights, limits, seed, acq, scal, iteration,
+              n_points, n_starts):
+    inputs = space.get_input_parameters()
+    n_train = len(data[objectives[0]])
+    fast = {}
+    for r in range(n_train):
+        fast[space.get_unique_hash_string_from_values({k: data[k][r] for k in inputs})] = r
+    d2 = copy.deepcopy(data)
+    s, _ = ns.utility_functions.compute_data_array_scalarization(d2, weights, copy.deepcopy(limits), scal)
+    key = config["scalarization_key"]
+    d2[key] = s.tolist()
+    params = {"regression_models": models, "iteration_number": iteration, "data_array": d2,
+              "classification_model": None, "param_space": space, "objective_weights": weights,
+              "model_type": "random_forest", "objective_limits": copy.deepcopy(limits), "acquisition_function": acq,
+              "scalarization_method": scal, "number_of_cpus": 1}
+    pools, states, colorder = [], [], []
+    orig_sample = space.get_random_configuration
+    orig_numpy = ns.local_search.dict_of_lists_to_numpy
+
+    def sample(*a, **kw):
+        r = orig_sample(*a, **kw)
+        if kw.get("return_as_array"):
+            pools.append(np.array(r, dtype=np.float64))
+            states.append(np.random.get_state())
+        return r
+
+    def to_numpy(d, return_col_of_key=False):
+        r = orig_numpy(d, return_col_of_key=return_col_of_key)
+        if return_col_of_key:
+            colorder.append([k for k, _ in sorted(r[1].items(), key=lambda kv: kv[1])])
+        return r
+
+    space.get_random_configuration = sample
+    ns.local_search.dict_of_lists_to_numpy = to_numpy
+    np.random.seed(seed)
+    random.seed(seed)
+    try:
+        with ref_harness.logger_stdout():
+            data_array, best = ns.local_search.local_search(
+                n_starts, n_points, space, fast, False, ns.random_scalarizations.run_acquisition_function, params, key, 1,
+                previous_points=d2, profiling=None)
+    finally:
+        space.get_random_configuration = orig_sample
+        ns.local_search.dict_of_lists_to_numpy = orig_numpy
+    assert len(pools) == 2 and len(colorder) == 1
+    pre = "%s_" % tag
+    out[pre + "pool_uniform"] = pools[0]
+    out[pre + "pool_prior"] = pools[1]
+    st = states[1]
+    assert st[0] == "MT19937"
+    out[pre + "rng_keys"] = np.asarray(st[1], dtype=np.uint32)
+    out[pre + "rng_pos"] = np.array([st[2], st[3]], dtype=np.int64)
+    out[pre + "rng_gauss"] = np.array([st[4]], dtype=np.float64)
+    out[pre + "dedup_columns"] = np.array(json.dumps(colorder[0]))
+    out[pre + "best"] = np.array([float(best[k]) for k in inputs])
+    out[pre + "data_array"] = np.array([[float(v) for v in data_array[k]] for k in inputs + [key]], dtype=np.float64)
+    out[pre + "meta"] = np.array(json.dumps({"seed": seed, "acq": acq, "scal": scal, "iteration": iteration,
+                                             "n_points": n_points, "n_starts": n_starts}))
+    return best
+
+
+def local_search_traj_case():
+    out = {}
+    summary = {}
+    plans = [
+        # tag, scenario, objective, n_train, pool size, starts, [(seed, acq, scal)]
+        ("branin", dict(BRANIN, models={"model": "random_forest", "number_of_trees": 10}), branin, 25, 1000, 10,
+         [(0, "EI", "tchebyshev"), (1, "EI", "tchebyshev"), (2, "UCB", "linear")]),
+        ("mixed", MIXED, objective_mixed, 70, 400, 5,
+         [(0, "EI", "tchebyshev"), (1, "UCB", "modified_tchebyshev"), (2, "TS", "linear")]),
+        ("discrete", DISCRETE, objective_discrete, 50, 300, 4,
+         [(0, "EI", "tchebyshev"), (1, "UCB", "linear"), (2, "EI", "linear"), (3, "TS", "tchebyshev")]),
+    ]
+    for name, scenario, fn, n_train, n_points, n_starts, runs in plans:
+        config = validated(scenario)
+        objectives = config["optimization_objectives"]
+        out[name + "_config_json"] = np.array(json.dumps(config))
+        out[name + "_params_json"] = np.array(json.dumps(params_desc(config)))
+        for seed, acq, scal in runs:
+            tag = "%s_s%d" % (name, seed)
+            np.random.seed(1000 + seed)            # a different training set (and forest) per run
+            random.seed(1000 + seed)
+            space = ns.space.Space(config)
+            inputs = space.get_input_parameters()
+            data = sample_data_array(space, n_train, fn, objectives)
+            models = fit(config, space, data, objectives)
+            for o in objectives:
+                out.update(oracle_forest(models[o]).to_npz_dict("%s_forest_%s_" % (tag, o)))
+                out["%s_data_%s" % (tag, o)] = np.array(data[o], dtype=np.float64)
+            out[tag + "_data_inputs"] = np.array([[float(data[k][r]) for k in inputs] for r in range(n_train)])
+            weights = {o: w for o, w in zip(objectives, [0.37, 0.63] if len(objectives) > 1 else [1.0])}
+            limits = {o: [min(data[o]), max(data[o])] for o in objectives}
+            out[tag + "_weights"] = np.array([weights[o] for o in objectives])
+            best = _traj_one(out, tag, config, space, models, data, objectives, weights, limits, seed, acq, scal,
+                             3 + seed, n_points, n_starts)
+            summary[tag] = [float(best[k]) for k in inputs]
+    np.savez_compressed(os.path.join(HERE, "local_search_traj.npz"), **out)
+    print("local_search_traj.npz", summary)
+
+
+def oracle_forest(model):
+    from oracle import oracle
+    return oracle.forest_arrays_from_model(model)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GP: the reference delegates to GPy (models.py:441-459, 997-1024), which is not installable here.  The restatement in
+# oracle/oracle.py is pinned to an INDEPENDENT exact-inference implementation instead: scikit-learn's
+# GaussianProcessRegressor with ConstantKernel * Matern(nu=2.5, ARD) [+ WhiteKernel], fixed hyper-parameters
+# (optimizer=None), normalize_y=True (population std, like GPy's Standardize), alpha = 1e-8 (the jitter GPy's
+# exact_gaussian_inference adds to the noise variance).  sklearn evaluates the kernel from explicit pairwise distances
+# (cdist), not GPy's GEMM form, and solves with its own Cholesky, so agreement is a genuine cross-check.
+# ---------------------------------------------------------------------------------------------------------------------
+def gp_case():
+    from sklearn.gaussian_process import GaussianProcessRegressor
+    from sklearn.gaussian_process.kernels import ConstantKernel, Matern, WhiteKernel, RBF
+    sys.path.insert(0, ROOT)
+    from hypermapper_b200 import workloads
+    out = {}
+    cases = [
+        ("c2_noise", 256, 6, 1e-4, 2, "matern52", 1.0, 1500),
+        ("c2_nonoise", 256, 6, 0.0, 2, "matern52", 1.0, 1500),
+        ("c5gp", 512, 32, 1e-4, 12, "matern52", 3.0, 1000),
+        ("small_rbf", 60, 4, 1e-3, 21, "rbf", 1.0, 500),
+        ("sf2", 200, 5, 1e-2, 22, "matern52", 1.0, 500),
+    ]
+    for tag, n, D, noise, seed, kernel, scale, N in cases:
+        rng = np.random.default_rng(seed)
+        X = rng.random((n, D))
+        if D == 6:
+            y = workloads.hartmann6(X)
+        elif D == 32:
+            y = np.sin(X[:, :8].sum(1)) + (X[:, 8:] ** 2).sum(1) * 0.1
+        else:
+            y = np.sin(3 * X[:, 0]) + (X ** 2).sum(1)
+        ls = np.random.default_rng(seed + 1).uniform(0.3, 1.0, D) * scale
+        sf2 = 1.0 if tag != "sf2" else 2.7
+        base = Matern(length_scale=ls, nu=2.5) if kernel == "matern52" else RBF(length_scale=ls)
+        k = ConstantKernel(sf2, constant_value_bounds="fixed") * base
+        if noise > 0:
+            k = k + WhiteKernel(noise, noise_level_bounds="fixed")
+        gpr = GaussianProcessRegressor(kernel=k, alpha=1e-8, optimizer=None, normalize_y=True)
+        gpr.fit(X, y)
+        Xs = np.random.default_rng(seed + 2).random((N, D))
+        Xs[:5] = X[:5]                     # candidates ON training points: the ill-conditioned end of the variance
+        Xs[5:10] = X[5:10] + 1e-4
+        mean, std = gpr.predict(Xs, return_std=True)
+        out[tag + "_X"] = X
+        out[tag + "_y"] = y
+        out[tag + "_lengthscale"] = ls
+        out[tag + "_hyper"] = np.array([sf2, noise])
+        out[tag + "_kernel"] = np.array(kernel)
+        out[tag + "_candidates"] = Xs
+        out[tag + "_sk_mean"] = mean
+        out[tag + "_sk_var"] = std ** 2
+    np.savez_compressed(os.path.join(HERE, "gp_sklearn.npz"), **out)
+    print("gp_sklearn.npz", {k: v.shape for k, v in out.items() if k.endswith("_sk_mean")})
+
+
+
 def neighbors_case():
     """get_neighbors (local_search.py:83-161) on the discrete and the mixed scenario, RNG seeded per call."""
     out = {}
@@ -458,9 +631,17 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "priors":
         priors_case()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "traj":
+        local_search_traj_case()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "gp":
+        gp_case()
+        sys.exit(0)
     rf_case(MIXED, objective_mixed, 90, 700, 1, "rf_mixed.npz")
     rf_case(BRANIN, branin, 40, 1500, 2, "rf_branin.npz")
     pareto_case()
     local_search_case()
     neighbors_case()
     priors_case()
+    local_search_traj_case()
+    gp_case()

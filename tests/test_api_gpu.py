@@ -278,3 +278,72 @@ def test_lockstep_hill_climb_equals_sequential():
         for k in inputs:
             assert [type(v) for v in data_array[k]] == [type(v) for v in results[0][0][k]], k
     assert len(results[0][0][config["scalarization_key"]]) > 800 + 60      # the climbs did evaluate neighbours
+
+
+def test_device_forest_cache_follows_in_place_refit():
+    """the reference's fit_RF (models.py:184-223) calls get_leaves_per_sample in the MIDDLE of the
+    fit -- before the Hutter tables exist and before tree_.threshold is rewritten in place.  Predictions made after the
+    fit must see the final thresholds and tables, not a forest cached during it."""
+    from hypermapper_b200 import forest, models as hm
+    from hypermapper_b200.hutter_forest import HutterForest, fit_hutter_forest
+    from hypermapper_b200.space_lite import SpaceLite
+    from oracle import oracle
+    rng = np.random.default_rng(0)
+    X = rng.random((200, 3))
+    y = np.sin(4 * X[:, 0]) + X[:, 1] * X[:, 2]
+    final = fit_hutter_forest(X, y, n_estimators=8, seed=3)
+    final_thr = [est.tree_.threshold.copy() for est in final.estimators_]
+    # rewind to the state fit_RF is in when it calls get_leaves_per_sample: no tables, other thresholds
+    means, variances = final.tree_means_per_leaf, final.tree_vars_per_leaf
+    model = HutterForest(final.estimators_, [], [], 3)
+    for est in model.estimators_:
+        internal = est.tree_.children_left != est.tree_.children_right
+        est.tree_.threshold[internal] += 0.05
+    leaves_mid = hm.rf_get_leaves_per_sample(model, X)
+    fa_mid = oracle.forest_arrays_from_model(model)
+    assert np.array_equal(leaves_mid, oracle.rf_apply(fa_mid, X))
+    _ = forest.device_forest(model)                       # anything cached now is stale after the next three lines
+    model.tree_means_per_leaf, model.tree_vars_per_leaf = means, variances
+    for est, thr in zip(model.estimators_, final_thr):
+        est.tree_.threshold[:] = thr
+    space = SpaceLite({"optimization_objectives": ["v"], "input_parameters": {
+        "a": {"parameter_type": "real", "values": [0, 1]}, "b": {"parameter_type": "real", "values": [0, 1]},
+        "c": {"parameter_type": "real", "values": [0, 1]}}})
+    Xc = rng.random((500, 3))
+    mean, var = hm.compute_rf_prediction_mean_and_uncertainty(Xc, {"v": model}, space, var=True)
+    fa = oracle.forest_arrays_from_model(model)
+    leaf = oracle.rf_apply(fa, Xc)
+    want = oracle.rf_prediction(fa, leaf)
+    assert np.array_equal(mean["v"], want)
+    assert rel_ok(var["v"], oracle.rf_prediction_variance(fa, leaf, want), 1e-10)
+
+
+def test_classifier_probability_is_normalised_per_leaf():
+    """tree_.value of a classifier holds weighted class COUNTS on scikit-learn < 1.4 (the versions
+    the unmodified reference runs on) and fractions later; the leaf payload must be the fraction either way."""
+    from sklearn.ensemble import RandomForestClassifier
+    from hypermapper_b200 import forest
+    rng = np.random.default_rng(1)
+    X = rng.random((300, 4))
+    y = X[:, 0] + X[:, 1] > 1.0
+    clf = RandomForestClassifier(n_estimators=5, random_state=0).fit(X, y)
+    tabs = forest.forest_tables(forest._NoHutter(clf), value_column=1, normalize_value=True)
+
+    class CountTree:
+        def __init__(self, tr, scale):
+            self.children_left, self.children_right = tr.children_left, tr.children_right
+            self.feature, self.threshold, self.node_count = tr.feature, tr.threshold, tr.node_count
+            self.value = tr.value * scale                     # what an old scikit-learn stores: counts, not fractions
+
+    class Est:
+        def __init__(self, tree):
+            self.tree_ = tree
+
+    class Old:
+        estimators_ = [Est(CountTree(e.tree_, 37.0 + i)) for i, e in enumerate(clf.estimators_)]
+        n_features_in_ = 4
+        tree_means_per_leaf = tree_vars_per_leaf = None
+    old = forest.forest_tables(Old, value_column=1, normalize_value=True)
+    assert np.allclose(old["value"], tabs["value"], rtol=1e-15, atol=0)
+    leaf = tabs["left"] < 0
+    assert np.all((tabs["value"][leaf] >= 0) & (tabs["value"][leaf] <= 1))

@@ -463,3 +463,47 @@ def test_neighbor_plan_enumerates_like_get_neighbors():
             row[j] = vals[pick]
             rows.append(row)
         assert rows == nb
+
+
+# ---- local_search host logic against recorded reference runs (real / integer / mixed / discrete spaces) -------------
+def _oracle_plugin():
+    """An acquisition plug-in with the reference's exact values that runs without a GPU (oracle = checker): used to pin
+    the HOST side of local_search -- RNG stream of the neighbourhoods, seed selection, duplicate filter, final pick."""
+    from oracle import oracle
+    from hypermapper_b200 import models as hm
+
+    def f(configurations, **p):
+        fas = p.setdefault("_oracle_forests", {o: oracle.forest_arrays_from_model(m)
+                                               for o, m in p["regression_models"].items()})
+        X = np.ascontiguousarray(hm.encode_host(configurations, p["param_space"]).T)
+        vals = oracle.rf_acquisition(p["acquisition_function"], fas, X, p["objective_weights"],
+                                     p["scalarization_method"], p["objective_limits"], p["iteration_number"],
+                                     p["data_array"])
+        return list(np.asarray(vals, dtype=np.float64)), [1] * len(configurations)
+    return f
+
+
+@pytest.mark.parametrize("tag", ["branin_s0", "branin_s1", "branin_s2", "mixed_s0", "mixed_s1", "mixed_s2",
+                                 "discrete_s0", "discrete_s1", "discrete_s2", "discrete_s3"])
+def test_local_search_host_logic_replays_reference_runs(tag):
+    """Every configuration the reference's local_search evaluated, in the same order, the same values (the plug-in is
+    the bit-exact oracle) and the same pick -- on spaces whose neighbourhoods consume numpy's RNG stream too."""
+    import ls_replay
+    from test_api_gpu import FrozenForest
+    z = ls_replay.load()
+    plugin = _oracle_plugin()
+
+    def wrapped(configurations, **p):
+        p.pop("_oracle_forests", None)
+        return plugin(configurations, **p)
+    out = ls_replay.replay(z, tag, wrapped, FrozenForest)
+    ls_replay.check(*out, rel=0.0)
+
+
+def test_local_search_goldens_discriminate():
+    """the recorded runs do not all end in the same configuration (a climb that ignored seed / acquisition would fail)"""
+    import ls_replay
+    z = ls_replay.load()
+    for name in ("branin", "mixed", "discrete"):
+        ends = {tuple(z[t + "_best"].tolist()) for t in ls_replay.TAGS if t.startswith(name)}
+        assert len(ends) >= 3, (name, ends)

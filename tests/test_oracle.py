@@ -172,3 +172,39 @@ def test_gp_restatement_self_consistency():
     vv = (st.variance - np.einsum("ij,ik,kj->j", Kx, Ki, Kx) + st.noise) * y.std() ** 2
     assert np.allclose(m2, mu, rtol=1e-6, atol=1e-8)
     assert np.allclose(v2, np.maximum(vv, 1e-11), rtol=1e-4, atol=1e-9)
+
+
+# ---- GP oracle pinned to an independent implementation --------------------------------------------------------------
+GP_TAGS = ["c2_noise", "c2_nonoise", "c5gp", "small_rbf", "sf2"]
+
+
+@pytest.mark.parametrize("tag", GP_TAGS)
+def test_gp_oracle_agrees_with_sklearn_gpr(tag):
+    """oracle.gp_predict (restatement of GPy's exact inference, models.py:441-459, 997-1024) against scikit-learn's
+    GaussianProcessRegressor on the same fixed hyper-parameters (tests/golden/gp_sklearn.npz, made by make_golden.py
+    gp_case): C2 shape (n = 256, D = 6, noise 1e-4 and 0), C5-GP shape (n = 512, D = 32), RBF, sf2 != 1.
+    sklearn builds the kernel from explicit pairwise distances and has its own Cholesky / normaliser code, so this is
+    an implementation the oracle's author did not write.  The one known GPy detail mirrored on the sklearn side is the
+    1e-8 jitter GPy adds to the noise variance (sklearn: alpha = 1e-8).
+    Tolerances: mean 1e-9 relative wherever |mean| > 1e-3 std(y) (absolute 1e-12 std(y) below that: the mean is a
+    cancelling sum); variance 1e-6 relative -- the worst case is a candidate ON a training point with zero noise, where
+    var = sf2 - |L^-1 k|^2 cancels down to the 1e-8 jitter."""
+    z = np.load(os.path.join(GOLDEN, "gp_sklearn.npz"), allow_pickle=False)
+    X, y, ls = z[tag + "_X"], z[tag + "_y"], z[tag + "_lengthscale"]
+    sf2, noise = z[tag + "_hyper"]
+    st = oracle.gp_fit(X, y, ls, float(sf2), float(noise), kernel=str(z[tag + "_kernel"]))
+    m, v = oracle.gp_predict(st, z[tag + "_candidates"])
+    sm, sv = z[tag + "_sk_mean"], z[tag + "_sk_var"]
+    big = np.abs(sm) > 1e-3 * y.std()
+    assert np.all(np.abs(m - sm)[big] <= 1e-9 * np.abs(sm)[big])
+    assert np.all(np.abs(m - sm)[~big] <= 1e-12 * y.std())
+    assert np.all(np.abs(v - sv) <= 1e-6 * sv)
+    assert np.all(np.abs(v - sv)[10:] <= 1e-9 * sv[10:])          # away from the training points: 1e-9
+
+
+@pytest.mark.parametrize("kind", ["branin_grid", "ordinal_branin"])
+def test_pareto_oracle_reference_known_answer_grids(kind):
+    """the two grid KATs of the reference's tests/test_system.py:36-64 (98 / 12 rows)"""
+    import pareto_kat
+    z = np.load(os.path.join(GOLDEN, "pareto.npz"), allow_pickle=False)
+    pareto_kat.check(z, kind, oracle.pareto)

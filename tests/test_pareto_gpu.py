@@ -34,6 +34,15 @@ def test_reference_known_answer_blackscholes():
     assert np.array_equal(got, z["kat_blackscholes"])        # tests/data/BlackScholes_real_pareto.csv, 88 rows
 
 
+@pytest.mark.parametrize("kind", ["branin_grid", "ordinal_branin"])
+def test_reference_known_answer_grids(kind):
+    """tests/test_system.py:36-64 of the reference: exhaustive 100 x 100 / 16 x 16 Branin grids -> the fronts in
+    tests/data/branin_grid_search_pareto.csv (98 rows) / ordinal_branin_real_pareto.csv (12 rows)"""
+    import pareto_kat
+    from hypermapper_b200 import compute_pareto
+    pareto_kat.check(golden(), kind, compute_pareto.sequential_is_pareto_efficient)
+
+
 def _branin_pair(x1, x2):
     a, b, c, r, s, t = 1.0, 5.1 / (4.0 * np.pi * np.pi), 5.0 / np.pi, 6.0, 10.0, 1.0 / (8.0 * np.pi)
     return a * (x2 - b * x1 * x1 + c * x1 - r) ** 2 + s * (1 - t) * np.cos(x1) + s
