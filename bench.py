@@ -2,13 +2,15 @@
 """bench.py -- acquisition evaluations / second on the surrogate-prediction + acquisition hot path.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
-                    [--workload c3|c1|c5rf|c2|c5gp|c4|c3raw|c3pool] [--candidates n]
+                    [--workload c3|c3f32|c1|c5rf|c2|c5gp|c4|c3raw|c3pool] [--candidates n]
 
 Default workload = BASELINE.json configs[2] ("C3"), the configuration the north-star's RF+EI target is quoted on:
 2-objective mixed ordinal/categorical space (D_enc = 23), two 256-tree Hutter forests, random_scalarizations
 EI + tchebyshev over 16 777 216 candidates per GPU, stable top-20.
 One "step" = one pass of the hot path over the whole pool:
   RF : fused forest traversal + Hutter reduction + EI scalarisation (hm_rf_eval) -> stable top-k (hm_topk)
+       c3 (all-discrete space): the candidates are held as packed 64-bit codes (hm_rf_eval_packed, csrc/hm_pack.cuh);
+       c3f32 is the same workload through the fp32 encoded matrix (the round-1 path), bit-identical results
   GP : hm_gp_mean_var -> hm_acq_score -> hm_topk                      (c2: Hartmann-6, n=256; c5gp: 20-D, n=512)
   c4 : hm_pareto_filter on 10^7 x 3 points (metric: points/s)
   c3raw : C3 with the candidates as RAW parameter values, the form the reference API takes: hm_encode -> RF step
@@ -37,19 +39,19 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOADS = ["c3", "c1", "c5rf", "c2", "c5gp", "c4", "c3raw", "c3pool"]
+WORKLOADS = ["c3", "c3f32", "c1", "c5rf", "c2", "c5gp", "c4", "c3raw", "c3pool"]
 
 # roofline.traffic: dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel from an
 # `ncu --set full` capture of the same command at the same size (profiles/<file>); None where no capture at that size exists
 # on-chip utilisation of the same launch in the same capture (per cent of peak): what actually bounds the kernel
 NCU_ONCHIP = {
-    ("c3", 1 << 24): {"l1tex_data_pipe_pct": 87.9, "issue_slots_pct": 63.5, "dram_pct": 0.7,
-                      "source": "profiles/r01_forest_c3_default_ncu_raw.csv"},
+    ("c3f32", 1 << 24): {"l1tex_data_pipe_pct": 87.9, "issue_slots_pct": 63.5, "dram_pct": 0.7,
+                         "source": "profiles/r01_forest_c3_default_ncu_raw.csv"},
     ("c1", 1 << 26): {"l1tex_data_pipe_pct": 71.0, "issue_slots_pct": 83.9, "dram_pct": 4.8,
                       "source": "profiles/r01_forest_c1_ncu_raw.csv"},
 }
 NCU_TRAFFIC = {
-    ("c3", 1 << 24): (2.234378e9 + 0.545148e9, "profiles/r01_forest_c3_default_ncu_raw.csv"),
+    ("c3f32", 1 << 24): (2.234378e9 + 0.545148e9, "profiles/r01_forest_c3_default_ncu_raw.csv"),
     ("c1", 1 << 26): (0.537153e9 + 0.501310e9, "profiles/r01_forest_c1_ncu_raw.csv"),
 }
 
@@ -138,6 +140,7 @@ class RFBench:
         self.name = name
         cache = os.path.join(os.environ.get("HM_BENCH_CACHE", "/tmp"),
                              "hm_bench_wl_v3_%s.pkl" % ("c3" if name.startswith("c3") else name))
+        self.packed = name == "c3"
         cached = None
         if os.path.exists(cache):
             import pickle
@@ -148,10 +151,16 @@ class RFBench:
                 cached = None
         if cached is not None:
             self.wl = cached
-        if name in ("c3", "c3raw", "c3pool"):
+        if name in ("c3", "c3f32", "c3raw", "c3pool"):
             self.wl = cached or workloads.RFWorkload(workloads.scenario_c3(), n_train=2000, seed=5)
             self.n_default = 1 << 24
             self.desc = "C3: 2-objective mixed ordinal/categorical (D_enc=23), 256-tree RF x2, EI+tchebyshev, top-20"
+            if name == "c3":
+                self.desc += "; candidates as packed 64-bit codes"
+                self.e2e_api = ("hm_rf_score_packed_host (C-ABI, pinned host codes, 8 B per candidate, 2M-candidate "
+                                "double-buffered chunks)")
+            elif name == "c3f32":
+                self.desc += "; candidates as the fp32 encoded matrix"
         elif name == "c1":
             self.wl = cached or workloads.RFWorkload(workloads.scenario_c1(), n_train=15, seed=0)
             self.n_default = 1 << 26
@@ -187,6 +196,7 @@ class RFBench:
             self._Xcpu = {}
         if sample not in self._Xcpu:
             self._Xcpu = {sample: np.ascontiguousarray(wl.candidates_encoded(sample, seed=1234).T)}
+            self._raw_sample = wl.candidates_raw(sample, seed=1234) if self.packed else None
         X = self._Xcpu[sample]
         t0 = time.perf_counter()
         means, variances = {}, {}
@@ -209,14 +219,22 @@ class RFBench:
         sample, means, vals, top = self._cpu_out
         X = self._Xcpu[sample]                                       # [sample][D_enc] float32 rows
         X32 = torch.from_numpy(np.ascontiguousarray(X.T)).cuda()
-        out = forest.rf_eval(self.forests, X32, want_mean=True, acq=self.acq)
+        if self.packed:
+            # the product path of this workload: packed codes of the same candidates
+            codes = torch.from_numpy(self.ds.pack_codes_host(self._raw_sample).view(np.int64)).cuda()
+            out = forest.rf_eval_packed(self.forests, codes, want_mean=True, acq=self.acq)
+        else:
+            out = forest.rf_eval(self.forests, X32, want_mean=True, acq=self.acq)
         mean_exact = all(np.array_equal(out["mean"][m].cpu().numpy(), means[o]) for m, o in enumerate(wl.objectives))
         sc = out["score"].cpu().numpy()
         with np.errstate(all="ignore"):
             err = np.abs(sc - vals) / np.maximum(np.abs(vals), 1e-300)
         err[sc == vals] = 0
         n_leaf = min(4096, sample)
-        lv = forest.rf_eval(self.forests, X32[:, :n_leaf].contiguous(), want_leaves=True)["leaves"]
+        if self.packed:
+            lv = forest.rf_eval_packed(self.forests, codes[:n_leaf].contiguous(), want_leaves=True)["leaves"]
+        else:
+            lv = forest.rf_eval(self.forests, X32[:, :n_leaf].contiguous(), want_leaves=True)["leaves"]
         leaf_exact = all(np.array_equal(lv[m].cpu().numpy().astype(np.int64),
                                         oracle.rf_apply(self._fas[o], np.ascontiguousarray(X[:n_leaf])))
                          for m, o in enumerate(wl.objectives))
@@ -229,7 +247,8 @@ class RFBench:
                                                          wl.iteration_number, wl.data_array)
         got = exact.exact_min_indices(out["score"], self.k, exact_rows)
         raw = forest.topk(out["score"], self.k)[1].cpu().numpy()
-        res = {"sample": sample, "leaves_bit_exact": bool(leaf_exact), "leaves_checked": n_leaf * wl.n_trees * len(wl.objectives),
+        res = {"sample": sample, "path": "packed codes (hm_rf_eval_packed)" if self.packed else "fp32 matrix (hm_rf_eval)",
+               "leaves_bit_exact": bool(leaf_exact), "leaves_checked": n_leaf * wl.n_trees * len(wl.objectives),
                "mean_bit_exact": bool(mean_exact), "score_max_rel_err": float(err.max()), "score_tol": 1e-5,
                "topk_identical": bool(np.array_equal(got, top)), "topk_identical_without_rescore": bool(np.array_equal(raw, top)),
                "near_tie_rescores": dict(exact.stats_counters)}
@@ -244,14 +263,36 @@ class RFBench:
         self.N, self.rank = N, rank
         self.forests = [forest.device_forest(wl.models[o]) for o in wl.objectives]
         self.acq = wl.acq_params()
-        self.x_host = torch.empty((wl.D_enc, N), dtype=torch.float32).pin_memory()
-        wl.candidates_encoded(N, seed=6 + rank, out=self.x_host.numpy())
-        self.x_dev = self.x_host.cuda()
         self.scores_host = torch.empty((N,), dtype=torch.float64).pin_memory()
         self.scorer = HostScorer(wl.D_enc, chunk=int(os.environ.get("HM_BENCH_CHUNK", 1 << 21)))
+        if self.packed:
+            from hypermapper_b200.space_device import device_space_for
+            self.ds = device_space_for(wl.space)
+            forest.attach_packing(self.forests, self.ds)
+            self.codes_host = torch.empty((N,), dtype=torch.int64).pin_memory()
+            raw = np.empty((min(N, 1 << 21), self.ds.D), dtype=np.float64)
+            rng = np.random.default_rng(6 + rank)
+            from hypermapper_b200 import workloads
+            inputs = wl.space.get_input_parameters()
+            ch = self.codes_host.numpy().view(np.uint64)
+            for lo in range(0, N, 1 << 21):                      # the candidates candidates_encoded(N, 6 + rank) encodes
+                hi = min(N, lo + (1 << 21))
+                cols = workloads.raw_uniform_columns(wl.space, hi - lo, rng)
+                for j, p in enumerate(inputs):
+                    raw[:hi - lo, j] = cols[p]
+                self.ds.pack_codes_host(raw[:hi - lo], out=ch[lo:hi])
+            self.codes_dev = self.codes_host.cuda()
+            # the fp32 form of the first candidates, for the per-evaluation shared-memory byte count
+            self.x_dev = torch.from_numpy(wl.candidates_encoded(min(N, 1 << 16), seed=6 + rank)).cuda()
+            n_groups = sum(f.packed_groups for f in self.forests)
+        else:
+            self.x_host = torch.empty((wl.D_enc, N), dtype=torch.float32).pin_memory()
+            wl.candidates_encoded(N, seed=6 + rank, out=self.x_host.numpy())
+            self.x_dev = self.x_host.cuda()
+            n_groups = sum(f.n_groups for f in self.forests if f.staged)
         # hm_forest_kernel + hm_topk_stage1/2; forests that stream through shared memory add the coherence pre-pass
-        # (hm_forest_sortkey, hm_forest_scan, hm_forest_scatter_rows) for pools of >= 2^17 candidates
-        self.prepass = sum(f.n_groups for f in self.forests if f.staged) > 2 and N >= (1 << 17)
+        # (hm_forest_sortkey, hm_forest_scan, hm_forest_scatter_rows / _codes) for pools of >= 2^17 candidates
+        self.prepass = n_groups > 2 and N >= (1 << 17)
         self.smem_bytes_per_eval = self._smem_bytes_per_eval()
         self.launches_per_step = 3 + (3 if self.prepass else 0)
 
@@ -262,7 +303,8 @@ class RFBench:
         import torch
         from hypermapper_b200 import forest
         wl = self.wl
-        n = min(sample, self.N)
+        n = min(sample, self.N, self.x_dev.shape[1])
+        per_visit = 8 if self.packed else 12           # packed codes: the node only; fp32 path: node + feature value
         leaves = forest.rf_eval(self.forests, self.x_dev[:, :n].contiguous(), want_leaves=True)["leaves"]
         total = 0.0
         for m, o in enumerate(wl.objectives):
@@ -275,7 +317,7 @@ class RFBench:
                     if l != r:
                         depth[l] = depth[node] + 1
                         depth[r] = depth[node] + 1
-                total += float(depth[lv[t]].mean()) * 12 + 8
+                total += float(depth[lv[t]].mean()) * per_visit + 8
         return total
 
     def step(self, record):
@@ -285,7 +327,10 @@ class RFBench:
         if record:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record()
-        out = forest.rf_eval(self.forests, self.x_dev, acq=self.acq)
+        if self.packed:
+            out = forest.rf_eval_packed(self.forests, self.codes_dev, acq=self.acq)
+        else:
+            out = forest.rf_eval(self.forests, self.x_dev, acq=self.acq)
         if record:
             ev[1].record()
         tv, ti = forest.topk(out["score"], self.k, index_base=self.rank * self.N)
@@ -293,11 +338,15 @@ class RFBench:
 
     def e2e_step(self):
         import torch
-        _, tv, ti = self.scorer.score(self.forests, self.x_host, self.acq, k=self.k, scores_out=self.scores_host)
+        if self.packed:
+            _, tv, ti = self.scorer.score_packed(self.forests, self.codes_host, self.acq, k=self.k,
+                                                 scores_out=self.scores_host)
+        else:
+            _, tv, ti = self.scorer.score(self.forests, self.x_host, self.acq, k=self.k, scores_out=self.scores_host)
         return torch.from_numpy(tv).cuda(), torch.from_numpy(ti + self.rank * self.N).cuda()
 
     def e2e_bytes(self, N):
-        return 4 * self.wl.D_enc * N, 8 * N + 16 * self.k
+        return (8 if self.packed else 4 * self.wl.D_enc) * N, 8 * N + 16 * self.k
 
     def roofline(self, N, kernel_ms):
         peak, src = measured_peaks()
@@ -309,14 +358,22 @@ class RFBench:
         smem_peak = 128.0 * prop.multi_processor_count * 1.965e9 / 1e9      # GB/s at clocks.max.sm = 1965 MHz
         smem_ach = self.smem_bytes_per_eval * N / (kernel_ms / 1e3) / 1e9
         traffic, traffic_src = NCU_TRAFFIC.get((self.name, N), (None, None))
+        compact = None
+        if self.packed:
+            compact = {"bytes_per_eval": 16, "achieved": 16 * N / (kernel_ms / 1e3) / 1e9,
+                       "how": "what this path actually has to move: 8 B packed code in + 8 B fp64 score out (SURVEY 8(d): "
+                              "secondary figure; `achieved` above stays on the contract's 4*D_enc + 8)"}
         return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                "compact": compact,
                 "traffic_source": traffic_src, "ncu_onchip": NCU_ONCHIP.get((self.name, N)),
                 "smem_pipe": {"achieved": smem_ach, "peak": smem_peak, "unit": "GB/s", "frac": smem_ach / smem_peak,
                               "bytes_per_eval": self.smem_bytes_per_eval,
-                              "how": "per tree: 12 B per internal node on the path (8 B node + 4 B feature) + 8 B leaf "
-                                     "node, path lengths measured on 65536 pool candidates; peak = 128 B/clk/SM x SMs "
-                                     "x 1965 MHz"},
-                "kernel": "hm_forest_kernel<false>" + (" (+ coherence pre-pass hm_forest_sortkey/scan/scatter_rows, inside "
+                              "how": ("per tree: 8 B per internal node on the path (the node; the candidate is a register "
+                                      "pair) + 8 B leaf node" if self.packed else
+                                      "per tree: 12 B per internal node on the path (8 B node + 4 B feature) + 8 B leaf "
+                                      "node") + ", path lengths measured on 65536 pool candidates; peak = 128 B/clk/SM x "
+                                     "SMs x 1965 MHz"},
+                "kernel": ("hm_forest_kernel<packed>" if self.packed else "hm_forest_kernel<fp32>") + (" (+ coherence pre-pass hm_forest_sortkey/scan/scatter_rows, inside "
                                                        "kernel_ms)" if getattr(self, "prepass", False) else ""),
                 "kernel_ms": kernel_ms, "algorithmic_bytes_per_eval": b, "peak_source": src,
                 "note": "forests with thousands of node visits per evaluation are bound by shared-memory load latency "
@@ -698,7 +755,7 @@ class ParetoBench:
 def make_bench(name):
     if name in ("c3raw", "c3pool"):
         return SpaceRFBench(name)
-    if name in ("c3", "c1", "c5rf"):
+    if name in ("c3", "c3f32", "c1", "c5rf"):
         return RFBench(name)
     if name in ("c2", "c5gp"):
         return GPBench(name)

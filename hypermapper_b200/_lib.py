@@ -9,7 +9,8 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-SO_PATH = os.path.join(CSRC, "libhm_b200.so")
+# HM_B200_LIB selects another build of the same C-ABI (the checked build, experiment variants); default = the in-tree one
+SO_PATH = os.environ.get("HM_B200_LIB") or os.path.join(CSRC, "libhm_b200.so")
 
 HM_MAX_OBJECTIVES = 8
 ACQ_KINDS = {"EI": 0, "UCB": 1, "TS": 2}
@@ -19,12 +20,15 @@ SCALARIZATIONS = {"linear": 0, "tchebyshev": 1, "modified_tchebyshev": 2}
 EXPORTED_SYMBOLS = [
     "hm_last_error", "hm_device_sm_count", "hm_version", "hm_fp64_peak_tflops",
     "hm_forest_create", "hm_forest_destroy", "hm_forest_n_trees", "hm_forest_n_features", "hm_forest_staged",
-    "hm_forest_set_coherence_mode", "hm_forest_n_groups",
+    "hm_forest_set_coherence", "hm_forest_n_groups",
+    "hm_forest_attach_packing", "hm_forest_packed", "hm_forest_packed_groups", "hm_rf_eval_packed",
     "hm_rf_eval", "hm_acq_score",
     "hm_topk_workspace_bytes", "hm_topk", "hm_topk_merge",
     "hm_gp_create", "hm_gp_destroy", "hm_gp_mean_var",
     "hm_pareto_workspace_bytes", "hm_pareto_filter", "hm_pareto_pass1",
     "hm_space_create", "hm_space_destroy", "hm_space_n_params", "hm_space_n_encoded",
+    "hm_space_packed_bits", "hm_space_packed_field", "hm_encode_packed", "hm_sample_pool_packed",
+    "hm_rf_score_packed_host",
     "hm_encode", "hm_sample_pool", "hm_sample_rows", "hm_prior_prob", "hm_prior_weight",
     "hm_minmax", "hm_bopro_ratio", "hm_bopro_finish", "hm_ls_neighbors", "hm_ls_move",
     "hm_host_ctx_create", "hm_host_ctx_destroy", "hm_rf_score_host", "hm_rf_score_raw_host", "hm_gp_score_host",
@@ -96,7 +100,12 @@ def lib():
     L.hm_forest_destroy.restype = None
     for f in ("hm_forest_n_trees", "hm_forest_n_features", "hm_forest_staged", "hm_forest_n_groups"):
         getattr(L, f).argtypes = [vp]
-    L.hm_forest_set_coherence_mode.argtypes = [i32]
+    for f in ("hm_forest_packed", "hm_forest_packed_groups"):
+        getattr(L, f).argtypes = [vp]
+    L.hm_forest_set_coherence.argtypes = [vp, i32]
+    L.hm_forest_attach_packing.argtypes = [vp, vp]
+    L.hm_rf_eval_packed.argtypes = [ctypes.POINTER(vp), i32, vp, i64, ctypes.POINTER(vp), vp, vp, vp,
+                                    ctypes.POINTER(AcqParams), vp, vp, vp]
     L.hm_rf_eval.argtypes = [ctypes.POINTER(vp), i32, vp, i64, i64, ctypes.POINTER(vp), vp, vp, vp,
                              ctypes.POINTER(AcqParams), vp, vp, vp]
     L.hm_acq_score.argtypes = [ctypes.POINTER(AcqParams), vp, vp, i64, vp, i64, vp, vp]
@@ -118,6 +127,10 @@ def lib():
     L.hm_space_destroy.restype = None
     L.hm_space_n_params.argtypes = [vp]
     L.hm_space_n_encoded.argtypes = [vp]
+    L.hm_space_packed_bits.argtypes = [vp]
+    L.hm_space_packed_field.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
+    L.hm_encode_packed.argtypes = [vp, vp, i32, i64, i64, vp, vp, vp]
+    L.hm_sample_pool_packed.argtypes = [vp, u64, i64, i64, i32, vp, vp, i64, vp]
     L.hm_encode.argtypes = [vp, vp, i32, i64, i64, vp, i64, vp, i64, vp, vp]
     L.hm_sample_pool.argtypes = [vp, u64, i64, i64, i32, vp, i64, vp, i64, vp, i64, vp, i32, vp, vp]
     L.hm_sample_rows.argtypes = [vp, u64, i32, vp, i64, vp, vp]
@@ -132,6 +145,7 @@ def lib():
     L.hm_host_ctx_destroy.argtypes = [vp]
     L.hm_host_ctx_destroy.restype = None
     L.hm_rf_score_host.argtypes = [vp, ctypes.POINTER(vp), i32, vp, i64, i64, ctypes.POINTER(AcqParams), vp, i32, vp, vp]
+    L.hm_rf_score_packed_host.argtypes = [vp, ctypes.POINTER(vp), i32, vp, i64, ctypes.POINTER(AcqParams), vp, i32, vp, vp]
     L.hm_rf_score_raw_host.argtypes = [vp, vp, ctypes.POINTER(vp), i32, vp, i64, ctypes.POINTER(AcqParams), vp, i32, vp,
                                        vp, ctypes.POINTER(ctypes.c_int32)]
     L.hm_gp_score_host.argtypes = [vp, ctypes.POINTER(vp), i32, i32, vp, i64, i64, ctypes.POINTER(AcqParams), vp, i32, vp,

@@ -39,6 +39,7 @@
 #include <utility>
 #include <vector>
 #include "hm_acq.cuh"
+#include "hm_pack.cuh"
 
 #define HM_LEFT_BITS 22
 #define HM_LEFT_MASK ((1u << HM_LEFT_BITS) - 1u)
@@ -56,6 +57,15 @@
 // larger tree groups do: C5-RF, D_enc = 32, 43.9 -> 40.3 ms when the block went from 512 to 1024 threads)
 #define HM_XTILE_MAX (132 * 1024)
 #define HM_NODEBUF_MAX (96 * 1024)
+// Packed candidates (hm_pack.cuh): a third node layout,
+//   word 0 = T (compare value)  |  forest-wide leaf ordinal (leaf)
+//   word 1 = (byte offset of the first child slot inside the group's node array) << 6 | s        (0 <=> leaf)
+// second slot <=> hi32(code << s) >= T.  There is no feature tile, so the two node buffers take all of shared memory.
+#ifndef HM_PACKED_BLOCK
+#define HM_PACKED_BLOCK 1024
+#endif
+#define HM_PACKED_CTAS (1024 / HM_PACKED_BLOCK)          // CTAs per SM of the packed kernel
+#define HM_PACKED_NODEBUF (((HM_SMEM_TOTAL - 1024 * HM_PACKED_CTAS) / HM_PACKED_CTAS - HM_SMEM_HEADER) / 2 / 16 * 16)
 
 struct HmGroupDesc {
     unsigned long long blob_off;
@@ -86,6 +96,15 @@ struct HmKeyTree {
     unsigned left_mask;          // left    = word1 & left_mask
 };
 
+// host copy of the trees in breadth-first order (children adjacent), kept so that further node layouts (the packed one)
+// can be built after hm_forest_create
+struct HmHostNode {
+    uint32_t w0;       // float32 threshold bits (internal)  |  forest-wide leaf ordinal (leaf)
+    int32_t feat;      // split feature, -1 at leaves (packed trees: the shift s)
+    uint32_t left;     // tree-local index of the left child (right = left + 1)
+};
+typedef std::vector<std::vector<HmHostNode> > HmHostTrees;
+
 struct hm_forest {
     HmForestDev dev;
     int n_trees, n_features, n_leaves, staged, block, nodebuf;
@@ -97,12 +116,31 @@ struct hm_forest {
     void* d_leaf_rank;
     int n_key;
     HmKeyTree key[2];
+    HmHostTrees* host_trees;
+    std::vector<long long>* tree_leaf_base;
+    int sort_mode;                 // coherence pre-pass: -1 auto, 0 off, 1 on
+    // packed layout (hm_forest_attach_packing)
+    int packed;                    // once the packed node arrays exist: 1 = FAST layout (every shift <= 31), 2 = wide
+    int packed_bits;
+    int nodebuf_p;                 // node-buffer size the packed groups were built for
+    HmForestDev devp;
+    void* d_blob_p;
+    void* d_groups_p;
+    HmKeyTree keyp[2];
+};
+
+// multipliers handed to the kernel as RUN-TIME values: as literals the compiler would strength-reduce the multiply-adds
+// that use them into alu-pipe shifts / adds, and the point of those instructions is to run on the fma pipe
+struct HmRtConst {
+    unsigned k26, k1, k8;
 };
 
 struct HmEvalArgs {
     HmForestDev f[HM_MAX_OBJECTIVES];
     int* leaf_out[HM_MAX_OBJECTIVES];
     int M, D, nodebuf, steps_per_tile;
+    const unsigned long long* codes;   // packed path: one 64-bit code per candidate (arrival order, or bucket order with perm)
+    HmRtConst k;                       // 1 << 26, 1, 8 as run-time values
     const float* X;
     long long ldx, N;
     double* mean_out;
@@ -120,11 +158,8 @@ struct HmEvalArgs {
 // block size / node-buffer size as a function of the encoded feature count (shared by create and launch)
 static void hm_forest_geometry(int D, int* block, int* nodebuf) {
     int b = 1024;
-    static long long xtile_max = -1;          // experiments: HM_B200_XTILE_MAX overrides the tile budget (bytes)
-    if (xtile_max < 0) {
-        const char* e = getenv("HM_B200_XTILE_MAX");
-        xtile_max = e ? atoll(e) : (long long)HM_XTILE_MAX;
-    }
+    const char* e = getenv("HM_B200_XTILE_MAX");          // experiments: overrides the tile budget (bytes)
+    const long long xtile_max = e ? atoll(e) : (long long)HM_XTILE_MAX;
     while (b > 128 && (long long)b * D * 4 > xtile_max) b >>= 1;
     size_t xt = (size_t)b * D * 4;
     long long nb = ((long long)HM_SMEM_TOTAL - HM_SMEM_HEADER - (long long)xt) / 2;
@@ -142,6 +177,78 @@ static float hm_floor_to_f32(double t) {
     return f;
 }
 
+// coherence pre-pass default of new handles: -1 auto, 0 off, 1 on (env HM_B200_FOREST_SORT); per handle afterwards
+static int hm_forest_default_sort_mode() {
+    const char* e = getenv("HM_B200_FOREST_SORT");
+    const int m = e ? atoi(e) : -1;
+    return (m < -1 || m > 1) ? -1 : m;
+}
+
+enum { HM_LAYOUT_F32_SMEM = 0, HM_LAYOUT_F32_L2 = 1, HM_LAYOUT_PACKED = 2 };
+
+// Groups the trees (as many consecutive trees as fit one node buffer when the forest is staged through shared memory, one
+// tree per group when it is walked in L2) and lays the node words out for `layout`.
+static int hm_build_blob(const HmHostTrees& trees, int layout, int nodebuf, int block, bool staged,
+                         std::vector<unsigned char>& blob, std::vector<HmGroupDesc>& groups,
+                         std::vector<unsigned>& tree_root, std::vector<long long>& tree_nodes_off) {
+    const int n_trees = (int)trees.size();
+    tree_root.assign(n_trees, 0);
+    tree_nodes_off.assign(n_trees, 0);
+    int t = 0;
+    while (t < n_trees) {
+        int t1 = t;
+        size_t nodes = 0;
+        while (t1 < n_trees) {
+            size_t nn = nodes + trees[t1].size();
+            size_t hdr = (((size_t)(t1 - t + 1) * 4) + 15) & ~(size_t)15;
+            size_t bytes = (hdr + nn * 8 + 15) & ~(size_t)15;
+            if (t1 > t && (!staged || bytes > (size_t)nodebuf)) break;
+            nodes = nn;
+            ++t1;
+            if (!staged) break;
+        }
+        const int ng = t1 - t;
+        const size_t hdr = (((size_t)ng * 4) + 15) & ~(size_t)15;
+        const size_t bytes = (hdr + nodes * 8 + 15) & ~(size_t)15;
+        HM_REQUIRE(nodes <= HM_LEFT_MASK, "group too large");
+        HM_REQUIRE(layout != HM_LAYOUT_F32_SMEM || nodes < (1u << 14), "shared-memory group too large for the packed-word node layout");
+        HmGroupDesc g;
+        g.blob_off = blob.size();
+        g.bytes = (unsigned)bytes;
+        g.first_tree = (unsigned)t;
+        g.n_trees = (unsigned)ng;
+        g.nodes_off = (unsigned)hdr;
+        blob.resize(blob.size() + bytes, 0);
+        unsigned char* gp = blob.data() + g.blob_off;
+        uint32_t* roots = (uint32_t*)gp;
+        uint32_t* nd32 = (uint32_t*)(gp + hdr);
+        uint32_t base = 0;
+        for (int tt = t; tt < t1; ++tt) {
+            const std::vector<HmHostNode>& T = trees[tt];
+            roots[tt - t] = base;
+            tree_root[tt] = base;
+            tree_nodes_off[tt] = (long long)(g.blob_off + hdr);
+            for (size_t h = 0; h < T.size(); ++h) {
+                uint32_t* slot = nd32 + 2 * (size_t)(base + h);
+                slot[0] = T[h].w0;
+                if (T[h].feat < 0) {
+                    slot[1] = 0u;
+                } else if (layout == HM_LAYOUT_F32_SMEM) {
+                    slot[1] = (((uint32_t)T[h].feat * (uint32_t)block) << 16) | (base + T[h].left);
+                } else if (layout == HM_LAYOUT_F32_L2) {
+                    slot[1] = ((uint32_t)T[h].feat << HM_LEFT_BITS) | (base + T[h].left);
+                } else {
+                    slot[1] = (((base + T[h].left) * 8u) << 6) | (uint32_t)T[h].feat;
+                }
+            }
+            base += (uint32_t)T.size();
+        }
+        groups.push_back(g);
+        t = t1;
+    }
+    return 0;
+}
+
 extern "C" int hm_forest_create(int n_trees, int n_features, const int64_t* off, const int32_t* feature,
                                 const double* threshold, const int32_t* left, const int32_t* right,
                                 const double* q, const double* s, const double* u, const double* value,
@@ -155,129 +262,109 @@ extern "C" int hm_forest_create(int n_trees, int n_features, const int64_t* off,
     hm_forest_geometry(n_features, &block, &nodebuf);
     HM_REQUIRE((size_t)block * n_features * 4 <= 160 * 1024, "n_features too large for the shared-memory tile");
 
-    // pass 1: per-tree BFS relayout (children adjacent), sizes
-    struct TreeLay { std::vector<int> order; std::vector<int> newidx; };
-    std::vector<TreeLay> lay(n_trees);
-    size_t max_tree_bytes = 0;
-    long long n_leaves = 0;
+    // pass 1: per-tree breadth-first relayout (children adjacent), leaf ordinals in (tree, breadth-first) order
+    long long n_leaves_total = 0;
     for (int t = 0; t < n_trees; ++t) {
-        long long b = off[t], e = off[t + 1];
-        HM_REQUIRE(e > b, "empty tree");
-        int n = (int)(e - b);
-        HM_REQUIRE(n <= (int)HM_LEFT_MASK, "tree too large (>4M nodes)");
-        TreeLay& L = lay[t];
-        L.order.reserve(n);
-        L.newidx.assign(n, -1);
-        L.order.push_back(0);
-        L.newidx[0] = 0;
-        for (size_t h = 0; h < L.order.size(); ++h) {
-            int nd = L.order[h];
-            int l = left[b + nd], r = right[b + nd];
+        HM_REQUIRE(off[t + 1] > off[t], "empty tree");
+        HM_REQUIRE(off[t + 1] - off[t] <= (long long)HM_LEFT_MASK, "tree too large (>4M nodes)");
+        for (long long i = off[t]; i < off[t + 1]; ++i) n_leaves_total += !(left[i] >= 0 && left[i] != right[i]);
+    }
+    HmHostTrees* trees = new (std::nothrow) HmHostTrees((size_t)n_trees);
+    std::vector<long long>* leaf_base = new (std::nothrow) std::vector<long long>((size_t)n_trees + 1, 0);
+    if (!trees || !leaf_base) {
+        delete trees;
+        delete leaf_base;
+        return HM_E_NOMEM;
+    }
+    struct Guard {
+        HmHostTrees* a;
+        std::vector<long long>* b;
+        ~Guard() { delete a; delete b; }
+    } guard = {trees, leaf_base};
+    std::vector<double> leaf_tab((size_t)n_leaves_total * 4, 0.0);
+    std::vector<int> leaf_node((size_t)n_leaves_total, 0);
+    std::vector<unsigned> leaf_rank((size_t)n_leaves_total, 0);
+    size_t max_tree_bytes = 0;
+    long long leaf_ord = 0;
+    for (int t = 0; t < n_trees; ++t) {
+        const long long b = off[t];
+        const int n = (int)(off[t + 1] - b);
+        std::vector<int> order, newidx(n, -1);
+        order.reserve(n);
+        order.push_back(0);
+        newidx[0] = 0;
+        for (size_t h = 0; h < order.size(); ++h) {
+            const int nd = order[h];
+            const int l = left[b + nd], r = right[b + nd];
             if (l >= 0 && l != r) {
                 HM_REQUIRE(l < n && r >= 0 && r < n, "child index out of range");
-                HM_REQUIRE(L.newidx[l] < 0 && L.newidx[r] < 0, "tree is not a tree");
-                int f = feature[b + nd];
+                HM_REQUIRE(newidx[l] < 0 && newidx[r] < 0, "tree is not a tree");
+                const int f = feature[b + nd];
                 HM_REQUIRE(f >= 0 && f < n_features, "feature index out of range");
-                L.newidx[l] = (int)L.order.size();
-                L.order.push_back(l);
-                L.newidx[r] = (int)L.order.size();
-                L.order.push_back(r);
-            } else {
-                ++n_leaves;
+                newidx[l] = (int)order.size();
+                order.push_back(l);
+                newidx[r] = (int)order.size();
+                order.push_back(r);
             }
         }
-        HM_REQUIRE((int)L.order.size() == n, "unreachable nodes in tree");
+        HM_REQUIRE((int)order.size() == n, "unreachable nodes in tree");
         max_tree_bytes = std::max(max_tree_bytes, (size_t)n * 8 + 16);
+        std::vector<HmHostNode>& T = (*trees)[t];
+        T.resize(n);
+        (*leaf_base)[t] = leaf_ord;
+        for (int h = 0; h < n; ++h) {
+            const int nd = order[h];
+            const int l = left[b + nd], r = right[b + nd];
+            if (l >= 0 && l != r) {
+                const float thr = hm_floor_to_f32(threshold[b + nd]);
+                memcpy(&T[h].w0, &thr, 4);
+                T[h].feat = feature[b + nd];
+                T[h].left = (uint32_t)newidx[l];
+            } else {
+                T[h].w0 = (uint32_t)leaf_ord;
+                T[h].feat = -1;
+                T[h].left = 0;
+                leaf_tab[4 * leaf_ord + 0] = q ? q[b + nd] : 0.0;
+                leaf_tab[4 * leaf_ord + 1] = s ? s[b + nd] : 0.0;
+                leaf_tab[4 * leaf_ord + 2] = u ? u[b + nd] : 0.0;
+                leaf_tab[4 * leaf_ord + 3] = value ? value[b + nd] : 0.0;
+                leaf_node[leaf_ord] = nd;
+                ++leaf_ord;
+            }
+        }
+        // DFS (= sklearn node id) rank of every leaf of this tree: neighbouring ranks are neighbouring regions
+        {
+            const long long lb = (*leaf_base)[t], le = leaf_ord;
+            std::vector<std::pair<int, long long> > byid;
+            byid.reserve((size_t)(le - lb));
+            for (long long o = lb; o < le; ++o) byid.push_back(std::make_pair(leaf_node[o], o));
+            std::sort(byid.begin(), byid.end());
+            for (size_t r = 0; r < byid.size(); ++r) leaf_rank[byid[r].second] = (unsigned)r;
+        }
     }
+    (*leaf_base)[n_trees] = leaf_ord;
+    const long long n_leaves = leaf_ord;
     const int staged = (max_tree_bytes <= (size_t)nodebuf) ? 1 : 0;
 
-    // pass 2: grouping
+    // pass 2: grouping + node words of the fp32 layout
     std::vector<HmGroupDesc> groups;
     std::vector<unsigned char> blob;
-    std::vector<double> leaf_tab((size_t)n_leaves * 4, 0.0);
-    std::vector<int> leaf_node((size_t)n_leaves, 0);
-    std::vector<unsigned> leaf_rank((size_t)n_leaves, 0);
-    std::vector<long long> tree_leaf_base(n_trees + 1, 0), tree_nodes_off(n_trees, 0);
-    std::vector<unsigned> tree_root(n_trees, 0);
-    long long leaf_ord = 0;
-    int t = 0;
-    while (t < n_trees) {
-        int t1 = t;
-        size_t nodes = 0;
-        // extend while the group fits (staged) / one tree per group (walked in L2)
-        while (t1 < n_trees) {
-            size_t nn = nodes + (size_t)(off[t1 + 1] - off[t1]);
-            size_t hdr = (((size_t)(t1 - t + 1) * 4) + 15) & ~(size_t)15;
-            size_t bytes = hdr + nn * 8;
-            bytes = (bytes + 15) & ~(size_t)15;
-            if (t1 > t && (!staged || bytes > (size_t)nodebuf)) break;
-            nodes = nn;
-            ++t1;
-            if (!staged) break;
-        }
-        const int ng = t1 - t;
-        const size_t hdr = (((size_t)ng * 4) + 15) & ~(size_t)15;
-        size_t bytes = (hdr + nodes * 8 + 15) & ~(size_t)15;
-        HM_REQUIRE(nodes <= HM_LEFT_MASK, "group too large");
-        HM_REQUIRE(!staged || nodes < (1u << 14), "shared-memory group too large for the packed node layout");
-        HmGroupDesc g;
-        g.blob_off = blob.size();
-        g.bytes = (unsigned)bytes;
-        g.first_tree = (unsigned)t;
-        g.n_trees = (unsigned)ng;
-        g.nodes_off = (unsigned)hdr;
-        blob.resize(blob.size() + bytes, 0);
-        unsigned char* gp = blob.data() + g.blob_off;
-        uint32_t* roots = (uint32_t*)gp;
-        uint32_t* nd32 = (uint32_t*)(gp + hdr);
-        uint32_t base = 0;
-        for (int tt = t; tt < t1; ++tt) {
-            const TreeLay& L = lay[tt];
-            const long long b = off[tt];
-            roots[tt - t] = base;
-            tree_root[tt] = base;
-            tree_nodes_off[tt] = (long long)(g.blob_off + hdr);
-            tree_leaf_base[tt] = leaf_ord;
-            for (size_t h = 0; h < L.order.size(); ++h) {
-                int nd = L.order[h];
-                int l = left[b + nd], r = right[b + nd];
-                uint32_t* slot = nd32 + 2 * (size_t)(base + h);
-                if (l >= 0 && l != r) {
-                    float thr = hm_floor_to_f32(threshold[b + nd]);
-                    uint32_t tb;
-                    memcpy(&tb, &thr, 4);
-                    slot[0] = tb;
-                    slot[1] = staged ? (((uint32_t)feature[b + nd] * (uint32_t)block) << 16) | (base + (uint32_t)L.newidx[l])
-                                     : ((uint32_t)feature[b + nd] << HM_LEFT_BITS) | (base + (uint32_t)L.newidx[l]);
-                } else {
-                    slot[0] = (uint32_t)leaf_ord;
-                    slot[1] = 0u;
-                    leaf_tab[4 * leaf_ord + 0] = q ? q[b + nd] : 0.0;
-                    leaf_tab[4 * leaf_ord + 1] = s ? s[b + nd] : 0.0;
-                    leaf_tab[4 * leaf_ord + 2] = u ? u[b + nd] : 0.0;
-                    leaf_tab[4 * leaf_ord + 3] = value ? value[b + nd] : 0.0;
-                    leaf_node[leaf_ord] = nd;
-                    ++leaf_ord;
-                }
-            }
-            base += (uint32_t)L.order.size();
-            // DFS (= sklearn node id) rank of every leaf of this tree: neighbouring ranks are neighbouring regions
-            {
-                const long long lb = tree_leaf_base[tt], le = leaf_ord;
-                std::vector<std::pair<int, long long>> byid;
-                byid.reserve((size_t)(le - lb));
-                for (long long o = lb; o < le; ++o) byid.push_back(std::make_pair(leaf_node[o], o));
-                std::sort(byid.begin(), byid.end());
-                for (size_t r = 0; r < byid.size(); ++r) leaf_rank[byid[r].second] = (unsigned)r;
-            }
-        }
-        groups.push_back(g);
-        t = t1;
+    std::vector<unsigned> tree_root;
+    std::vector<long long> tree_nodes_off;
+    {
+        int rc = hm_build_blob(*trees, staged ? HM_LAYOUT_F32_SMEM : HM_LAYOUT_F32_L2, nodebuf, block, staged != 0, blob,
+                               groups, tree_root, tree_nodes_off);
+        if (rc) return rc;
     }
 
     hm_forest* F = new (std::nothrow) hm_forest();
     if (!F) return HM_E_NOMEM;
     memset(F, 0, sizeof(*F));
+    F->host_trees = trees;
+    F->tree_leaf_base = leaf_base;
+    guard.a = nullptr;
+    guard.b = nullptr;
+    F->sort_mode = hm_forest_default_sort_mode();
     F->n_trees = n_trees;
     F->n_features = n_features;
     F->n_leaves = (int)n_leaves;
@@ -294,9 +381,9 @@ extern "C" int hm_forest_create(int n_trees, int n_features, const int64_t* off,
     }
     HM_F_TRY(cudaMalloc(&F->d_blob, blob.size()));
     HM_F_TRY(cudaMalloc(&F->d_groups, groups.size() * sizeof(HmGroupDesc)));
-    HM_F_TRY(cudaMalloc(&F->d_leaf_tab, leaf_tab.size() * sizeof(double)));
-    HM_F_TRY(cudaMalloc(&F->d_leaf_node, leaf_node.size() * sizeof(int)));
-    HM_F_TRY(cudaMalloc(&F->d_leaf_rank, leaf_rank.size() * sizeof(unsigned)));
+    HM_F_TRY(cudaMalloc(&F->d_leaf_tab, std::max<size_t>(leaf_tab.size(), 1) * sizeof(double)));
+    HM_F_TRY(cudaMalloc(&F->d_leaf_node, std::max<size_t>(leaf_node.size(), 1) * sizeof(int)));
+    HM_F_TRY(cudaMalloc(&F->d_leaf_rank, std::max<size_t>(leaf_rank.size(), 1) * sizeof(unsigned)));
     HM_F_TRY(cudaMemcpy(F->d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
     HM_F_TRY(cudaMemcpy(F->d_groups, groups.data(), groups.size() * sizeof(HmGroupDesc), cudaMemcpyHostToDevice));
     HM_F_TRY(cudaMemcpy(F->d_leaf_tab, leaf_tab.data(), leaf_tab.size() * sizeof(double), cudaMemcpyHostToDevice));
@@ -313,19 +400,143 @@ extern "C" int hm_forest_create(int n_trees, int n_features, const int64_t* off,
     F->dev.n_groups = (int)groups.size();
     F->dev.n_trees = n_trees;
     F->dev.staged = staged;
-    tree_leaf_base[n_trees] = leaf_ord;
     F->n_key = std::min(n_trees, 2);
     for (int kk = 0; kk < F->n_key; ++kk) {
         F->key[kk].nodes = (const uint2*)((const unsigned char*)F->d_blob + tree_nodes_off[kk]);
         F->key[kk].leaf_rank = (const unsigned*)F->d_leaf_rank;
         F->key[kk].root = tree_root[kk];
-        F->key[kk].n_leaves = (unsigned)(tree_leaf_base[kk + 1] - tree_leaf_base[kk]);
+        F->key[kk].n_leaves = (unsigned)((*leaf_base)[kk + 1] - (*leaf_base)[kk]);
         unsigned lg = 0;
         while ((1 << lg) < block) ++lg;
         F->key[kk].feat_shift = staged ? 16u + lg : (unsigned)HM_LEFT_BITS;
         F->key[kk].left_mask = staged ? HM_PK_LEFT_MASK : HM_LEFT_MASK;
     }
     *out = F;
+    return 0;
+}
+
+// Builds the packed node arrays of `F` for the all-discrete space `S` (hm_pack.cuh): every split (feature column,
+// float32 threshold) becomes (shift, compare value) on the candidate's 64-bit code; splits that cannot separate any two
+// values of their parameter are bypassed.  Decisions are identical to the fp32 path for every candidate of the space.
+extern "C" int hm_forest_attach_packing(hm_forest_t* F, const hm_space_t* S) {
+    HM_REQUIRE(F != nullptr && S != nullptr, "forest/space");
+    HM_REQUIRE(S->pack_bits > 0, "the space has real / integer parameters or needs more than 64 bits: not packable");
+    HM_REQUIRE(S->D_enc == F->n_features, "encoded width of the space must equal the forest's n_features");
+    if (F->packed) return 0;
+    // encoded column -> (parameter, category)
+    std::vector<int> col_param(F->n_features, -1), col_cat(F->n_features, -1);
+    for (int j = 0; j < S->D; ++j) {
+        const HmPackField& f = S->pack[j];
+        const int ncol = f.kind == HM_P_CATEGORICAL ? f.n_values : 1;
+        for (int c = 0; c < ncol; ++c) {
+            HM_REQUIRE(f.out_col + c < F->n_features && col_param[f.out_col + c] < 0, "encoded columns of the space overlap");
+            col_param[f.out_col + c] = j;
+            col_cat[f.out_col + c] = f.kind == HM_P_CATEGORICAL ? c : -1;
+        }
+    }
+    // float32 encoded values of every ordinal, ascending (models.py:962-965, cast as sklearn's check_array does)
+    std::vector<std::vector<float> > enc32(S->D);
+    for (int j = 0; j < S->D; ++j) {
+        if (S->pack[j].kind != HM_P_ORDINAL) continue;
+        const hm_param_desc_t& d = S->params[j];
+        enc32[j].resize(d.n_values);
+        for (int r = 0; r < d.n_values; ++r) {
+            enc32[j][r] = (float)S->tables[(size_t)d.values_off + d.n_values + r];
+            HM_REQUIRE(r == 0 || enc32[j][r] >= enc32[j][r - 1], "encoded ordinal values must ascend");
+        }
+    }
+    const HmHostTrees& src = *F->host_trees;
+    HmHostTrees dst(src.size());
+    size_t max_tree_bytes = 0;
+    bool all_fast = true;                 // every surviving split shifts by <= 31: the 32-bit funnel-shift kernel applies
+    for (size_t t = 0; t < src.size(); ++t) {
+        const std::vector<HmHostNode>& T = src[t];
+        // direction of every split on the space's value sets: 0 = both possible, 1 = always left, 2 = always right
+        std::vector<unsigned char> fixed(T.size(), 0), swapped(T.size(), 0);
+        std::vector<uint32_t> cmp(T.size(), 0), shift(T.size(), 0);
+        for (size_t h = 0; h < T.size(); ++h) {
+            if (T[h].feat < 0) continue;
+            HM_REQUIRE(col_param[T[h].feat] >= 0, "a split uses an encoded column the space does not produce");
+            const int j = col_param[T[h].feat];
+            const HmPackField& f = S->pack[j];
+            float thr;
+            memcpy(&thr, &T[h].w0, 4);
+            if (col_cat[T[h].feat] >= 0) {
+                const int c = col_cat[T[h].feat];
+                if (!(thr >= 0.0f)) fixed[h] = 2;            // 0 > thr and 1 > thr (also a NaN threshold: x <= NaN is false)
+                else if (thr >= 1.0f) fixed[h] = 1;
+                else if (f.n_values == 1) fixed[h] = 2;      // the column of a one-category categorical is always 1.0
+                else if (c < f.n_values - 1) {               // right <=> the category's bit is set
+                    shift[h] = (uint32_t)(63 - (f.low + c));
+                    cmp[h] = 0x80000000u;
+                } else {                                     // last category: right <=> the whole field is zero
+                    shift[h] = (uint32_t)(63 - f.top);
+                    cmp[h] = 1u << (32 - f.width);
+                    swapped[h] = 1;
+                }
+            } else {
+                int r1 = 0;
+                while (r1 < f.n_values && enc32[j][r1] <= thr) ++r1;
+                if (r1 == 0) fixed[h] = 2;
+                else if (r1 == f.n_values) fixed[h] = 1;
+                else {
+                    shift[h] = (uint32_t)(63 - f.top);
+                    cmp[h] = (uint32_t)r1 << (32 - f.width);
+                }
+            }
+            if (!fixed[h] && shift[h] > 31) all_fast = false;
+        }
+        auto resolve = [&](uint32_t h) {
+            while (T[h].feat >= 0 && fixed[h]) h = T[h].left + (fixed[h] == 2 ? 1u : 0u);
+            return h;
+        };
+        std::vector<uint32_t> order;
+        order.push_back(resolve(0));
+        std::vector<HmHostNode>& O = dst[t];
+        for (size_t k = 0; k < order.size(); ++k) {
+            const uint32_t h = order[k];
+            HmHostNode nd;
+            if (T[h].feat < 0) {
+                nd = T[h];
+            } else {
+                nd.w0 = cmp[h];
+                nd.feat = (int32_t)shift[h];
+                nd.left = (uint32_t)order.size();
+                // first slot: taken when the test fails = sklearn's left child, unless the test is the swapped one
+                order.push_back(resolve(T[h].left + (swapped[h] ? 1u : 0u)));
+                order.push_back(resolve(T[h].left + (swapped[h] ? 0u : 1u)));
+            }
+            O.push_back(nd);
+        }
+        max_tree_bytes = std::max(max_tree_bytes, O.size() * 8 + 16);
+    }
+    int nodebuf_p = HM_PACKED_NODEBUF;      // experiments: a smaller buffer leaves part of the 228 KB to the L1 cache
+    if (const char* e = getenv("HM_B200_PACKED_NODEBUF")) nodebuf_p = std::min(HM_PACKED_NODEBUF, std::max(4096, atoi(e) & ~15));
+    const int staged = max_tree_bytes <= (size_t)nodebuf_p ? 1 : 0;
+    std::vector<HmGroupDesc> groups;
+    std::vector<unsigned char> blob;
+    std::vector<unsigned> tree_root;
+    std::vector<long long> tree_nodes_off;
+    int rc = hm_build_blob(dst, HM_LAYOUT_PACKED, nodebuf_p, 0, staged != 0, blob, groups, tree_root, tree_nodes_off);
+    if (rc) return rc;
+    HM_CUDA_TRY(cudaMalloc(&F->d_blob_p, blob.size()));
+    HM_CUDA_TRY(cudaMalloc(&F->d_groups_p, groups.size() * sizeof(HmGroupDesc)));
+    HM_CUDA_TRY(cudaMemcpy(F->d_blob_p, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+    HM_CUDA_TRY(cudaMemcpy(F->d_groups_p, groups.data(), groups.size() * sizeof(HmGroupDesc), cudaMemcpyHostToDevice));
+    HM_CUDA_TRY(cudaDeviceSynchronize());
+    F->devp = F->dev;
+    F->devp.blob = (const unsigned char*)F->d_blob_p;
+    F->devp.groups = (const HmGroupDesc*)F->d_groups_p;
+    F->devp.n_groups = (int)groups.size();
+    F->devp.staged = staged;
+    for (int kk = 0; kk < F->n_key; ++kk) {
+        F->keyp[kk] = F->key[kk];
+        F->keyp[kk].nodes = (const uint2*)((const unsigned char*)F->d_blob_p + tree_nodes_off[kk]);
+        F->keyp[kk].root = tree_root[kk];
+    }
+    F->packed_bits = S->pack_bits;
+    F->nodebuf_p = nodebuf_p;
+    F->packed = all_fast ? 1 : 2;
     return 0;
 }
 
@@ -336,18 +547,26 @@ extern "C" void hm_forest_destroy(hm_forest_t* F) {
     cudaFree(F->d_leaf_tab);
     cudaFree(F->d_leaf_node);
     cudaFree(F->d_leaf_rank);
+    cudaFree(F->d_blob_p);
+    cudaFree(F->d_groups_p);
+    delete F->host_trees;
+    delete F->tree_leaf_base;
     delete F;
 }
 extern "C" int hm_forest_n_trees(const hm_forest_t* f) { return f ? f->n_trees : 0; }
 extern "C" int hm_forest_n_features(const hm_forest_t* f) { return f ? f->n_features : 0; }
 extern "C" int hm_forest_staged(const hm_forest_t* f) { return f ? f->staged : 0; }
 extern "C" int hm_forest_n_groups(const hm_forest_t* f) { return f ? f->dev.n_groups : 0; }
+extern "C" int hm_forest_packed(const hm_forest_t* f) { return f ? f->packed : 0; }
+extern "C" int hm_forest_packed_groups(const hm_forest_t* f) { return (f && f->packed) ? f->devp.n_groups : 0; }
 
 // ------------------------------------------------------------------------------------------------------------
 // Running sums of one objective + the leaf records of the previous round of trees, still in flight: a round's leaf
 // gathers (L2 latency, ~30 % of a round when waited for on the spot) are issued when its walk ends and added -- in tree
 // order -- only after the NEXT round's walk, so their latency hides behind that walk.
+#ifndef HM_MAX_CHAINS
 #define HM_MAX_CHAINS 3
+#endif
 struct HmAcc {
     double q, s, u, v;
     double pq[HM_MAX_CHAINS], ps[HM_MAX_CHAINS], pu[HM_MAX_CHAINS], pv[HM_MAX_CHAINS];
@@ -377,14 +596,99 @@ __device__ __forceinline__ void hm_acc_clear_pending(HmAcc& acc) {
 // ...); the chains of different trees are independent, so their loads overlap; a chain that has reached its leaf
 // idles (predicated off) until the slowest of the NCH is done.  The leaf records are then added in tree order, so the
 // fp64 sums are unchanged.
-template <bool APPLY, bool NEED_V, bool SMEM, int NCH>
+template <bool APPLY, bool NEED_V, bool SMEM, int NCH, int PACKED>
 __device__ __forceinline__ void hm_walk_round(const uint32_t* __restrict__ roots, const uint2* __restrict__ nodes,
                                               int t0, const float* __restrict__ xs_t, int BD,
+                                              unsigned long long code, HmRtConst k,
                                               const double* __restrict__ leaf_tab, const int* __restrict__ leaf_node,
                                               HmAcc& acc, int* __restrict__ leaf_out, long long N, long long i,
                                               bool valid, int first_tree) {
     uint2 nd[NCH];
-    if (SMEM) {
+    if (SMEM && PACKED) {
+        // packed candidates: the split is a shift and an unsigned compare on the 64-bit code held in a register pair
+        // (hm_pack.cuh); word 1 = (byte offset of the first child slot) << 6 | shift, 0 at a leaf.  One shared-memory load
+        // per visit (the node).  The loop is bound by the alu pipe (one warp instruction per two cycles; shift, leaf test,
+        // compare, predicated add), so everything that can run elsewhere does: the slot address is an IMAD.HI with its
+        // multiplier in a register (fma pipe; as a literal it would be strength-reduced to an alu-pipe LEA.HI), the node
+        // stays in one aligned register pair (no moves around the load) and the loop condition is one three-input OR.
+        const uint32_t nodes_a = hm_smem_u32(nodes);
+        const uint32_t c_lo = (uint32_t)code, c_hi = (uint32_t)(code >> 32);
+        unsigned long long nq[NCH];
+        uint32_t yy[NCH];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            nq[c] = reinterpret_cast<const unsigned long long*>(nodes)[roots[t0 + c]];
+            asm volatile("{\n\t.reg .b32 lo;\n\tmov.b64 {lo, %0}, %1;\n\t}" : "=r"(yy[c]) : "l"(nq[c]));
+        }
+        uint32_t live = 0;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) live |= yy[c];
+        while (live) {
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                if (PACKED == 1) {
+                    asm volatile(
+                        "{\n\t"
+                        ".reg .pred p, q;\n\t"
+                        ".reg .b32 th, y, hi, na;\n\t"
+                        "mov.b64 {th, y}, %0;\n\t"
+                        "setp.ne.u32 p, y, 0;\n\t"
+                        "shf.l.wrap.b32 hi, %3, %4, y;\n\t"          // hi32(code << (y & 31)): every shift is <= 31
+                        "mad.hi.u32 na, y, %5, %2;\n\t"              // nodes + (y >> 6)
+                        "setp.ge.u32 q, hi, th;\n\t"                 // second slot <=> hi32(code << s) >= T
+                        "@q add.u32 na, na, 8;\n\t"
+                        "@p ld.shared.b64 %0, [na];\n\t"
+                        "mov.b64 {th, %1}, %0;\n\t"
+                        "}"
+                        : "+l"(nq[c]), "=r"(yy[c])
+                        : "r"(nodes_a), "r"(c_lo), "r"(c_hi), "r"(k.k26));
+                } else {
+                    asm volatile(
+                        "{\n\t"
+                        ".reg .pred p, q;\n\t"
+                        ".reg .b32 th, y, sft, lo, hi, na;\n\t"
+                        ".reg .b64 sh;\n\t"
+                        "mov.b64 {th, y}, %0;\n\t"
+                        "setp.ne.u32 p, y, 0;\n\t"
+                        "and.b32 sft, y, 63;\n\t"
+                        "shl.b64 sh, %3, sft;\n\t"
+                        "mov.b64 {lo, hi}, sh;\n\t"
+                        "mad.hi.u32 na, y, %4, %2;\n\t"
+                        "setp.ge.u32 q, hi, th;\n\t"
+                        "@q add.u32 na, na, 8;\n\t"
+                        "@p ld.shared.b64 %0, [na];\n\t"
+                        "mov.b64 {th, %1}, %0;\n\t"
+                        "}"
+                        : "+l"(nq[c]), "=r"(yy[c])
+                        : "r"(nodes_a), "l"(code), "r"(k.k26));
+                }
+            }
+            live = 0;
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) live |= yy[c];
+        }
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) nd[c] = make_uint2((uint32_t)nq[c], (uint32_t)(nq[c] >> 32));
+    } else if (PACKED) {
+        // packed candidates, trees too large for a node buffer: walked in L2
+        const unsigned char* nb = reinterpret_cast<const unsigned char*>(nodes);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) nd[c] = nodes[roots[t0 + c]];
+        bool any = false;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) any = any || (nd[c].y != 0u);
+        while (any) {
+            any = false;
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                if (nd[c].y != 0u) {
+                    const uint32_t hi = (uint32_t)((code << (nd[c].y & 63u)) >> 32);
+                    nd[c] = *reinterpret_cast<const uint2*>(nb + (nd[c].y >> 6) + (hi >= nd[c].x ? 8u : 0u));
+                    any = any || (nd[c].y != 0u);
+                }
+            }
+        }
+    } else if (SMEM) {
         // shared-memory forest.  One visit = one PTX block per chain (ptxas interleaves the chains): both loads are
         // predicated on "this chain is still at an internal node", so a finished chain issues no load and no branch;
         // the node lives in one 64-bit register {threshold bits | leaf ordinal, feature << 22 | left}.
@@ -470,14 +774,15 @@ __device__ __forceinline__ void hm_walk_round(const uint32_t* __restrict__ roots
 
 // Walk `ntrees` trees whose roots/nodes are at the given pointers (shared or global), in tree order: rounds of 3,
 // then what is left as a round of 2 and/or 1 (4 = 2 + 2).
-template <bool APPLY, bool NEED_V, bool SMEM>
+template <bool APPLY, bool NEED_V, bool SMEM, int PACKED>
 __device__ __forceinline__ void hm_walk_group(const uint32_t* __restrict__ roots, const uint2* __restrict__ nodes,
-                                              int ntrees, const float* __restrict__ xs_t, int BD,
+                                              int ntrees, const float* __restrict__ xs_t, int BD, unsigned long long code,
+                                              HmRtConst k,
                                               const double* __restrict__ leaf_tab, const int* __restrict__ leaf_node,
                                               HmAcc& acc, int* __restrict__ leaf_out, long long N, long long i,
                                               bool valid, int first_tree) {
     int t = 0;
-#define HM_ROUND(K) hm_walk_round<APPLY, NEED_V, SMEM, K>(roots, nodes, t, xs_t, BD, leaf_tab, leaf_node, acc, leaf_out, N, i, valid, first_tree)
+#define HM_ROUND(K) hm_walk_round<APPLY, NEED_V, SMEM, K, PACKED>(roots, nodes, t, xs_t, BD, code, k, leaf_tab, leaf_node, acc, leaf_out, N, i, valid, first_tree)
 #if HM_FOREST_MAXCH >= 5
     while (ntrees - t >= 5) { HM_ROUND(5); t += 5; }
 #endif
@@ -490,12 +795,12 @@ __device__ __forceinline__ void hm_walk_group(const uint32_t* __restrict__ roots
 #undef HM_ROUND
 }
 
-template <bool APPLY, bool NEED_V, int BDT>
-__global__ void __launch_bounds__(BDT, 1) hm_forest_kernel(const __grid_constant__ HmEvalArgs a) {
+template <bool APPLY, bool NEED_V, int BDT, int PACKED>
+__global__ void __launch_bounds__(BDT, (PACKED && BDT < 1024) ? 1024 / BDT : 1) hm_forest_kernel(const __grid_constant__ HmEvalArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
     unsigned char* nbuf0 = smem + HM_SMEM_HEADER;
-    float* xs = reinterpret_cast<float*>(smem + HM_SMEM_HEADER + 2 * (size_t)a.nodebuf);
+    float* xs = reinterpret_cast<float*>(smem + HM_SMEM_HEADER + 2 * (size_t)a.nodebuf);     // unused when PACKED
 
     const int tid = threadIdx.x;
     constexpr int BD = BDT;      // compile-time block size: the x-tile stride folds into the address arithmetic
@@ -544,7 +849,10 @@ __global__ void __launch_bounds__(BDT, 1) hm_forest_kernel(const __grid_constant
         const long long sl = valid ? slot : a.N - 1;
         // i = the candidate this thread evaluates: arrival order, or the coherence order of the pre-pass
         const long long i = a.perm ? (long long)__ldg(a.perm + sl) : sl;
-        if (a.Xrows) {
+        unsigned long long code = 0ull;
+        if (PACKED) {
+            code = __ldg(a.codes + sl);          // arrival order, or the bucket-ordered copy of the pre-pass (with perm)
+        } else if (a.Xrows) {
             // the pre-pass left this slot's candidate as one contiguous row: Dp/4 128-bit loads
             const float4* row = reinterpret_cast<const float4*>(a.Xrows + (size_t)sl * (size_t)a.Dp);
             for (int q = 0; 4 * q < a.D; ++q) {
@@ -575,8 +883,8 @@ __global__ void __launch_bounds__(BDT, 1) hm_forest_kernel(const __grid_constant
                     const unsigned ntr = __ldg(&F.groups[g].n_trees);
                     const unsigned noff = __ldg(&F.groups[g].nodes_off);
                     const unsigned ft = __ldg(&F.groups[g].first_tree);
-                    hm_walk_group<APPLY, NEED_V, true>(reinterpret_cast<const uint32_t*>(gb),
-                                         reinterpret_cast<const uint2*>(gb + noff), (int)ntr, xs_t, BD, F.leaf_tab,
+                    hm_walk_group<APPLY, NEED_V, true, PACKED>(reinterpret_cast<const uint32_t*>(gb),
+                                         reinterpret_cast<const uint2*>(gb + noff), (int)ntr, xs_t, BD, code, a.k, F.leaf_tab,
                                          F.leaf_node, acc, lo, a.N, i, valid, (int)ft);
                     if (!resident) {
                         __syncthreads();   // everyone is done reading this buffer
@@ -589,9 +897,9 @@ __global__ void __launch_bounds__(BDT, 1) hm_forest_kernel(const __grid_constant
                 for (int g = 0; g < F.n_groups; ++g) {
                     const HmGroupDesc gd = F.groups[g];
                     const unsigned char* gb = F.blob + gd.blob_off;
-                    hm_walk_group<APPLY, NEED_V, false>(reinterpret_cast<const uint32_t*>(gb),
+                    hm_walk_group<APPLY, NEED_V, false, PACKED>(reinterpret_cast<const uint32_t*>(gb),
                                          reinterpret_cast<const uint2*>(gb + gd.nodes_off), (int)gd.n_trees, xs_t, BD,
-                                         F.leaf_tab, F.leaf_node, acc, lo, a.N, i, valid, (int)gd.first_tree);
+                                         code, a.k, F.leaf_tab, F.leaf_node, acc, lo, a.N, i, valid, (int)gd.first_tree);
                 }
             }
             hm_acc_flush<NEED_V>(acc);
@@ -724,33 +1032,79 @@ __global__ void __launch_bounds__(256) hm_forest_scatter_rows(const unsigned* __
     }
 }
 
-static int g_forest_sort_mode = -2;       // -1 auto, 0 off, 1 on; -2 = not read yet (env HM_B200_FOREST_SORT)
-static int hm_forest_sort_mode() {
-    if (g_forest_sort_mode == -2) {
-        const char* e = getenv("HM_B200_FOREST_SORT");
-        g_forest_sort_mode = e ? atoi(e) : -1;
+// packed candidates: the same key, the key trees walked with the packed split test
+__global__ void __launch_bounds__(256) hm_forest_sortkey_packed(const HmKeyArgs a, const unsigned long long* __restrict__ codes,
+                                                                unsigned* __restrict__ key, unsigned* __restrict__ hist) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.N) return;
+    const unsigned long long code = __ldg(codes + i);
+    unsigned k = 0;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        if (q < a.n_key) {
+            const unsigned char* nb = reinterpret_cast<const unsigned char*>(a.t[q].nodes);
+            uint2 nd = __ldg(a.t[q].nodes + a.t[q].root);
+            while (nd.y != 0u) {
+                const uint32_t hi = (uint32_t)((code << (nd.y & 63u)) >> 32);
+                nd = __ldg(reinterpret_cast<const uint2*>(nb + (nd.y >> 6) + (hi >= nd.x ? 8u : 0u)));
+            }
+            const unsigned r = __ldg(a.t[q].leaf_rank + nd.x) >> a.shift[q];
+            k = (q == 0) ? r : k * a.nB + r;
+        }
     }
-    return g_forest_sort_mode;
+    key[i] = k;
+    atomicAdd(hist + k, 1u);
 }
-extern "C" int hm_forest_set_coherence_mode(int mode) {
+
+// pos = offset[key[i]]++;  perm[pos] = i;  sorted[pos] = code i
+__global__ void __launch_bounds__(256) hm_forest_scatter_codes(const unsigned* __restrict__ key, unsigned* __restrict__ offs,
+                                                               const unsigned long long* __restrict__ codes, long long N,
+                                                               unsigned* __restrict__ perm,
+                                                               unsigned long long* __restrict__ sorted) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const unsigned pos = atomicAdd(offs + key[i], 1u);
+    perm[pos] = (unsigned)i;
+    sorted[pos] = __ldg(codes + i);
+}
+
+extern "C" int hm_forest_set_coherence(hm_forest_t* f, int mode) {
+    HM_REQUIRE(f != nullptr, "forest");
     HM_REQUIRE(mode >= -1 && mode <= 1, "mode in {-1 auto, 0 off, 1 on}");
-    g_forest_sort_mode = mode;
+    f->sort_mode = mode;
     return 0;
 }
 
-// builds the coherence permutation of the N candidates in *perm_out (stream-ordered allocation, freed by the caller)
-static int hm_forest_build_perm(const hm_forest_t* const* forests, int M, const float* Xcm, int64_t ldx, int64_t N,
-                                cudaStream_t st, unsigned** perm_out, float** rows_out, int* Dp_out, void** scratch_out) {
+// keep freed stream-ordered blocks in the pool: the next call reuses them without a driver round trip (once per device)
+static void hm_forest_keep_pool() {
+    static unsigned done_mask = 0;                  // bit per device; a benign race sets the same attribute twice
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 32 && (done_mask >> dev & 1u)) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    if (dev < 32) done_mask |= 1u << dev;
+}
+
+// builds the coherence permutation of the N candidates in *perm_out (stream-ordered allocation, freed by the caller);
+// fp32 path: candidates also copied as contiguous rows in bucket order; packed path: the codes in bucket order
+static int hm_forest_build_perm(const hm_forest_t* const* forests, int M, const float* Xcm, int64_t ldx,
+                                const unsigned long long* codes, int64_t N, cudaStream_t st, unsigned** perm_out,
+                                float** rows_out, int* Dp_out, unsigned long long** codes_out, void** scratch_out) {
+    const bool packed = codes != nullptr;
     HmKeyArgs ka;
     memset(&ka, 0, sizeof(ka));
     // key trees: one from each of the first two forests, or the first two trees of a single forest
     if (M >= 2) {
-        ka.t[0] = forests[0]->key[0];
-        ka.t[1] = forests[1]->key[0];
+        ka.t[0] = packed ? forests[0]->keyp[0] : forests[0]->key[0];
+        ka.t[1] = packed ? forests[1]->keyp[0] : forests[1]->key[0];
         ka.n_key = 2;
     } else {
         ka.n_key = forests[0]->n_key;
-        for (int q = 0; q < ka.n_key; ++q) ka.t[q] = forests[0]->key[q];
+        for (int q = 0; q < ka.n_key; ++q) ka.t[q] = packed ? forests[0]->keyp[q] : forests[0]->key[q];
     }
     unsigned bits[2] = {0, 0};
     for (int q = 0; q < ka.n_key; ++q)
@@ -766,63 +1120,88 @@ static int hm_forest_build_perm(const hm_forest_t* const* forests, int M, const 
     ka.X = Xcm;
     ka.ldx = ldx;
     ka.N = N;
-    static bool pool_set = false;
-    if (!pool_set) {            // keep freed blocks in the pool: the next call reuses them without a driver round trip
-        cudaMemPool_t pool;
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-            unsigned long long thr = ~0ull;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-        }
-        pool_set = true;
-    }
+    hm_forest_keep_pool();
     unsigned* buf = nullptr;
-    const int D = forests[0]->n_features, Dp = (D + 3) & ~3;
+    const int D = forests[0]->n_features, Dp = packed ? 2 : (D + 3) & ~3;      // words per candidate in the sorted copy
     const size_t rows_words = (size_t)N * Dp;                       // 16-byte aligned rows at the front
     const size_t words = rows_words + (size_t)N * 2 + bins;
     HM_CUDA_TRY(cudaMallocAsync((void**)&buf, words * sizeof(unsigned), st));
-    float* rows = reinterpret_cast<float*>(buf);
     unsigned* key = buf + rows_words;
     unsigned* perm = key + N;
     unsigned* hist = perm + N;
     HM_CUDA_TRY(cudaMemsetAsync(hist, 0, bins * sizeof(unsigned), st));
     const unsigned grid = (unsigned)((N + 255) / 256);
-    hm_forest_sortkey<<<grid, 256, 0, st>>>(ka, key, hist);
-    hm_forest_scan<<<1, 1024, 0, st>>>(hist, (unsigned)bins);
-    hm_forest_scatter_rows<<<grid, 256, 0, st>>>(key, hist, Xcm, ldx, N, D, Dp, perm, rows);
-    HM_CUDA_TRY(cudaGetLastError());
+    if (packed) {
+        hm_forest_sortkey_packed<<<grid, 256, 0, st>>>(ka, codes, key, hist);
+        hm_forest_scan<<<1, 1024, 0, st>>>(hist, (unsigned)bins);
+        hm_forest_scatter_codes<<<grid, 256, 0, st>>>(key, hist, codes, N, perm, reinterpret_cast<unsigned long long*>(buf));
+        *codes_out = reinterpret_cast<unsigned long long*>(buf);
+    } else {
+        hm_forest_sortkey<<<grid, 256, 0, st>>>(ka, key, hist);
+        hm_forest_scan<<<1, 1024, 0, st>>>(hist, (unsigned)bins);
+        hm_forest_scatter_rows<<<grid, 256, 0, st>>>(key, hist, Xcm, ldx, N, D, Dp, perm, reinterpret_cast<float*>(buf));
+        *rows_out = reinterpret_cast<float*>(buf);
+        *Dp_out = Dp;
+    }
+    {
+        const cudaError_t le = cudaGetLastError();
+        if (le != cudaSuccess) {
+            cudaFreeAsync(buf, st);
+            HM_CUDA_TRY(le);
+        }
+    }
     *perm_out = perm;
-    *rows_out = rows;
-    *Dp_out = Dp;
     *scratch_out = buf;
     return 0;
 }
 
-extern "C" int hm_rf_eval(const hm_forest_t* const* forests, int M, const float* Xcm, int64_t ldx, int64_t N,
-                          int32_t* const* leaf_out, double* mean_out, double* var_out, double* pred_out,
-                          const hm_acq_params_t* acq, const double* feas, double* score_out, void* stream) {
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel instantiation, device) instead of on every call
+// (the hill climb issues thousands of small launches)
+template <bool AP, bool NV, int B, int PK>
+static cudaError_t hm_forest_kernel_attr() {
+    static unsigned done_mask = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 32 && (done_mask >> dev & 1u)) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(hm_forest_kernel<AP, NV, B, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               HM_SMEM_TOTAL);
+    if (e == cudaSuccess && dev < 32) done_mask |= 1u << dev;
+    return e;
+}
+
+static int hm_rf_eval_impl(const hm_forest_t* const* forests, int M, const float* Xcm, int64_t ldx,
+                           const unsigned long long* codes, int64_t N, int32_t* const* leaf_out, double* mean_out,
+                           double* var_out, double* pred_out, const hm_acq_params_t* acq, const double* feas,
+                           double* score_out, void* stream) {
+    const bool packed = codes != nullptr;
     HM_REQUIRE(forests != nullptr && M >= 1 && M <= HM_MAX_OBJECTIVES, "1 <= M <= 8");
-    HM_REQUIRE(N >= 0 && ldx >= N, "ldx >= N >= 0");
+    HM_REQUIRE(N >= 0 && (packed || ldx >= N), "ldx >= N >= 0");
     if (N == 0) return 0;
-    HM_REQUIRE(Xcm != nullptr, "Xcm");
+    HM_REQUIRE(packed || Xcm != nullptr, "Xcm");
     HmEvalArgs a;
     memset(&a, 0, sizeof(a));
     a.M = M;
     a.D = forests[0] ? forests[0]->n_features : 0;
     int steps = 0;
-    bool any_leaf = false;
+    bool any_leaf = false, wide = false;
     for (int m = 0; m < M; ++m) {
         HM_REQUIRE(forests[m] != nullptr, "forest handle");
         HM_REQUIRE(forests[m]->n_features == a.D, "all forests must share n_features");
-        a.f[m] = forests[m]->dev;
-        if (forests[m]->staged) steps += forests[m]->dev.n_groups;
+        HM_REQUIRE(!packed || forests[m]->packed, "hm_forest_attach_packing has not been called on this forest");
+        if (packed && forests[m]->packed == 2) wide = true;
+        a.f[m] = packed ? forests[m]->devp : forests[m]->dev;
+        if (a.f[m].staged) steps += a.f[m].n_groups;
         a.leaf_out[m] = leaf_out ? leaf_out[m] : nullptr;
         any_leaf = any_leaf || (a.leaf_out[m] != nullptr);
     }
-    a.nodebuf = forests[0]->nodebuf;
+    a.nodebuf = packed ? forests[0]->nodebuf_p : forests[0]->nodebuf;
+    for (int m = 1; packed && m < M; ++m) a.nodebuf = std::max(a.nodebuf, forests[m]->nodebuf_p);
     a.steps_per_tile = steps;
     a.X = Xcm;
+    a.codes = codes;
+    a.k.k26 = 1u << 26;
+    a.k.k1 = 1u;
+    a.k.k8 = 8u;
     a.ldx = ldx;
     a.N = N;
     a.mean_out = mean_out;
@@ -843,39 +1222,43 @@ extern "C" int hm_rf_eval(const hm_forest_t* const* forests, int M, const float*
     } else {
         HM_REQUIRE(score_out == nullptr, "score_out without acq");
     }
-    const int block = forests[0]->block;
+    const int block = packed ? HM_PACKED_BLOCK : forests[0]->block;
+    cudaStream_t st = (cudaStream_t)stream;
     // coherence pre-pass: pays when the forest streams through shared memory (not resident) and the pool is large
     void* scratch = nullptr;
     {
-        const int mode = hm_forest_sort_mode();
+        const int mode = forests[0]->sort_mode;
         const bool big = steps > 2 && N >= HM_SORT_MIN_N && N < 4294967295ll;
-        if (!any_leaf && (mode == 1 || (mode == -1 && big))) {
+        if (!any_leaf && N < 4294967295ll && (mode == 1 || (mode == -1 && big))) {
             unsigned* perm = nullptr;
             float* rows = nullptr;
-            int rc = hm_forest_build_perm(forests, M, Xcm, ldx, N, (cudaStream_t)stream, &perm, &rows, &a.Dp, &scratch);
+            unsigned long long* sorted = nullptr;
+            int rc = hm_forest_build_perm(forests, M, Xcm, ldx, codes, N, st, &perm, &rows, &a.Dp, &sorted, &scratch);
             if (rc) return rc;
             a.perm = perm;
-            a.Xrows = rows;
+            if (packed) a.codes = sorted;
+            else a.Xrows = rows;
         }
     }
-    const size_t smem = HM_SMEM_HEADER + 2 * (size_t)a.nodebuf + (size_t)block * a.D * 4;
+    const size_t smem = HM_SMEM_HEADER + 2 * (size_t)a.nodebuf + (packed ? 0 : (size_t)block * a.D * 4);
     const long long n_tiles = (N + block - 1) / block;
-    const int grid = (int)std::min<long long>(n_tiles, hm_num_sms());
-    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = (int)std::min<long long>(n_tiles, (long long)hm_num_sms() * (packed ? HM_PACKED_CTAS : 1));
     // the plain-predict column of the leaf records is only read for pred_out and Thompson sampling
     const bool need_v = pred_out != nullptr || (acq && a.acq.kind == HM_ACQ_TS);
-#define HM_LAUNCH_B(AP, NV, B)                                                                                         \
+    cudaError_t attr_err = cudaSuccess;
+#define HM_LAUNCH_B(AP, NV, B, PK)                                                                                     \
     do {                                                                                                               \
-        HM_CUDA_TRY(cudaFuncSetAttribute(hm_forest_kernel<AP, NV, B>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
-                                         (int)smem));                                                                  \
-        hm_forest_kernel<AP, NV, B><<<grid, B, smem, st>>>(a);                                                         \
+        attr_err = hm_forest_kernel_attr<AP, NV, B, PK>();                                                             \
+        if (attr_err == cudaSuccess) hm_forest_kernel<AP, NV, B, PK><<<grid, B, smem, st>>>(a);                        \
     } while (0)
 #define HM_LAUNCH(AP, NV)                                                                                              \
     do {                                                                                                               \
-        if (block == 1024) HM_LAUNCH_B(AP, NV, 1024);                                                                  \
-        else if (block == 512) HM_LAUNCH_B(AP, NV, 512);                                                               \
-        else if (block == 256) HM_LAUNCH_B(AP, NV, 256);                                                               \
-        else HM_LAUNCH_B(AP, NV, 128);                                                                                 \
+        if (packed && !wide) HM_LAUNCH_B(AP, NV, HM_PACKED_BLOCK, 1);                                                  \
+        else if (packed) HM_LAUNCH_B(AP, NV, HM_PACKED_BLOCK, 2);                                                      \
+        else if (block == 1024) HM_LAUNCH_B(AP, NV, 1024, 0);                                                          \
+        else if (block == 512) HM_LAUNCH_B(AP, NV, 512, 0);                                                            \
+        else if (block == 256) HM_LAUNCH_B(AP, NV, 256, 0);                                                            \
+        else HM_LAUNCH_B(AP, NV, 128, 0);                                                                              \
     } while (0)
     if (any_leaf) {
         if (need_v) HM_LAUNCH(true, true); else HM_LAUNCH(true, false);
@@ -884,8 +1267,23 @@ extern "C" int hm_rf_eval(const hm_forest_t* const* forests, int M, const float*
     }
 #undef HM_LAUNCH
 #undef HM_LAUNCH_B
-    const cudaError_t launch_err = cudaGetLastError();
+    const cudaError_t launch_err = attr_err != cudaSuccess ? attr_err : cudaGetLastError();
     if (scratch) cudaFreeAsync(scratch, st);          // also on a failed launch: the scratch must not leak
     HM_CUDA_TRY(launch_err);
     return 0;
+}
+
+extern "C" int hm_rf_eval(const hm_forest_t* const* forests, int M, const float* Xcm, int64_t ldx, int64_t N,
+                          int32_t* const* leaf_out, double* mean_out, double* var_out, double* pred_out,
+                          const hm_acq_params_t* acq, const double* feas, double* score_out, void* stream) {
+    return hm_rf_eval_impl(forests, M, Xcm, ldx, nullptr, N, leaf_out, mean_out, var_out, pred_out, acq, feas, score_out,
+                           stream);
+}
+
+extern "C" int hm_rf_eval_packed(const hm_forest_t* const* forests, int M, const uint64_t* codes, int64_t N,
+                                 int32_t* const* leaf_out, double* mean_out, double* var_out, double* pred_out,
+                                 const hm_acq_params_t* acq, const double* feas, double* score_out, void* stream) {
+    HM_REQUIRE(N == 0 || codes != nullptr, "codes");
+    return hm_rf_eval_impl(forests, M, nullptr, 0, reinterpret_cast<const unsigned long long*>(codes), N, leaf_out,
+                           mean_out, var_out, pred_out, acq, feas, score_out, stream);
 }

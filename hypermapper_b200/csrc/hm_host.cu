@@ -41,6 +41,7 @@ struct hm_host_ctx {
     int32_t* d_invalid;
     double* d_mv[2];        // [2 M][chunk] posterior mean / variance of a chunk (hm_gp_score_host), lazily sized
     int mv_objectives;
+    uint64_t* d_codes[2];   // [chunk] packed codes of a chunk (hm_rf_score_packed_host), lazily allocated
 };
 
 extern "C" int hm_host_ctx_create(int64_t max_candidates_per_chunk, int max_features, hm_host_ctx_t** out) {
@@ -82,6 +83,8 @@ extern "C" void hm_host_ctx_destroy(hm_host_ctx_t* c) {
         if (c->d_raw[i]) cudaFree(c->d_raw[i]);
     for (int i = 0; i < 2; ++i)
         if (c->d_mv[i]) cudaFree(c->d_mv[i]);
+    for (int i = 0; i < 2; ++i)
+        if (c->d_codes[i]) cudaFree(c->d_codes[i]);
     if (c->d_invalid) cudaFree(c->d_invalid);
     if (c->d_scores) cudaFree(c->d_scores);
     if (c->d_topk_ws) cudaFree(c->d_topk_ws);
@@ -123,6 +126,55 @@ extern "C" int hm_rf_score_host(hm_host_ctx_t* c, const hm_forest_t* const* fore
     }
     if (k > 0) {
         // stream 0 waits for stream 1's kernels, then selects over the whole score vector
+        if (n_chunks > 1) {
+            HM_HOST_TRY(c, cudaEventRecord(c->ev[1], c->st[1]));
+            HM_HOST_TRY(c, cudaStreamWaitEvent(c->st[0], c->ev[1], 0));
+        }
+        int rc = hm_topk(c->d_scores, N, 0, k, c->d_topk_vals, c->d_topk_idx, c->d_topk_ws, (void*)c->st[0]);
+        if (rc) HM_HOST_FAIL(c, rc);
+        HM_HOST_TRY(c, cudaMemcpyAsync(topk_vals_host, c->d_topk_vals, (size_t)k * sizeof(double), cudaMemcpyDeviceToHost,
+                                    c->st[0]));
+        HM_HOST_TRY(c, cudaMemcpyAsync(topk_idx_host, c->d_topk_idx, (size_t)k * sizeof(int64_t), cudaMemcpyDeviceToHost,
+                                    c->st[0]));
+    }
+    HM_HOST_TRY(c, cudaStreamSynchronize(c->st[0]));
+    HM_HOST_TRY(c, cudaStreamSynchronize(c->st[1]));
+    return 0;
+}
+
+
+// Packed candidates (all-discrete spaces, hm_pack.cuh): 8 bytes per candidate over PCIe instead of 4 * D_enc.  Per chunk
+// H2D of the codes -> fused forest + acquisition kernel on the codes -> D2H of the scores, double-buffered.
+extern "C" int hm_rf_score_packed_host(hm_host_ctx_t* c, const hm_forest_t* const* forests, int M,
+                                       const uint64_t* codes_host, int64_t N, const hm_acq_params_t* acq,
+                                       double* score_out_host, int k, double* topk_vals_host, int64_t* topk_idx_host) {
+    HM_REQUIRE(c != nullptr && forests != nullptr && acq != nullptr, "ctx/forests/acq");
+    HM_REQUIRE(N >= 0 && (N == 0 || codes_host != nullptr), "codes_host");
+    HM_REQUIRE(k >= 0 && k <= 1024, "0 <= k <= 1024");
+    HM_REQUIRE(k == 0 || (topk_vals_host && topk_idx_host), "top-k outputs");
+    for (int i = 0; i < 2; ++i)
+        if (!c->d_codes[i]) HM_CUDA_TRY(cudaMalloc((void**)&c->d_codes[i], (size_t)c->chunk * sizeof(uint64_t)));
+    if (N > c->cap_scores) {
+        if (c->d_scores) cudaFree(c->d_scores);
+        c->d_scores = nullptr;
+        c->cap_scores = 0;
+        HM_CUDA_TRY(cudaMalloc((void**)&c->d_scores, (size_t)N * sizeof(double)));
+        c->cap_scores = N;
+    }
+    int n_chunks = 0;
+    for (int64_t lo = 0; lo < N; lo += c->chunk, ++n_chunks) {
+        const int b = n_chunks & 1;
+        const int64_t n = std::min<int64_t>(c->chunk, N - lo);
+        cudaStream_t st = c->st[b];
+        HM_HOST_TRY(c, cudaMemcpyAsync(c->d_codes[b], codes_host + lo, (size_t)n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        int rc = hm_rf_eval_packed(forests, M, c->d_codes[b], n, nullptr, nullptr, nullptr, nullptr, acq, nullptr,
+                                   c->d_scores + lo, (void*)st);
+        if (rc) HM_HOST_FAIL(c, rc);
+        if (score_out_host)
+            HM_HOST_TRY(c, cudaMemcpyAsync(score_out_host + lo, c->d_scores + lo, (size_t)n * sizeof(double),
+                                        cudaMemcpyDeviceToHost, st));
+    }
+    if (k > 0) {
         if (n_chunks > 1) {
             HM_HOST_TRY(c, cudaEventRecord(c->ev[1], c->st[1]));
             HM_HOST_TRY(c, cudaStreamWaitEvent(c->st[0], c->ev[1], 0));

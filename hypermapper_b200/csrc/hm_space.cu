@@ -14,17 +14,10 @@
 #include <new>
 #include <vector>
 #include "hm_acq.cuh"
+#include "hm_pack.cuh"
 
 #define HM_SPACE_MAX_PARAMS 256
 #define HM_SPACE_SMEM_TABLES 4096          // doubles of table data cached in shared memory (32 KB); larger stay in L2
-
-struct hm_space {
-    int D, D_enc;
-    long long n_tables;
-    hm_param_desc_t* d_params;
-    double* d_tables;
-    std::vector<hm_param_desc_t> params;
-};
 
 static int hm_check_desc(const hm_param_desc_t& p, long long n_tables, int j) {
     (void)j;
@@ -66,6 +59,12 @@ extern "C" int hm_space_create(int n_params, const hm_param_desc_t* params_host,
     S->D_enc = d_enc;
     S->n_tables = n_tables;
     S->params.assign(params_host, params_host + n_params);
+    if (n_tables) S->tables.assign(tables_host, tables_host + n_tables);
+    S->pack.resize(n_params);
+    S->pack_fast = 0;
+    S->pack_bits = hm_pack_layout(params_host, n_params, S->pack.data(), &S->pack_fast);
+    if (!S->pack_bits) S->pack.clear();
+    S->d_pack_low = nullptr;
     S->d_params = nullptr;
     S->d_tables = nullptr;
 #define HM_S_TRY(expr)                                                                                       \
@@ -82,6 +81,12 @@ extern "C" int hm_space_create(int n_params, const hm_param_desc_t* params_host,
     HM_S_TRY(cudaMalloc((void**)&S->d_tables, sizeof(double) * std::max<long long>(n_tables, 1)));
     if (n_tables)
         HM_S_TRY(cudaMemcpy(S->d_tables, tables_host, sizeof(double) * n_tables, cudaMemcpyHostToDevice));
+    if (S->pack_bits) {
+        std::vector<int> lows(n_params);
+        for (int j = 0; j < n_params; ++j) lows[j] = S->pack[j].low;
+        HM_S_TRY(cudaMalloc((void**)&S->d_pack_low, sizeof(int) * n_params));
+        HM_S_TRY(cudaMemcpy(S->d_pack_low, lows.data(), sizeof(int) * n_params, cudaMemcpyHostToDevice));
+    }
     HM_S_TRY(cudaDeviceSynchronize());      // consumed on non-blocking caller streams (see hm_forest_create)
 #undef HM_S_TRY
     *out = S;
@@ -92,10 +97,19 @@ extern "C" void hm_space_destroy(hm_space_t* S) {
     if (!S) return;
     cudaFree(S->d_params);
     cudaFree(S->d_tables);
+    cudaFree(S->d_pack_low);
     delete S;
 }
 extern "C" int hm_space_n_params(const hm_space_t* s) { return s ? s->D : 0; }
 extern "C" int hm_space_n_encoded(const hm_space_t* s) { return s ? s->D_enc : 0; }
+extern "C" int hm_space_packed_bits(const hm_space_t* s) { return s ? s->pack_bits : 0; }
+extern "C" int hm_space_packed_field(const hm_space_t* s, int param, int* low_bit, int* width) {
+    HM_REQUIRE(s != nullptr && s->pack_bits > 0, "space is not packable");
+    HM_REQUIRE(param >= 0 && param < s->D && low_bit && width, "param");
+    *low_bit = s->pack[param].low;
+    *width = s->pack[param].width;
+    return 0;
+}
 
 // ---- Philox4x32-10: one stream per (seed, candidate index, pool kind), consumed sequentially over the parameters ------
 struct HmPhilox {
@@ -175,7 +189,7 @@ struct HmPhilox {
 struct HmP {
     int kind, n_values, out_col, flags;          // flags: 1 = z-score, 2 = discrete parameter sampled as Beta(a, b)
     int prior_kind, n_prior, n_cdf, values_off;
-    int prior_off, cdf_off, pad0, pad1;
+    int prior_off, cdf_off, pack_low, pad1;       // pack_low: bit index of the parameter's field in a packed code
     double lo, hi, mean, std, a, b, lbeta, pad2;
 };
 #define HM_PF_NORMALIZE 1
@@ -320,6 +334,8 @@ struct HmSpaceArgs {
     int n_obj;
     double w[HM_MAX_OBJECTIVES];
     int* n_invalid;
+    unsigned long long* codes;    // packed 64-bit code per candidate (hm_pack.cuh), all-discrete spaces only
+    const int* pack_low;          // device [D]: bit index of every parameter's field
 };
 
 // descriptors (compact form) and the first n_tab table entries into shared memory; ends with a CTA barrier
@@ -337,7 +353,8 @@ __device__ __forceinline__ void hm_space_load_shared(const HmSpaceArgs& a, HmP* 
         p.values_off = (int)d.values_off;
         p.prior_off = (int)d.prior_off;
         p.cdf_off = (int)d.cdf_off;
-        p.pad0 = p.pad1 = 0;
+        p.pack_low = a.pack_low ? a.pack_low[j] : 0;
+        p.pad1 = 0;
         p.lo = d.lo; p.hi = d.hi; p.mean = d.mean; p.std = d.std; p.a = d.a; p.b = d.b; p.lbeta = d.lbeta; p.pad2 = 0.0;
         sp[j] = p;
     }
@@ -386,6 +403,7 @@ __global__ void __launch_bounds__(HM_SPACE_BLOCK) hm_space_kernel(const HmSpaceA
         const long long i = base + threadIdx.x;
         if (i >= a.N) continue;
         double prob = 1.0;
+        unsigned long long code = 0ull;
         HmPhilox g;
         if (GENERATE) {
             const unsigned long long gi = (unsigned long long)(a.gather ? __ldg(a.gather + i) : a.index_base + i);
@@ -407,12 +425,15 @@ __global__ void __launch_bounds__(HM_SPACE_BLOCK) hm_space_kernel(const HmSpaceA
                 if (a.raw_out_rows) a.raw_out[(size_t)i * (size_t)a.D + j] = x;
                 else a.raw_out[(size_t)j * (size_t)a.ldro + (size_t)i] = x;
             }
-            if (!GENERATE && p.kind >= HM_P_ORDINAL && (want_enc || a.prob)) {
+            if (!GENERATE && p.kind >= HM_P_ORDINAL && (want_enc || a.prob || a.codes)) {
                 // value index of a discrete parameter: ordinal -> position in its value list, categorical -> the value
                 if (p.kind == HM_P_ORDINAL) idx = hm_find_value(tab + p.values_off, p.n_values, x);
                 else idx = (x >= 0.0 && x < (double)p.n_values && x == rint(x)) ? (int)x : -1;
                 bad_any |= idx < 0;
             }
+            if (a.codes && idx >= 0)      // ordinal: rank; categorical: one-hot over the first n - 1 categories (hm_pack.cuh)
+                code |= (p.kind == HM_P_CATEGORICAL ? (idx < p.n_values - 1 ? (1ull << idx) : 0ull)
+                                                    : (unsigned long long)idx) << p.pack_low;
             if (want_enc) {
                 // models.py:957-984
                 if (p.kind == HM_P_CATEGORICAL) {
@@ -441,6 +462,7 @@ __global__ void __launch_bounds__(HM_SPACE_BLOCK) hm_space_kernel(const HmSpaceA
             }
         }
         if (a.prob) a.prob[i] = prob;
+        if (a.codes) a.codes[i] = code;
     }
     if (a.n_invalid && bad_any) atomicAdd(a.n_invalid, 1);
 }
@@ -590,7 +612,7 @@ __global__ void __launch_bounds__(HM_SPACE_BLOCK) hm_encode_tile_kernel(const Hm
 // launches the tile kernel when its preconditions hold; *done = 0 otherwise
 static int hm_space_launch_tile(const hm_space_t* s, HmSpaceArgs& a, cudaStream_t st, int* done) {
     *done = 0;
-    if (a.raw_col_major || a.ldr != s->D || s->n_tables > HM_SPACE_SMEM_TABLES || a.raw_out) return 0;
+    if (a.raw_col_major || a.ldr != s->D || s->n_tables > HM_SPACE_SMEM_TABLES || a.raw_out || a.codes) return 0;
     const bool w32 = a.x32 != nullptr, w64 = a.x64 != nullptr, wp = a.prob != nullptr;
     if (wp == (w32 || w64)) return 0;             // exactly one of {encode, prior}: what hm_encode / hm_prior_prob ask for
     const int mode = wp ? 3 : (w32 && w64 ? 2 : (w64 ? 1 : 0));
@@ -725,6 +747,40 @@ extern "C" int hm_sample_pool(const hm_space_t* s, uint64_t seed, int64_t index_
     a.prob = prob_out;
     a.n_obj = prob_out ? n_objectives : 0;
     for (int o = 0; o < a.n_obj; ++o) a.w[o] = objective_weights_host[o];
+    return hm_space_launch(s, a, true, stream);
+}
+
+// packed 64-bit codes (hm_pack.cuh) instead of encoded columns: K5 / K6 for all-discrete spaces
+extern "C" int hm_encode_packed(const hm_space_t* s, const double* raw, int raw_col_major, int64_t ldr, int64_t N,
+                                uint64_t* codes_out, int32_t* n_invalid_dev, void* stream) {
+    HM_REQUIRE(s != nullptr && (raw != nullptr || N == 0) && codes_out != nullptr, "space/raw/codes_out");
+    HM_REQUIRE(s->pack_bits > 0, "the space has real / integer parameters or needs more than 64 bits: not packable");
+    HM_REQUIRE(N >= 0 && (raw_col_major ? ldr >= N : ldr >= s->D), "leading dimension of raw");
+    HmSpaceArgs a = {};
+    a.raw = raw;
+    a.raw_col_major = raw_col_major;
+    a.ldr = ldr;
+    a.N = N;
+    a.codes = reinterpret_cast<unsigned long long*>(codes_out);
+    a.pack_low = s->d_pack_low;
+    a.n_invalid = n_invalid_dev;
+    return hm_space_launch(s, a, false, stream);
+}
+
+extern "C" int hm_sample_pool_packed(const hm_space_t* s, uint64_t seed, int64_t index_base, int64_t N, int use_priors,
+                                     uint64_t* codes_out, double* raw_cm_out, int64_t ldr, void* stream) {
+    HM_REQUIRE(s != nullptr && N >= 0 && index_base >= 0 && codes_out != nullptr, "space/N/index_base/codes_out");
+    HM_REQUIRE(s->pack_bits > 0, "the space has real / integer parameters or needs more than 64 bits: not packable");
+    HM_REQUIRE(raw_cm_out == nullptr || ldr >= N, "ldr >= N");
+    HmSpaceArgs a = {};
+    a.N = N;
+    a.seed = seed;
+    a.index_base = index_base;
+    a.use_priors = use_priors ? 1 : 0;
+    a.raw_out = raw_cm_out;
+    a.ldro = ldr;
+    a.codes = reinterpret_cast<unsigned long long*>(codes_out);
+    a.pack_low = s->d_pack_low;
     return hm_space_launch(s, a, true, stream);
 }
 

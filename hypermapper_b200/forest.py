@@ -214,6 +214,47 @@ def rf_eval(forests, Xcm, want_leaves=False, want_mean=False, want_var=False, wa
     return out
 
 
+def attach_packing(forests, device_space):
+    """hm_forest_attach_packing on every forest (idempotent): needed once before rf_eval_packed / score_packed"""
+    L = _lib.lib()
+    for f in forests:
+        _lib.check(L.hm_forest_attach_packing(f.handle, device_space.handle), "hm_forest_attach_packing")
+        f.packed_groups = int(L.hm_forest_packed_groups(f.handle))
+    return forests
+
+
+def rf_eval_packed(forests, codes, want_leaves=False, want_mean=False, want_var=False, want_pred=False, acq=None,
+                   feas=None):
+    """rf_eval on packed candidates: codes = CUDA int64 tensor [N] (64-bit codes of an all-discrete space,
+    DeviceSpace.encode_packed / sample_pool_packed); the forests must have been through attach_packing."""
+    torch = _lib.require_cuda()
+    L = _lib.lib()
+    M = len(forests)
+    assert codes.dtype == torch.int64 and codes.is_cuda and codes.dim() == 1 and codes.is_contiguous()
+    N = codes.numel()
+    dev = codes.device
+    out = {}
+    handles = (ctypes.c_void_p * M)(*[f.handle for f in forests])
+    leaf_ptrs = None
+    if want_leaves:
+        out["leaves"] = [torch.empty((f.n_trees, N), dtype=torch.int32, device=dev) for f in forests]
+        leaf_ptrs = (ctypes.c_void_p * M)(*[t.data_ptr() for t in out["leaves"]])
+    for key, flag in (("mean", want_mean), ("var", want_var), ("pred", want_pred)):
+        if flag:
+            out[key] = torch.empty((M, N), dtype=torch.float64, device=dev)
+    acq_ref = None
+    if acq is not None:
+        out["score"] = torch.empty((N,), dtype=torch.float64, device=dev)
+        acq_ref = ctypes.byref(acq)
+    if N == 0:
+        return out
+    rc = L.hm_rf_eval_packed(handles, M, _lib.dptr(codes), N, leaf_ptrs, _lib.dptr(out.get("mean")),
+                             _lib.dptr(out.get("var")), _lib.dptr(out.get("pred")), acq_ref, _lib.dptr(feas),
+                             _lib.dptr(out.get("score")), _lib.stream_ptr())
+    _lib.check(rc, "hm_rf_eval_packed")
+    return out
+
+
 def topk(values, k, index_base=0):
     """Stable k smallest of a CUDA fp64 vector: (values[k], indices[k]) CUDA tensors, (+inf,-1) padded."""
     torch = _lib.require_cuda()

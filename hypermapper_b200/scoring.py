@@ -48,6 +48,30 @@ class HostScorer:
         _lib.check(rc, "hm_rf_score_host")
         return scores_out, tv[:k], ti[:k]
 
+    def score_packed(self, forests, codes_host, acq, k=0, scores_out=None):
+        """Like score(), from packed 64-bit codes of an all-discrete space (DeviceSpace.pack_codes_host): codes_host is a
+        uint64 / int64 [N] host array (numpy, or a pinned torch CPU tensor); 8 bytes per candidate cross PCIe.  The
+        forests must have been through forest.attach_packing."""
+        if hasattr(codes_host, "data_ptr"):
+            N = codes_host.shape[0]
+            assert codes_host.is_contiguous() and not codes_host.is_cuda and codes_host.element_size() == 8
+            cp = ctypes.c_void_p(codes_host.data_ptr())
+        else:
+            assert codes_host.dtype in (np.uint64, np.int64) and codes_host.flags.c_contiguous
+            N = codes_host.shape[0]
+            cp = _lib.hptr(codes_host)
+        sp = None
+        if scores_out is not None:
+            sp = ctypes.c_void_p(scores_out.data_ptr()) if hasattr(scores_out, "data_ptr") else _lib.hptr(scores_out)
+        tv = np.empty(max(k, 1), dtype=np.float64)
+        ti = np.empty(max(k, 1), dtype=np.int64)
+        M = len(forests)
+        handles = (ctypes.c_void_p * M)(*[f.handle for f in forests])
+        rc = _lib.lib().hm_rf_score_packed_host(self.handle, handles, M, cp, N, ctypes.byref(acq), sp, int(k),
+                                                _lib.hptr(tv), _lib.hptr(ti))
+        _lib.check(rc, "hm_rf_score_packed_host")
+        return scores_out, tv[:k], ti[:k]
+
     def score_raw(self, device_space, forests, raw_host, acq, k=0, scores_out=None):
         """Like score(), from RAW parameter values: raw_host is a float64 row-major [N][D] host array (numpy, or a pinned
         torch CPU tensor) in input-parameter order, categoricals as indices.  Raises ValueError like the reference when

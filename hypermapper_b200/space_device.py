@@ -217,6 +217,92 @@ class DeviceSpace:
             raise ValueError("a discrete parameter value is not in its list of values (models.py:962-983)")
         return x32, x64
 
+    # -- packed candidates (all-discrete spaces; include/hm_b200.h "Packed candidates", csrc/hm_pack.cuh) -------
+    @property
+    def packed_bits(self):
+        """bits of a candidate's 64-bit code, 0 when the space cannot be packed (real / integer parameters, > 64 bits)"""
+        return int(_lib.lib().hm_space_packed_bits(self.handle))
+
+    def packed_fields(self):
+        """[(low bit, width)] per input parameter"""
+        out = []
+        for j in range(self.D):
+            lo, w = ctypes.c_int(0), ctypes.c_int(0)
+            _lib.check(_lib.lib().hm_space_packed_field(self.handle, j, ctypes.byref(lo), ctypes.byref(w)),
+                       "hm_space_packed_field")
+            out.append((lo.value, w.value))
+        return out
+
+    def encode_packed(self, raw):
+        """raw [N][D] values (host or device) -> CUDA uint64-as-int64 tensor [N] of packed codes (hm_encode_packed)."""
+        torch = _lib.require_cuda()
+        rd = self.raw_to_device(raw)
+        N = rd.shape[0]
+        codes = torch.empty((N,), dtype=torch.int64, device="cuda")
+        if N == 0:
+            return codes
+        bad = self._invalid_counter()
+        rc = _lib.lib().hm_encode_packed(self.handle, _lib.dptr(rd), 0, self.D, N, _lib.dptr(codes), _lib.dptr(bad),
+                                         _lib.stream_ptr())
+        _lib.check(rc, "hm_encode_packed")
+        if int(bad.item()) != 0:
+            raise ValueError("a discrete parameter value is not in its list of values (models.py:962-983)")
+        return codes
+
+    def sample_pool_packed(self, seed, N, use_priors, index_base=0, want_raw=False):
+        """hm_sample_pool_packed: the same pool as sample_pool (same Philox stream), as packed codes.
+        -> dict(codes=int64 [N], raw=[D][N] fp64 | None)"""
+        torch = _lib.require_cuda()
+        codes = torch.empty((N,), dtype=torch.int64, device="cuda")
+        raw = torch.empty((self.D, N), dtype=torch.float64, device="cuda") if want_raw else None
+        rc = _lib.lib().hm_sample_pool_packed(self.handle, ctypes.c_uint64(int(seed) & (2 ** 64 - 1)), int(index_base), N,
+                                              1 if use_priors else 0, _lib.dptr(codes), _lib.dptr(raw), N,
+                                              _lib.stream_ptr())
+        _lib.check(rc, "hm_sample_pool_packed")
+        return {"codes": codes, "raw": raw}
+
+    def pack_codes_host(self, raw, out=None):
+        """numpy restatement of the packing for host-resident candidates: raw [N][D] values (categoricals as indices,
+        ordinals as values) -> uint64 [N].  What a caller that samples on the host hands to hm_rf_score_packed_host."""
+        raw = np.asarray(raw, dtype=np.float64)
+        N = raw.shape[0]
+        codes = np.zeros((N,), dtype=np.uint64) if out is None else out
+        if out is not None:
+            codes[:] = 0
+        objs = self.space.get_input_parameters_objects()
+        for j, ((low, width), name) in enumerate(zip(self.packed_fields(), self.inputs)):
+            col = raw[:, j]
+            if self.descs[j].kind == P_ORDINAL:
+                sv = np.asarray(objs[name].get_values(), dtype=np.float64)
+                idx = np.clip(np.searchsorted(sv, col), 0, len(sv) - 1)
+                if not np.array_equal(sv[idx], col):
+                    raise ValueError("a discrete parameter value is not in its list of values (models.py:962-983)")
+                codes |= idx.astype(np.uint64) << np.uint64(low)
+            else:
+                idx = col.astype(np.int64)
+                n_cat = int(self.descs[j].n_values)
+                if N and (idx.min() < 0 or idx.max() >= n_cat or not np.array_equal(idx, col)):
+                    raise ValueError("a categorical index is out of range")
+                # one-hot over the first n - 1 categories; the last category is the all-zero field (csrc/hm_pack.cuh)
+                bit = np.where(idx < n_cat - 1, np.left_shift(np.uint64(1), np.minimum(idx, 62).astype(np.uint64)),
+                               np.uint64(0)).astype(np.uint64)
+                codes |= bit << np.uint64(low)
+        return codes
+
+    def unpack_codes_host(self, codes):
+        """inverse of pack_codes_host: uint64 [n] -> raw fp64 rows [n][D]"""
+        codes = np.asarray(codes).astype(np.uint64)
+        objs = self.space.get_input_parameters_objects()
+        out = np.empty((len(codes), self.D), dtype=np.float64)
+        for j, ((low, width), name) in enumerate(zip(self.packed_fields(), self.inputs)):
+            field = (codes >> np.uint64(low)) & np.uint64((1 << width) - 1)
+            if self.descs[j].kind == P_ORDINAL:
+                out[:, j] = np.asarray(objs[name].get_values(), dtype=np.float64)[field.astype(np.int64)]
+            else:
+                n_cat = int(self.descs[j].n_values)
+                out[:, j] = np.where(field == 0, float(n_cat - 1), np.log2(np.maximum(field, 1).astype(np.float64)))
+        return out
+
     # -- K7 -------------------------------------------------------------------------------------------
     def prior_prob(self, raw, objective_weights, col_major=False):
         """compute_probability_from_prior on the device -> CUDA fp64 tensor [N].

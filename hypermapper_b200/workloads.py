@@ -143,6 +143,20 @@ class RFWorkload:
         self.scalarization = scalarization
         self.iteration_number = iteration_number
 
+    def candidates_raw(self, n, seed, out=None):
+        """float64 [n][D] raw parameter values of the SAME candidates candidates_encoded(n, seed) encodes"""
+        rng = np.random.default_rng(seed)
+        inputs = self.space.get_input_parameters()
+        if out is None:
+            out = np.empty((n, len(inputs)), dtype=np.float64)
+        chunk = 1 << 21
+        for lo in range(0, n, chunk):
+            hi = min(n, lo + chunk)
+            cols = raw_uniform_columns(self.space, hi - lo, rng)
+            for j, p in enumerate(inputs):
+                out[lo:hi, j] = cols[p]
+        return out
+
     def candidates_encoded(self, n, seed, out=None):
         """float32 [D_enc][n] column-major candidates, uniform over every parameter's values."""
         rng = np.random.default_rng(seed)

@@ -101,13 +101,30 @@ typedef struct hm_acq_params {
  *   feas         : fp64 [N] or NULL  feasibility probability multiplied into the score
  */
 /* Coherence pre-pass of hm_rf_eval (candidates bucketed by the leaves of two key trees so that the lanes of a warp
- * walk the same nodes): -1 = automatic (forests that stream through shared memory, N >= 2^17; the default, also
- * settable with the environment variable HM_B200_FOREST_SORT), 0 = never, 1 = always.  Results are bit-identical
- * either way; this only exists for tests and measurements. */
-int hm_forest_set_coherence_mode(int mode);
+ * walk the same nodes), a property of the handle (the first forest of a call decides): -1 = automatic (forests that
+ * stream through shared memory, N >= 2^17; the default of a new handle, which the environment variable
+ * HM_B200_FOREST_SORT overrides at creation), 0 = never, 1 = always.  Results are bit-identical either way; this only
+ * exists for tests and measurements. */
+int hm_forest_set_coherence(hm_forest_t* f, int mode);
 int hm_rf_eval(const hm_forest_t* const* forests, int M, const float* Xcm, int64_t ldx, int64_t N,
                int32_t* const* leaf_out, double* mean_out, double* var_out, double* pred_out,
                const hm_acq_params_t* acq, const double* feas, double* score_out, void* stream);
+
+/* Packed candidates (all-discrete search spaces: ordinal / categorical parameters only).  A candidate is ONE 64-bit code
+ * -- the rank of every ordinal value and a one-hot field per categorical, parameters in input order from bit 63 downwards
+ * (hm_space_packed_field gives every field; csrc/hm_pack.cuh states the layout) -- instead of D_enc float32 columns:
+ * 8 bytes per candidate in HBM and over PCIe, and no per-visit feature load in the traversal (the split becomes a shift
+ * and an unsigned compare on the code, exact because the encoding of models.py:957-984 is monotone in the rank).
+ *   hm_forest_attach_packing  builds the packed node arrays of a forest for the space its model was fitted on (once)
+ *   hm_rf_eval_packed         hm_rf_eval on codes; every output is bit-identical to hm_rf_eval on the encoded form of the
+ *                             same candidates (sklearn's decision (double)x32 <= threshold, models.py:174-182) */
+typedef struct hm_space hm_space_t;
+int hm_forest_attach_packing(hm_forest_t* f, const hm_space_t* space);
+int hm_forest_packed(const hm_forest_t* f);
+int hm_forest_packed_groups(const hm_forest_t* f);
+int hm_rf_eval_packed(const hm_forest_t* const* forests, int M, const uint64_t* codes, int64_t N,
+                      int32_t* const* leaf_out, double* mean_out, double* var_out, double* pred_out,
+                      const hm_acq_params_t* acq, const double* feas, double* score_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * K3  scalarised acquisition on precomputed mean/variance (GP path, or RF mean/var API users)
@@ -207,12 +224,16 @@ typedef struct hm_param_desc {
     double a, b;         /* Beta alpha/beta, or Gaussian mean/std */
     double lbeta;        /* log B(a, b) */
 } hm_param_desc_t;
-typedef struct hm_space hm_space_t;
 int hm_space_create(int n_params, const hm_param_desc_t* params_host, const double* tables_host, int64_t n_tables,
                     hm_space_t** out);
 void hm_space_destroy(hm_space_t* s);
 int hm_space_n_params(const hm_space_t* s);
 int hm_space_n_encoded(const hm_space_t* s);
+/* packed codes: number of bits a candidate of this space takes (0: the space has real / integer parameters or needs
+ * more than 64 bits and cannot be packed); bit range [low_bit, low_bit + width) of one parameter's field (ordinal: the
+ * rank of the value; categorical: one-hot, category c = bit low_bit + c) */
+int hm_space_packed_bits(const hm_space_t* s);
+int hm_space_packed_field(const hm_space_t* s, int param, int* low_bit, int* width);
 
 /* K5  replaces models.preprocess_data_array (models.py:941-984), bit-exact.
  *   raw: fp64 raw parameter values, row-major [N][ldr >= D] (raw_col_major = 0, the layout of the reference's
@@ -222,6 +243,13 @@ int hm_space_n_encoded(const hm_space_t* s);
  *        categorical index is out of range (the reference raises ValueError there); such entries encode as NaN. */
 int hm_encode(const hm_space_t* s, const double* raw, int raw_col_major, int64_t ldr, int64_t N, float* X32cm,
               int64_t ld32, double* X64cm, int64_t ld64, int32_t* n_invalid_dev, void* stream);
+
+/* K5 / K6 for packed codes: hm_encode / hm_sample_pool writing one 64-bit code per candidate instead of the encoded
+ * columns (same value search, same Philox stream: candidate i of a pool is the same configuration either way). */
+int hm_encode_packed(const hm_space_t* s, const double* raw, int raw_col_major, int64_t ldr, int64_t N,
+                     uint64_t* codes_out, int32_t* n_invalid_dev, void* stream);
+int hm_sample_pool_packed(const hm_space_t* s, uint64_t seed, int64_t index_base, int64_t N, int use_priors,
+                          uint64_t* codes_out, double* raw_cm_out, int64_t ldr, void* stream);
 
 /* K6  replaces space.get_random_configuration(size=N, use_priors, return_as_array=True) (space.py:1263-1311) followed
  * by the encoding: candidate i of the pool = f(seed, index_base + i, use_priors) (Philox4x32-10; same distributions as
@@ -296,6 +324,12 @@ void hm_host_ctx_destroy(hm_host_ctx_t* c);
 int hm_rf_score_host(hm_host_ctx_t* c, const hm_forest_t* const* forests, int M, const float* X_host,
                      int64_t ldx, int64_t N, const hm_acq_params_t* acq, double* score_out_host, int k,
                      double* topk_vals_host, int64_t* topk_idx_host);
+
+/* The same from packed 64-bit codes in host memory (all-discrete spaces; hm_forest_attach_packing done on every forest):
+ * 8 bytes per candidate H2D instead of 4 * n_features. */
+int hm_rf_score_packed_host(hm_host_ctx_t* c, const hm_forest_t* const* forests, int M, const uint64_t* codes_host,
+                            int64_t N, const hm_acq_params_t* acq, double* score_out_host, int k,
+                            double* topk_vals_host, int64_t* topk_idx_host);
 
 /* The same from RAW parameter values, row-major fp64 [N][n_params] in host memory -- the form the reference's API is
  * handed (run_acquisition_function's configurations, random_scalarizations.py:75-157): per chunk H2D -> hm_encode ->

@@ -224,12 +224,14 @@ def test_coherence_prepass_is_invisible(T, D, N):
     outs = []
     try:
         for mode in (0, 1):
-            _lib.check(_lib.lib().hm_forest_set_coherence_mode(mode), "hm_forest_set_coherence_mode")
+            for f in dfs:
+                _lib.check(_lib.lib().hm_forest_set_coherence(f.handle, mode), "hm_forest_set_coherence")
             o = forest.rf_eval(dfs, Xd, want_mean=True, want_var=True, want_pred=True, acq=acq)
             outs.append({k: [t.cpu().numpy() for t in v] if isinstance(v, (list, tuple)) else v.cpu().numpy()
                          for k, v in o.items() if v is not None})
     finally:
-        _lib.lib().hm_forest_set_coherence_mode(-1)
+        for f in dfs:
+            _lib.lib().hm_forest_set_coherence(f.handle, -1)
     for k in outs[0]:
         a, b = outs[0][k], outs[1][k]
         if isinstance(a, list):
