@@ -25,17 +25,27 @@ class EncodedCandidates:
     """Candidates that are already encoded and resident on the GPU (column-major [D_enc][N]); `raw_cm` optionally
     holds their raw parameter values (column-major [D][N] fp64) for the prior-weighted acquisitions."""
 
-    def __init__(self, x32=None, x64=None, raw_cm=None):
+    def __init__(self, x32=None, x64=None, raw_cm=None, codes=None, device_space=None):
         self.x32 = x32
         self.x64 = x64
         self.raw_cm = raw_cm
+        self.codes = codes                  # packed 64-bit codes (all-discrete spaces, csrc/hm_pack.cuh) as int64 [N]
+        self.device_space = device_space    # the DeviceSpace the codes / raw values belong to
 
     def __len__(self):
+        if self.codes is not None:
+            return int(self.codes.shape[0])
         t = self.x32 if self.x32 is not None else self.x64
         return int(t.shape[1])
 
     def get(self, dtype):
         torch = _lib.require_cuda()
+        if self.x32 is None and self.x64 is None:
+            # a packed pool: the encoded matrix is only built when something other than the forest kernel asks for it
+            # (a feasibility classifier, a GP)
+            x32, x64 = self.device_space.encode(self.raw_cm, want32=(dtype == "float32"), want64=(dtype != "float32"),
+                                                col_major=True)
+            self.x32, self.x64 = x32, x64
         if dtype == "float32":
             if self.x32 is None:
                 self.x32 = self.x64.to(torch.float32)

@@ -62,10 +62,17 @@ def acquisition_scores_device(acquisition_function, candidates, objective_weight
                                                  objective_weights, objective_limits, data_array, iteration_number)
     params = _lib.make_acq_params(acquisition_function, scalarization_method, weights, f_min, beta)
     if model_type == "random_forest":
-        from .forest import device_forest, rf_eval
+        from .forest import attach_packing, device_forest, rf_eval, rf_eval_packed
+        forests = [device_forest(regression_models[o]) for o in objectives]
+        if isinstance(candidates, models.EncodedCandidates) and candidates.codes is not None:
+            # packed pool of an all-discrete space: the forest kernel walks the 64-bit codes (bit-identical results)
+            feas = None
+            if classification_model is not None:
+                feas = _feasibility_tensor(candidates.get("float32"), classification_model, param_space)
+            attach_packing(forests, candidates.device_space)
+            return rf_eval_packed(forests, candidates.codes, acq=params, feas=feas)["score"]
         X32 = models.encode_to_device(candidates, param_space, "float32")
         feas = _feasibility_tensor(X32, classification_model, param_space)
-        forests = [device_forest(regression_models[o]) for o in objectives]
         return rf_eval(forests, X32, acq=params, feas=feas)["score"]
     if model_type == "gaussian_process":
         import torch

@@ -199,19 +199,20 @@ class DeviceSpace:
         return torch.zeros((1,), dtype=torch.int32, device="cuda")
 
     # -- K5 -------------------------------------------------------------------------------------------
-    def encode(self, raw, want32=True, want64=False):
+    def encode(self, raw, want32=True, want64=False, col_major=False):
         """-> (x32 [D_enc][N] or None, x64 [D_enc][N] or None).  Raises ValueError like the reference
-        (list.index / OneHotEncoder) when a discrete value is not one of the parameter's values."""
+        (list.index / OneHotEncoder) when a discrete value is not one of the parameter's values.
+        col_major: raw is a CUDA fp64 tensor [D][N] (the layout of device pools)."""
         torch = _lib.require_cuda()
-        rd = self.raw_to_device(raw)
-        N = rd.shape[0]
+        rd = raw if col_major else self.raw_to_device(raw)
+        N = rd.shape[1] if col_major else rd.shape[0]
         x32 = torch.empty((self.n_encoded, N), dtype=torch.float32, device="cuda") if want32 else None
         x64 = torch.empty((self.n_encoded, N), dtype=torch.float64, device="cuda") if want64 else None
         if N == 0:
             return x32, x64
         bad = self._invalid_counter()
-        rc = _lib.lib().hm_encode(self.handle, _lib.dptr(rd), 0, self.D, N, _lib.dptr(x32), N, _lib.dptr(x64), N,
-                                  _lib.dptr(bad), _lib.stream_ptr())
+        rc = _lib.lib().hm_encode(self.handle, _lib.dptr(rd), 1 if col_major else 0, N if col_major else self.D, N,
+                                  _lib.dptr(x32), N, _lib.dptr(x64), N, _lib.dptr(bad), _lib.stream_ptr())
         _lib.check(rc, "hm_encode")
         if int(bad.item()) != 0:
             raise ValueError("a discrete parameter value is not in its list of values (models.py:962-983)")
@@ -380,8 +381,14 @@ class DevicePool:
     def __init__(self, device_space, seed, use_priors, n, want64=False):
         from .models import EncodedCandidates
         self.ds, self.seed, self.use_priors, self.n = device_space, int(seed), bool(use_priors), int(n)
-        out = device_space.sample_pool(seed, n, use_priors, want_raw=True, want32=True, want64=want64)
-        self.candidates = EncodedCandidates(x32=out["x32"], x64=out["x64"], raw_cm=out["raw"])
+        if device_space.packed_bits > 0 and not want64:
+            # all-discrete space: the pool is one 64-bit code per candidate (same Philox stream, same candidates)
+            out = device_space.sample_pool_packed(seed, n, use_priors, want_raw=True)
+            self.candidates = EncodedCandidates(raw_cm=out["raw"], codes=out["codes"], device_space=device_space)
+        else:
+            out = device_space.sample_pool(seed, n, use_priors, want_raw=True, want32=True, want64=want64)
+            self.candidates = EncodedCandidates(x32=out["x32"], x64=out["x64"], raw_cm=out["raw"],
+                                                device_space=device_space)
 
     def __len__(self):
         return self.n

@@ -172,3 +172,25 @@ def test_packed_host_entry_and_errors():
         mixed.encode_packed(np.array([[0.5, 2.0]]))
     with pytest.raises(ValueError):
         ds.encode_packed(np.full((3, ds.D), 12345.0))
+
+
+def test_device_pools_of_discrete_spaces_are_packed_and_score_identically():
+    """local_search's device pools on an all-discrete space are 64-bit codes; acquisition_scores_device walks them with
+    the packed kernel and returns the very scores the fp32 encoded pool gets; the encoded matrix is still available on
+    demand (feasibility classifier / GP consumers)."""
+    import torch
+    from hypermapper_b200 import random_scalarizations as rs, workloads
+    from hypermapper_b200.models import EncodedCandidates
+    from hypermapper_b200.space_device import DevicePool, device_space_for
+    wl = workloads.RFWorkload(dict(workloads.scenario_c3(), models={"model": "random_forest", "number_of_trees": 12}),
+                              n_train=300, seed=3)
+    ds = device_space_for(wl.space)
+    pool = DevicePool(ds, 99, False, 200_000)
+    assert pool.candidates.codes is not None and pool.candidates.x32 is None
+    args = ("EI", None, wl.objective_weights, wl.models, wl.space, "tchebyshev", wl.objective_limits, 5, wl.data_array,
+            "random_forest")
+    got = rs.acquisition_scores_device(args[0], pool.candidates, *args[2:])
+    ref_pool = ds.sample_pool(99, 200_000, False)
+    want = rs.acquisition_scores_device(args[0], EncodedCandidates(x32=ref_pool["x32"]), *args[2:])
+    assert torch.equal(got.view(torch.int64), want.view(torch.int64))
+    assert torch.equal(pool.candidates.get("float32"), ref_pool["x32"])
