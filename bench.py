@@ -64,6 +64,9 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3", choices=WORKLOADS)
     ap.add_argument("--candidates", type=int, default=0, help="units per GPU (default: the workload's)")
+    ap.add_argument("--total-candidates", type=int, default=0,
+                    help="STRONG scaling: units of the whole job, split evenly over the GPUs (BASELINE configs[4]: "
+                         "67108864 over 2/4/8 GPUs); the JSON line then says \"scaling\": \"strong\"")
     ap.add_argument("--cpu-sample", type=int, default=0, help="units in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -136,7 +139,7 @@ class RFBench:
     e2e_api = "hm_rf_score_host (C-ABI, pinned host candidates, 2M-candidate double-buffered chunks)"
 
     def __init__(self, name):
-        from hypermapper_b200 import workloads
+        from bench_support import workloads
         self.name = name
         cache = os.path.join(os.environ.get("HM_BENCH_CACHE", "/tmp"),
                              "hm_bench_wl_v3_%s.pkl" % ("c3" if name.startswith("c3") else name))
@@ -272,7 +275,7 @@ class RFBench:
             self.codes_host = torch.empty((N,), dtype=torch.int64).pin_memory()
             raw = np.empty((min(N, 1 << 21), self.ds.D), dtype=np.float64)
             rng = np.random.default_rng(6 + rank)
-            from hypermapper_b200 import workloads
+            from bench_support import workloads
             inputs = wl.space.get_input_parameters()
             ch = self.codes_host.numpy().view(np.uint64)
             for lo in range(0, N, 1 << 21):                      # the candidates candidates_encoded(N, 6 + rank) encodes
@@ -402,7 +405,7 @@ class SpaceRFBench(RFBench):
                                   "D2H top-k + hm_sample_rows of the winners (no candidate crosses PCIe)"}[name]
 
     def raw_rows(self, n, seed):
-        from hypermapper_b200 import workloads
+        from bench_support import workloads
         wl = self.wl
         rng = np.random.default_rng(seed)
         inputs = wl.space.get_input_parameters()
@@ -525,7 +528,8 @@ class GPBench:
                "hm_gp_mean_var -> hm_acq_score -> D2H scores; hm_topk -> D2H top-k)")
 
     def __init__(self, name):
-        from hypermapper_b200 import gp, workloads
+        from hypermapper_b200 import gp
+        from bench_support import workloads
         self.name = name
         if name == "c2":
             n, D, self.n_default = 256, 6, 1 << 20
@@ -815,6 +819,10 @@ def main():
 
     b = make_bench(args.workload)
     N = args.candidates or b.n_default
+    strong = args.total_candidates > 0
+    if strong:
+        assert args.total_candidates % world == 0, "--total-candidates must be a multiple of the number of GPUs"
+        N = args.total_candidates // world
     b.setup_device(N, rank)
     ev_pairs = []
 
@@ -882,10 +890,13 @@ def main():
         roof["share_of_step"] = kernel_ms / ms_per_step
         line = {
             "metric": b.metric, "value": value, "unit": b.unit, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong" if strong else "weak",
             "vs_baseline": None, "dtype": b.dtype, "data": "synthetic", "impl": "b200", "config": b.config(N, world),
             "roofline": roof, "clocks": clocks, "gpu_launches": launches * args.steps,
         }
+        if strong:
+            line["config"]["total_candidates"] = args.total_candidates
         if e2e is not None:
             line["e2e"] = e2e
         if world == 1 and not args.no_cpu_baseline:

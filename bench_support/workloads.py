@@ -5,8 +5,9 @@ import math
 
 import numpy as np
 
-from . import _lib
-from .encoding import Encoder
+from hypermapper_b200 import _lib
+from hypermapper_b200.encoding import Encoder
+
 from .hutter_forest import fit_hutter_forest
 from .space_lite import SpaceLite
 
@@ -170,7 +171,7 @@ class RFWorkload:
         return out
 
     def acq_params(self):
-        from .random_scalarizations import acquisition_constants
+        from hypermapper_b200.random_scalarizations import acquisition_constants
         w, fmin, beta = acquisition_constants(self.acquisition, self.scalarization, self.objectives,
                                               self.objective_weights, self.objective_limits, self.data_array,
                                               self.iteration_number)

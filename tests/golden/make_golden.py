@@ -560,7 +560,7 @@ def gp_case():
     from sklearn.gaussian_process import GaussianProcessRegressor
     from sklearn.gaussian_process.kernels import ConstantKernel, Matern, WhiteKernel, RBF
     sys.path.insert(0, ROOT)
-    from hypermapper_b200 import workloads
+    from bench_support import workloads
     out = {}
     cases = [
         ("c2_noise", 256, 6, 1e-4, 2, "matern52", 1.0, 1500),

@@ -31,7 +31,7 @@ def replay(z, tag, optimization_function, frozen_forest_cls):
     """Runs hypermapper_b200.local_search.local_search on the frozen inputs of run `tag`.
     Returns (data_array, best, golden data_array [D+1][n], golden best, inputs, scalarization key)."""
     from hypermapper_b200 import local_search as ls, utility_functions as uf
-    from hypermapper_b200.space_lite import SpaceLite
+    from bench_support.space_lite import SpaceLite
     name = tag.rsplit("_", 1)[0]
     config = json.loads(str(z[name + "_config_json"]))
     params_desc = json.loads(str(z[name + "_params_json"]))

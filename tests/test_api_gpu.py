@@ -48,7 +48,7 @@ class FrozenForest:
 
 
 def setup_case(name):
-    from hypermapper_b200.space_lite import SpaceLite
+    from bench_support.space_lite import SpaceLite
     z = load(name)
     config = json.loads(str(z["config_json"]))
     space = SpaceLite(config)
@@ -149,7 +149,7 @@ def test_feasibility_classifier_probability_matches_sklearn():
     models.py:574-578), and it multiplies the acquisition value."""
     from sklearn.ensemble import RandomForestClassifier
     from hypermapper_b200 import models as hm, random_scalarizations as rs
-    from hypermapper_b200.space_lite import SpaceLite
+    from bench_support.space_lite import SpaceLite
     z, space, objectives, models, bufferx, data, weights, limits = setup_case("rf_mixed.npz")
     config = json.loads(str(z["config_json"]))
     config["feasible_output"] = {"enable_feasible_predictor": True, "name": "Valid", "true_value": "True", "false_value": "False"}
@@ -173,7 +173,7 @@ def test_local_search_matches_reference_golden():
     """local_search() end point on the discrete golden scenario: same pools (frozen from the reference's RNG draws),
     same fitted forest -> same best configuration as the reference picked."""
     from hypermapper_b200 import random_scalarizations as rs, utility_functions as uf
-    from hypermapper_b200.space_lite import SpaceLite
+    from bench_support.space_lite import SpaceLite
     z = load("local_search.npz")
     config = json.loads(str(z["config_json"]))
     space = SpaceLite(config)
@@ -213,7 +213,7 @@ def test_local_search_generic_callable_and_return_shape():
     """the plug-in seam: any f(configurations=[dict], **params) -> (values, feasibility) works, and the returned
     data_array holds every evaluated point (LS points first, then both pools, then previous points)."""
     from hypermapper_b200 import local_search as ls
-    from hypermapper_b200.space_lite import SpaceLite
+    from bench_support.space_lite import SpaceLite
     config = {"optimization_objectives": ["v"], "input_parameters": {
         "a": {"parameter_type": "ordinal", "values": list(range(40)), "parameter_default": 0},
         "b": {"parameter_type": "integer", "values": [0, 30], "parameter_default": 0},
@@ -240,7 +240,7 @@ def test_lockstep_hill_climb_equals_sequential():
     """The lock-step hill climb (all starts advance together, one scoring launch per round) returns exactly what the
     start-after-start climb returns on a discrete space: same data_array (order included), same pick."""
     from hypermapper_b200 import local_search as ls, random_scalarizations as rs, utility_functions as uf
-    from hypermapper_b200.space_lite import SpaceLite
+    from bench_support.space_lite import SpaceLite
     z = load("local_search.npz")
     config = json.loads(str(z["config_json"]))
     space = SpaceLite(config)
@@ -285,8 +285,8 @@ def test_device_forest_cache_follows_in_place_refit():
     fit -- before the Hutter tables exist and before tree_.threshold is rewritten in place.  Predictions made after the
     fit must see the final thresholds and tables, not a forest cached during it."""
     from hypermapper_b200 import forest, models as hm
-    from hypermapper_b200.hutter_forest import HutterForest, fit_hutter_forest
-    from hypermapper_b200.space_lite import SpaceLite
+    from bench_support.hutter_forest import HutterForest, fit_hutter_forest
+    from bench_support.space_lite import SpaceLite
     from oracle import oracle
     rng = np.random.default_rng(0)
     X = rng.random((200, 3))

@@ -17,7 +17,8 @@ REL = 1e-5
 
 
 def _setup(n, D, noise, seed, kernel="matern52"):
-    from hypermapper_b200 import gp, workloads
+    from hypermapper_b200 import gp
+    from bench_support import workloads
     from oracle import oracle
     rng = np.random.default_rng(seed)
     X = rng.random((n, D))

@@ -18,7 +18,7 @@ def load(name):
 
 
 def space_of(z, key="config_json"):
-    from hypermapper_b200.space_lite import SpaceLite
+    from bench_support.space_lite import SpaceLite
     return SpaceLite(json.loads(str(z[key])))
 
 
@@ -66,7 +66,7 @@ def test_encoder_rejects_unknown_values():
 
 def test_encoder_normalize_inputs():
     from hypermapper_b200.encoding import Encoder
-    from hypermapper_b200.space_lite import SpaceLite
+    from bench_support.space_lite import SpaceLite
     from oracle import oracle
     z = load("rf_mixed.npz")
     cfg = json.loads(str(z["config_json"]))

@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 
 
 def _space(params):
-    from hypermapper_b200.space_lite import SpaceLite
+    from bench_support.space_lite import SpaceLite
     return SpaceLite({"optimization_objectives": ["v"], "input_parameters": params})
 
 
@@ -38,15 +38,15 @@ SPACES = {
 
 
 def _make(name):
-    from hypermapper_b200 import workloads
-    from hypermapper_b200.space_lite import SpaceLite
+    from bench_support import workloads
+    from bench_support.space_lite import SpaceLite
     from hypermapper_b200.space_device import DeviceSpace
     space = SpaceLite(workloads.scenario_c3()) if name == "c3" else _space(SPACES[name])
     return space, DeviceSpace(space)
 
 
 def _raw(space, n, rng):
-    from hypermapper_b200 import workloads
+    from bench_support import workloads
     cols = workloads.raw_uniform_columns(space, n, rng)
     return np.stack([np.asarray(cols[p], dtype=np.float64) for p in space.get_input_parameters()], axis=1)
 
@@ -112,7 +112,7 @@ def test_packed_path_on_the_reference_golden_forest():
     import torch
     from hypermapper_b200 import forest
     from hypermapper_b200.space_device import DeviceSpace
-    from hypermapper_b200.space_lite import SpaceLite
+    from bench_support.space_lite import SpaceLite
     from oracle import oracle
     z = load("local_search.npz")
     space = SpaceLite(json.loads(str(z["config_json"])))
@@ -179,7 +179,8 @@ def test_device_pools_of_discrete_spaces_are_packed_and_score_identically():
     the packed kernel and returns the very scores the fp32 encoded pool gets; the encoded matrix is still available on
     demand (feasibility classifier / GP consumers)."""
     import torch
-    from hypermapper_b200 import random_scalarizations as rs, workloads
+    from hypermapper_b200 import random_scalarizations as rs
+    from bench_support import workloads
     from hypermapper_b200.models import EncodedCandidates
     from hypermapper_b200.space_device import DevicePool, device_space_for
     wl = workloads.RFWorkload(dict(workloads.scenario_c3(), models={"model": "random_forest", "number_of_trees": 12}),

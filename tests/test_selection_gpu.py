@@ -91,7 +91,8 @@ def test_bench_workload_top20_equals_oracle_selection(which):
     """the bench's own fitted 2 x 256-tree (C3) / 256-tree (C5) forests, a seeded 2^20-candidate pool: the GPU's top-20
     == the oracle's get_min_configurations on the oracle's values; leaves / means bit-exact on a sample."""
     import torch
-    from hypermapper_b200 import exact, forest, workloads
+    from hypermapper_b200 import exact, forest
+    from bench_support import workloads
     from oracle import oracle
     if which == "c3":
         wl = workloads.RFWorkload(workloads.scenario_c3(), n_train=2000, seed=5)
@@ -137,7 +138,7 @@ def test_final_pick_when_the_best_of_a_pool_is_already_evaluated():
     """more than 256 of the best pool entries were evaluated before (late in a run on a small discrete space): the
     search goes past the k <= 1024 limit of hm_topk instead of raising (local_search.py:789-807 keeps deleting)."""
     from hypermapper_b200 import local_search as ls, random_scalarizations as rs, utility_functions as uf
-    from hypermapper_b200.space_lite import SpaceLite
+    from bench_support.space_lite import SpaceLite
     import copy
     z = load("local_search.npz")
     config = json.loads(str(z["config_json"]))

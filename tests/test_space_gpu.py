@@ -25,7 +25,7 @@ def load(name):
 
 
 def space_of(z, key="config_json"):
-    from hypermapper_b200.space_lite import SpaceLite
+    from bench_support.space_lite import SpaceLite
     return SpaceLite(json.loads(str(z[key])))
 
 
@@ -81,7 +81,7 @@ def test_device_encode_zscore_matches_host_encoder():
     z = load("rf_mixed.npz")
     cfg = json.loads(str(z["config_json"]))
     cfg["normalize_inputs"] = True
-    from hypermapper_b200.space_lite import SpaceLite
+    from bench_support.space_lite import SpaceLite
     space = SpaceLite(cfg)
     for rep, (m, s) in enumerate(((1.25, 3.5), (-0.3, 0.07))):
         for p in ("x_real", "x_int"):
@@ -165,7 +165,7 @@ def test_local_search_runs_with_prior_weighted_plugins():
         # get_neighbors maps 0 -> round(0 * size - 0.5 + min) (space.py:437-453): with min = 1 that is 0, outside the
         # range, and the reference's list.index raises for a "distribution" prior.  [0, 4] has no such boundary case.
         cfg["input_parameters"]["i_list"].update({"values": [0, 4], "prior": [0.1, 0.2, 0.3, 0.2, 0.2]})
-        from hypermapper_b200.space_lite import SpaceLite
+        from bench_support.space_lite import SpaceLite
         space = SpaceLite(cfg)
         inputs = space.get_input_parameters()
         np.random.seed(5)
@@ -294,7 +294,7 @@ def test_local_search_with_device_pools():
     np.random.seed."""
     import random
     from hypermapper_b200 import local_search as ls, random_scalarizations as rs, utility_functions as uf
-    from hypermapper_b200.space_lite import SpaceLite
+    from bench_support.space_lite import SpaceLite
     z = load("local_search.npz")
     config = json.loads(str(z["config_json"]))
     config["local_search_random_points"] = 20000
@@ -435,7 +435,7 @@ def test_random_spaces_encode_and_prior_match_host(seed):
     from hypermapper_b200 import _lib
     from hypermapper_b200.encoding import Encoder
     from hypermapper_b200.space_device import DeviceSpace
-    from hypermapper_b200.space_lite import SpaceLite
+    from bench_support.space_lite import SpaceLite
     torch = __import__("torch")
     rng = np.random.default_rng(1000 + seed)
     space = SpaceLite(_random_space_config(rng, normalize=seed % 2 == 0))
@@ -490,7 +490,7 @@ def test_device_neighbourhoods_equal_get_neighbors():
     from hypermapper_b200 import _lib
     from hypermapper_b200.local_search import get_neighbors, neighbor_plan
     from hypermapper_b200.space_device import device_space_for
-    from hypermapper_b200.space_lite import SpaceLite
+    from bench_support.space_lite import SpaceLite
     cfg = {"optimization_objectives": ["y"], "input_parameters": {
         "big": {"parameter_type": "ordinal", "values": [1, 2, 4, 8, 16, 32, 64, 128, 256], "parameter_default": 1},
         "cat": {"parameter_type": "categorical", "values": ["a", "b", "c"], "parameter_default": "a"},

@@ -7,7 +7,7 @@ bucket, not between buckets.
 """
 import sys, time, numpy as np
 sys.path.insert(0,'/root/repo')
-from hypermapper_b200 import workloads
+from bench_support import workloads
 t=time.time()
 wl=workloads.RFWorkload(workloads.scenario_c3(), n_train=2000, seed=5)
 print('fit',time.time()-t)

@@ -25,7 +25,7 @@ def main():
     ap.add_argument("--scenario", default="c1", choices=["c1", "c3"])
     ap.add_argument("--reps", type=int, default=3)
     args = ap.parse_args()
-    from hypermapper_b200 import workloads
+    from bench_support import workloads
     scen = workloads.scenario_c1() if args.scenario == "c1" else workloads.scenario_c3()
     if args.scenario == "c3":
         scen["models"]["number_of_trees"] = 32
