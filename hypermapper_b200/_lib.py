@@ -25,7 +25,7 @@ EXPORTED_SYMBOLS = [
     "hm_rf_eval", "hm_acq_score",
     "hm_topk_workspace_bytes", "hm_topk", "hm_topk_merge",
     "hm_gp_create", "hm_gp_destroy", "hm_gp_mean_var",
-    "hm_pareto_workspace_bytes", "hm_pareto_filter", "hm_pareto_pass1",
+    "hm_pareto_workspace_bytes", "hm_pareto_filter", "hm_pareto_pass1", "hm_pareto_pass1_compact",
     "hm_space_create", "hm_space_destroy", "hm_space_n_params", "hm_space_n_encoded",
     "hm_space_packed_bits", "hm_space_packed_field", "hm_encode_packed", "hm_sample_pool_packed",
     "hm_rf_score_packed_host",
@@ -121,6 +121,8 @@ def lib():
     L.hm_pareto_workspace_bytes.restype = i64
     L.hm_pareto_filter.argtypes = [vp, i64, i32, vp, vp, ctypes.POINTER(i64), vp]
     L.hm_pareto_pass1.argtypes = [vp, i64, i32, vp, vp, ctypes.POINTER(i64), vp]
+    L.hm_pareto_pass1_compact.argtypes = [vp, i64, i32, vp, vp, vp, vp, i64, i64, ctypes.POINTER(i64),
+                                          ctypes.POINTER(ctypes.c_int32), vp]
     u64 = ctypes.c_uint64
     L.hm_space_create.argtypes = [i32, vp, vp, i64, ctypes.POINTER(vp)]
     L.hm_space_destroy.argtypes = [vp]

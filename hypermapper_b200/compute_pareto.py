@@ -38,6 +38,30 @@ def pareto_mask_device(costs_dev, pass2=True):
     return mask
 
 
+def pareto_pass1_compact(costs_dev, cap, index_base=0):
+    """hm_pareto_pass1_compact: pass 1 on the device block + its survivors compacted in index order.
+    -> (mask uint8 [N], rows fp64 [cap][M], idx int64 [cap], n_alive, saw_nan); rows / idx valid for j < min(n_alive, cap)"""
+    torch = _lib.require_cuda()
+    L = _lib.lib()
+    assert costs_dev.is_cuda and costs_dev.dtype == torch.float64 and costs_dev.dim() == 2 and costs_dev.is_contiguous()
+    N, M = costs_dev.shape
+    dev = costs_dev.device
+    mask = torch.empty((N,), dtype=torch.uint8, device=dev)
+    rows = torch.empty((cap, M), dtype=torch.float64, device=dev)
+    idx = torch.empty((cap,), dtype=torch.int64, device=dev)
+    if N == 0:
+        return mask, rows, idx, 0, False
+    if M > _lib.HM_MAX_OBJECTIVES:
+        raise _lib.HmError("at most %d cost columns are supported" % _lib.HM_MAX_OBJECTIVES)
+    ws = torch.empty((int(L.hm_pareto_workspace_bytes(N, M)),), dtype=torch.uint8, device=dev)
+    n_alive, saw_nan = ctypes.c_int64(0), ctypes.c_int32(0)
+    rc = L.hm_pareto_pass1_compact(_lib.dptr(costs_dev), N, M, _lib.dptr(mask), _lib.dptr(ws), _lib.dptr(rows),
+                                   _lib.dptr(idx), int(cap), int(index_base), ctypes.byref(n_alive),
+                                   ctypes.byref(saw_nan), _lib.stream_ptr())
+    _lib.check(rc, "hm_pareto_pass1_compact")
+    return mask, rows, idx, int(n_alive.value), bool(saw_nan.value)
+
+
 def sequential_is_pareto_efficient(costs):
     """:param costs: An (n_points, n_costs) array  :return: A (n_points, ) boolean array (compute_pareto.py:89-117)"""
     torch = _lib.require_cuda()

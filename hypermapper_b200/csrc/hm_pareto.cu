@@ -602,7 +602,7 @@ __global__ void __launch_bounds__(HM_PF_THREADS) hm_px_count_flags(const unsigne
                                                                    unsigned* __restrict__ block_counts,
                                                                    const unsigned* __restrict__ run_flag) {
     __shared__ unsigned blk;
-    if (!*run_flag) return;
+    if (run_flag && !*run_flag) return;
     if (threadIdx.x == 0) blk = 0;
     __syncthreads();
     const unsigned base = blockIdx.x * HM_PF_CHUNK;
@@ -1003,17 +1003,19 @@ static int hm_pareto_run_fast(const double* costs, int64_t N, uint8_t* mask, voi
 
 template <int M>
 static int hm_pareto_run(const double* costs, int64_t N, uint8_t* mask, void* workspace, int64_t* n_out, bool pass2,
-                         cudaStream_t st) {
+                         cudaStream_t st, int* saw_nan_out) {
     int saw_nan = 0;
     int rc = hm_pareto_run_fast<M>(costs, N, mask, workspace, n_out, pass2, st, &saw_nan);
+    if (saw_nan_out) *saw_nan_out = saw_nan;
     if (rc || !saw_nan) return rc;
     return hm_pareto_run_exact<M>(costs, N, mask, workspace, n_out, pass2, st);
 }
 
 static int hm_pareto_dispatch(const double* costs, int64_t N, int M, uint8_t* mask, void* workspace, int64_t* n_out,
-                              bool pass2, void* stream) {
+                              bool pass2, void* stream, int* saw_nan_out = nullptr) {
     HM_REQUIRE(N >= 0 && N < 2147483647ll, "0 <= N < 2^31");
     HM_REQUIRE(M >= 1 && M <= HM_MAX_OBJECTIVES, "1 <= M <= 8");
+    if (saw_nan_out) *saw_nan_out = 0;
     if (N == 0) {
         if (n_out) *n_out = 0;
         return 0;
@@ -1021,14 +1023,14 @@ static int hm_pareto_dispatch(const double* costs, int64_t N, int M, uint8_t* ma
     HM_REQUIRE(costs && mask && workspace, "costs/mask/workspace");
     cudaStream_t st = (cudaStream_t)stream;
     switch (M) {
-        case 1: return hm_pareto_run<1>(costs, N, mask, workspace, n_out, pass2, st);
-        case 2: return hm_pareto_run<2>(costs, N, mask, workspace, n_out, pass2, st);
-        case 3: return hm_pareto_run<3>(costs, N, mask, workspace, n_out, pass2, st);
-        case 4: return hm_pareto_run<4>(costs, N, mask, workspace, n_out, pass2, st);
-        case 5: return hm_pareto_run<5>(costs, N, mask, workspace, n_out, pass2, st);
-        case 6: return hm_pareto_run<6>(costs, N, mask, workspace, n_out, pass2, st);
-        case 7: return hm_pareto_run<7>(costs, N, mask, workspace, n_out, pass2, st);
-        default: return hm_pareto_run<8>(costs, N, mask, workspace, n_out, pass2, st);
+        case 1: return hm_pareto_run<1>(costs, N, mask, workspace, n_out, pass2, st, saw_nan_out);
+        case 2: return hm_pareto_run<2>(costs, N, mask, workspace, n_out, pass2, st, saw_nan_out);
+        case 3: return hm_pareto_run<3>(costs, N, mask, workspace, n_out, pass2, st, saw_nan_out);
+        case 4: return hm_pareto_run<4>(costs, N, mask, workspace, n_out, pass2, st, saw_nan_out);
+        case 5: return hm_pareto_run<5>(costs, N, mask, workspace, n_out, pass2, st, saw_nan_out);
+        case 6: return hm_pareto_run<6>(costs, N, mask, workspace, n_out, pass2, st, saw_nan_out);
+        case 7: return hm_pareto_run<7>(costs, N, mask, workspace, n_out, pass2, st, saw_nan_out);
+        default: return hm_pareto_run<8>(costs, N, mask, workspace, n_out, pass2, st, saw_nan_out);
     }
 }
 
@@ -1040,4 +1042,46 @@ extern "C" int hm_pareto_filter(const double* costs, int64_t N, int M, uint8_t* 
 extern "C" int hm_pareto_pass1(const double* costs, int64_t N, int M, uint8_t* mask, void* workspace,
                                int64_t* n_alive_out_host, void* stream) {
     return hm_pareto_dispatch(costs, N, M, mask, workspace, n_alive_out_host, false, stream);
+}
+
+// rows_out[j][M] = costs[list[j]], idx_out[j] = index_base + list[j]   for j < n
+__global__ void hm_pareto_gather_rows(const double* __restrict__ costs, int M, const unsigned* __restrict__ list, unsigned n,
+                                      long long index_base, double* __restrict__ rows_out, long long* __restrict__ idx_out) {
+    const unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const unsigned i = list[j];
+    for (int d = 0; d < M; ++d) rows_out[(size_t)j * M + d] = costs[(size_t)i * M + d];
+    idx_out[j] = index_base + (long long)i;
+}
+
+// Pass 1 followed by the ordered compaction of its survivors, for the sharded path (distributed.pareto_mask_sharded):
+// what a rank sends to the others is on the device, in index order, when this returns -- no host-side nonzero / gather
+// and no separate NaN scan of the block (the filter itself detects NaNs).
+extern "C" int hm_pareto_pass1_compact(const double* costs, int64_t N, int M, uint8_t* mask, void* workspace,
+                                       double* rows_out, int64_t* idx_out, int64_t cap, int64_t index_base,
+                                       int64_t* n_alive_out_host, int32_t* saw_nan_out_host, void* stream) {
+    HM_REQUIRE(rows_out != nullptr && idx_out != nullptr && cap >= 0 && n_alive_out_host != nullptr, "outputs");
+    int saw_nan = 0;
+    int64_t n_alive = 0;
+    int rc = hm_pareto_dispatch(costs, N, M, mask, workspace, &n_alive, false, stream, &saw_nan);
+    if (rc) return rc;
+    *n_alive_out_host = n_alive;
+    if (saw_nan_out_host) *saw_nan_out_host = saw_nan;
+    const int64_t take = std::min<int64_t>(n_alive, cap);
+    if (N == 0 || take == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    HmParetoWs ws;
+    unsigned char* base = (unsigned char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    hm_pareto_layout(N, M, base, &ws);
+    const unsigned n = (unsigned)N;
+    const unsigned nblk = (n + HM_PF_CHUNK - 1) / HM_PF_CHUNK;
+    hm_px_count_flags<<<nblk, HM_PF_THREADS, 0, st>>>(mask, n, ws.block_counts, nullptr);
+    hm_pareto_scan<<<1, 1024, 0, st>>>(ws.block_counts, nblk, ws.round, nullptr);
+    hm_pareto_scatter<<<nblk, HM_PF_THREADS, 0, st>>>(nullptr, n, mask, ws.block_counts, ws.alive[0], 0xffffffffu, ws.round,
+                                                      nullptr);
+    hm_pareto_gather_rows<<<(unsigned)((take + 255) / 256), 256, 0, st>>>(costs, M, ws.alive[0], (unsigned)take,
+                                                                          (long long)index_base, rows_out,
+                                                                          reinterpret_cast<long long*>(idx_out));
+    HM_CUDA_TRY(cudaGetLastError());
+    return 0;
 }

@@ -73,6 +73,8 @@ def pareto_mask_sharded(costs_local, filter_fn=None, group=None):
     filter_fn(costs, pass2) -> uint8/bool mask tensor on the same device; default: the K4 kernels."""
     import torch
     import torch.distributed as dist
+    if filter_fn is None and costs_local.is_cuda:
+        return _pareto_mask_sharded_device(costs_local, group)
     if filter_fn is None:
         from .compute_pareto import pareto_mask_device as filter_fn
     world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -116,4 +118,58 @@ def pareto_mask_sharded(costs_local, filter_fn=None, group=None):
     keep = filter_fn(union, True).to(torch.bool) if union.shape[0] else torch.zeros((0,), dtype=torch.bool, device=dev)
     start = sum(counts[:rank])
     out[rows[keep[start: start + counts[rank]]]] = 1
+    return out
+
+
+def _pareto_mask_sharded_device(costs_local, group=None):
+    """pareto_mask_sharded on CUDA tensors with the K4 kernels: the local survivors come back from ONE library call
+    already compacted in index order on the device (hm_pareto_pass1_compact, which also reports NaNs -- no separate
+    isnan pass, no torch.nonzero, no row gather through the host); the exchange is ONE all-gather of fixed-capacity
+    blocks whose header row carries the count and the NaN flag; the only host reads are the two scalars that call
+    returns, the world-size headers (they size the union) and the final filter's own completion.
+    Measured (profiles/r02_bench_c4_*gpu.json): the fixed cost of the exchange is ~0.2 ms, so sharding pays from a few
+    10^7 points per rank on; below that one rank filters everything faster than the ranks can talk."""
+    import torch
+    import torch.distributed as dist
+    from .compute_pareto import pareto_mask_device, pareto_pass1_compact
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    dev = costs_local.device
+    n_local, M = costs_local.shape
+    nan_msg = ("pareto_mask_sharded: NaN costs (the dominance relation is not transitive with NaNs; filter them on one "
+               "rank with sequential_is_pareto_efficient)")
+    out = torch.zeros((n_local,), dtype=torch.uint8, device=dev)
+    cap = _PARETO_EXCHANGE_ROWS
+    _, rows, idx, n_alive, saw_nan = pareto_pass1_compact(costs_local.contiguous(), cap)
+    if world == 1:
+        if saw_nan:
+            raise ValueError(nan_msg)
+        if n_alive > cap:
+            _, rows, idx, n_alive, saw_nan = pareto_pass1_compact(costs_local.contiguous(), n_alive)
+        if n_alive:
+            keep = pareto_mask_device(rows[:n_alive].contiguous(), True).to(torch.bool)
+            out[idx[:n_alive][keep]] = 1
+        return out
+    cdev = dev if dist.get_backend(group) == "nccl" else torch.device("cpu")     # gloo: collectives through the host
+    rank = dist.get_rank(group)
+    while True:
+        block = torch.zeros((1 + cap, M), dtype=torch.float64, device=dev)
+        block[0, 0] = float(n_alive) + (0.5 if saw_nan else 0.0)
+        take = min(n_alive, cap)
+        block[1: 1 + take] = rows[:take]
+        gathered = torch.empty((world * (1 + cap), M), dtype=torch.float64, device=cdev)
+        dist.all_gather_into_tensor(gathered, block.to(cdev), group=group)
+        gathered = gathered.view(world, 1 + cap, M)
+        heads = gathered[:, 0, 0].cpu().tolist()
+        if any(h != int(h) for h in heads):
+            raise ValueError(nan_msg)                    # every rank sees the same headers and raises together
+        counts = [int(h) for h in heads]
+        if max(counts) <= cap:
+            break
+        cap = max(counts)                                # rare: a rank kept more rows than the block holds
+        _, rows, idx, n_alive, saw_nan = pareto_pass1_compact(costs_local.contiguous(), cap)
+    union = torch.cat([gathered[r, 1: 1 + counts[r]] for r in range(world)], dim=0).to(dev).contiguous()
+    if union.shape[0]:
+        keep = pareto_mask_device(union, True).to(torch.bool)
+        start = sum(counts[:rank])
+        out[idx[:counts[rank]][keep[start: start + counts[rank]]]] = 1
     return out

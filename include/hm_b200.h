@@ -187,6 +187,13 @@ int hm_pareto_filter(const double* costs, int64_t N, int M, uint8_t* mask, void*
 int hm_pareto_pass1(const double* costs, int64_t N, int M, uint8_t* mask, void* workspace,
                     int64_t* n_alive_out_host, void* stream);
 
+/* pass 1 + ordered compaction of its survivors, for the sharded path: rows_out[j][M] / idx_out[j] = the j-th surviving
+ * row (ascending index; idx = index_base + row) for j < min(*n_alive_out_host, cap), all on the device and ordered on
+ * `stream`; *saw_nan_out_host = 1 when the block holds NaN costs (the filter detects them itself). */
+int hm_pareto_pass1_compact(const double* costs, int64_t N, int M, uint8_t* mask, void* workspace, double* rows_out,
+                            int64_t* idx_out, int64_t cap, int64_t index_base, int64_t* n_alive_out_host,
+                            int32_t* saw_nan_out_host, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * K5 / K6 / K7  search-space side of the path on the device
  * A space is the list of input parameters in input-parameter order (space.py Real/Integer/Ordinal/
