@@ -36,6 +36,11 @@
 #define HM_GP_MAX_STAGES 4
 #define HM_GP_SMEM_LIMIT (227 * 1024)
 #define HM_GP_SMEM_HEADER 256     // 8 warps x 4 stages mbarriers
+// large-n path (n_pad > HM_GP_MAX_NPAD): 64 x 64 output tiles, 32-deep k stages
+#define HM_GPB_T 64
+#define HM_GPB_K 32
+#define HM_GPB_MAX_NPAD 16384
+#define HM_GPB_CHUNK 8192         // candidates per pass (Kx chunk = n_pad x 8192 x 8 B of stream-ordered scratch)
 
 struct hm_gp {
     int n, n_pad, D, kind;
@@ -48,6 +53,11 @@ struct hm_gp {
     double* d_alpha;   // [n_pad]     (zero padded)
     double* d_LpF;     // panels r = 0..R-1, panel r = [(r+1)*8 k4][4 nb][32 lanes] in B-fragment order
     double* d_ls;      // [D]
+    // n_pad > HM_GP_MAX_NPAD: the Kx tile no longer fits shared memory; the model is kept row-major and the prediction
+    // runs as two plain kernels over candidate chunks (hm_gp_big_*)
+    int big;
+    double* d_Xs_rm;    // [n_pad][D]   training inputs / lengthscale, row-major (zero padded)
+    double* d_Linv_rm;  // [n_pad][n_pad] inverse Cholesky factor, row-major (lower triangular, zero padded)
 };
 
 struct HmGpArgs {
@@ -118,6 +128,10 @@ static int hm_gp_plan(int n_pad, int D, int* warps_out, int* G_out, int* stage_k
     return hm_gp_plan_w(n_pad, D, 8, HM_GP_SMEM_LIMIT, G_out, stage_k_out, n_stages_out, aliased_out, smem_out);
 }
 
+static int hm_gp_create_big(hm_gp* g, int n, int n_pad, int D, const double* Xs, const double* ls, const double* alpha,
+                            const double* Linv, double sf2, double noise, double y_mean, double y_std, int kernel_kind,
+                            hm_gp_t** out);
+
 extern "C" int hm_gp_create(int n, int D, const double* Xs, const double* ls, const double* alpha, const double* Linv,
                             double sf2, double noise, double y_mean, double y_std, int kernel_kind, hm_gp_t** out) {
     HM_REQUIRE(out != nullptr, "out");
@@ -125,14 +139,14 @@ extern "C" int hm_gp_create(int n, int D, const double* Xs, const double* ls, co
     HM_REQUIRE(n >= 1 && D >= 1 && D <= HM_GP_MAX_D, "n >= 1, 1 <= D <= 64");
     HM_REQUIRE(Xs && ls && alpha && Linv, "arrays");
     HM_REQUIRE(kernel_kind == 0 || kernel_kind == 1, "kernel_kind");
-    const int n_pad = (n + HM_GP_BLK - 1) / HM_GP_BLK * HM_GP_BLK;
-    if (n_pad > HM_GP_MAX_NPAD) {
-        hm_set_error("hm_gp_create: n = %d training points exceeds the supported %d", n, HM_GP_MAX_NPAD);
-        return HM_E_UNSUPPORTED;
-    }
+    int n_pad = (n + HM_GP_BLK - 1) / HM_GP_BLK * HM_GP_BLK;
+    const bool big = n_pad > HM_GP_MAX_NPAD || getenv("HM_B200_GP_FORCE_BIG") != nullptr;
+    if (big) n_pad = (n + HM_GPB_T - 1) / HM_GPB_T * HM_GPB_T;
+    HM_REQUIRE(n_pad <= HM_GPB_MAX_NPAD, "n <= 16384 training points");
     hm_gp* g = new (std::nothrow) hm_gp();
     if (!g) return HM_E_NOMEM;
     memset(g, 0, sizeof(*g));
+    if (big) return hm_gp_create_big(g, n, n_pad, D, Xs, ls, alpha, Linv, sf2, noise, y_mean, y_std, kernel_kind, out);
     g->n = n;
     g->n_pad = n_pad;
     g->D = D;
@@ -192,6 +206,8 @@ extern "C" int hm_gp_create(int n, int D, const double* Xs, const double* ls, co
 
 extern "C" void hm_gp_destroy(hm_gp_t* g) {
     if (!g) return;
+    cudaFree(g->d_Xs_rm);
+    cudaFree(g->d_Linv_rm);
     cudaFree(g->d_XsF);
     cudaFree(g->d_b2);
     cudaFree(g->d_alpha);
@@ -496,12 +512,238 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? 2 : 1) hm_gp_kernel(const _
     }
 }
 
+// ============================================================================================================
+// Large models (n_pad > 768): the [candidates x n] cross-covariance tile does not fit shared memory any more, so the
+// prediction runs over chunks of HM_GPB_CHUNK candidates as
+//   hm_gp_big_kx      Kt[k][i] = k(x_i, X_k) (fp64, stream-ordered scratch, k-major so both kernels touch it coalesced),
+//                     mu_i = sum_k Kt[k][i] alpha_k (fixed order)
+//   hm_gp_big_tri     P[i][rj] = sum_{r in row tile rj} ( sum_{k <= r} Kt[k][i] Linv[r][k] )^2 : a lower-triangular
+//                     fp64 GEMM on the FP64 tensor path (DMMA.8x8x4), 64 candidates x 64 rows per CTA, operands staged
+//                     through shared memory in 32-deep k slices, the squares reduced in registers
+//   hm_gp_big_finish  var_i from sum_rj P[i][rj] (fixed order) with the same epilogue as hm_gp_kernel
+// Same arithmetic model as the fused kernel (GPy's GEMM-form distance, clip, lean sqrt / exp); throughput is lower (the
+// operands come from L2 instead of a per-warp TMA ring) -- this path exists so that n has no hard limit.
+// ============================================================================================================
+struct HmGpBigArgs {
+    const double* Xs;      // [n_pad][D]
+    const double* b2;
+    const double* alpha;
+    const double* Linv;    // [n_pad][n_pad]
+    const double* ls;
+    const double* X;       // [D][ldx]
+    long long ldx, i0;
+    int nc, nc_pad;        // candidates of this chunk, rounded up to 64
+    int n, n_pad, D;
+    double sf2, noise, y_mean, y_std, y_std2;
+    double* Kt;            // [n_pad][nc_pad]
+    double* mu;            // [nc_pad]
+    double* a2;            // [nc_pad]  |x_i / ls|^2 (NaN / inf marks a bad candidate)
+    double* P;             // [nc_pad][n_pad / 64]
+    double* mean;
+    double* var;
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(128) hm_gp_big_kx(const HmGpBigArgs a) {
+    extern __shared__ double xs_sh[];                       // [D][128] this CTA's candidates / lengthscale
+    const int t = threadIdx.x;
+    const int i = blockIdx.x * 128 + t;                      // chunk-relative candidate
+    const bool live = i < a.nc;
+    double a2 = 0.0;
+    for (int d = 0; d < a.D; ++d) {
+        const double x = live ? a.X[(size_t)d * (size_t)a.ldx + (size_t)(a.i0 + i)] / a.ls[d] : 0.0;
+        xs_sh[d * 128 + t] = x;
+        a2 = __dadd_rn(a2, __dmul_rn(x, x));
+    }
+    const bool bad = !(a2 < 1.7976931348623157e308);
+    double mu = 0.0;
+    for (int k = 0; k < a.n_pad; ++k) {
+        double kv = 0.0;
+        if (k < a.n && !bad) {
+            const double* xk = a.Xs + (size_t)k * a.D;       // the same address for the whole warp: broadcast
+            double dot = 0.0;
+            for (int d = 0; d < a.D; ++d) dot = fma(xs_sh[d * 128 + t], xk[d], dot);
+            double r2 = __dadd_rn(__dmul_rn(-2.0, dot), __dadd_rn(a2, a.b2[k]));
+            r2 = r2 > 0.0 ? r2 : 0.0;                        // np.clip(r2, 0, inf)
+            kv = hm_gp_k_of_r2<KIND>(r2, a.sf2);
+            mu = fma(kv, a.alpha[k], mu);
+        }
+        if (i < a.nc_pad) a.Kt[(size_t)k * a.nc_pad + i] = kv;
+    }
+    if (i < a.nc_pad) {
+        a.mu[i] = mu;
+        a.a2[i] = live ? a2 : 0.0;
+    }
+}
+
+// CTA (ci, rj): candidates [64 ci, 64 ci + 64) x rows [64 rj, 64 rj + 64); 8 warps, warp w owns candidates 8 w .. 8 w + 7
+__global__ void __launch_bounds__(256) hm_gp_big_tri(const HmGpBigArgs a) {
+    constexpr int SA = HM_GPB_T + 4, SB = HM_GPB_K + 4;     // padded strides (in doubles): conflict-free fragment loads
+    extern __shared__ double big_sh[];
+    double (*As)[HM_GPB_K * SA] = reinterpret_cast<double (*)[HM_GPB_K * SA]>(big_sh);                         // [k][candidate]
+    double (*Bs)[HM_GPB_T * SB] = reinterpret_cast<double (*)[HM_GPB_T * SB]>(big_sh + 2 * HM_GPB_K * SA);     // [row][k]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gid = lane >> 2, tig = lane & 3;
+    const int c0 = blockIdx.x * HM_GPB_T, r0 = blockIdx.y * HM_GPB_T;
+    const int k_end = r0 + HM_GPB_T;                         // Linv[r][k] = 0 for k > r
+    double acc[8][2];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) acc[t][0] = acc[t][1] = 0.0;
+    // a thread moves 8 doubles of each operand per stage: A rows k (64 contiguous candidates), B rows r (32 contiguous k)
+    auto load = [&](int buf, int k0) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int e = q * 256 + tid;
+            const int ka = e >> 6, ca = e & 63;
+            As[buf][ka * SA + ca] = a.Kt[(size_t)(k0 + ka) * a.nc_pad + c0 + ca];
+            const int rb = e >> 5, kb = e & 31;
+            Bs[buf][rb * SB + kb] = a.Linv[(size_t)(r0 + rb) * a.n_pad + k0 + kb];
+        }
+    };
+    load(0, 0);
+    __syncthreads();
+    int buf = 0;
+    for (int k0 = 0; k0 < k_end; k0 += HM_GPB_K) {
+        if (k0 + HM_GPB_K < k_end) load(buf ^ 1, k0 + HM_GPB_K);
+#pragma unroll
+        for (int kk = 0; kk < HM_GPB_K; kk += 4) {
+            const double av = As[buf][(kk + tig) * SA + warp * 8 + gid];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) hm_dmma(acc[t], av, Bs[buf][(t * 8 + gid) * SB + kk + tig]);
+        }
+        __syncthreads();
+        buf ^= 1;
+    }
+    double ss = 0.0;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) ss += acc[t][0] * acc[t][0] + acc[t][1] * acc[t][1];
+    ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+    ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+    if (tig == 0) a.P[(size_t)(c0 + warp * 8 + gid) * (a.n_pad / HM_GPB_T) + blockIdx.y] = ss;
+}
+
+__global__ void hm_gp_big_finish(const HmGpBigArgs a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.nc) return;
+    const int R = a.n_pad / HM_GPB_T;
+    double tot = 0.0;
+    for (int r = 0; r < R; ++r) tot += a.P[(size_t)i * R + r];
+    double v = a.sf2 - tot;
+    v = v > 1e-15 ? v : 1e-15;                     // np.clip(var, 1e-15, inf)
+    v += a.noise;                                   // Gaussian likelihood
+    const double mean = a.mu[i] * a.y_std + a.y_mean;
+    double var = v * a.y_std2;
+    if (var < 1e-11) var = 1e-11;                   // models.py:1018
+    const double a2 = a.a2[i];
+    const bool bad = !(a2 < 1.7976931348623157e308);
+    a.mean[a.i0 + i] = bad ? a2 - a2 : mean;
+    a.var[a.i0 + i] = bad ? a2 - a2 : var;
+}
+
+static int hm_gp_create_big(hm_gp* g, int n, int n_pad, int D, const double* Xs, const double* ls, const double* alpha,
+                            const double* Linv, double sf2, double noise, double y_mean, double y_std, int kernel_kind,
+                            hm_gp_t** out) {
+    g->big = 1;
+    g->n = n;
+    g->n_pad = n_pad;
+    g->D = D;
+    g->kind = kernel_kind;
+    g->sf2 = sf2;
+    g->noise = noise;
+    g->y_mean = y_mean;
+    g->y_std = y_std;
+    g->y_std2 = pow(y_std, 2.0);
+    std::vector<double> hXs((size_t)n_pad * D, 0.0), hb2(n_pad, 0.0), ha(n_pad, 0.0), hL((size_t)n_pad * n_pad, 0.0);
+    for (int j = 0; j < n; ++j) {
+        double s = 0.0;
+        for (int d = 0; d < D; ++d) {
+            hXs[(size_t)j * D + d] = Xs[(size_t)j * D + d];
+            s += Xs[(size_t)j * D + d] * Xs[(size_t)j * D + d];
+        }
+        hb2[j] = s;
+        ha[j] = alpha[j];
+        for (int k = 0; k <= j; ++k) hL[(size_t)j * n_pad + k] = Linv[(size_t)j * n + k];
+    }
+    cudaError_t e;
+#define HM_G_TRY(x)                                             \
+    if ((e = (x)) != cudaSuccess) {                             \
+        hm_set_error("%s: %s", #x, cudaGetErrorString(e));      \
+        hm_gp_destroy(g);                                       \
+        return (int)e;                                          \
+    }
+    HM_G_TRY(cudaMalloc((void**)&g->d_Xs_rm, hXs.size() * 8));
+    HM_G_TRY(cudaMalloc((void**)&g->d_b2, hb2.size() * 8));
+    HM_G_TRY(cudaMalloc((void**)&g->d_alpha, ha.size() * 8));
+    HM_G_TRY(cudaMalloc((void**)&g->d_Linv_rm, hL.size() * 8));
+    HM_G_TRY(cudaMalloc((void**)&g->d_ls, (size_t)D * 8));
+    HM_G_TRY(cudaMemcpy(g->d_Xs_rm, hXs.data(), hXs.size() * 8, cudaMemcpyHostToDevice));
+    HM_G_TRY(cudaMemcpy(g->d_b2, hb2.data(), hb2.size() * 8, cudaMemcpyHostToDevice));
+    HM_G_TRY(cudaMemcpy(g->d_alpha, ha.data(), ha.size() * 8, cudaMemcpyHostToDevice));
+    HM_G_TRY(cudaMemcpy(g->d_Linv_rm, hL.data(), hL.size() * 8, cudaMemcpyHostToDevice));
+    HM_G_TRY(cudaMemcpy(g->d_ls, ls, (size_t)D * 8, cudaMemcpyHostToDevice));
+    HM_G_TRY(cudaDeviceSynchronize());
+#undef HM_G_TRY
+    *out = g;
+    return 0;
+}
+
+static int hm_gp_mean_var_big(const hm_gp_t* g, const double* Xcm, int64_t ldx, int64_t N, double* mean_out,
+                              double* var_out, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const int R = g->n_pad / HM_GPB_T;
+    const int chunk = (int)std::min<int64_t>(HM_GPB_CHUNK, (N + HM_GPB_T - 1) / HM_GPB_T * HM_GPB_T);
+    const size_t words = (size_t)g->n_pad * chunk + 2 * (size_t)chunk + (size_t)chunk * R;
+    const size_t kx_smem = (size_t)g->D * 128 * sizeof(double);
+    const size_t tri_smem = sizeof(double) * 2 * (HM_GPB_K * (HM_GPB_T + 4) + HM_GPB_T * (HM_GPB_K + 4));
+    HM_CUDA_TRY(cudaFuncSetAttribute(hm_gp_big_tri, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tri_smem));
+    HM_CUDA_TRY(cudaFuncSetAttribute(hm_gp_big_kx<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kx_smem));
+    HM_CUDA_TRY(cudaFuncSetAttribute(hm_gp_big_kx<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kx_smem));
+    double* buf = nullptr;
+    HM_CUDA_TRY(cudaMallocAsync((void**)&buf, words * sizeof(double), st));
+    HmGpBigArgs a;
+    a.Xs = g->d_Xs_rm;
+    a.b2 = g->d_b2;
+    a.alpha = g->d_alpha;
+    a.Linv = g->d_Linv_rm;
+    a.ls = g->d_ls;
+    a.X = Xcm;
+    a.ldx = ldx;
+    a.n = g->n;
+    a.n_pad = g->n_pad;
+    a.D = g->D;
+    a.sf2 = g->sf2;
+    a.noise = g->noise;
+    a.y_mean = g->y_mean;
+    a.y_std = g->y_std;
+    a.y_std2 = g->y_std2;
+    a.Kt = buf;
+    a.mu = buf + (size_t)g->n_pad * chunk;
+    a.a2 = a.mu + chunk;
+    a.P = a.a2 + chunk;
+    a.mean = mean_out;
+    a.var = var_out;
+    for (int64_t i0 = 0; i0 < N; i0 += chunk) {
+        a.i0 = i0;
+        a.nc = (int)std::min<int64_t>(chunk, N - i0);
+        a.nc_pad = (a.nc + HM_GPB_T - 1) / HM_GPB_T * HM_GPB_T;
+        const int kx_grid = (a.nc_pad + 127) / 128;
+        if (g->kind == 0) hm_gp_big_kx<0><<<kx_grid, 128, kx_smem, st>>>(a);
+        else hm_gp_big_kx<1><<<kx_grid, 128, kx_smem, st>>>(a);
+        hm_gp_big_tri<<<dim3(a.nc_pad / HM_GPB_T, R), 256, tri_smem, st>>>(a);
+        hm_gp_big_finish<<<(a.nc + 255) / 256, 256, 0, st>>>(a);
+    }
+    const cudaError_t le = cudaGetLastError();
+    cudaFreeAsync(buf, st);
+    HM_CUDA_TRY(le);
+    return 0;
+}
+
 extern "C" int hm_gp_mean_var(const hm_gp_t* g, const double* Xcm, int64_t ldx, int64_t N, double* mean_out,
                               double* var_out, void* stream) {
     HM_REQUIRE(g != nullptr, "gp handle");
     HM_REQUIRE(N >= 0 && ldx >= N, "ldx >= N >= 0");
     if (N == 0) return 0;
     HM_REQUIRE(Xcm && mean_out && var_out, "Xcm/mean/var");
+    if (g->big) return hm_gp_mean_var_big(g, Xcm, ldx, N, mean_out, var_out, stream);
     HmGpArgs a;
     a.XsF = g->d_XsF;
     a.b2 = g->d_b2;

@@ -158,7 +158,9 @@ int hm_topk_merge(const double* vals, const int64_t* idx, int64_t n, int k, doub
  *   ls_host    : fp64 [D]    ARD lengthscales (candidates are divided by them on the device, as GPy does)
  *   alpha_host : fp64 [n]    K_y^-1 y_normalised
  *   Linv_host  : fp64 [n][n] row-major inverse of the lower Cholesky factor of K_y (lower triangular)
- *   kernel_kind: 0 = Matern-5/2, 1 = RBF;  n <= 768 training points, D <= 64
+ *   kernel_kind: 0 = Matern-5/2, 1 = RBF;  D <= 64.  Up to 768 training points the prediction is ONE fused kernel (Kx tile
+ *   in shared memory, L^-1 panels through per-warp TMA rings); larger models (n <= 16384) run as a chunked Kx kernel +
+ *   a lower-triangular fp64 tensor-path GEMM through stream-ordered scratch (same arithmetic, lower throughput)
  * ------------------------------------------------------------------------------------------ */
 typedef struct hm_gp hm_gp_t;
 int hm_gp_create(int n, int D, const double* Xs_host, const double* ls_host, const double* alpha_host,

@@ -168,3 +168,43 @@ def test_gp_full_size_properties_c2():
     mo, vo = oracle.gp_predict(st_o, base[:, torch.from_numpy(sub).cuda()].T.cpu().numpy())
     m, v = bm[0].cpu().numpy()[sub], bv[0].cpu().numpy()[sub]
     assert_mean_var(m, v, mo, vo, 256, st)
+
+
+@pytest.mark.parametrize("n,D,noise,N", [(1000, 8, 1e-3, 3000), (1537, 20, 1e-4, 700), (2048, 6, 1e-2, 9000)])
+def test_gp_large_models_beyond_the_fused_kernel(n, D, noise, N):
+    """n > 768 training points (a 1000-evaluation BO run gets there): the chunked Kx + triangular DMMA GEMM path,
+    against the oracle (pinned to scikit-learn); chunk boundary (N > 8192) and padding (n not a multiple of 64) included"""
+    import torch
+    from hypermapper_b200 import gp
+    from oracle import oracle
+    st_o, st = _setup(n, D, noise, seed=n + D)
+    Xs = np.random.default_rng(4).random((N, D))
+    Xs[:5] = st.X[:5]
+    Xs[7, 0] = np.nan
+    mean_o, var_o = oracle.gp_predict(st_o, np.where(np.isnan(Xs), 0.5, Xs))
+    X64 = torch.from_numpy(np.ascontiguousarray(Xs.T)).cuda()
+    mean = torch.empty(N, dtype=torch.float64, device="cuda")
+    var = torch.empty_like(mean)
+    gp.gp_mean_var(gp.DeviceGP(st), X64, mean, var)
+    m, v = mean.cpu().numpy(), var.cpu().numpy()
+    assert np.isnan(m[7]) and np.isnan(v[7])                # NaN coordinates: GPy's K is NaN there
+    ok = np.arange(N) != 7
+    assert_mean_var(m[ok], v[ok], mean_o[ok], var_o[ok], n, st)
+
+
+def test_gp_large_path_agrees_with_fused_kernel(monkeypatch):
+    """the two K2 paths on the same model (HM_B200_GP_FORCE_BIG routes a small model through the large-n path)"""
+    import torch
+    from hypermapper_b200 import gp
+    _, st = _setup(300, 6, 1e-4, seed=5)
+    Xs = np.random.default_rng(6).random((5000, 6))
+    X64 = torch.from_numpy(np.ascontiguousarray(Xs.T)).cuda()
+    outs = []
+    for force in (False, True):
+        if force:
+            monkeypatch.setenv("HM_B200_GP_FORCE_BIG", "1")
+        mean = torch.empty(5000, dtype=torch.float64, device="cuda")
+        var = torch.empty_like(mean)
+        gp.gp_mean_var(gp.DeviceGP(st), X64, mean, var)
+        outs.append((mean.cpu().numpy(), var.cpu().numpy()))
+    assert_mean_var(outs[1][0], outs[1][1], outs[0][0], outs[0][1], 300, st)
