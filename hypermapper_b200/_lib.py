@@ -18,7 +18,7 @@ SCALARIZATIONS = {"linear": 0, "tchebyshev": 1, "modified_tchebyshev": 2}
 
 # every symbol include/hm_b200.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = [
-    "hm_last_error", "hm_device_sm_count", "hm_version", "hm_fp64_peak_tflops",
+    "hm_last_error", "hm_device_sm_count", "hm_version", "hm_fp64_peak_tflops", "hm_checked_failures",
     "hm_forest_create", "hm_forest_destroy", "hm_forest_n_trees", "hm_forest_n_features", "hm_forest_staged",
     "hm_forest_set_coherence", "hm_forest_n_groups",
     "hm_forest_attach_packing", "hm_forest_packed", "hm_forest_packed_groups", "hm_rf_eval_packed",
@@ -95,6 +95,7 @@ def lib():
     L.hm_device_sm_count.restype = i32
     L.hm_version.restype = i32
     L.hm_fp64_peak_tflops.restype = dbl
+    L.hm_checked_failures.argtypes = [ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
     L.hm_forest_create.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, ctypes.POINTER(vp)]
     L.hm_forest_destroy.argtypes = [vp]
     L.hm_forest_destroy.restype = None

@@ -149,7 +149,11 @@ __device__ const HmPair* hm_select_k(Load load, long long lo, long long hi, int 
     // so that they sort 512 entries, not 2048 -- the sorts, not the stream, were most of the kernel
     {
         const long long p = lo + threadIdx.x;
-        if (p < hi) buf[atomicAdd(&count, 1)] = load.pair(load.item(p), p);
+        if (p < hi) {
+            const int pos = atomicAdd(&count, 1);
+            HM_DEV_ASSERT(pos >= 0 && pos < HM_TK_CAP);
+            buf[pos] = load.pair(load.item(p), p);
+        }
         __syncthreads();
         if (hi - lo > HM_TK_BLOCK) hm_sel_compact(s, k);
     }
@@ -196,7 +200,11 @@ __device__ const HmPair* hm_select_k(Load load, long long lo, long long hi, int 
                     const long long p = t0 + r * HM_TK_BLOCK + threadIdx.x;
                     if (p < e1 && p < t0 + HM_TK_TILE) {
                         const HmPair e = load.pair(load.item(p), p);
-                        if (hm_pair_less(e, tl2)) buf[atomicAdd(&count, 1)] = e;
+                        if (hm_pair_less(e, tl2)) {
+                            const int pos = atomicAdd(&count, 1);
+                            HM_DEV_ASSERT(pos >= 0 && pos < HM_TK_CAP);      // the compaction above left room for a whole tile
+                            buf[pos] = e;
+                        }
                     }
                 }
                 __syncthreads();
@@ -206,6 +214,7 @@ __device__ const HmPair* hm_select_k(Load load, long long lo, long long hi, int 
         }
     }
     hm_sel_compact(s, k);
+    HM_DEV_ASSERT(count >= 0 && count <= k && count <= HM_TK_CAP && overflow == 0);
     *n_selected = count;
     return buf;
 }
@@ -318,3 +327,5 @@ extern "C" int hm_topk_merge(const double* vals, const int64_t* idx, int64_t n, 
     HmLoadValIdx load = {vals, (const long long*)idx};
     return hm_topk_run(load, n, k, out_vals, out_idx, workspace, (cudaStream_t)stream);
 }
+
+HM_CHECKED_EXPORT(acq)

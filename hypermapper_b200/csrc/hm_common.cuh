@@ -27,6 +27,35 @@ void hm_set_error(const char* fmt, ...);
 
 int hm_num_sms();
 
+// ---- checked build (make checked -> libhm_b200_checked.so, -DHM_CHECKED) ---------------------------------------------
+// compute-sanitizer is not available on the GPU pool this library is developed on (profiles/r02_sanitizer_unavailable.txt),
+// so the hand-rolled synchronisation code carries its own invariants: every index into a shared-memory ring / queue /
+// candidate buffer and every staged-node address is checked in the checked build; a violation is COUNTED (the kernel
+// keeps running, nothing traps, so a failing run cannot wedge the GPU) and hm_checked_failures() reports the total and
+// the source line of the last one.  The normal build compiles the checks away.
+#ifdef HM_CHECKED
+static __device__ unsigned hm_chk_fails = 0;
+static __device__ int hm_chk_line = 0;
+#define HM_DEV_ASSERT(cond)                     \
+    do {                                        \
+        if (!(cond)) {                          \
+            atomicAdd(&hm_chk_fails, 1u);       \
+            hm_chk_line = __LINE__;             \
+        }                                       \
+    } while (0)
+#define HM_CHECKED_EXPORT(tu)                                                        \
+    extern "C" unsigned hm_chk_##tu(int* line) {                                     \
+        unsigned v = 0;                                                              \
+        cudaDeviceSynchronize();                                                     \
+        cudaMemcpyFromSymbol(&v, hm_chk_fails, sizeof(v));                           \
+        if (line) cudaMemcpyFromSymbol(line, hm_chk_line, sizeof(int));              \
+        return v;                                                                    \
+    }
+#else
+#define HM_DEV_ASSERT(cond) ((void)0)
+#define HM_CHECKED_EXPORT(tu)
+#endif
+
 // ---- order-preserving key for the stable (value, index) selection ---------------------------
 // np.argmin semantics: NaN is "smallest" (first NaN wins), -0.0 == +0.0, ties -> lowest index.
 __host__ __device__ __forceinline__ unsigned long long hm_order_key(double v) {

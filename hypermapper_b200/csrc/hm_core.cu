@@ -80,3 +80,33 @@ extern "C" double hm_fp64_peak_tflops(void) {
     const double flops = 2.0 * 8.0 * (double)iters * (double)grid * (double)block;
     return flops / (best * 1e-3) / 1e12;
 }
+
+// -1: not a checked build; otherwise the number of violated device-side invariants since the library was loaded
+// (*line_out = source line of the last one, *tu_out = 0 forest, 1 top-k, 2 GP, 3 Pareto, 4 space)
+#ifdef HM_CHECKED
+extern "C" unsigned hm_chk_forest(int*);
+extern "C" unsigned hm_chk_acq(int*);
+extern "C" unsigned hm_chk_gp(int*);
+extern "C" unsigned hm_chk_pareto(int*);
+extern "C" unsigned hm_chk_space(int*);
+#endif
+extern "C" int hm_checked_failures(int* tu_out, int* line_out) {
+#ifdef HM_CHECKED
+    unsigned (*fns[5])(int*) = {hm_chk_forest, hm_chk_acq, hm_chk_gp, hm_chk_pareto, hm_chk_space};
+    long long total = 0;
+    for (int t = 0; t < 5; ++t) {
+        int line = 0;
+        const unsigned v = fns[t](&line);
+        if (v) {
+            if (tu_out) *tu_out = t;
+            if (line_out) *line_out = line;
+        }
+        total += v;
+    }
+    return (int)(total > 2147483647ll ? 2147483647ll : total);
+#else
+    (void)tu_out;
+    (void)line_out;
+    return -1;
+#endif
+}

@@ -133,6 +133,8 @@ struct hm_forest {
 // that use them into alu-pipe shifts / adds, and the point of those instructions is to run on the fma pipe
 struct HmRtConst {
     unsigned k26, k1, k8;
+    int nodebuf;          // node-buffer bytes (checked build: staged node addresses are verified against it)
+    int xtile_bytes;      // fp32 path: bytes of the [feature][thread] tile
 };
 
 struct HmEvalArgs {
@@ -613,6 +615,8 @@ __device__ __forceinline__ void hm_walk_round(const uint32_t* __restrict__ roots
         // stays in one aligned register pair (no moves around the load) and the loop condition is one three-input OR.
         const uint32_t nodes_a = hm_smem_u32(nodes);
         const uint32_t c_lo = (uint32_t)code, c_hi = (uint32_t)(code >> 32);
+        const int nodebuf_bytes = k.nodebuf;
+        (void)nodebuf_bytes;
         unsigned long long nq[NCH];
         uint32_t yy[NCH];
 #pragma unroll
@@ -626,6 +630,7 @@ __device__ __forceinline__ void hm_walk_round(const uint32_t* __restrict__ roots
         while (live) {
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
+                HM_DEV_ASSERT((yy[c] >> 6) + 16u <= (unsigned)nodebuf_bytes);     // both child slots inside the staged group
                 if (PACKED == 1) {
                     asm volatile(
                         "{\n\t"
@@ -702,6 +707,9 @@ __device__ __forceinline__ void hm_walk_round(const uint32_t* __restrict__ roots
         while (any) {
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
+                // both child slots inside the staged group, feature column inside the tile
+                HM_DEV_ASSERT((((uint32_t)(nq[c] >> 32) & HM_PK_LEFT_MASK) * 8u + 16u <= (unsigned)k.nodebuf) &&
+                              ((uint32_t)(nq[c] >> 32) >> 14) + 4u <= (unsigned)k.xtile_bytes);
                 // packed word 1: tile byte offset = y >> 14 (as the high half of y * 2^18, one IMAD.HI), child = y & 0xffff
                 asm volatile(
                     "{\n\t"
@@ -747,6 +755,10 @@ __device__ __forceinline__ void hm_walk_round(const uint32_t* __restrict__ roots
             }
         }
     }
+#ifdef HM_CHECKED
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) HM_DEV_ASSERT(PACKED ? nd[c].y == 0u : (nd[c].y & (SMEM ? HM_PK_LEFT_MASK : HM_LEFT_MASK)) == 0u);
+#endif
     // add the previous round's leaf records (they had this whole walk to arrive), then put this round's in flight:
     // one 256-bit load per 32-byte record (LDG.E.256), or 128 + 64 bits when the `value` column is not needed
     hm_acc_flush<NEED_V>(acc);
@@ -826,6 +838,7 @@ __global__ void __launch_bounds__(BDT, (PACKED && BDT < 1024) ? 1024 / BDT : 1) 
     auto issue = [&](int buf) {
         const HmGroupDesc* gd = a.f[pm].groups + pg;
         const unsigned bytes = gd->bytes;
+        HM_DEV_ASSERT(bytes <= (unsigned)a.nodebuf && (bytes & 15u) == 0u && pg < a.f[pm].n_groups && pm < a.M);
         hm_mbar_expect_tx(&bars[buf], bytes);
         hm_bulk_g2s(nbuf0 + (size_t)buf * a.nodebuf, a.f[pm].blob + gd->blob_off, bytes, &bars[buf]);
         ++issued;
@@ -1202,6 +1215,8 @@ static int hm_rf_eval_impl(const hm_forest_t* const* forests, int M, const float
     a.k.k26 = 1u << 26;
     a.k.k1 = 1u;
     a.k.k8 = 8u;
+    a.k.nodebuf = a.nodebuf;
+    a.k.xtile_bytes = packed ? 0 : forests[0]->block * a.D * 4;
     a.ldx = ldx;
     a.N = N;
     a.mean_out = mean_out;
@@ -1287,3 +1302,5 @@ extern "C" int hm_rf_eval_packed(const hm_forest_t* const* forests, int M, const
     return hm_rf_eval_impl(forests, M, nullptr, 0, reinterpret_cast<const unsigned long long*>(codes), N, leaf_out,
                            mean_out, var_out, pred_out, acq, feas, score_out, stream);
 }
+
+HM_CHECKED_EXPORT(forest)

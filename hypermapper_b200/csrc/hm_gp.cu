@@ -345,6 +345,8 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? 2 : 1) hm_gp_kernel(const _
                 p_in_panel = ((r + 1) * HM_GP_BLK) >> stage_shift;
                 p_src = a.LpF + (size_t)512 * r * (r + 1);
             }
+            HM_DEV_ASSERT(p_stage >= 0 && p_stage < NS && p_left > 0 && p_in_panel > 0 && p_round < 2 * R &&
+                          p_src + stage_dbl <= a.LpF + (size_t)512 * R * (R + 1));
             hm_mbar_expect_tx(&wbar[p_stage], stage_bytes);
             hm_bulk_g2s(ring + (size_t)p_stage * stage_dbl, p_src, stage_bytes, &wbar[p_stage]);
             p_src += stage_dbl;
@@ -444,6 +446,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 4 ? 2 : 1) hm_gp_kernel(const _
             const int nch = ((r + 1) * HM_GP_BLK) >> stage_shift;
             int k4 = 0;
             for (int ch = 0; ch < nch; ++ch) {
+                HM_DEV_ASSERT(c_stage >= 0 && c_stage < NS && (c_par == 0 || c_par == 1));
                 hm_mbar_wait(&wbar[c_stage], (uint32_t)c_par);
                 const double* sb = ring + (size_t)c_stage * stage_dbl + lane;
                 for (int q = 0; q < k4_per_chunk; ++q, ++k4) {
@@ -788,3 +791,5 @@ extern "C" int hm_gp_mean_var(const hm_gp_t* g, const double* Xcm, int64_t ldx, 
     HM_CUDA_TRY(cudaGetLastError());
     return 0;
 }
+
+HM_CHECKED_EXPORT(gp)

@@ -490,6 +490,7 @@ __global__ void __launch_bounds__(HM_PX_THREADS, 3) hm_px_stream(const double* _
         unsigned base = 0;
         if (lane == 0) base = atomicAdd(out_count, m);
         base = __shfl_sync(0xffffffffu, base, 0);
+        HM_DEV_ASSERT(m <= 32u && m <= n2 && n2 <= (unsigned)HM_PS_Q2 && (unsigned long long)base + m <= (unsigned long long)n_total);
         if ((unsigned)lane < m) out_list[base + lane] = q2[lane];
         __syncwarp();
         if ((unsigned)lane + 32 < n2) {                    // move the tail down (n2 <= 64)
@@ -515,6 +516,7 @@ __global__ void __launch_bounds__(HM_PX_THREADS, 3) hm_px_stream(const double* _
         }
         n1 -= m;
         const unsigned ballot = __ballot_sync(0xffffffffu, !dead);
+        HM_DEV_ASSERT(n2 + __popc(ballot) <= (unsigned)HM_PS_Q2 && m <= 32u);
         if (!dead) q2[n2 + __popc(ballot & ((1u << lane) - 1u))] = sidx;
         n2 += __popc(ballot);
         __syncwarp();
@@ -553,6 +555,7 @@ __global__ void __launch_bounds__(HM_PX_THREADS, 3) hm_px_stream(const double* _
             }
             const bool keep = !dead && pos < count;
             const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+            HM_DEV_ASSERT(n1 + __popc(ballot) <= (unsigned)HM_PS_Q1);
             if (keep) q1[n1 + __popc(ballot & ((1u << lane) - 1u))] = src[r];
             n1 += __popc(ballot);
         }
@@ -1085,3 +1088,5 @@ extern "C" int hm_pareto_pass1_compact(const double* costs, int64_t N, int M, ui
     HM_CUDA_TRY(cudaGetLastError());
     return 0;
 }
+
+HM_CHECKED_EXPORT(pareto)

@@ -1100,3 +1100,5 @@ extern "C" int hm_ls_move(const double* scores, const double* rows, int K, int D
     HM_CUDA_TRY(cudaGetLastError());
     return 0;
 }
+
+HM_CHECKED_EXPORT(space)

@@ -40,6 +40,11 @@ int hm_device_sm_count(void);
 int hm_version(void);
 /* burst FP64 DFMA rate of the current device in TFLOP/s (roofline denominator for K2; not on a data path) */
 double hm_fp64_peak_tflops(void);
+/* -1 in a normal build.  In the checked build (make -C hypermapper_b200/csrc checked; HM_B200_LIB selects it) every index
+ * into a hand-rolled shared-memory ring / queue / candidate buffer and every staged-node address is verified on the
+ * device; this returns how many of those invariants were violated since the library was loaded (0 = clean) and where
+ * (*tu_out: 0 forest, 1 top-k, 2 GP, 3 Pareto, 4 space; *line_out: source line of the last one). */
+int hm_checked_failures(int* tu_out, int* line_out);
 
 /* ------------------------------------------------------------------------------------------
  * K1  forest traversal + per-leaf table reduction

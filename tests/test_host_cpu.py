@@ -507,3 +507,12 @@ def test_local_search_goldens_discriminate():
     for name in ("branin", "mixed", "discrete"):
         ends = {tuple(z[t + "_best"].tolist()) for t in ls_replay.TAGS if t.startswith(name)}
         assert len(ends) >= 3, (name, ends)
+
+
+def test_checked_build_reports_itself():
+    """the normal build answers -1 to hm_checked_failures (no device-side checks compiled in); the symbol exists"""
+    from hypermapper_b200 import _lib
+    L = ctypes.CDLL(_lib.SO_PATH)
+    L.hm_checked_failures.argtypes = [ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
+    if "checked" not in os.path.basename(_lib.SO_PATH):
+        assert L.hm_checked_failures(None, None) == -1
