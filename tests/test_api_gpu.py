@@ -347,3 +347,22 @@ def test_classifier_probability_is_normalised_per_leaf():
     assert np.allclose(old["value"], tabs["value"], rtol=1e-15, atol=0)
     leaf = tabs["left"] < 0
     assert np.all((tabs["value"][leaf] >= 0) & (tabs["value"][leaf] <= 1))
+
+
+def test_integration_md_snippet_runs():
+    """INTEGRATION.md section 2 (the ctypes binding a maintainer of the reference would add) is executed as written:
+    extracted from the markdown, run against the built library with a fitted model of the golden file, and compared with
+    the reference's own values."""
+    import re
+    from conftest import ROOT
+    from hypermapper_b200 import _lib
+    from hypermapper_b200.random_scalarizations import acquisition_constants
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    m = re.search(r"# integration-snippet-begin\n(.*?)# integration-snippet-end", text, re.S)
+    assert m, "snippet markers missing"
+    z, space, objectives, models, bufferx, data, weights, limits = setup_case("rf_mixed.npz")
+    w, fmin, _ = acquisition_constants("EI", "tchebyshev", objectives, weights, limits, data, int(z["iteration_number"]))
+    ns = {"LIB_PATH": _lib.SO_PATH, "rf_models": models, "X_enc": z["encoded"], "weights": w, "f_min": fmin}
+    exec(compile(m.group(1), "INTEGRATION.md", "exec"), ns)
+    assert rel_ok(ns["scores"], z["acq_EI_tchebyshev"], REL)
+    assert np.array_equal(ns["topk_idx"], z["topk_idx_20"])
