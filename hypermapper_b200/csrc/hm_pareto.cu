@@ -490,7 +490,7 @@ __global__ void __launch_bounds__(HM_PX_THREADS, 3) hm_px_stream(const double* _
         unsigned base = 0;
         if (lane == 0) base = atomicAdd(out_count, m);
         base = __shfl_sync(0xffffffffu, base, 0);
-        HM_DEV_ASSERT(m <= 32u && m <= n2 && n2 <= (unsigned)HM_PS_Q2 && (unsigned long long)base + m <= (unsigned long long)n_total);
+        HM_DEV_ASSERT(m <= 32u && m <= n2 && n2 <= (unsigned)HM_PS_Q2 && (unsigned long long)base + m <= (unsigned long long)count);
         if ((unsigned)lane < m) out_list[base + lane] = q2[lane];
         __syncwarp();
         if ((unsigned)lane + 32 < n2) {                    // move the tail down (n2 <= 64)
