@@ -711,10 +711,10 @@ class ParetoBench:
         self.c_dev = self.c_host.cuda()
         self.c_stage = torch.empty_like(self.c_dev)
         self.mask_host = torch.empty((N,), dtype=torch.uint8).pin_memory()
-        # fast path: ctl_init, 2 x (gather_sample, exact, sort_pivots, stream), exact, sort_front, count_flags, scan,
-        # scatter, pass2_a, pass2_b
-        # sharded: pass 1 on the block (fast path up to hm_px_exact = 9 launches) + full filter on the union (16)
-        self.launches_per_step = 16 if self.world == 1 else 25
+        # fast path (one CUDA graph): ctl_init, 2 x (prep, stream), exact, tail_small, sort_front, pass2_a, pass2_b, publish
+        # sharded: pass 1 on the block (ctl_init, 2 x (prep, stream), exact, publish = 7) + sort_front + gather_rows + the
+        # full filter on the union (11)
+        self.launches_per_step = 11 if self.world == 1 else 20
 
     def step(self, record):
         import torch
@@ -751,8 +751,8 @@ class ParetoBench:
         b = 8 * self.M + 1
         ach = b * N / (kernel_ms / 1e3) / 1e9
         return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                "kernel": "hm_px_* (whole filter call: 2 x {sample front, stream filter}, exact all-pairs, pass 2; the level-1 "
-                          "hm_px_stream launch is the only one that touches all N points)",
+                "kernel": "hm_px_* (whole filter call, one CUDA graph: 2 x {pivot preparation, stream filter}, exact all-pairs, "
+                          "one-CTA pass 2, publish; the level-1 hm_px_stream launch is the only one that touches all N points)",
                 "kernel_ms": kernel_ms, "algorithmic_bytes_per_point": b, "peak_source": src}
 
 

@@ -38,7 +38,9 @@ def scenario_c3():
     ip = {}
     for j, size in enumerate((4, 8, 16, 16, 32, 64)):
         ip["o%d" % j] = _ordinal([2 ** i for i in range(size)] if size <= 16 else list(range(1, size + 1)))
-    for j, size in enumerate((2, 3, 4, 8)):
+    import os
+    cats = tuple(int(v) for v in os.environ.get("HM_BENCH_C3_CATS", "2,3,4,8").split(","))      # experiments only
+    for j, size in enumerate(cats):
         ip["c%d" % j] = _categorical(size, "v")
     return {"application_name": "c3_mixed", "optimization_objectives": ["obj0", "obj1"],
             "models": {"model": "random_forest", "number_of_trees": 256}, "input_parameters": ip}

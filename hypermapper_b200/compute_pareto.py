@@ -19,6 +19,24 @@ def _as_cost_matrix(costs):
     return np.ascontiguousarray(costs, dtype=np.float64)
 
 
+# workspaces of the last few (device, N, M) shapes: a BO loop filters the same shape over and over, and the library replays
+# one CUDA graph per (costs, mask, workspace) triple -- a fresh workspace per call would also mean a fresh graph capture.
+# Calls are stream-ordered on the current stream, so sequential calls may share a workspace.
+_WS_CACHE = {}
+_WS_CACHE_MAX = 2
+
+
+def _workspace(torch, L, N, M, device):
+    key = (device.index, int(N), int(M))
+    ws = _WS_CACHE.get(key)
+    if ws is None:
+        while len(_WS_CACHE) >= _WS_CACHE_MAX:
+            _WS_CACHE.pop(next(iter(_WS_CACHE)))
+        ws = torch.empty((int(L.hm_pareto_workspace_bytes(N, M)),), dtype=torch.uint8, device=device)
+        _WS_CACHE[key] = ws
+    return ws
+
+
 def pareto_mask_device(costs_dev, pass2=True):
     """costs_dev: CUDA fp64 tensor [N][M] row-major -> CUDA uint8 mask [N]."""
     torch = _lib.require_cuda()
@@ -30,7 +48,7 @@ def pareto_mask_device(costs_dev, pass2=True):
         return mask
     if M > _lib.HM_MAX_OBJECTIVES:
         raise _lib.HmError("at most %d cost columns are supported" % _lib.HM_MAX_OBJECTIVES)
-    ws = torch.empty((int(L.hm_pareto_workspace_bytes(N, M)),), dtype=torch.uint8, device=costs_dev.device)
+    ws = _workspace(torch, L, N, M, costs_dev.device)
     n_front = ctypes.c_int64(0)
     fn = L.hm_pareto_filter if pass2 else L.hm_pareto_pass1
     rc = fn(_lib.dptr(costs_dev), N, M, _lib.dptr(mask), _lib.dptr(ws), ctypes.byref(n_front), _lib.stream_ptr())
@@ -38,22 +56,27 @@ def pareto_mask_device(costs_dev, pass2=True):
     return mask
 
 
-def pareto_pass1_compact(costs_dev, cap, index_base=0):
+def pareto_pass1_compact(costs_dev, cap, index_base=0, rows_out=None):
     """hm_pareto_pass1_compact: pass 1 on the device block + its survivors compacted in index order.
-    -> (mask uint8 [N], rows fp64 [cap][M], idx int64 [cap], n_alive, saw_nan); rows / idx valid for j < min(n_alive, cap)"""
+    -> (mask uint8 [N], rows fp64 [cap][M], idx int64 [cap], n_alive, saw_nan); rows / idx valid for j < min(n_alive, cap).
+    rows_out (optional): a contiguous CUDA fp64 [cap][M] view the rows are written to (e.g. inside an exchange buffer)."""
     torch = _lib.require_cuda()
     L = _lib.lib()
     assert costs_dev.is_cuda and costs_dev.dtype == torch.float64 and costs_dev.dim() == 2 and costs_dev.is_contiguous()
     N, M = costs_dev.shape
     dev = costs_dev.device
     mask = torch.empty((N,), dtype=torch.uint8, device=dev)
-    rows = torch.empty((cap, M), dtype=torch.float64, device=dev)
+    if rows_out is None:
+        rows = torch.empty((cap, M), dtype=torch.float64, device=dev)
+    else:
+        rows = rows_out
+        assert rows.is_cuda and rows.dtype == torch.float64 and rows.shape == (cap, M) and rows.is_contiguous()
     idx = torch.empty((cap,), dtype=torch.int64, device=dev)
     if N == 0:
         return mask, rows, idx, 0, False
     if M > _lib.HM_MAX_OBJECTIVES:
         raise _lib.HmError("at most %d cost columns are supported" % _lib.HM_MAX_OBJECTIVES)
-    ws = torch.empty((int(L.hm_pareto_workspace_bytes(N, M)),), dtype=torch.uint8, device=dev)
+    ws = _workspace(torch, L, N, M, dev)
     n_alive, saw_nan = ctypes.c_int64(0), ctypes.c_int32(0)
     rc = L.hm_pareto_pass1_compact(_lib.dptr(costs_dev), N, M, _lib.dptr(mask), _lib.dptr(ws), _lib.dptr(rows),
                                    _lib.dptr(idx), int(cap), int(index_base), ctypes.byref(n_alive),

@@ -3,6 +3,7 @@
 // contraction: every product/sum goes through __dmul_rn/__dadd_rn).
 #pragma once
 #include "hm_common.cuh"
+#include "hm_lean_math.cuh"
 
 struct HmAcqDev {
     int kind, scal, M, pad;
@@ -48,13 +49,43 @@ __device__ __forceinline__ double hm_norm_pdf(double v) {
     return exp(-hm_mul(v, v) / 2.0) / NORM_PDF_C;
 }
 
-// per-objective expected improvement (random_scalarizations.py:432-437)
-__device__ __forceinline__ double hm_ei_term(double mean, double var, double f_min) {
+// per-objective expected improvement (random_scalarizations.py:432-437), the reference's operations one by one on the
+// CUDA library functions: the slow path of hm_ei_term (non-finite or extreme inputs) and the yardstick of its lean path
+static __device__ __noinline__ double hm_ei_term_ref(double mean, double var, double f_min) {
     double x_std = sqrt(var);
     double x_mean = hm_sub(1.0, mean);
     double d = hm_sub(x_mean, f_min);
     double v = d / x_std;
     return hm_add(hm_mul(d, hm_ndtr(v)), hm_mul(x_std, hm_norm_pdf(v)));
+}
+
+// The same value for ordinary inputs (1e-30 <= var <= 1e30, |d| <= 1e30, |v| <= 36: nothing near underflow, nothing
+// non-finite), ~110 fp64 instructions instead of ~330 and no branch inside:
+//   x_std, 1/x_std   one coupled Newton iteration (hm_sqrt_rsqrt_pos); v = d / x_std finished with one residual step, so v
+//                    is the correctly rounded quotient the reference computes (the far tail is sensitive to the last bit
+//                    of v: a relative 1e-16 there moves d*Phi + x_std*phi by ~v^4 * 1e-16)
+//   E = exp(-v^2/2)  once, shared: phi(v) = E / sqrt(2 pi),  Phi(-|v|) = E * erfcx(|v| / sqrt 2) / 2
+//   erfcx            one degree-20 polynomial on the whole range (hm_erfcx_pos), no erf / erfc branch
+// Against 40-digit arithmetic it is closer to the true EI than the reference's own fp64 formula (tools/lean_ei_fit.py);
+// the two differ by <= 2e-13 relative for |v| <= 6 and by the reference's own cancellation error (<= 3e-10) in the far
+// negative tail -- inside the near-tie window (exact.NEAR_TIE_REL) the host re-scores with the reference's arithmetic.
+__device__ __forceinline__ double hm_ei_term(double mean, double var, double f_min) {
+    const double d = hm_sub(hm_sub(1.0, mean), f_min);
+    if (var >= 1e-30 && var <= 1e30 && fabs(d) <= 1e30) {          // false for NaNs
+        double x_std, r_std;
+        hm_sqrt_rsqrt_pos(var, &x_std, &r_std);
+        double v = __dmul_rn(d, r_std);
+        v = fma(fma(-v, x_std, d), r_std, v);
+        const double a = fabs(v);
+        if (a <= 36.0) {
+            const double E = hm_exp_neg(__dmul_rn(__dmul_rn(-0.5, a), a));
+            const double tail = __dmul_rn(__dmul_rn(0.5, E), hm_erfcx_pos(__dmul_rn(a, 7.07106781186547524401E-1)));
+            const double Phi = v <= 0.0 ? tail : __dadd_rn(1.0, -tail);
+            const double phi = __dmul_rn(E, 0.3989422804014327);
+            return fma(d, Phi, __dmul_rn(x_std, phi));
+        }
+    }
+    return hm_ei_term_ref(mean, var, f_min);
 }
 
 // mean[m], var[m]: per-objective prediction (TS: mean[m] holds the plain prediction).

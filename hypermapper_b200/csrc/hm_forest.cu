@@ -61,8 +61,18 @@
 //   word 0 = T (compare value)  |  forest-wide leaf ordinal (leaf)
 //   word 1 = (byte offset of the first child slot inside the group's node array) << 6 | s        (0 <=> leaf)
 // second slot <=> hi32(code << s) >= T.  There is no feature tile, so the two node buffers take all of shared memory.
+// Layout kinds (hm_forest.packed): 1 = FAST (every shift <= 31), leaf word 1 = 0; 2 = wide (64-bit shift), leaf word 1 = 0;
+// 3 = FAST with self-looping leaves (hm_pack.cuh: T = bound + leaf ordinal, word 1 = own offset << 6 | 32 | sentinel shift).
 #ifndef HM_PACKED_BLOCK
 #define HM_PACKED_BLOCK 1024
+#endif
+// levels walked between two "is any chain still at an internal node" tests of the shared-memory walks (a finished chain's
+// visit is predicated off, so extra levels are harmless): the test + branch cost 2 of the 20 instructions of a 3-chain level
+#ifndef HM_WALK_LEVELS
+#define HM_WALK_LEVELS 2
+#endif
+#ifndef HM_LOOP_LEVELS
+#define HM_LOOP_LEVELS 2             // the same for the self-looping-leaf walk (packed kind 3)
 #endif
 #define HM_PACKED_CTAS (1024 / HM_PACKED_BLOCK)          // CTAs per SM of the packed kernel
 #define HM_PACKED_NODEBUF (((HM_SMEM_TOTAL - 1024 * HM_PACKED_CTAS) / HM_PACKED_CTAS - HM_SMEM_HEADER) / 2 / 16 * 16)
@@ -94,6 +104,7 @@ struct HmKeyTree {
     unsigned n_leaves;
     unsigned feat_shift;         // feature = word1 >> feat_shift      (22, or 16 + log2(block) for the packed layout)
     unsigned left_mask;          // left    = word1 & left_mask
+    unsigned leaf_and, leaf_eq;  // packed trees: leaf <=> (word1 & leaf_and) == leaf_eq;  leaf_rank is biased by the leaf bound
 };
 
 // host copy of the trees in breadth-first order (children adjacent), kept so that further node layouts (the packed one)
@@ -120,7 +131,9 @@ struct hm_forest {
     std::vector<long long>* tree_leaf_base;
     int sort_mode;                 // coherence pre-pass: -1 auto, 0 off, 1 on
     // packed layout (hm_forest_attach_packing)
-    int packed;                    // once the packed node arrays exist: 1 = FAST layout (every shift <= 31), 2 = wide
+    int packed;                    // once the packed node arrays exist: 1 = FAST layout (every shift <= 31), 2 = wide,
+                                   // 3 = FAST with self-looping leaves
+    unsigned loop_shift, loop_bound;   // kind 3: the sentinel field's shift and bound (hm_pack.cuh)
     int packed_bits;
     int nodebuf_p;                 // node-buffer size the packed groups were built for
     HmForestDev devp;
@@ -135,6 +148,8 @@ struct HmRtConst {
     unsigned k26, k1, k8;
     int nodebuf;          // node-buffer bytes (checked build: staged node addresses are verified against it)
     int xtile_bytes;      // fp32 path: bytes of the [feature][thread] tile
+    unsigned leaf_and, leaf_eq;        // packed trees walked in L2: leaf <=> (word1 & leaf_and) == leaf_eq
+    unsigned loop_shift, loop_bound;   // packed kind 3: sentinel field of the self-looping leaves
 };
 
 struct HmEvalArgs {
@@ -186,13 +201,14 @@ static int hm_forest_default_sort_mode() {
     return (m < -1 || m > 1) ? -1 : m;
 }
 
-enum { HM_LAYOUT_F32_SMEM = 0, HM_LAYOUT_F32_L2 = 1, HM_LAYOUT_PACKED = 2 };
+enum { HM_LAYOUT_F32_SMEM = 0, HM_LAYOUT_F32_L2 = 1, HM_LAYOUT_PACKED = 2, HM_LAYOUT_PACKED_LOOP = 3 };
 
 // Groups the trees (as many consecutive trees as fit one node buffer when the forest is staged through shared memory, one
 // tree per group when it is walked in L2) and lays the node words out for `layout`.
 static int hm_build_blob(const HmHostTrees& trees, int layout, int nodebuf, int block, bool staged,
                          std::vector<unsigned char>& blob, std::vector<HmGroupDesc>& groups,
-                         std::vector<unsigned>& tree_root, std::vector<long long>& tree_nodes_off) {
+                         std::vector<unsigned>& tree_root, std::vector<long long>& tree_nodes_off,
+                         unsigned loop_shift = 0, unsigned loop_bound = 0) {
     const int n_trees = (int)trees.size();
     tree_root.assign(n_trees, 0);
     tree_nodes_off.assign(n_trees, 0);
@@ -235,6 +251,10 @@ static int hm_build_blob(const HmHostTrees& trees, int layout, int nodebuf, int 
                 slot[0] = T[h].w0;
                 if (T[h].feat < 0) {
                     slot[1] = 0u;
+                    if (layout == HM_LAYOUT_PACKED_LOOP) {      // the always-false sentinel test: first slot = the leaf itself
+                        slot[0] = loop_bound + T[h].w0;
+                        slot[1] = (((base + (uint32_t)h) * 8u) << 6) | 32u | loop_shift;
+                    }
                 } else if (layout == HM_LAYOUT_F32_SMEM) {
                     slot[1] = (((uint32_t)T[h].feat * (uint32_t)block) << 16) | (base + T[h].left);
                 } else if (layout == HM_LAYOUT_F32_L2) {
@@ -519,7 +539,12 @@ extern "C" int hm_forest_attach_packing(hm_forest_t* F, const hm_space_t* S) {
     std::vector<unsigned char> blob;
     std::vector<unsigned> tree_root;
     std::vector<long long> tree_nodes_off;
-    int rc = hm_build_blob(dst, HM_LAYOUT_PACKED, nodebuf_p, 0, staged != 0, blob, groups, tree_root, tree_nodes_off);
+    // self-looping leaves: a FAST space with a sentinel field (every forest of the space then takes the same kind)
+    unsigned loop_shift = 0, loop_bound = 0;
+    const bool loop = all_fast && S->pack_fast && hm_pack_sentinel(S->pack.data(), S->D, &loop_shift, &loop_bound) &&
+                      (unsigned long long)loop_bound + (unsigned long long)F->n_leaves < 0xFFFFFFFFull && !getenv("HM_B200_PACKED_NOLOOP");
+    int rc = hm_build_blob(dst, loop ? HM_LAYOUT_PACKED_LOOP : HM_LAYOUT_PACKED, nodebuf_p, 0, staged != 0, blob, groups,
+                           tree_root, tree_nodes_off, loop_shift, loop_bound);
     if (rc) return rc;
     HM_CUDA_TRY(cudaMalloc(&F->d_blob_p, blob.size()));
     HM_CUDA_TRY(cudaMalloc(&F->d_groups_p, groups.size() * sizeof(HmGroupDesc)));
@@ -531,14 +556,28 @@ extern "C" int hm_forest_attach_packing(hm_forest_t* F, const hm_space_t* S) {
     F->devp.groups = (const HmGroupDesc*)F->d_groups_p;
     F->devp.n_groups = (int)groups.size();
     F->devp.staged = staged;
+    if (loop) {
+        // word 0 of a leaf is bound + ordinal: the tables are addressed through pointers moved down by `bound` entries
+        F->devp.leaf_tab = reinterpret_cast<const double*>(reinterpret_cast<uintptr_t>(F->d_leaf_tab) -
+                                                           (uintptr_t)loop_bound * 32u);
+        F->devp.leaf_node = reinterpret_cast<const int*>(reinterpret_cast<uintptr_t>(F->d_leaf_node) -
+                                                         (uintptr_t)loop_bound * sizeof(int));
+    }
     for (int kk = 0; kk < F->n_key; ++kk) {
         F->keyp[kk] = F->key[kk];
         F->keyp[kk].nodes = (const uint2*)((const unsigned char*)F->d_blob_p + tree_nodes_off[kk]);
         F->keyp[kk].root = tree_root[kk];
+        F->keyp[kk].leaf_and = loop ? 32u : 0xffffffffu;
+        F->keyp[kk].leaf_eq = loop ? 32u : 0u;
+        if (loop)
+            F->keyp[kk].leaf_rank = reinterpret_cast<const unsigned*>(reinterpret_cast<uintptr_t>(F->d_leaf_rank) -
+                                                                      (uintptr_t)loop_bound * sizeof(unsigned));
     }
     F->packed_bits = S->pack_bits;
     F->nodebuf_p = nodebuf_p;
-    F->packed = all_fast ? 1 : 2;
+    F->packed = loop ? 3 : (all_fast ? 1 : 2);
+    F->loop_shift = loop_shift;
+    F->loop_bound = loop_bound;
     return 0;
 }
 
@@ -624,13 +663,47 @@ __device__ __forceinline__ void hm_walk_round(const uint32_t* __restrict__ roots
             nq[c] = reinterpret_cast<const unsigned long long*>(nodes)[roots[t0 + c]];
             asm volatile("{\n\t.reg .b32 lo;\n\tmov.b64 {lo, %0}, %1;\n\t}" : "=r"(yy[c]) : "l"(nq[c]));
         }
+        if (PACKED == 3) {
+            // self-looping leaves (hm_pack.cuh): no leaf predicate, five instructions per visit -- funnel shift, compare,
+            // slot address, +8, load; a chain that has arrived re-loads its leaf (the sentinel test is false for every
+            // candidate of the space) until the slowest chain of the warp is there.  "Everyone has arrived" = bit 5 of
+            // every word 1, tested once per HM_LOOP_LEVELS levels.
+            uint32_t arrived;
+            do {
+#pragma unroll
+                for (int lvl = 0; lvl < HM_LOOP_LEVELS; ++lvl) {
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) {
+                        HM_DEV_ASSERT(((uint32_t)(nq[c] >> 32) >> 6) + 16u <= (unsigned)nodebuf_bytes);
+                        asm volatile(
+                            "{\n\t"
+                            ".reg .pred q;\n\t"
+                            ".reg .b32 th, y, hi, na;\n\t"
+                            "mov.b64 {th, y}, %0;\n\t"
+                            "shf.l.wrap.b32 hi, %2, %3, y;\n\t"        // hi32(code << (y & 31))
+                            "mad.hi.u32 na, y, %4, %1;\n\t"            // nodes + (y >> 6)
+                            "setp.ge.u32 q, hi, th;\n\t"               // second slot <=> hi32(code << s) >= T
+                            "@q add.u32 na, na, 8;\n\t"
+                            "ld.shared.b64 %0, [na];\n\t"
+                            "}"
+                            : "+l"(nq[c])
+                            : "r"(nodes_a), "r"(c_lo), "r"(c_hi), "r"(k.k26));
+                    }
+                }
+                arrived = 32u;
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) arrived &= (uint32_t)(nq[c] >> 32);
+            } while (!arrived);
+        } else {
         uint32_t live = 0;
 #pragma unroll
         for (int c = 0; c < NCH; ++c) live |= yy[c];
         while (live) {
 #pragma unroll
+            for (int lvl = 0; lvl < HM_WALK_LEVELS; ++lvl) {
+#pragma unroll
             for (int c = 0; c < NCH; ++c) {
-                HM_DEV_ASSERT((yy[c] >> 6) + 16u <= (unsigned)nodebuf_bytes);     // both child slots inside the staged group
+                HM_DEV_ASSERT(yy[c] == 0u || (yy[c] >> 6) + 16u <= (unsigned)nodebuf_bytes);     // both child slots inside the staged group
                 if (PACKED == 1) {
                     asm volatile(
                         "{\n\t"
@@ -668,9 +741,11 @@ __device__ __forceinline__ void hm_walk_round(const uint32_t* __restrict__ roots
                         : "r"(nodes_a), "l"(code), "r"(k.k26));
                 }
             }
+            }
             live = 0;
 #pragma unroll
             for (int c = 0; c < NCH; ++c) live |= yy[c];
+        }
         }
 #pragma unroll
         for (int c = 0; c < NCH; ++c) nd[c] = make_uint2((uint32_t)nq[c], (uint32_t)(nq[c] >> 32));
@@ -681,15 +756,15 @@ __device__ __forceinline__ void hm_walk_round(const uint32_t* __restrict__ roots
         for (int c = 0; c < NCH; ++c) nd[c] = nodes[roots[t0 + c]];
         bool any = false;
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) any = any || (nd[c].y != 0u);
+        for (int c = 0; c < NCH; ++c) any = any || ((nd[c].y & k.leaf_and) != k.leaf_eq);
         while (any) {
             any = false;
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
-                if (nd[c].y != 0u) {
+                if ((nd[c].y & k.leaf_and) != k.leaf_eq) {
                     const uint32_t hi = (uint32_t)((code << (nd[c].y & 63u)) >> 32);
                     nd[c] = *reinterpret_cast<const uint2*>(nb + (nd[c].y >> 6) + (hi >= nd[c].x ? 8u : 0u));
-                    any = any || (nd[c].y != 0u);
+                    any = any || ((nd[c].y & k.leaf_and) != k.leaf_eq);
                 }
             }
         }
@@ -705,6 +780,8 @@ __device__ __forceinline__ void hm_walk_round(const uint32_t* __restrict__ roots
 #pragma unroll
         for (int c = 0; c < NCH; ++c) any = any || ((uint32_t)(nq[c] >> 32) & HM_PK_LEFT_MASK);
         while (any) {
+#pragma unroll
+            for (int lvl = 0; lvl < HM_WALK_LEVELS; ++lvl) {
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
                 // both child slots inside the staged group, feature column inside the tile
@@ -729,6 +806,7 @@ __device__ __forceinline__ void hm_walk_round(const uint32_t* __restrict__ roots
                     "}"
                     : "+l"(nq[c])
                     : "r"(xs_a), "r"(nodes_a));
+            }
             }
             any = false;
 #pragma unroll
@@ -757,7 +835,7 @@ __device__ __forceinline__ void hm_walk_round(const uint32_t* __restrict__ roots
     }
 #ifdef HM_CHECKED
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) HM_DEV_ASSERT(PACKED ? nd[c].y == 0u : (nd[c].y & (SMEM ? HM_PK_LEFT_MASK : HM_LEFT_MASK)) == 0u);
+    for (int c = 0; c < NCH; ++c) HM_DEV_ASSERT(PACKED ? (nd[c].y & k.leaf_and) == k.leaf_eq : (nd[c].y & (SMEM ? HM_PK_LEFT_MASK : HM_LEFT_MASK)) == 0u);
 #endif
     // add the previous round's leaf records (they had this whole walk to arrive), then put this round's in flight:
     // one 256-bit load per 32-byte record (LDG.E.256), or 128 + 64 bits when the `value` column is not needed
@@ -865,6 +943,12 @@ __global__ void __launch_bounds__(BDT, (PACKED && BDT < 1024) ? 1024 / BDT : 1) 
         unsigned long long code = 0ull;
         if (PACKED) {
             code = __ldg(a.codes + sl);          // arrival order, or the bucket-ordered copy of the pre-pass (with perm)
+            if (PACKED == 3) {
+                // self-looping leaves rely on the sentinel field's bound: a malformed code (not one of the space's
+                // candidates) is replaced by the all-zero code instead of walking out of the staged nodes
+                const uint32_t hi = (uint32_t)((code << a.k.loop_shift) >> 32);
+                if (hi >= a.k.loop_bound) code = 0ull;
+            }
         } else if (a.Xrows) {
             // the pre-pass left this slot's candidate as one contiguous row: Dp/4 128-bit loads
             const float4* row = reinterpret_cast<const float4*>(a.Xrows + (size_t)sl * (size_t)a.Dp);
@@ -1057,7 +1141,7 @@ __global__ void __launch_bounds__(256) hm_forest_sortkey_packed(const HmKeyArgs 
         if (q < a.n_key) {
             const unsigned char* nb = reinterpret_cast<const unsigned char*>(a.t[q].nodes);
             uint2 nd = __ldg(a.t[q].nodes + a.t[q].root);
-            while (nd.y != 0u) {
+            while ((nd.y & a.t[q].leaf_and) != a.t[q].leaf_eq) {
                 const uint32_t hi = (uint32_t)((code << (nd.y & 63u)) >> 32);
                 nd = __ldg(reinterpret_cast<const uint2*>(nb + (nd.y >> 6) + (hi >= nd.x ? 8u : 0u)));
             }
@@ -1197,11 +1281,13 @@ static int hm_rf_eval_impl(const hm_forest_t* const* forests, int M, const float
     a.D = forests[0] ? forests[0]->n_features : 0;
     int steps = 0;
     bool any_leaf = false, wide = false;
+    int n_loop = 0;
     for (int m = 0; m < M; ++m) {
         HM_REQUIRE(forests[m] != nullptr, "forest handle");
         HM_REQUIRE(forests[m]->n_features == a.D, "all forests must share n_features");
         HM_REQUIRE(!packed || forests[m]->packed, "hm_forest_attach_packing has not been called on this forest");
         if (packed && forests[m]->packed == 2) wide = true;
+        if (packed && forests[m]->packed == 3) ++n_loop;
         a.f[m] = packed ? forests[m]->devp : forests[m]->dev;
         if (a.f[m].staged) steps += a.f[m].n_groups;
         a.leaf_out[m] = leaf_out ? leaf_out[m] : nullptr;
@@ -1217,6 +1303,14 @@ static int hm_rf_eval_impl(const hm_forest_t* const* forests, int M, const float
     a.k.k8 = 8u;
     a.k.nodebuf = a.nodebuf;
     a.k.xtile_bytes = packed ? 0 : forests[0]->block * a.D * 4;
+    HM_REQUIRE(n_loop == 0 || n_loop == M, "forests of one call must be packed for the same space");
+    a.k.leaf_and = n_loop ? 32u : 0xffffffffu;
+    a.k.leaf_eq = n_loop ? 32u : 0u;
+    a.k.loop_shift = n_loop ? forests[0]->loop_shift : 0u;
+    a.k.loop_bound = n_loop ? forests[0]->loop_bound : 0u;
+    for (int m = 1; m < n_loop; ++m)
+        HM_REQUIRE(forests[m]->loop_shift == a.k.loop_shift && forests[m]->loop_bound == a.k.loop_bound,
+                   "forests of one call must be packed for the same space");
     a.ldx = ldx;
     a.N = N;
     a.mean_out = mean_out;
@@ -1268,7 +1362,8 @@ static int hm_rf_eval_impl(const hm_forest_t* const* forests, int M, const float
     } while (0)
 #define HM_LAUNCH(AP, NV)                                                                                              \
     do {                                                                                                               \
-        if (packed && !wide) HM_LAUNCH_B(AP, NV, HM_PACKED_BLOCK, 1);                                                  \
+        if (packed && n_loop) HM_LAUNCH_B(AP, NV, HM_PACKED_BLOCK, 3);                                                 \
+        else if (packed && !wide) HM_LAUNCH_B(AP, NV, HM_PACKED_BLOCK, 1);                                             \
         else if (packed) HM_LAUNCH_B(AP, NV, HM_PACKED_BLOCK, 2);                                                      \
         else if (block == 1024) HM_LAUNCH_B(AP, NV, 1024, 0);                                                          \
         else if (block == 512) HM_LAUNCH_B(AP, NV, 512, 0);                                                            \

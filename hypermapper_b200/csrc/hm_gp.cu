@@ -27,6 +27,7 @@
 #include <algorithm>
 #include <vector>
 #include "hm_common.cuh"
+#include "hm_lean_math.cuh"
 
 #define HM_GP_THREADS 256
 #define HM_GP_WARPS 8
@@ -216,51 +217,7 @@ extern "C" void hm_gp_destroy(hm_gp_t* g) {
     delete g;
 }
 
-// ---- lean fp64 elementary functions for the covariance transform ------------------------------------------------
-// The CUDA library sqrt()/exp() carry inline slow paths (denormals, infinities, huge arguments) and cost ~160 SASS
-// instructions per covariance entry; here the argument ranges are known (r2 >= 0, exponent argument <= 0), so
-// branch-free versions with <= 1-2 ulp error do the same job in ~40.
-// sqrt(x) for x >= 1e-30 (callers clamp): fp32 rsqrt seed + two coupled Newton steps (Goldschmidt form) + one residual
-// correction.
-__device__ __forceinline__ double hm_sqrt_pos(double x) {
-    float yf;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(yf) : "f"((float)x));
-    const double y = (double)yf;                     // ~2^-22
-    double g = __dmul_rn(x, y);                      // ~ sqrt(x)
-    double h = __dmul_rn(0.5, y);                    // ~ 1 / (2 sqrt(x))
-    double e = fma(-g, h, 0.5);
-    g = fma(g, e, g);
-    h = fma(h, e, h);                                // ~2^-43
-    e = fma(-g, h, 0.5);
-    g = fma(g, e, g);                                // rounding-limited
-    const double d = fma(-g, g, x);                  // exact residual
-    return fma(d, h, g);
-}
-// exp(x) for -708 <= x <= 0 (callers clamp): n = rint(x log2 e), f = x - n ln2 (two-constant Cody-Waite), degree-13
-// Taylor polynomial on |f| <= ln2/2 (truncation 4e-18), scaled by 2^n through the exponent field (result stays normal).
-__device__ __forceinline__ double hm_exp_neg(double x) {
-    const double MAGIC = 6755399441055744.0;         // 1.5 * 2^52: the low mantissa word of (t + MAGIC) is rint(t)
-    const double t = fma(x, 1.4426950408889634, MAGIC);
-    const int n = __double2loint(t);
-    const double nf = __dsub_rn(t, MAGIC);
-    double f = fma(nf, -6.93147180559945290e-01, x);
-    f = fma(nf, -2.31904681384629956e-17, f);
-    double p = 1.6059043836821613e-10;               // 1/13!
-    p = fma(p, f, 2.08767569878681e-09);             // 1/12!
-    p = fma(p, f, 2.505210838544172e-08);            // 1/11!
-    p = fma(p, f, 2.755731922398589e-07);            // 1/10!
-    p = fma(p, f, 2.7557319223985893e-06);           // 1/9!
-    p = fma(p, f, 2.48015873015873e-05);             // 1/8!
-    p = fma(p, f, 1.984126984126984e-04);            // 1/7!
-    p = fma(p, f, 1.388888888888889e-03);            // 1/6!
-    p = fma(p, f, 8.333333333333333e-03);            // 1/5!
-    p = fma(p, f, 4.1666666666666664e-02);           // 1/4!
-    p = fma(p, f, 1.6666666666666666e-01);           // 1/3!
-    p = fma(p, f, 0.5);
-    p = fma(p, f, 1.0);
-    p = fma(p, f, 1.0);
-    return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
-}
+// lean sqrt / exp of the covariance transform: hm_lean_math.cuh (shared with the EI epilogue)
 
 // min(x, cap) for x >= 0 and a cap whose low word is zero: non-negative doubles order like their high words
 __device__ __forceinline__ double hm_cap_pos(double x, double cap) {

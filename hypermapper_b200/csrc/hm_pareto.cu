@@ -6,18 +6,22 @@
 // FAST PATH (NaN-free input).  Strict dominance in every coordinate is transitive, so the survivors of the sweep are
 // exactly the points that NO other point kills -- independent of the order, and ANY subset of the points may be used
 // as pivots to thin the set out first.  Two thinning levels, then an exact all-pairs test on what is left:
-//   sample  : a strided sample of the (remaining) points is gathered, its own exact front computed (all-pairs, tiled
-//             through shared memory, one candidate per warp) and sorted by coordinate sum -> <= 1024 strong pivots.
+//   prep    : the exact front of a strided sample of the (remaining) points, strongest first = <= 1024 pivots; ONE
+//             launch (hm_px_prep: sample read in place and staged whole in shared memory, a warp drops out when its
+//             candidates are dead, the last CTA to finish rank-sorts the front by coordinate sum).
 //   stream  : every point is tested against the 8 strongest pivots unconditionally (branch-free), block survivors are
 //             compacted in shared memory and tested warp-cooperatively against the remaining pivots; survivors'
 //             indices are appended to a list.  Level 1 streams the cost matrix once at HBM speed (8 M + 1 bytes/point
 //             algorithmic), level 2 re-filters the ~1 % survivors against pivots sampled from among them.
 //   exact   : all-pairs on the level-2 survivors -> mask.
-// Everything is sized by device-side counters: no host round trip until the final (count, NaN flag) read-back.
+// Everything is sized by device-side counters, the chain is one CUDA graph, and its last node publishes the counters to
+// mapped pinned memory: the only host interaction is the graph launch and one stream synchronisation.
 // Pass 2 (compute_pareto.py:107-115; sequential and order dependent by definition): at point i's turn every later point
 // still has its pass-1 state and every earlier point its final state, so  dead(i) = A(i) or B(i)  with
 // A(i) = exists j > i: rel(j, i)  (fully parallel) and B(i) = exists j < i alive: rel(j, i)  (one CTA walks only the
-// points that have such a candidate, in index order);  rel(j, i) = any(c_j == c_i) and any(c_j < c_i).
+// points that have such a candidate, in index order);  rel(j, i) = any(c_j == c_i) and any(c_j < c_i).  A front of <= 256
+// points (the normal case) is sorted, tested and cleaned up by ONE CTA (hm_px_tail_small); up to 8192 points by the
+// one-CTA sort + grid-wide A + one-CTA B; beyond that the host runs an ordered mask compaction first.
 //
 // EXACT PATH (input contains NaN: the kill relation is no longer transitive, the sweep order matters).  The sweep is
 // reproduced literally, a batch of B pivot candidates at a time:
@@ -272,10 +276,9 @@ __global__ void hm_pareto_write_mask(const unsigned* __restrict__ alive, const u
 // ============================================================================================================
 #define HM_PX_THREADS 256
 #define HM_PX_WARPS 8
-#define HM_PX_CPW 2                 // candidates per warp
-#define HM_PX_GROUP (HM_PX_WARPS * HM_PX_CPW)
 #define HM_PX_TILE 1024             // points per shared-memory tile
 #define HM_PIV_MAX 1024
+#define HM_PIV1_MAX 1024            // level-1 cap (experiments: HM_B200_PARETO_PIV1)
 #define HM_SAMPLE1 4096
 #define HM_SAMPLE2 4096
 #define HM_SORT_MAX 8192            // longest list the one-CTA sorts take
@@ -283,7 +286,7 @@ __global__ void hm_pareto_write_mask(const unsigned* __restrict__ alive, const u
 #define HM_PS_ITEMS2 1              // level 2: few points, spread them over many CTAs
 
 struct HmParetoCtl {
-    unsigned n_sample;      // gathered sample size
+    unsigned n_sample;      // size of the last level's sample
     unsigned n_piv_raw;     // front of the sample (unsorted)
     unsigned n_piv;         // pivots after sort / cap
     unsigned n_list1;       // survivors of level 1
@@ -291,158 +294,244 @@ struct HmParetoCtl {
     unsigned n_front1;      // pass-1 survivors
     unsigned nan_flag;
     unsigned n_dead2;       // points removed by pass 2
-    unsigned need_scan;     // pass-1 front too long for the one-CTA index sort
-    unsigned pad[7];
+    unsigned need_scan;     // pass-1 front too long for the one-CTA index sort: the host runs the ordered-compaction tail
+    unsigned tail_done;     // pass 2 was finished by hm_px_tail_small (front of <= HM_TAIL_SMALL points)
+    unsigned prep_ticket;   // CTAs of hm_px_prep that are done (the last one sorts the pivots and resets it)
+    unsigned pad[5];
 };
 
 __global__ void hm_px_ctl_init(HmParetoCtl* ctl) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         ctl->n_sample = ctl->n_piv_raw = ctl->n_piv = 0;
         ctl->n_list1 = ctl->n_list2 = ctl->n_front1 = 0;
-        ctl->nan_flag = ctl->n_dead2 = ctl->need_scan = 0;
+        ctl->nan_flag = ctl->n_dead2 = ctl->need_scan = ctl->tail_done = ctl->prep_ticket = 0;
     }
 }
 
-// strided sample of a point list (idx == nullptr: the identity list 0..n_total-1) into a compact [S][M] array
+// exact front of a point list (the level-2 survivors): every candidate is tested against every point of the list (tiles
+// staged in shared memory, SoA, 2-4 candidates per warp at a time, lanes stride over the tile);  mask[index] = 1 for
+// the survivors, their indices appended to front_list.
 template <int M>
-__global__ void hm_px_gather_sample(const double* __restrict__ costs, const unsigned* __restrict__ idx,
-                                    const unsigned* __restrict__ count_ptr, unsigned n_total, unsigned s_max,
-                                    double* __restrict__ sample, HmParetoCtl* ctl) {
-    const unsigned count = count_ptr ? *count_ptr : n_total;
-    const unsigned S = min(s_max, count);
-    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) {
-        ctl->n_sample = S;
-        ctl->n_piv_raw = 0;
-    }
-    if (i >= S) return;
-    const unsigned pos = (unsigned)(((unsigned long long)i * count) / S);
-    const size_t src = idx ? (size_t)idx[pos] : (size_t)pos;
-#pragma unroll
-    for (int d = 0; d < M; ++d) sample[(size_t)i * M + d] = costs[src * M + d];
-}
-
-// exact front of a point list: every candidate is tested against every point of the list (tiles staged in shared
-// memory, SoA, one candidate per warp at a time, lanes stride over the tile).
-//   TO_MASK = false : survivors' costs are appended to out_costs (count in *out_count)       [sample -> pivots]
-//   TO_MASK = true  : mask[index] = 1 for survivors, their indices appended to (unsigned*)out_costs [final exact step]
-template <int M, bool TO_MASK>
 __global__ void __launch_bounds__(HM_PX_THREADS) hm_px_exact(const double* __restrict__ costs,
                                                              const unsigned* __restrict__ idx,
-                                                             const unsigned* __restrict__ count_ptr,
-                                                             double* __restrict__ out_costs, unsigned char* __restrict__ mask,
+                                                             const unsigned* __restrict__ count_ptr, unsigned tile_pts,
+                                                             unsigned* __restrict__ front_list, unsigned char* __restrict__ mask,
                                                              unsigned* __restrict__ out_count,
                                                              const unsigned* __restrict__ abort_flag) {
+    constexpr int CPW = M <= 4 ? 4 : 2;                  // candidates per warp
+    constexpr unsigned GROUP = HM_PX_WARPS * CPW;
     extern __shared__ __align__(16) unsigned char exact_smem[];
     if (*abort_flag) return;        // a NaN was seen: the exact path will redo the call
-    double (*tile)[HM_PX_TILE] = reinterpret_cast<double (*)[HM_PX_TILE]>(exact_smem);   // [M][HM_PX_TILE]
+    double* tile = reinterpret_cast<double*>(exact_smem);             // [M][tile_pts]
     const unsigned count = *count_ptr;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (unsigned g0 = blockIdx.x * HM_PX_GROUP; g0 < count; g0 += gridDim.x * HM_PX_GROUP) {
-        double cc[HM_PX_CPW][M];
+    for (unsigned g0 = blockIdx.x * GROUP; g0 < count; g0 += gridDim.x * GROUP) {
+        double cc[CPW][M];
         unsigned alive = 0;          // bit c: candidate c exists and is not killed yet (warp uniform)
 #pragma unroll
-        for (int c = 0; c < HM_PX_CPW; ++c) {
-            const unsigned q = g0 + warp * HM_PX_CPW + c;
+        for (int c = 0; c < CPW; ++c) {
+            const unsigned q = g0 + warp * CPW + c;
             const bool ok = q < count;
             const size_t src = ok ? (idx ? (size_t)idx[q] : (size_t)q) : 0;
 #pragma unroll
             for (int d = 0; d < M; ++d) cc[c][d] = costs[src * M + d];
             if (ok) alive |= 1u << c;
         }
-        for (unsigned t0 = 0; t0 < count; t0 += HM_PX_TILE) {
+        for (unsigned t0 = 0; t0 < count; t0 += tile_pts) {
             if (!__syncthreads_or(alive != 0)) break;        // also: everyone is done with the previous tile
-            const unsigned tn = min((unsigned)HM_PX_TILE, count - t0);
+            const unsigned tn = min(tile_pts, count - t0);
             for (unsigned t = threadIdx.x; t < tn; t += HM_PX_THREADS) {
                 const size_t src = idx ? (size_t)idx[t0 + t] : (size_t)(t0 + t);
 #pragma unroll
-                for (int d = 0; d < M; ++d) tile[d][t] = costs[src * M + d];
+                for (int d = 0; d < M; ++d) tile[(size_t)d * tile_pts + t] = costs[src * M + d];
             }
             __syncthreads();
-            if (alive) {
+            // a warp leaves the tile as soon as its candidates are dead (tested every 128 points)
+            for (unsigned j0 = 0; j0 < tn && alive; j0 += 128) {
                 unsigned killed = 0;
-                for (unsigned j = lane; j < tn; j += 32) {
-                    double p[M];
 #pragma unroll
-                    for (int d = 0; d < M; ++d) p[d] = tile[d][j];
+                for (int u = 0; u < 4; ++u) {
+                    const unsigned j = j0 + u * 32 + lane;
+                    if (j < tn) {
+                        double p[M];
 #pragma unroll
-                    for (int c = 0; c < HM_PX_CPW; ++c)
-                        if (hm_kills<M>(p, cc[c])) killed |= 1u << c;
+                        for (int d = 0; d < M; ++d) p[d] = tile[(size_t)d * tile_pts + j];
+#pragma unroll
+                        for (int c = 0; c < CPW; ++c)
+                            if (hm_kills<M>(p, cc[c])) killed |= 1u << c;
+                    }
                 }
 #pragma unroll
-                for (int c = 0; c < HM_PX_CPW; ++c)
+                for (int c = 0; c < CPW; ++c)
                     if (__any_sync(0xffffffffu, (killed >> c) & 1u)) alive &= ~(1u << c);
             }
         }
         if (lane == 0) {
 #pragma unroll
-            for (int c = 0; c < HM_PX_CPW; ++c) {
+            for (int c = 0; c < CPW; ++c) {
                 if (!((alive >> c) & 1u)) continue;
-                const unsigned q = g0 + warp * HM_PX_CPW + c;
-                if (TO_MASK) {
-                    const unsigned gi = idx ? idx[q] : q;
-                    mask[gi] = 1;
-                    reinterpret_cast<unsigned*>(out_costs)[atomicAdd(out_count, 1u)] = gi;     // front list (indices)
-                } else {
-                    const unsigned pos = atomicAdd(out_count, 1u);
-#pragma unroll
-                    for (int d = 0; d < M; ++d) out_costs[(size_t)pos * M + d] = cc[c][d];
-                }
+                const unsigned q = g0 + warp * CPW + c;
+                const unsigned gi = idx ? idx[q] : q;
+                mask[gi] = 1;
+                front_list[atomicAdd(out_count, 1u)] = gi;
             }
         }
         __syncthreads();
     }
 }
 
-// sort the raw pivots by coordinate sum (strongest killers first) and keep at most HM_PIV_MAX of them.  One CTA.
+// Pivot preparation of one thinning level in ONE launch (was: gather_sample + exact + sort_pivots): the exact front of a
+// strided sample of a point list, strongest points first.
+//   * the sample is read in place (point q of the sample = list position q * count / S); a CTA stages the whole sample
+//     in shared memory at once when it fits (M <= 4: one load phase instead of four load / barrier / compute rounds);
+//   * a warp owns CPW candidates and leaves the tile loop as soon as all of them are dead (most die within the first
+//     few dozen points), so the launch lasts as long as one front member takes to meet every sample point;
+//   * the last CTA to finish (ticket) sorts the front by coordinate sum -- a rank sort in shared memory for the usual
+//     few hundred points -- and writes the <= HM_PIV_MAX strongest as the level's pivots.
+#define HM_PREP_RANK_MAX 1024
 template <int M>
-__global__ void __launch_bounds__(1024, 1) hm_px_sort_pivots(const double* __restrict__ raw, double* __restrict__ sorted,
-                                                             HmParetoCtl* ctl) {
-    extern __shared__ __align__(16) unsigned char sort_smem[];
-    double* key = reinterpret_cast<double*>(sort_smem);                                  // [HM_SORT_MAX]
-    unsigned short* ord = reinterpret_cast<unsigned short*>(key + HM_SORT_MAX);          // [HM_SORT_MAX]
-    const unsigned n = ctl->n_piv_raw;
-    unsigned n2 = 1;
-    while (n2 < n) n2 <<= 1;
-    for (unsigned i = threadIdx.x; i < n2; i += 1024) {
-        double s = INFINITY;
-        if (i < n) {
-            s = 0.0;
+__global__ void __launch_bounds__(HM_PX_THREADS) hm_px_prep(const double* __restrict__ costs,
+                                                            const unsigned* __restrict__ idx,
+                                                            const unsigned* __restrict__ count_ptr, unsigned n_total,
+                                                            unsigned s_max, unsigned tile_pts, unsigned piv_max,
+                                                            double* __restrict__ piv_raw, double* __restrict__ pivots,
+                                                            HmParetoCtl* ctl) {
+    constexpr int CPW = M <= 4 ? 4 : 2;
+    constexpr unsigned GROUP = HM_PX_WARPS * CPW;
+    extern __shared__ __align__(16) unsigned char prep_smem[];
+    double* tile = reinterpret_cast<double*>(prep_smem);              // [M][tile_pts]
+    __shared__ unsigned s_last;
+    const unsigned count = count_ptr ? *count_ptr : n_total;
+    const unsigned S = min(s_max, count);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    auto sample_src = [&](unsigned q) -> size_t {
+        const unsigned pos = (unsigned)(((unsigned long long)q * count) / S);
+        return idx ? (size_t)idx[pos] : (size_t)pos;
+    };
+    if (!*(volatile unsigned*)&ctl->nan_flag && blockIdx.x * GROUP < S) {
+        double cc[CPW][M];
+        unsigned alive = 0;          // bit c: candidate c exists and is not killed yet (warp uniform)
 #pragma unroll
-            for (int d = 0; d < M; ++d) s += raw[(size_t)i * M + d];
-            if (s != s) s = INFINITY;       // inf - inf
+        for (int c = 0; c < CPW; ++c) {
+            const unsigned q = blockIdx.x * GROUP + warp * CPW + c;
+            const bool ok = q < S;
+            const size_t src = ok ? sample_src(q) : 0;
+#pragma unroll
+            for (int d = 0; d < M; ++d) cc[c][d] = __ldg(costs + src * M + d);
+            if (ok) alive |= 1u << c;
         }
-        key[i] = s;
-        ord[i] = (unsigned short)i;
-    }
-    __syncthreads();
-    for (unsigned k = 2; k <= n2; k <<= 1) {
-        for (unsigned j = k >> 1; j > 0; j >>= 1) {
-            for (unsigned i = threadIdx.x; i < n2; i += 1024) {
-                const unsigned l = i ^ j;
-                if (l > i) {
-                    const bool up = (i & k) == 0;
-                    const double a = key[i], b = key[l];
-                    const unsigned short oa = ord[i], ob = ord[l];
-                    const bool gt = (a > b) || (a == b && oa > ob);
-                    if (gt == up) {
-                        key[i] = b;
-                        key[l] = a;
-                        ord[i] = ob;
-                        ord[l] = oa;
-                    }
-                }
+        for (unsigned t0 = 0; t0 < S; t0 += tile_pts) {
+            if (t0 && !__syncthreads_or(alive != 0)) break;           // also: everyone is done with the previous tile
+            const unsigned tn = min(tile_pts, S - t0);
+            for (unsigned t = threadIdx.x; t < tn; t += HM_PX_THREADS) {
+                const size_t src = sample_src(t0 + t);
+#pragma unroll
+                for (int d = 0; d < M; ++d) tile[(size_t)d * tile_pts + t] = __ldg(costs + src * M + d);
             }
             __syncthreads();
+            for (unsigned j0 = 0; j0 < tn && alive; j0 += 128) {
+                unsigned killed = 0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const unsigned j = j0 + u * 32 + lane;
+                    if (j < tn) {
+                        double p[M];
+#pragma unroll
+                        for (int d = 0; d < M; ++d) p[d] = tile[(size_t)d * tile_pts + j];
+#pragma unroll
+                        for (int c = 0; c < CPW; ++c)
+                            if (hm_kills<M>(p, cc[c])) killed |= 1u << c;
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < CPW; ++c)
+                    if (__any_sync(0xffffffffu, (killed >> c) & 1u)) alive &= ~(1u << c);
+            }
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int c = 0; c < CPW; ++c) {
+                if (!((alive >> c) & 1u)) continue;
+                const unsigned pos = atomicAdd(&ctl->n_piv_raw, 1u);
+                HM_DEV_ASSERT(pos < s_max);
+#pragma unroll
+                for (int d = 0; d < M; ++d) piv_raw[(size_t)pos * M + d] = cc[c][d];
+            }
         }
     }
-    const unsigned P = min(n, (unsigned)HM_PIV_MAX);
-    for (unsigned i = threadIdx.x; i < P; i += 1024) {
-        const unsigned src = ord[i];
+    // ---- the last CTA sorts ----
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&ctl->prep_ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const unsigned n = *(volatile unsigned*)&ctl->n_piv_raw;
+    double* key = reinterpret_cast<double*>(prep_smem);                               // [n2]
+    unsigned short* ord = reinterpret_cast<unsigned short*>(key + HM_SAMPLE2);        // [n2]  (bitonic path only)
+    unsigned n2 = 1;
+    while (n2 < n) n2 <<= 1;
+    for (unsigned i = threadIdx.x; i < n2; i += HM_PX_THREADS) {
+        double sum = INFINITY;
+        if (i < n) {
+            sum = 0.0;
 #pragma unroll
-        for (int d = 0; d < M; ++d) sorted[(size_t)i * M + d] = raw[(size_t)src * M + d];
+            for (int d = 0; d < M; ++d) sum += __ldcg(piv_raw + (size_t)i * M + d);
+            if (sum != sum) sum = INFINITY;       // inf - inf
+        }
+        key[i] = sum;
     }
-    if (threadIdx.x == 0) ctl->n_piv = P;
+    __syncthreads();
+    const unsigned P = min(n, piv_max);
+    if (n <= HM_PREP_RANK_MAX) {
+        // rank of (key, position): distinct by construction
+        for (unsigned i = threadIdx.x; i < n; i += HM_PX_THREADS) {
+            const double k = key[i];
+            unsigned r = 0;
+            for (unsigned j = 0; j < n; ++j) {
+                const double kj = key[j];
+                r += (kj < k || (kj == k && j < i)) ? 1u : 0u;
+            }
+            if (r < P) {
+#pragma unroll
+                for (int d = 0; d < M; ++d) pivots[(size_t)r * M + d] = __ldcg(piv_raw + (size_t)i * M + d);
+            }
+        }
+    } else {
+        for (unsigned i = threadIdx.x; i < n2; i += HM_PX_THREADS) ord[i] = (unsigned short)i;
+        __syncthreads();
+        for (unsigned k = 2; k <= n2; k <<= 1) {
+            for (unsigned j = k >> 1; j > 0; j >>= 1) {
+                for (unsigned i = threadIdx.x; i < n2; i += HM_PX_THREADS) {
+                    const unsigned l = i ^ j;
+                    if (l > i) {
+                        const bool up = (i & k) == 0;
+                        const double a = key[i], b = key[l];
+                        const unsigned short oa = ord[i], ob = ord[l];
+                        const bool gt = (a > b) || (a == b && oa > ob);
+                        if (gt == up) {
+                            key[i] = b;
+                            key[l] = a;
+                            ord[i] = ob;
+                            ord[l] = oa;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        for (unsigned i = threadIdx.x; i < P; i += HM_PX_THREADS) {
+            const unsigned src = ord[i];
+#pragma unroll
+            for (int d = 0; d < M; ++d) pivots[(size_t)i * M + d] = __ldcg(piv_raw + (size_t)src * M + d);
+        }
+    }
+    if (threadIdx.x == 0) {
+        ctl->n_piv = P;
+        ctl->n_piv_raw = 0;          // ready for the next level
+        ctl->prep_ticket = 0;
+        ctl->n_sample = S;
+    }
 }
 
 // streaming filter of a point list against the sorted pivots; survivors' indices are appended to out_list.
@@ -572,7 +661,7 @@ __global__ void __launch_bounds__(HM_PX_THREADS, 3) hm_px_stream(const double* _
 __global__ void __launch_bounds__(1024, 1) hm_px_sort_front(unsigned* __restrict__ list, HmParetoCtl* ctl) {
     __shared__ unsigned key[HM_SORT_MAX];
     const unsigned n = ctl->n_front1;
-    if (ctl->nan_flag) return;
+    if (ctl->nan_flag || ctl->tail_done) return;
     if (n > HM_SORT_MAX) {
         if (threadIdx.x == 0) ctl->need_scan = 1;
         return;
@@ -638,8 +727,10 @@ __global__ void __launch_bounds__(HM_PX_THREADS) hm_px_pass2_a(const double* __r
                                                                const unsigned* __restrict__ sorted,
                                                                const unsigned* __restrict__ count_ptr,
                                                                unsigned char* __restrict__ state,
-                                                               const unsigned* __restrict__ abort_flag) {
-    if (*abort_flag) return;
+                                                               const HmParetoCtl* __restrict__ ctl, int forced) {
+    // in the graph: nothing to do when the small tail finished pass 2, or when the front was too long to sort in one
+    // CTA (the host then runs the ordered compaction and calls this kernel again, forced)
+    if (ctl->nan_flag || (!forced && (ctl->tail_done || ctl->need_scan))) return;
     const unsigned S = *count_ptr;
     const int lane = threadIdx.x & 31;
     const unsigned gw = (blockIdx.x * HM_PX_THREADS + threadIdx.x) >> 5, nw = (gridDim.x * HM_PX_THREADS) >> 5;
@@ -674,8 +765,8 @@ __global__ void __launch_bounds__(1024, 1) hm_px_pass2_b(const double* __restric
                                                          const unsigned* __restrict__ sorted,
                                                          const unsigned* __restrict__ count_ptr,
                                                          volatile unsigned char* state, unsigned char* __restrict__ mask,
-                                                         HmParetoCtl* ctl) {
-    if (ctl->nan_flag) return;
+                                                         HmParetoCtl* ctl, int forced) {
+    if (ctl->nan_flag || (!forced && (ctl->tail_done || ctl->need_scan))) return;
     const unsigned S = *count_ptr;
     __shared__ unsigned pending[1024];
     __shared__ unsigned n_pending;
@@ -727,6 +818,96 @@ __global__ void __launch_bounds__(1024, 1) hm_px_pass2_b(const double* __restric
     if ((threadIdx.x & 31) == 0 && dead_count) atomicAdd(&ctl->n_dead2, dead_count);
 }
 
+
+// Pass 2 on a short pass-1 front (the normal case: a front has a few hundred points), everything in ONE CTA: rank sort
+// of the front's indices, the costs staged in shared memory, A(i) / B(i) candidates all-pairs, the rare sequential
+// resolution of the undecided points, mask clean-up.  Replaces sort_front + pass2_a + pass2_b (+ the three launches of
+// the ordered compaction, which the host now runs only when the front is longer than HM_SORT_MAX).
+#define HM_TAIL_SMALL 256
+template <int M>
+__global__ void __launch_bounds__(HM_TAIL_SMALL, 1) hm_px_tail_small(const double* __restrict__ costs,
+                                                                     unsigned* __restrict__ list,
+                                                                     unsigned char* __restrict__ mask, HmParetoCtl* ctl) {
+    __shared__ unsigned key[HM_TAIL_SMALL], sorted[HM_TAIL_SMALL];
+    __shared__ double c[M][HM_TAIL_SMALL];
+    __shared__ unsigned char stt[HM_TAIL_SMALL];
+    __shared__ unsigned n_dead;
+    if (ctl->nan_flag) return;
+    const unsigned n = ctl->n_front1;
+    if (n > HM_TAIL_SMALL) return;          // sort_front / pass2_a / pass2_b (grid-wide) take it
+    const unsigned t = threadIdx.x;
+    if (t == 0) n_dead = 0;
+    if (t < n) key[t] = list[t];
+    __syncthreads();
+    if (t < n) {                            // rank sort: the indices are distinct
+        const unsigned k = key[t];
+        unsigned r = 0;
+        for (unsigned j = 0; j < n; ++j) r += key[j] < k ? 1u : 0u;
+        HM_DEV_ASSERT(r < n);
+        sorted[r] = k;
+    }
+    __syncthreads();
+    double ci[M];
+#pragma unroll
+    for (int d = 0; d < M; ++d) ci[d] = 0.0;
+    if (t < n) {
+        const size_t si = sorted[t];
+        list[t] = (unsigned)si;             // the front list is left in index order, as hm_px_sort_front leaves it
+#pragma unroll
+        for (int d = 0; d < M; ++d) {
+            ci[d] = __ldg(costs + si * M + d);
+            c[d][t] = ci[d];
+        }
+    }
+    __syncthreads();
+    bool later = false, earlier = false;
+    if (t < n) {
+        for (unsigned j = 0; j < n; ++j) {
+            double cj[M];
+#pragma unroll
+            for (int d = 0; d < M; ++d) cj[d] = c[d][j];
+            if (hm_rel2<M>(cj, ci)) {
+                later = later || (j > t);
+                earlier = earlier || (j < t);
+            }
+        }
+    }
+    const unsigned char s0 = later ? 0 : (earlier ? 2 : 1);
+    if (t < n) stt[t] = s0;
+    // B(i): the undecided points (they share a coordinate value with an earlier point: rare) in index order
+    if (__syncthreads_or(t < n && s0 == 2)) {
+        for (unsigned i = 0; i < n; ++i) {
+            if (stt[i] != 2) continue;      // uniform: shared memory, written behind a barrier
+            bool found = false;
+            if (t < i && stt[t] == 1) {
+                double cI[M];
+#pragma unroll
+                for (int d = 0; d < M; ++d) cI[d] = c[d][i];
+                found = hm_rel2<M>(ci, cI);
+            }
+            const int kill = __syncthreads_or(found);
+            if (t == 0) stt[i] = kill ? 0 : 1;
+            __syncthreads();
+        }
+    }
+    if (t < n && stt[t] == 0) {
+        mask[sorted[t]] = 0;
+        atomicAdd(&n_dead, 1u);
+    }
+    __syncthreads();
+    if (t == 0) {
+        ctl->n_dead2 = n_dead;
+        ctl->tail_done = 1;
+    }
+}
+
+// last node of the chain: the control block goes to the host through mapped pinned memory (no D2H copy behind the graph)
+__global__ void hm_px_publish(const HmParetoCtl* __restrict__ ctl, volatile unsigned* host_result) {
+    const unsigned t = threadIdx.x;
+    if (t < sizeof(HmParetoCtl) / 4) host_result[t] = reinterpret_cast<const unsigned*>(ctl)[t];
+    __threadfence_system();
+}
+
 // ------------------------------------------------------------------------------------------------------------
 struct HmParetoWs {
     unsigned* alive[2];          // exact path: ping-pong index lists; fast path: level-1 / level-2 survivor lists
@@ -735,7 +916,6 @@ struct HmParetoWs {
     double* pivots;              // exact path: batch pivots; fast path: sorted pivots   [HM_PB][M]
     unsigned char* state;
     HmParetoRound* round;
-    double* sample;              // [HM_SAMPLE2][M]
     double* piv_raw;             // [HM_SAMPLE2][M]
     HmParetoCtl* ctl;
 };
@@ -758,7 +938,6 @@ static size_t hm_pareto_layout(int64_t N, int M, unsigned char* base, HmParetoWs
     unsigned char* pv = take((size_t)HM_PB * M * 8);
     unsigned char* stt = take(n);
     unsigned char* rd = take(sizeof(HmParetoRound));
-    unsigned char* sm = take((size_t)HM_SAMPLE2 * M * 8);
     unsigned char* pr = take((size_t)HM_SAMPLE2 * M * 8);
     unsigned char* ct = take(sizeof(HmParetoCtl));
     if (ws) {
@@ -769,7 +948,6 @@ static size_t hm_pareto_layout(int64_t N, int M, unsigned char* base, HmParetoWs
         ws->pivots = (double*)pv;
         ws->state = stt;
         ws->round = (HmParetoRound*)rd;
-        ws->sample = (double*)sm;
         ws->piv_raw = (double*)pr;
         ws->ctl = (HmParetoCtl*)ct;
     }
@@ -858,6 +1036,9 @@ static struct {
 static int g_graph_next = 0, g_graph_off = -1;
 static cudaStream_t g_graph_stream = nullptr;
 static std::mutex g_graph_mutex;
+// one mapped pinned control block per graph slot: the chain's last node (hm_px_publish) writes the counters there, the
+// host reads them after the stream synchronisation -- no D2H copy node behind the graph
+static HmParetoCtl* g_results = nullptr;
 
 static bool hm_graph_enabled() {
     if (g_graph_off < 0) {
@@ -873,28 +1054,59 @@ static cudaStream_t hm_graph_capture_stream() {     // the caller's stream may b
         g_graph_stream = nullptr;
     return g_graph_stream;
 }
-static cudaGraphExec_t hm_graph_lookup(const HmGraphKey& k) {
+static HmParetoCtl* hm_graph_results() {
+    std::lock_guard<std::mutex> lk(g_graph_mutex);
+    if (!g_results) {
+        void* p = nullptr;
+        if (cudaHostAlloc(&p, sizeof(HmParetoCtl) * HM_GRAPH_SLOTS, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        g_results = (HmParetoCtl*)p;
+    }
+    return g_results;
+}
+// -> slot of the instantiated graph for this key on the current device, or -1
+static int hm_graph_lookup(const HmGraphKey& k, cudaGraphExec_t* exec) {
     int dev = 0;
     cudaGetDevice(&dev);
     std::lock_guard<std::mutex> lk(g_graph_mutex);
     for (int i = 0; i < HM_GRAPH_SLOTS; ++i)
         if (g_graphs[i].exec && g_graphs[i].device == dev && g_graphs[i].key.costs == k.costs &&
             g_graphs[i].key.mask == k.mask && g_graphs[i].key.workspace == k.workspace && g_graphs[i].key.N == k.N &&
-            g_graphs[i].key.M == k.M && g_graphs[i].key.pass2 == k.pass2)
-            return g_graphs[i].exec;
-    return nullptr;
+            g_graphs[i].key.M == k.M && g_graphs[i].key.pass2 == k.pass2) {
+            *exec = g_graphs[i].exec;
+            return i;
+        }
+    return -1;
 }
-static void hm_graph_store(const HmGraphKey& k, cudaGraphExec_t exec) {
-    int dev = 0;
-    cudaGetDevice(&dev);
+// the slot the next graph will live in (its old graph, if any, is destroyed: the slot's result block is about to be
+// baked into a new chain)
+static int hm_graph_reserve() {
     std::lock_guard<std::mutex> lk(g_graph_mutex);
     const int i = g_graph_next;
     g_graph_next = (g_graph_next + 1) % HM_GRAPH_SLOTS;
     if (g_graphs[i].exec) cudaGraphExecDestroy(g_graphs[i].exec);
-    g_graphs[i].key = k;
-    g_graphs[i].exec = exec;
-    g_graphs[i].device = dev;
+    g_graphs[i].exec = nullptr;
+    return i;
 }
+static void hm_graph_store(int slot, const HmGraphKey& k, cudaGraphExec_t exec) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(g_graph_mutex);
+    g_graphs[slot].key = k;
+    g_graphs[slot].exec = exec;
+    g_graphs[slot].device = dev;
+}
+
+// kernel attributes and occupancy of the fast path: set / queried once per (M, device)
+template <int M>
+struct HmPxSetup {
+    static unsigned done_mask;       // bit per device; a benign race repeats the same calls
+    static int occ1[32];
+};
+template <int M> unsigned HmPxSetup<M>::done_mask = 0;
+template <int M> int HmPxSetup<M>::occ1[32] = {0};
 
 // NaN-free fast path; *saw_nan_out = 1 means the result is void and the exact path must run.
 template <int M>
@@ -905,33 +1117,48 @@ static int hm_pareto_run_fast(const double* costs, int64_t N, uint8_t* mask, voi
     unsigned char* base = (unsigned char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     hm_pareto_layout(N, M, base, &ws);
     static_assert(HM_PIV_MAX <= HM_PB, "sorted pivots share the exact path's pivot buffer");
-    const size_t exact_smem = sizeof(double) * M * HM_PX_TILE;
-    const size_t sort_smem = (sizeof(double) + sizeof(unsigned short)) * HM_SORT_MAX;
     const size_t stream_smem1 = sizeof(double) * M * HM_PIV_MAX + sizeof(unsigned) * HM_PX_WARPS * (HM_PS_Q1 + HM_PS_Q2);
     const size_t stream_smem2 = stream_smem1;
-    HM_CUDA_TRY(cudaFuncSetAttribute(hm_px_exact<M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)exact_smem));
-    HM_CUDA_TRY(cudaFuncSetAttribute(hm_px_exact<M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)exact_smem));
-    HM_CUDA_TRY(cudaFuncSetAttribute(hm_px_sort_pivots<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
-    HM_CUDA_TRY(cudaFuncSetAttribute(hm_px_stream<M, IT1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_smem1));
-    HM_CUDA_TRY(cudaFuncSetAttribute(hm_px_stream<M, HM_PS_ITEMS2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_smem2));
+    static_assert(HM_SAMPLE1 == HM_SAMPLE2, "one pivot-preparation geometry for both levels");
+    // the whole sample in shared memory when it fits 128 KB, else 1024-point tiles; the last CTA's sort needs 10 B / point
+    const unsigned prep_tile = (size_t)M * HM_SAMPLE1 * 8 <= 128 * 1024 ? HM_SAMPLE1 : HM_PX_TILE;
+    const size_t prep_smem = std::max<size_t>((size_t)M * prep_tile * 8, (size_t)HM_SAMPLE1 * 10);
+    const unsigned prep_grid = (HM_SAMPLE1 + HM_PX_WARPS * (M <= 4 ? 4 : 2) - 1) / (HM_PX_WARPS * (M <= 4 ? 4 : 2));
+    // level 1 keeps only its strongest pivots: every stage-1 survivor batch walks ALL of them (it nearly always holds a
+    // final survivor), and that walk is time the warp is not streaming; what the weaker pivots would have killed is left
+    // to level 2, whose pivots are stronger anyway
+    unsigned piv1_max = HM_PIV1_MAX;
+    if (const char* e = getenv("HM_B200_PARETO_PIV1")) piv1_max = (unsigned)std::min(std::max(atoi(e), 8), HM_PIV_MAX);
+    int dev = 0;
+    HM_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev >= 32 || !(HmPxSetup<M>::done_mask >> dev & 1u)) {
+        HM_CUDA_TRY(cudaFuncSetAttribute(hm_px_exact<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem));
+        HM_CUDA_TRY(cudaFuncSetAttribute(hm_px_prep<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem));
+        HM_CUDA_TRY(cudaFuncSetAttribute(hm_px_stream<M, IT1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_smem1));
+        HM_CUDA_TRY(cudaFuncSetAttribute(hm_px_stream<M, HM_PS_ITEMS2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_smem2));
+        int occ = 0;
+        HM_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hm_px_stream<M, IT1>, HM_PX_THREADS, stream_smem1));
+        if (dev < 32) {
+            HmPxSetup<M>::occ1[dev] = occ < 1 ? 1 : occ;
+            HmPxSetup<M>::done_mask |= 1u << dev;
+        }
+    }
     const unsigned n = (unsigned)N;
     const int sms = hm_num_sms();
-    int occ1 = 0;
-    HM_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, hm_px_stream<M, IT1>, HM_PX_THREADS, stream_smem1));
+    int occ1 = dev < 32 ? HmPxSetup<M>::occ1[dev] : 1;
     if (occ1 < 1) occ1 = 1;
     HmParetoCtl* ctl = ws.ctl;
     unsigned* list1 = ws.alive[0];
     unsigned* list2 = ws.alive[1];
 
-    // the whole launch chain (17 nodes, every size a device-side counter) as a function of the stream
-    auto enqueue = [&](cudaStream_t s) -> int {
+    // the whole launch chain (every size a device-side counter) as a function of the stream; `result` (nullable): mapped
+    // host block the last node publishes the counters to
+    auto enqueue = [&](cudaStream_t s, HmParetoCtl* result) -> int {
     hm_px_ctl_init<<<1, 32, 0, s>>>(ctl);
     HM_CUDA_TRY(cudaMemsetAsync(mask, 0, (size_t)N, s));
     // ---- level 1: pivots from a strided sample of everything, stream the whole cost matrix ----
-    hm_px_gather_sample<M><<<(HM_SAMPLE1 + 255) / 256, 256, 0, s>>>(costs, nullptr, nullptr, n, HM_SAMPLE1, ws.sample, ctl);
-    hm_px_exact<M, false><<<(HM_SAMPLE1 + HM_PX_GROUP - 1) / HM_PX_GROUP, HM_PX_THREADS, exact_smem, s>>>(
-        ws.sample, nullptr, &ctl->n_sample, ws.piv_raw, nullptr, &ctl->n_piv_raw, &ctl->nan_flag);
-    hm_px_sort_pivots<M><<<1, 1024, sort_smem, s>>>(ws.piv_raw, ws.pivots, ctl);
+    hm_px_prep<M><<<prep_grid, HM_PX_THREADS, prep_smem, s>>>(costs, nullptr, nullptr, n, HM_SAMPLE1, prep_tile, piv1_max,
+                                                               ws.piv_raw, ws.pivots, ctl);
     {
         const unsigned chunk = HM_PX_THREADS * IT1;
         const unsigned chunks = (n + chunk - 1) / chunk;
@@ -942,44 +1169,48 @@ static int hm_pareto_run_fast(const double* costs, int64_t N, uint8_t* mask, voi
                                                                               list1, &ctl->n_list1);
     }
     // ---- level 2: pivots sampled from the survivors, re-filter the survivors ----
-    hm_px_gather_sample<M><<<(HM_SAMPLE2 + 255) / 256, 256, 0, s>>>(costs, list1, &ctl->n_list1, 0, HM_SAMPLE2, ws.sample, ctl);
-    hm_px_exact<M, false><<<(HM_SAMPLE2 + HM_PX_GROUP - 1) / HM_PX_GROUP, HM_PX_THREADS, exact_smem, s>>>(
-        ws.sample, nullptr, &ctl->n_sample, ws.piv_raw, nullptr, &ctl->n_piv_raw, &ctl->nan_flag);
-    hm_px_sort_pivots<M><<<1, 1024, sort_smem, s>>>(ws.piv_raw, ws.pivots, ctl);
+    hm_px_prep<M><<<prep_grid, HM_PX_THREADS, prep_smem, s>>>(costs, list1, &ctl->n_list1, 0, HM_SAMPLE2, prep_tile, HM_PIV_MAX,
+                                                               ws.piv_raw, ws.pivots, ctl);
     hm_px_stream<M, HM_PS_ITEMS2><<<sms * 4, HM_PX_THREADS, stream_smem2, s>>>(costs, list1, &ctl->n_list1, 0, ws.pivots,
                                                                              ctl, list2, &ctl->n_list2);
     // ---- exact all-pairs on what is left -> mask, and the front's indices into list1 ----
-    hm_px_exact<M, true><<<sms * 4, HM_PX_THREADS, exact_smem, s>>>(costs, list2, &ctl->n_list2, (double*)list1, mask,
+    hm_px_exact<M><<<sms * 2, HM_PX_THREADS, prep_smem, s>>>(costs, list2, &ctl->n_list2, prep_tile, list1, mask,
                                                                      &ctl->n_front1, &ctl->nan_flag);
     HM_CUDA_TRY(cudaGetLastError());
     if (pass2) {
-        // survivors in index order (one-CTA sort of the front list; the ordered mask compaction only runs, device
-        // side decision, when the front is too long for that), then the order-dependent clean-up pass
-        const unsigned nblk = (n + HM_PF_CHUNK - 1) / HM_PF_CHUNK;
+        // the order-dependent clean-up pass.  A front of <= HM_TAIL_SMALL points (the normal case) is finished by one CTA
+        // (hm_px_tail_small); up to HM_SORT_MAX points: one-CTA index sort, A(i) grid-wide, B(i) in one CTA (the three
+        // kernels return at once when the small tail did the job); longer: sort_front raises need_scan and the HOST runs
+        // the ordered mask compaction + pass 2 behind the graph (below).
+        hm_px_tail_small<M><<<1, HM_TAIL_SMALL, 0, s>>>(costs, list1, mask, ctl);
         hm_px_sort_front<<<1, 1024, 0, s>>>(list1, ctl);
-        hm_px_count_flags<<<nblk, HM_PF_THREADS, 0, s>>>(mask, n, ws.block_counts, &ctl->need_scan);
-        hm_pareto_scan<<<1, 1024, 0, s>>>(ws.block_counts, nblk, ws.round, &ctl->need_scan);
-        hm_pareto_scatter<<<nblk, HM_PF_THREADS, 0, s>>>(nullptr, n, mask, ws.block_counts, list1, 0xffffffffu, ws.round,
-                                                          &ctl->need_scan);
-        hm_px_pass2_a<M><<<sms * 4, HM_PX_THREADS, 0, s>>>(costs, list1, &ctl->n_front1, ws.state, &ctl->nan_flag);
-        hm_px_pass2_b<M><<<1, 1024, 0, s>>>(costs, list1, &ctl->n_front1, ws.state, mask, ctl);
+        hm_px_pass2_a<M><<<sms * 4, HM_PX_THREADS, 0, s>>>(costs, list1, &ctl->n_front1, ws.state, ctl, 0);
+        hm_px_pass2_b<M><<<1, 1024, 0, s>>>(costs, list1, &ctl->n_front1, ws.state, mask, ctl, 0);
+        HM_CUDA_TRY(cudaGetLastError());
+    }
+    if (result) {
+        hm_px_publish<<<1, 32, 0, s>>>(ctl, reinterpret_cast<volatile unsigned*>(result));
         HM_CUDA_TRY(cudaGetLastError());
     }
         return 0;
     };
-    // 16 back-to-back launches cost more CPU time than the GPU needs to run them (10^7 x 3: ~0.19 ms of work), so the
-    // chain is captured once per (buffers, N, pass 2) into a CUDA graph and replayed with one launch.
+    // The chain costs more CPU time to launch than the GPU needs to run it (10^7 x 3: ~0.15 ms of work), so it is
+    // captured once per (buffers, N, pass 2) into a CUDA graph and replayed with one launch.
+    HmParetoCtl h;
     {
         HmGraphKey key = {costs, mask, workspace, N, M, pass2 ? 1 : 0};
-        cudaGraphExec_t exec = hm_graph_lookup(key);
-        if (!exec && hm_graph_enabled()) {
+        cudaGraphExec_t exec = nullptr;
+        int slot = hm_graph_lookup(key, &exec);
+        HmParetoCtl* results = hm_graph_enabled() ? hm_graph_results() : nullptr;
+        if (slot < 0 && results) {
             cudaStream_t cap = hm_graph_capture_stream();
             cudaGraph_t graph = nullptr;
+            slot = hm_graph_reserve();
             if (cap && cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-                const int rc = enqueue(cap);
+                const int rc = enqueue(cap, results + slot);
                 const cudaError_t e = cudaStreamEndCapture(cap, &graph);
                 if (rc == 0 && e == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess)
-                    hm_graph_store(key, exec);
+                    hm_graph_store(slot, key, exec);
                 else
                     exec = nullptr;
                 if (graph) cudaGraphDestroy(graph);
@@ -987,18 +1218,33 @@ static int hm_pareto_run_fast(const double* costs, int64_t N, uint8_t* mask, voi
             if (!exec) {
                 cudaGetLastError();
                 hm_graph_disable();
+                slot = -1;
             }
         }
-        if (exec) {
+        if (exec && slot >= 0) {
             HM_CUDA_TRY(cudaGraphLaunch(exec, st));
+            HM_CUDA_TRY(cudaStreamSynchronize(st));
+            h = results[slot];
         } else {
-            const int rc = enqueue(st);
+            const int rc = enqueue(st, nullptr);
             if (rc) return rc;
+            HM_CUDA_TRY(cudaMemcpyAsync(&h, ctl, sizeof(h), cudaMemcpyDeviceToHost, st));
+            HM_CUDA_TRY(cudaStreamSynchronize(st));
         }
     }
-    HmParetoCtl h;
-    HM_CUDA_TRY(cudaMemcpyAsync(&h, ctl, sizeof(h), cudaMemcpyDeviceToHost, st));
-    HM_CUDA_TRY(cudaStreamSynchronize(st));
+    if (pass2 && !h.nan_flag && h.need_scan) {
+        // pass-1 front longer than HM_SORT_MAX: survivors in index order by ordered mask compaction, then pass 2
+        const unsigned nblk = (n + HM_PF_CHUNK - 1) / HM_PF_CHUNK;
+        hm_px_count_flags<<<nblk, HM_PF_THREADS, 0, st>>>(mask, n, ws.block_counts, nullptr);
+        hm_pareto_scan<<<1, 1024, 0, st>>>(ws.block_counts, nblk, ws.round, nullptr);
+        hm_pareto_scatter<<<nblk, HM_PF_THREADS, 0, st>>>(nullptr, n, mask, ws.block_counts, list1, 0xffffffffu, ws.round,
+                                                          nullptr);
+        hm_px_pass2_a<M><<<sms * 4, HM_PX_THREADS, 0, st>>>(costs, list1, &ctl->n_front1, ws.state, ctl, 1);
+        hm_px_pass2_b<M><<<1, 1024, 0, st>>>(costs, list1, &ctl->n_front1, ws.state, mask, ctl, 1);
+        HM_CUDA_TRY(cudaGetLastError());
+        HM_CUDA_TRY(cudaMemcpyAsync(&h, ctl, sizeof(h), cudaMemcpyDeviceToHost, st));
+        HM_CUDA_TRY(cudaStreamSynchronize(st));
+    }
     *saw_nan_out = h.nan_flag ? 1 : 0;
     if (n_out) *n_out = (int64_t)h.n_front1 - (int64_t)h.n_dead2;
     return 0;
@@ -1077,11 +1323,16 @@ extern "C" int hm_pareto_pass1_compact(const double* costs, int64_t N, int M, ui
     unsigned char* base = (unsigned char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     hm_pareto_layout(N, M, base, &ws);
     const unsigned n = (unsigned)N;
-    const unsigned nblk = (n + HM_PF_CHUNK - 1) / HM_PF_CHUNK;
-    hm_px_count_flags<<<nblk, HM_PF_THREADS, 0, st>>>(mask, n, ws.block_counts, nullptr);
-    hm_pareto_scan<<<1, 1024, 0, st>>>(ws.block_counts, nblk, ws.round, nullptr);
-    hm_pareto_scatter<<<nblk, HM_PF_THREADS, 0, st>>>(nullptr, n, mask, ws.block_counts, ws.alive[0], 0xffffffffu, ws.round,
-                                                      nullptr);
+    if (!saw_nan && n_alive <= HM_SORT_MAX) {
+        // the fast path left the survivors' indices (unordered) in alive[0]: one-CTA index sort
+        hm_px_sort_front<<<1, 1024, 0, st>>>(ws.alive[0], ws.ctl);
+    } else {
+        const unsigned nblk = (n + HM_PF_CHUNK - 1) / HM_PF_CHUNK;
+        hm_px_count_flags<<<nblk, HM_PF_THREADS, 0, st>>>(mask, n, ws.block_counts, nullptr);
+        hm_pareto_scan<<<1, 1024, 0, st>>>(ws.block_counts, nblk, ws.round, nullptr);
+        hm_pareto_scatter<<<nblk, HM_PF_THREADS, 0, st>>>(nullptr, n, mask, ws.block_counts, ws.alive[0], 0xffffffffu,
+                                                          ws.round, nullptr);
+    }
     hm_pareto_gather_rows<<<(unsigned)((take + 255) / 256), 256, 0, st>>>(costs, M, ws.alive[0], (unsigned)take,
                                                                           (long long)index_base, rows_out,
                                                                           reinterpret_cast<long long*>(idx_out));

@@ -139,23 +139,25 @@ def _pareto_mask_sharded_device(costs_local, group=None):
                "rank with sequential_is_pareto_efficient)")
     out = torch.zeros((n_local,), dtype=torch.uint8, device=dev)
     cap = _PARETO_EXCHANGE_ROWS
-    _, rows, idx, n_alive, saw_nan = pareto_pass1_compact(costs_local.contiguous(), cap)
+    costs_local = costs_local.contiguous()
     if world == 1:
+        _, rows, idx, n_alive, saw_nan = pareto_pass1_compact(costs_local, cap)
         if saw_nan:
             raise ValueError(nan_msg)
         if n_alive > cap:
-            _, rows, idx, n_alive, saw_nan = pareto_pass1_compact(costs_local.contiguous(), n_alive)
+            _, rows, idx, n_alive, saw_nan = pareto_pass1_compact(costs_local, n_alive)
         if n_alive:
-            keep = pareto_mask_device(rows[:n_alive].contiguous(), True).to(torch.bool)
-            out[idx[:n_alive][keep]] = 1
+            keep = pareto_mask_device(rows[:n_alive].contiguous(), True)
+            out.scatter_(0, idx[:n_alive], keep)                 # the survivors' indices are distinct
         return out
     cdev = dev if dist.get_backend(group) == "nccl" else torch.device("cpu")     # gloo: collectives through the host
     rank = dist.get_rank(group)
     while True:
-        block = torch.zeros((1 + cap, M), dtype=torch.float64, device=dev)
+        # the exchange block [1 + cap][M]: header row (count + 0.5 if a NaN was seen), then the survivors' rows, which
+        # hm_pareto_pass1_compact writes in place
+        block = torch.empty((1 + cap, M), dtype=torch.float64, device=dev)
+        _, _, idx, n_alive, saw_nan = pareto_pass1_compact(costs_local, cap, rows_out=block[1:])
         block[0, 0] = float(n_alive) + (0.5 if saw_nan else 0.0)
-        take = min(n_alive, cap)
-        block[1: 1 + take] = rows[:take]
         gathered = torch.empty((world * (1 + cap), M), dtype=torch.float64, device=cdev)
         dist.all_gather_into_tensor(gathered, block.to(cdev), group=group)
         gathered = gathered.view(world, 1 + cap, M)
@@ -166,10 +168,10 @@ def _pareto_mask_sharded_device(costs_local, group=None):
         if max(counts) <= cap:
             break
         cap = max(counts)                                # rare: a rank kept more rows than the block holds
-        _, rows, idx, n_alive, saw_nan = pareto_pass1_compact(costs_local.contiguous(), cap)
-    union = torch.cat([gathered[r, 1: 1 + counts[r]] for r in range(world)], dim=0).to(dev).contiguous()
-    if union.shape[0]:
-        keep = pareto_mask_device(union, True).to(torch.bool)
+    if sum(counts):
+        union = torch.cat([gathered[r, 1: 1 + counts[r]] for r in range(world)], dim=0).to(dev)
+        keep = pareto_mask_device(union, True)
         start = sum(counts[:rank])
-        out[idx[:counts[rank]][keep[start: start + counts[rank]]]] = 1
+        if counts[rank]:
+            out.scatter_(0, idx[:counts[rank]], keep[start: start + counts[rank]])      # distinct indices, no host sync
     return out

@@ -220,6 +220,7 @@ def attach_packing(forests, device_space):
     for f in forests:
         _lib.check(L.hm_forest_attach_packing(f.handle, device_space.handle), "hm_forest_attach_packing")
         f.packed_groups = int(L.hm_forest_packed_groups(f.handle))
+        f.packed_kind = int(L.hm_forest_packed(f.handle))     # 1 FAST, 2 wide (64-bit shift), 3 FAST + self-looping leaves
     return forests
 
 

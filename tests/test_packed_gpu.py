@@ -34,7 +34,18 @@ SPACES = {
     "wide": dict([("k%d" % i, {"parameter_type": "categorical", "values": list("abcdefghi")}) for i in range(5)] +
                  [("o8", {"parameter_type": "ordinal", "values": [1, 2, 4, 8, 16, 32, 64, 128]}),
                   ("o33", {"parameter_type": "ordinal", "values": list(range(33))})]),
+    # every ordinal a power of two, no categorical with three or more values: a FAST layout WITHOUT a sentinel field,
+    # i.e. the predicated walk (kind 1) instead of the self-looping leaves (kind 3) that "c3" and "odd" get
+    "pow2": {
+        "a2": {"parameter_type": "ordinal", "values": [0.25, 0.75]},
+        "b4": {"parameter_type": "ordinal", "values": [1, 2, 3, 4]},
+        "c2": {"parameter_type": "categorical", "values": ["x", "y"]},
+        "d16": {"parameter_type": "ordinal", "values": list(range(16))},
+        "e8": {"parameter_type": "ordinal", "values": [1, 2, 4, 8, 16, 32, 64, 128]},
+        "f2": {"parameter_type": "categorical", "values": ["u", "v"]},
+    },
 }
+PACKED_KIND = {"c3": 3, "odd": 3, "wide": 2, "pow2": 1}
 
 
 def _make(name):
@@ -75,13 +86,15 @@ def _edge_thresholds(f, x32_rows, rng):
 @pytest.mark.parametrize("name,N,T,dlo,dhi", [("c3", 5000, 7, 3, 9), ("odd", 4000, 5, 2, 8), ("c3", 300_000, 40, 8, 12),
                                               ("odd", 140_000, 48, 7, 11), ("c3", 3000, 3, 13, 15),
                                               ("wide", 6000, 6, 3, 9), ("wide", 150_000, 40, 8, 11),
-                                              ("wide", 2500, 3, 13, 15)])
+                                              ("wide", 2500, 3, 13, 15),
+                                              ("pow2", 5000, 6, 3, 9), ("pow2", 140_000, 40, 8, 11),
+                                              ("pow2", 2500, 3, 13, 15)])
 def test_packed_path_is_bit_identical_to_fp32_path(name, N, T, dlo, dhi):
     """resident / streamed + coherence pre-pass / walked-in-L2 forests on two spaces, edge thresholds included"""
     import torch
     from hypermapper_b200 import forest, _lib
     space, ds = _make(name)
-    assert ds.packed_bits == {"c3": 37, "odd": 1 + 2 + 0 + 3 + 4 + 7 + 1, "wide": 49}[name]
+    assert ds.packed_bits == {"c3": 37, "odd": 1 + 2 + 0 + 3 + 4 + 7 + 1, "wide": 49, "pow2": 1 + 2 + 1 + 4 + 3 + 1}[name]
     rng = np.random.default_rng(N + T)
     raw = _raw(space, N, rng)
     x32, _ = ds.encode(raw)
@@ -92,6 +105,7 @@ def test_packed_path_is_bit_identical_to_fp32_path(name, N, T, dlo, dhi):
     fs = [_edge_thresholds(_synthetic_forest(rng, T, ds.n_encoded, dlo, dhi), rows32, rng) for _ in range(2)]
     dfs = [forest.DeviceForest(forest.tables_from_arrays(**f)) for f in fs]
     forest.attach_packing(dfs, ds)
+    assert [f.packed_kind for f in dfs] == [PACKED_KIND[name]] * 2
     acq = _lib.make_acq_params("EI", "tchebyshev", [0.3, 0.7], [0.1, 0.2], 0.0)
     a = forest.rf_eval(dfs, x32, want_leaves=True, want_mean=True, want_var=True, want_pred=True)
     b = forest.rf_eval_packed(dfs, codes, want_leaves=True, want_mean=True, want_var=True, want_pred=True)
@@ -105,6 +119,37 @@ def test_packed_path_is_bit_identical_to_fp32_path(name, N, T, dlo, dhi):
         sa = forest.rf_eval(dfs, x32, acq=p)["score"]
         sb = forest.rf_eval_packed(dfs, codes, acq=p)["score"]
         assert torch.equal(sa.view(torch.int64), sb.view(torch.int64)), kind
+
+
+@pytest.mark.parametrize("name,N,T", [("c3", 200_000, 24), ("odd", 50_000, 12), ("pow2", 50_000, 12), ("wide", 50_000, 12)])
+def test_malformed_codes_stay_inside_the_forest(name, N, T):
+    """codes that are no candidate of the space (random 64-bit words: several one-hot bits set, ranks beyond the value
+    list) must still end in SOME leaf of every tree -- in particular with self-looping leaves (kind 3), whose sentinel test
+    is only guaranteed false for well-formed codes: the kernel replaces a code that breaks the sentinel bound by the
+    all-zero code.  The checked build (tools/checked_run.py) verifies every staged-node address on the way."""
+    import torch
+    from hypermapper_b200 import forest
+    space, ds = _make(name)
+    rng = np.random.default_rng(T)
+    raw = _raw(space, 4096, rng)
+    x32, _ = ds.encode(raw)
+    fs = [_synthetic_forest(rng, T, ds.n_encoded, 6, 11) for _ in range(2)]
+    dfs = [forest.DeviceForest(forest.tables_from_arrays(**f)) for f in fs]
+    forest.attach_packing(dfs, ds)
+    garbage = torch.from_numpy(rng.integers(-2 ** 63, 2 ** 63, size=N, dtype=np.int64)).cuda()
+    out = forest.rf_eval_packed(dfs, garbage, want_leaves=True, want_mean=True)
+    torch.cuda.synchronize()
+    for m in range(2):
+        leaves = out["leaves"][m].cpu().numpy()
+        for t in range(T):
+            lo, hi = fs[m]["tree_off"][t], fs[m]["tree_off"][t + 1]
+            is_leaf = fs[m]["left"][lo:hi] < 0
+            assert np.all((leaves[t] >= 0) & (leaves[t] < hi - lo)) and np.all(is_leaf[leaves[t]])
+    assert bool(torch.isfinite(out["mean"]).all())
+    # and the big-pool launch (coherence pre-pass walks the key trees with the same codes)
+    big = garbage.repeat(max(1, (1 << 18) // N + 1))
+    forest.rf_eval_packed(dfs, big, want_mean=True)
+    torch.cuda.synchronize()
 
 
 def test_packed_path_on_the_reference_golden_forest():

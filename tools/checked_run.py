@@ -6,7 +6,7 @@ GPU pool where compute-sanitizer is closed (profiles/r02_sanitizer_unavailable.t
     HM_B200_LIB=hypermapper_b200/csrc/libhm_b200_checked.so python tools/checked_run.py
 
 Coverage: forest kernel (resident / streamed through the TMA double buffer + coherence pre-pass / walked in L2; fp32,
-packed-fast and packed-wide layouts), top-k (k = 20 and k = 1024, heavy ties: the roll-back path), GP (4- and 8-warp
+packed-fast, packed-wide and self-looping-leaf layouts, malformed codes), top-k (k = 20 and k = 1024, heavy ties: the roll-back path), GP (4- and 8-warp
 plans, per-warp TMA rings; the large-n path), Pareto (fast path with warp queues, exact NaN path), encode / sample,
 device hill climb.  Every case also checks its results against the oracle / goldens (they are the GPU tests' own
 functions), so a wrong result fails here too."""
@@ -46,6 +46,11 @@ def main():
         (pk.test_packed_path_is_bit_identical_to_fp32_path, ("odd", 4000, 5, 2, 8)),
         (pk.test_packed_path_is_bit_identical_to_fp32_path, ("wide", 150_000, 40, 8, 11)),
         (pk.test_packed_path_is_bit_identical_to_fp32_path, ("c3", 3000, 3, 13, 15)),
+        (pk.test_packed_path_is_bit_identical_to_fp32_path, ("pow2", 140_000, 40, 8, 11)),
+        (pk.test_malformed_codes_stay_inside_the_forest, ("c3", 200_000, 24)),
+        (pk.test_malformed_codes_stay_inside_the_forest, ("odd", 50_000, 12)),
+        (pk.test_malformed_codes_stay_inside_the_forest, ("pow2", 50_000, 12)),
+        (pk.test_malformed_codes_stay_inside_the_forest, ("wide", 50_000, 12)),
         (pk.test_packed_host_entry_and_errors, ()),
         (gp.test_gp_mean_var_vs_oracle, (256, 6, 1e-4, 20000, "matern52")),
         (gp.test_gp_mean_var_vs_oracle, (512, 32, 1e-4, 4000, "matern52")),
