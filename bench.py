@@ -70,6 +70,8 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="units in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--fused-topk", action="store_true",
+                    help="RF workloads: device-timed step = hm_rf_score_topk (no score array) instead of hm_rf_eval + hm_topk")
     return ap.parse_args()
 
 
@@ -144,6 +146,7 @@ class RFBench:
         cache = os.path.join(os.environ.get("HM_BENCH_CACHE", "/tmp"),
                              "hm_bench_wl_v3_%s.pkl" % ("c3" if name.startswith("c3") else name))
         self.packed = name == "c3"
+        self.fused_topk = False
         cached = None
         if os.path.exists(cache):
             import pickle
@@ -330,6 +333,13 @@ class RFBench:
         if record:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record()
+        if self.fused_topk:
+            # hm_rf_score_topk: prefix pass + filtered pass + merge of the short list; no score array (what local_search
+            # needs from its random pools); the events bracket the whole call
+            tv, ti = forest.score_topk(self.forests, self.codes_dev if self.packed else self.x_dev, self.acq, self.k)
+            if record:
+                ev[1].record()
+            return (tv, ti + self.rank * self.N), ev
         if self.packed:
             out = forest.rf_eval_packed(self.forests, self.codes_dev, acq=self.acq)
         else:
@@ -377,7 +387,9 @@ class RFBench:
                                       "node") + ", path lengths measured on 65536 pool candidates; peak = 128 B/clk/SM x "
                                      "SMs x 1965 MHz"},
                 "kernel": ("hm_forest_kernel<packed>" if self.packed else "hm_forest_kernel<fp32>") + (" (+ coherence pre-pass hm_forest_sortkey/scan/scatter_rows, inside "
-                                                       "kernel_ms)" if getattr(self, "prepass", False) else ""),
+                                                       "kernel_ms)" if getattr(self, "prepass", False) else "") +
+                          (" -- fused mode: kernel_ms = the whole hm_rf_score_topk call (65536-candidate prefix pass + hm_topk, "
+                           "filtered pass over the pool, hm_topk_merge of the list)" if self.fused_topk else ""),
                 "kernel_ms": kernel_ms, "algorithmic_bytes_per_eval": b, "peak_source": src,
                 "note": "forests with thousands of node visits per evaluation are bound by shared-memory load latency "
                         "and the L1/shared-memory data pipe, not HBM (profiles/, DESIGN.md section 3)"}
@@ -818,6 +830,10 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     b = make_bench(args.workload)
+    if args.fused_topk:
+        assert hasattr(b, "fused_topk"), "--fused-topk applies to the forest workloads"
+        b.fused_topk = True
+        b.desc += "; fused scoring + selection (hm_rf_score_topk: no score array)"
     N = args.candidates or b.n_default
     strong = args.total_candidates > 0
     if strong:

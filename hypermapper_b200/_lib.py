@@ -23,6 +23,7 @@ EXPORTED_SYMBOLS = [
     "hm_forest_set_coherence", "hm_forest_n_groups",
     "hm_forest_attach_packing", "hm_forest_packed", "hm_forest_packed_groups", "hm_rf_eval_packed",
     "hm_rf_eval", "hm_acq_score",
+    "hm_rf_score_topk_workspace_bytes", "hm_rf_score_topk", "hm_rf_score_topk_packed",
     "hm_topk_workspace_bytes", "hm_topk", "hm_topk_merge",
     "hm_gp_create", "hm_gp_destroy", "hm_gp_mean_var",
     "hm_pareto_workspace_bytes", "hm_pareto_filter", "hm_pareto_pass1", "hm_pareto_pass1_compact",
@@ -110,6 +111,11 @@ def lib():
     L.hm_rf_eval.argtypes = [ctypes.POINTER(vp), i32, vp, i64, i64, ctypes.POINTER(vp), vp, vp, vp,
                              ctypes.POINTER(AcqParams), vp, vp, vp]
     L.hm_acq_score.argtypes = [ctypes.POINTER(AcqParams), vp, vp, i64, vp, i64, vp, vp]
+    L.hm_rf_score_topk_workspace_bytes.argtypes = [i32]
+    L.hm_rf_score_topk_workspace_bytes.restype = i64
+    L.hm_rf_score_topk.argtypes = [ctypes.POINTER(vp), i32, vp, i64, i64, ctypes.POINTER(AcqParams), vp, i32, vp, vp, vp, vp]
+    L.hm_rf_score_topk_packed.argtypes = [ctypes.POINTER(vp), i32, vp, i64, ctypes.POINTER(AcqParams), vp, i32, vp, vp,
+                                          vp, vp]
     L.hm_topk_workspace_bytes.argtypes = [i32]
     L.hm_topk_workspace_bytes.restype = i64
     L.hm_topk.argtypes = [vp, i64, i64, i32, vp, vp, vp, vp]

@@ -170,6 +170,23 @@ struct HmEvalArgs {
     int Dp;                   // row stride of Xrows (D rounded up to a multiple of 4)
     HmAcqDev acq;
     int has_acq;
+    // fused scoring + selection (hm_rf_score_topk): instead of writing every score, a candidate that can still be among
+    // the k best -- score < *filter_tau, or == *filter_tau with an index below filter_n0, or NaN -- is appended to a list
+    const double* filter_tau;
+    double* list_val;
+    long long* list_idx;
+    unsigned* list_count;
+    unsigned list_cap;
+    long long filter_n0;
+};
+
+struct HmScoreFilter {
+    const double* tau;
+    double* list_val;
+    long long* list_idx;
+    unsigned* list_count;
+    unsigned list_cap;
+    long long n0;
 };
 
 // block size / node-buffer size as a function of the encoded feature count (shared by create and launch)
@@ -934,6 +951,7 @@ __global__ void __launch_bounds__(BDT, (PACKED && BDT < 1024) ? 1024 / BDT : 1) 
 
     long long step = 0;
     float* xs_t = xs + tid;
+    const double filter_tau = a.filter_tau ? __ldg(a.filter_tau) : 0.0;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long long slot = tile * BD + tid;
         const bool valid = slot < a.N;
@@ -1023,7 +1041,18 @@ __global__ void __launch_bounds__(BDT, (PACKED && BDT < 1024) ? 1024 / BDT : 1) 
         }
         if (a.has_acq && valid) {
             const double feas = a.feas ? __ldg(a.feas + i) : 1.0;
-            a.score_out[i] = hm_acq_value(a.acq, mean_l, var_l, feas);
+            const double sc = hm_acq_value(a.acq, mean_l, var_l, feas);
+            if (a.filter_tau) {
+                if (sc < filter_tau || sc != sc || (sc == filter_tau && i < a.filter_n0)) {
+                    const unsigned pos = atomicAdd(a.list_count, 1u);
+                    if (pos < a.list_cap) {
+                        a.list_val[pos] = sc;
+                        a.list_idx[pos] = i;
+                    }
+                }
+            } else {
+                a.score_out[i] = sc;
+            }
         }
     }
 }
@@ -1269,7 +1298,7 @@ static cudaError_t hm_forest_kernel_attr() {
 static int hm_rf_eval_impl(const hm_forest_t* const* forests, int M, const float* Xcm, int64_t ldx,
                            const unsigned long long* codes, int64_t N, int32_t* const* leaf_out, double* mean_out,
                            double* var_out, double* pred_out, const hm_acq_params_t* acq, const double* feas,
-                           double* score_out, void* stream) {
+                           double* score_out, void* stream, const HmScoreFilter* filter = nullptr) {
     const bool packed = codes != nullptr;
     HM_REQUIRE(forests != nullptr && M >= 1 && M <= HM_MAX_OBJECTIVES, "1 <= M <= 8");
     HM_REQUIRE(N >= 0 && (packed || ldx >= N), "ldx >= N >= 0");
@@ -1319,8 +1348,16 @@ static int hm_rf_eval_impl(const hm_forest_t* const* forests, int M, const float
     a.score_out = score_out;
     a.feas = feas;
     a.has_acq = 0;
+    if (filter) {
+        a.filter_tau = filter->tau;
+        a.list_val = filter->list_val;
+        a.list_idx = filter->list_idx;
+        a.list_count = filter->list_count;
+        a.list_cap = filter->list_cap;
+        a.filter_n0 = filter->n0;
+    }
     if (acq) {
-        HM_REQUIRE(score_out != nullptr, "score_out required with acq");
+        HM_REQUIRE(score_out != nullptr || filter != nullptr, "score_out required with acq");
         HM_REQUIRE(acq->n_objectives == M, "acq->n_objectives == M");
         int rc = hm_acq_to_dev(acq, &a.acq);
         if (rc) {
@@ -1396,6 +1433,129 @@ extern "C" int hm_rf_eval_packed(const hm_forest_t* const* forests, int M, const
     HM_REQUIRE(N == 0 || codes != nullptr, "codes");
     return hm_rf_eval_impl(forests, M, nullptr, 0, reinterpret_cast<const unsigned long long*>(codes), N, leaf_out,
                            mean_out, var_out, pred_out, acq, feas, score_out, stream);
+}
+
+// ---- fused scoring + selection -------------------------------------------------------------------------------------------
+// hm_rf_score_topk: the k best candidates of a pool WITHOUT the score array ever existing in HBM (local_search only needs
+// the seeds of its random pools, local_search.py:625-645).  Two passes, both through the forest kernel:
+//   1. the first HM_ST_PREFIX candidates are scored the plain way and hm_topk gives tau = their k-th best value;
+//   2. the whole pool is scored with the kernel's epilogue in filter mode: a candidate is appended to a short list (one
+//      atomic) only if it can still be among the k best -- score < tau, or == tau with an index inside the prefix (k
+//      candidates with value <= tau and a smaller index exist already, so a later tie can never be selected: tie classes,
+//      the norm on discrete spaces, do not flood the list), or NaN (np.argmin puts NaN first);
+//   3. hm_topk_merge on the list (value, global index) = the stable top-k of the whole pool.
+// Expected list length ~ k * N / HM_ST_PREFIX; if the list overflows (scores that keep improving along the pool) the call
+// falls back to the plain score array + hm_topk.  Results are identical to hm_rf_eval + hm_topk by construction.
+#define HM_ST_PREFIX (1 << 16)
+#define HM_ST_CAP (1 << 18)
+struct HmStWs {
+    void* topk_ws;
+    double* prefix_scores;   // [HM_ST_PREFIX]
+    double* tmp_vals;        // [1024]
+    long long* tmp_idx;      // [1024]
+    unsigned* count;
+    double* list_val;        // [HM_ST_CAP]
+    long long* list_idx;     // [HM_ST_CAP]
+};
+static size_t hm_st_layout(int k, unsigned char* base, HmStWs* ws) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        unsigned char* p = base ? base + off : nullptr;
+        off += (bytes + 255) & ~(size_t)255;
+        return p;
+    };
+    unsigned char* a = take((size_t)hm_topk_workspace_bytes(k));
+    unsigned char* b = take(sizeof(double) * HM_ST_PREFIX);
+    unsigned char* c = take(sizeof(double) * 1024);
+    unsigned char* d = take(sizeof(long long) * 1024);
+    unsigned char* e = take(256);
+    unsigned char* f = take(sizeof(double) * HM_ST_CAP);
+    unsigned char* g = take(sizeof(long long) * HM_ST_CAP);
+    if (ws) {
+        ws->topk_ws = a;
+        ws->prefix_scores = (double*)b;
+        ws->tmp_vals = (double*)c;
+        ws->tmp_idx = (long long*)d;
+        ws->count = (unsigned*)e;
+        ws->list_val = (double*)f;
+        ws->list_idx = (long long*)g;
+    }
+    return off;
+}
+extern "C" int64_t hm_rf_score_topk_workspace_bytes(int k) {
+    if (k < 1) k = 1;
+    return (int64_t)hm_st_layout(k, nullptr, nullptr) + 256;
+}
+
+__global__ void hm_st_fill(double* __restrict__ val, long long* __restrict__ idx, unsigned n, unsigned* __restrict__ count) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *count = 0;
+    if (i < n) {
+        val[i] = __longlong_as_double(0x7ff0000000000000ll);        // +inf with the largest index: behind every real entry
+        idx[i] = 0x7fffffffffffffffll;
+    }
+}
+
+static int hm_rf_score_topk_impl(const hm_forest_t* const* forests, int M, const float* Xcm, int64_t ldx,
+                                 const unsigned long long* codes, int64_t N, const hm_acq_params_t* acq, const double* feas,
+                                 int k, double* out_vals, int64_t* out_idx, void* workspace, void* stream) {
+    HM_REQUIRE(acq != nullptr, "acq");
+    HM_REQUIRE(k >= 1 && k <= 1024, "1 <= k <= 1024");
+    HM_REQUIRE(out_vals && out_idx && workspace, "outputs/workspace");
+    HM_REQUIRE(N >= 0, "N >= 0");
+    cudaStream_t st = (cudaStream_t)stream;
+    HmStWs ws;
+    unsigned char* base = (unsigned char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    hm_st_layout(k, base, &ws);
+    if (N <= HM_ST_CAP) {
+        // short pool: the list area holds the whole score array
+        int rc = hm_rf_eval_impl(forests, M, Xcm, ldx, codes, N, nullptr, nullptr, nullptr, nullptr, acq, feas, ws.list_val,
+                                 stream);
+        if (rc) return rc;
+        return hm_topk(ws.list_val, N, 0, k, out_vals, out_idx, ws.topk_ws, stream);
+    }
+    const int64_t n0 = HM_ST_PREFIX;
+    int rc = hm_rf_eval_impl(forests, M, Xcm, ldx, codes, n0, nullptr, nullptr, nullptr, nullptr, acq, feas,
+                             ws.prefix_scores, stream);
+    if (rc) return rc;
+    rc = hm_topk(ws.prefix_scores, n0, 0, k, ws.tmp_vals, reinterpret_cast<int64_t*>(ws.tmp_idx), ws.topk_ws, stream);
+    if (rc) return rc;
+    hm_st_fill<<<HM_ST_CAP / 256, 256, 0, st>>>(ws.list_val, ws.list_idx, HM_ST_CAP, ws.count);
+    HM_CUDA_TRY(cudaGetLastError());
+    HmScoreFilter filt = {ws.tmp_vals + (k - 1), ws.list_val, ws.list_idx, ws.count, HM_ST_CAP, (long long)n0};
+    rc = hm_rf_eval_impl(forests, M, Xcm, ldx, codes, N, nullptr, nullptr, nullptr, nullptr, acq, feas, nullptr, stream, &filt);
+    if (rc) return rc;
+    rc = hm_topk_merge(ws.list_val, reinterpret_cast<const int64_t*>(ws.list_idx), HM_ST_CAP, k, out_vals, out_idx,
+                       ws.topk_ws, stream);
+    if (rc) return rc;
+    unsigned pushed = 0;
+    HM_CUDA_TRY(cudaMemcpyAsync(&pushed, ws.count, sizeof(pushed), cudaMemcpyDeviceToHost, st));
+    HM_CUDA_TRY(cudaStreamSynchronize(st));
+    if (pushed > HM_ST_CAP) {
+        // the list overflowed: plain score array + hm_topk (correct for any input, twice the time)
+        double* scores = nullptr;
+        HM_CUDA_TRY(cudaMallocAsync((void**)&scores, sizeof(double) * (size_t)N, st));
+        rc = hm_rf_eval_impl(forests, M, Xcm, ldx, codes, N, nullptr, nullptr, nullptr, nullptr, acq, feas, scores, stream);
+        if (!rc) rc = hm_topk(scores, N, 0, k, out_vals, out_idx, ws.topk_ws, stream);
+        cudaFreeAsync(scores, st);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+extern "C" int hm_rf_score_topk(const hm_forest_t* const* forests, int M, const float* Xcm, int64_t ldx, int64_t N,
+                                const hm_acq_params_t* acq, const double* feas, int k, double* out_vals, int64_t* out_idx,
+                                void* workspace, void* stream) {
+    HM_REQUIRE(N == 0 || Xcm != nullptr, "Xcm");
+    return hm_rf_score_topk_impl(forests, M, Xcm, ldx, nullptr, N, acq, feas, k, out_vals, out_idx, workspace, stream);
+}
+
+extern "C" int hm_rf_score_topk_packed(const hm_forest_t* const* forests, int M, const uint64_t* codes, int64_t N,
+                                       const hm_acq_params_t* acq, const double* feas, int k, double* out_vals,
+                                       int64_t* out_idx, void* workspace, void* stream) {
+    HM_REQUIRE(N == 0 || codes != nullptr, "codes");
+    return hm_rf_score_topk_impl(forests, M, nullptr, 0, reinterpret_cast<const unsigned long long*>(codes), N, acq, feas, k,
+                                 out_vals, out_idx, workspace, stream);
 }
 
 HM_CHECKED_EXPORT(forest)

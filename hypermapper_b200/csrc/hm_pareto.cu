@@ -6,9 +6,9 @@
 // FAST PATH (NaN-free input).  Strict dominance in every coordinate is transitive, so the survivors of the sweep are
 // exactly the points that NO other point kills -- independent of the order, and ANY subset of the points may be used
 // as pivots to thin the set out first.  Two thinning levels, then an exact all-pairs test on what is left:
-//   prep    : the exact front of a strided sample of the (remaining) points, strongest first = <= 1024 pivots; ONE
-//             launch (hm_px_prep: sample read in place and staged whole in shared memory, a warp drops out when its
-//             candidates are dead, the last CTA to finish rank-sorts the front by coordinate sum).
+//   prep    : the exact front of a strided sample of the (remaining) points, strongest first = <= 1024 pivots
+//             (hm_px_gather_sample + hm_px_prep: all-pairs through 1024-point shared-memory tiles, two candidates per
+//             warp; the last CTA to finish sorts the front by coordinate sum).
 //   stream  : every point is tested against the 8 strongest pivots unconditionally (branch-free), block survivors are
 //             compacted in shared memory and tested warp-cooperatively against the remaining pivots; survivors'
 //             indices are appended to a list.  Level 1 streams the cost matrix once at HBM speed (8 M + 1 bytes/point
@@ -278,7 +278,6 @@ __global__ void hm_pareto_write_mask(const unsigned* __restrict__ alive, const u
 #define HM_PX_WARPS 8
 #define HM_PX_TILE 1024             // points per shared-memory tile
 #define HM_PIV_MAX 1024
-#define HM_PIV1_MAX 1024            // level-1 cap (experiments: HM_B200_PARETO_PIV1)
 #define HM_SAMPLE1 4096
 #define HM_SAMPLE2 4096
 #define HM_SORT_MAX 8192            // longest list the one-CTA sorts take
@@ -308,157 +307,121 @@ __global__ void hm_px_ctl_init(HmParetoCtl* ctl) {
     }
 }
 
-// exact front of a point list (the level-2 survivors): every candidate is tested against every point of the list (tiles
-// staged in shared memory, SoA, 2-4 candidates per warp at a time, lanes stride over the tile);  mask[index] = 1 for
-// the survivors, their indices appended to front_list.
-template <int M>
-__global__ void __launch_bounds__(HM_PX_THREADS) hm_px_exact(const double* __restrict__ costs,
-                                                             const unsigned* __restrict__ idx,
-                                                             const unsigned* __restrict__ count_ptr, unsigned tile_pts,
-                                                             unsigned* __restrict__ front_list, unsigned char* __restrict__ mask,
-                                                             unsigned* __restrict__ out_count,
-                                                             const unsigned* __restrict__ abort_flag) {
-    constexpr int CPW = M <= 4 ? 4 : 2;                  // candidates per warp
-    constexpr unsigned GROUP = HM_PX_WARPS * CPW;
-    extern __shared__ __align__(16) unsigned char exact_smem[];
-    if (*abort_flag) return;        // a NaN was seen: the exact path will redo the call
-    double* tile = reinterpret_cast<double*>(exact_smem);             // [M][tile_pts]
-    const unsigned count = *count_ptr;
+// Exact front of a point list: every candidate is tested against every point of the list (1024-point tiles staged in
+// shared memory, SoA, two candidates per warp, lanes stride over the tile; a CTA leaves the tile loop when all its
+// candidates are dead).  Every thread of the CTA must call it.
+//   TO_MASK = false : survivors' costs are appended to out_costs (count in *out_count)                 [sample -> pivots]
+//   TO_MASK = true  : mask[index] = 1 for survivors, their indices appended to (unsigned*)out_costs     [final exact step]
+// (Measured alternatives that lost, profiles/r02_pareto_timeline_v3..v5.txt: four candidates per warp with the whole list
+// staged at once -- half the CTAs, twice the serial work per warp, 28-32 us against 9-10; a warp-level first phase on 256
+// points followed by the whole CTA on each candidate still alive -- three barriers per candidate, 18 us on a uniform
+// sample and 36 us on the level-2 sample, whose points are mostly mutually non-dominated.)
+#define HM_PX_CPW 2                 // candidates per warp
+#define HM_PX_GROUP (HM_PX_WARPS * HM_PX_CPW)
+template <int M, bool TO_MASK>
+__device__ __forceinline__ void hm_px_front_core(const double* __restrict__ costs, const unsigned* __restrict__ idx,
+                                                 unsigned count, double* __restrict__ out_costs,
+                                                 unsigned char* __restrict__ mask, unsigned* __restrict__ out_count,
+                                                 unsigned char* smem) {
+    double (*tile)[HM_PX_TILE] = reinterpret_cast<double (*)[HM_PX_TILE]>(smem);   // [M][HM_PX_TILE]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (unsigned g0 = blockIdx.x * GROUP; g0 < count; g0 += gridDim.x * GROUP) {
-        double cc[CPW][M];
+    for (unsigned g0 = blockIdx.x * HM_PX_GROUP; g0 < count; g0 += gridDim.x * HM_PX_GROUP) {
+        double cc[HM_PX_CPW][M];
         unsigned alive = 0;          // bit c: candidate c exists and is not killed yet (warp uniform)
 #pragma unroll
-        for (int c = 0; c < CPW; ++c) {
-            const unsigned q = g0 + warp * CPW + c;
+        for (int c = 0; c < HM_PX_CPW; ++c) {
+            const unsigned q = g0 + warp * HM_PX_CPW + c;
             const bool ok = q < count;
             const size_t src = ok ? (idx ? (size_t)idx[q] : (size_t)q) : 0;
 #pragma unroll
             for (int d = 0; d < M; ++d) cc[c][d] = costs[src * M + d];
             if (ok) alive |= 1u << c;
         }
-        for (unsigned t0 = 0; t0 < count; t0 += tile_pts) {
+        for (unsigned t0 = 0; t0 < count; t0 += HM_PX_TILE) {
             if (!__syncthreads_or(alive != 0)) break;        // also: everyone is done with the previous tile
-            const unsigned tn = min(tile_pts, count - t0);
+            const unsigned tn = min((unsigned)HM_PX_TILE, count - t0);
             for (unsigned t = threadIdx.x; t < tn; t += HM_PX_THREADS) {
                 const size_t src = idx ? (size_t)idx[t0 + t] : (size_t)(t0 + t);
 #pragma unroll
-                for (int d = 0; d < M; ++d) tile[(size_t)d * tile_pts + t] = costs[src * M + d];
+                for (int d = 0; d < M; ++d) tile[d][t] = costs[src * M + d];
             }
             __syncthreads();
-            // a warp leaves the tile as soon as its candidates are dead (tested every 128 points)
-            for (unsigned j0 = 0; j0 < tn && alive; j0 += 128) {
+            if (alive) {
                 unsigned killed = 0;
+                for (unsigned j = lane; j < tn; j += 32) {
+                    double p[M];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const unsigned j = j0 + u * 32 + lane;
-                    if (j < tn) {
-                        double p[M];
+                    for (int d = 0; d < M; ++d) p[d] = tile[d][j];
 #pragma unroll
-                        for (int d = 0; d < M; ++d) p[d] = tile[(size_t)d * tile_pts + j];
-#pragma unroll
-                        for (int c = 0; c < CPW; ++c)
-                            if (hm_kills<M>(p, cc[c])) killed |= 1u << c;
-                    }
+                    for (int c = 0; c < HM_PX_CPW; ++c)
+                        if (hm_kills<M>(p, cc[c])) killed |= 1u << c;
                 }
 #pragma unroll
-                for (int c = 0; c < CPW; ++c)
+                for (int c = 0; c < HM_PX_CPW; ++c)
                     if (__any_sync(0xffffffffu, (killed >> c) & 1u)) alive &= ~(1u << c);
             }
         }
         if (lane == 0) {
 #pragma unroll
-            for (int c = 0; c < CPW; ++c) {
+            for (int c = 0; c < HM_PX_CPW; ++c) {
                 if (!((alive >> c) & 1u)) continue;
-                const unsigned q = g0 + warp * CPW + c;
-                const unsigned gi = idx ? idx[q] : q;
-                mask[gi] = 1;
-                front_list[atomicAdd(out_count, 1u)] = gi;
+                const unsigned q = g0 + warp * HM_PX_CPW + c;
+                if (TO_MASK) {
+                    const unsigned gi = idx ? idx[q] : q;
+                    mask[gi] = 1;
+                    reinterpret_cast<unsigned*>(out_costs)[atomicAdd(out_count, 1u)] = gi;     // front list (indices)
+                } else {
+                    const unsigned pos = atomicAdd(out_count, 1u);
+#pragma unroll
+                    for (int d = 0; d < M; ++d) out_costs[(size_t)pos * M + d] = cc[c][d];
+                }
             }
         }
         __syncthreads();
     }
 }
 
-// Pivot preparation of one thinning level in ONE launch (was: gather_sample + exact + sort_pivots): the exact front of a
-// strided sample of a point list, strongest points first.
-//   * the sample is read in place (point q of the sample = list position q * count / S); a CTA stages the whole sample
-//     in shared memory at once when it fits (M <= 4: one load phase instead of four load / barrier / compute rounds);
-//   * a warp owns CPW candidates and leaves the tile loop as soon as all of them are dead (most die within the first
-//     few dozen points), so the launch lasts as long as one front member takes to meet every sample point;
-//   * the last CTA to finish (ticket) sorts the front by coordinate sum -- a rank sort in shared memory for the usual
-//     few hundred points -- and writes the <= HM_PIV_MAX strongest as the level's pivots.
-#define HM_PREP_RANK_MAX 1024
+// the final exact step: front of the level-2 survivors -> mask, and the front's indices into front_list
 template <int M>
-__global__ void __launch_bounds__(HM_PX_THREADS) hm_px_prep(const double* __restrict__ costs,
-                                                            const unsigned* __restrict__ idx,
-                                                            const unsigned* __restrict__ count_ptr, unsigned n_total,
-                                                            unsigned s_max, unsigned tile_pts, unsigned piv_max,
-                                                            double* __restrict__ piv_raw, double* __restrict__ pivots,
-                                                            HmParetoCtl* ctl) {
-    constexpr int CPW = M <= 4 ? 4 : 2;
-    constexpr unsigned GROUP = HM_PX_WARPS * CPW;
-    extern __shared__ __align__(16) unsigned char prep_smem[];
-    double* tile = reinterpret_cast<double*>(prep_smem);              // [M][tile_pts]
-    __shared__ unsigned s_last;
+__global__ void __launch_bounds__(HM_PX_THREADS) hm_px_exact(const double* __restrict__ costs,
+                                                             const unsigned* __restrict__ idx,
+                                                             const unsigned* __restrict__ count_ptr,
+                                                             unsigned* __restrict__ front_list, unsigned char* __restrict__ mask,
+                                                             unsigned* __restrict__ out_count,
+                                                             const unsigned* __restrict__ abort_flag) {
+    extern __shared__ __align__(16) unsigned char exact_smem[];
+    if (*abort_flag) return;        // a NaN was seen: the exact path will redo the call
+    hm_px_front_core<M, true>(costs, idx, *count_ptr, reinterpret_cast<double*>(front_list), mask, out_count, exact_smem);
+}
+
+// Pivot preparation of one thinning level = the exact front of a strided sample of a point list, strongest first:
+//   hm_px_gather_sample  the sample as a compact array [S][M] (point q of the sample = list position q * count / S);
+//   hm_px_prep           its exact front (hm_px_front_core) into piv_raw; the last CTA to finish (ticket) sorts the front
+//                        by coordinate sum (bitonic, shared memory) and writes the <= piv_max strongest as the level's
+//                        pivots -- one launch where there were two (exact, sort_pivots).
+template <int M>
+__global__ void hm_px_gather_sample(const double* __restrict__ costs, const unsigned* __restrict__ idx,
+                                    const unsigned* __restrict__ count_ptr, unsigned n_total, unsigned s_max,
+                                    double* __restrict__ sample, HmParetoCtl* ctl) {
     const unsigned count = count_ptr ? *count_ptr : n_total;
     const unsigned S = min(s_max, count);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    auto sample_src = [&](unsigned q) -> size_t {
-        const unsigned pos = (unsigned)(((unsigned long long)q * count) / S);
-        return idx ? (size_t)idx[pos] : (size_t)pos;
-    };
-    if (!*(volatile unsigned*)&ctl->nan_flag && blockIdx.x * GROUP < S) {
-        double cc[CPW][M];
-        unsigned alive = 0;          // bit c: candidate c exists and is not killed yet (warp uniform)
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) ctl->n_sample = S;
+    if (i >= S) return;
+    const unsigned pos = (unsigned)(((unsigned long long)i * count) / S);
+    const size_t src = idx ? (size_t)idx[pos] : (size_t)pos;
 #pragma unroll
-        for (int c = 0; c < CPW; ++c) {
-            const unsigned q = blockIdx.x * GROUP + warp * CPW + c;
-            const bool ok = q < S;
-            const size_t src = ok ? sample_src(q) : 0;
-#pragma unroll
-            for (int d = 0; d < M; ++d) cc[c][d] = __ldg(costs + src * M + d);
-            if (ok) alive |= 1u << c;
-        }
-        for (unsigned t0 = 0; t0 < S; t0 += tile_pts) {
-            if (t0 && !__syncthreads_or(alive != 0)) break;           // also: everyone is done with the previous tile
-            const unsigned tn = min(tile_pts, S - t0);
-            for (unsigned t = threadIdx.x; t < tn; t += HM_PX_THREADS) {
-                const size_t src = sample_src(t0 + t);
-#pragma unroll
-                for (int d = 0; d < M; ++d) tile[(size_t)d * tile_pts + t] = __ldg(costs + src * M + d);
-            }
-            __syncthreads();
-            for (unsigned j0 = 0; j0 < tn && alive; j0 += 128) {
-                unsigned killed = 0;
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const unsigned j = j0 + u * 32 + lane;
-                    if (j < tn) {
-                        double p[M];
-#pragma unroll
-                        for (int d = 0; d < M; ++d) p[d] = tile[(size_t)d * tile_pts + j];
-#pragma unroll
-                        for (int c = 0; c < CPW; ++c)
-                            if (hm_kills<M>(p, cc[c])) killed |= 1u << c;
-                    }
-                }
-#pragma unroll
-                for (int c = 0; c < CPW; ++c)
-                    if (__any_sync(0xffffffffu, (killed >> c) & 1u)) alive &= ~(1u << c);
-            }
-        }
-        if (lane == 0) {
-#pragma unroll
-            for (int c = 0; c < CPW; ++c) {
-                if (!((alive >> c) & 1u)) continue;
-                const unsigned pos = atomicAdd(&ctl->n_piv_raw, 1u);
-                HM_DEV_ASSERT(pos < s_max);
-#pragma unroll
-                for (int d = 0; d < M; ++d) piv_raw[(size_t)pos * M + d] = cc[c][d];
-            }
-        }
-    }
+    for (int d = 0; d < M; ++d) sample[(size_t)i * M + d] = costs[src * M + d];
+}
+
+template <int M>
+__global__ void __launch_bounds__(HM_PX_THREADS) hm_px_prep(const double* __restrict__ sample, unsigned piv_max,
+                                                            double* __restrict__ piv_raw, double* __restrict__ pivots,
+                                                            HmParetoCtl* ctl) {
+    extern __shared__ __align__(16) unsigned char prep_smem[];
+    __shared__ unsigned s_last;
+    if (!*(volatile unsigned*)&ctl->nan_flag)
+        hm_px_front_core<M, false>(sample, nullptr, ctl->n_sample, piv_raw, nullptr, &ctl->n_piv_raw, prep_smem);
     // ---- the last CTA sorts ----
     __threadfence();
     __syncthreads();
@@ -468,7 +431,7 @@ __global__ void __launch_bounds__(HM_PX_THREADS) hm_px_prep(const double* __rest
     __threadfence();
     const unsigned n = *(volatile unsigned*)&ctl->n_piv_raw;
     double* key = reinterpret_cast<double*>(prep_smem);                               // [n2]
-    unsigned short* ord = reinterpret_cast<unsigned short*>(key + HM_SAMPLE2);        // [n2]  (bitonic path only)
+    unsigned short* ord = reinterpret_cast<unsigned short*>(key + HM_SAMPLE2);        // [n2]
     unsigned n2 = 1;
     while (n2 < n) n2 <<= 1;
     for (unsigned i = threadIdx.x; i < n2; i += HM_PX_THREADS) {
@@ -483,54 +446,37 @@ __global__ void __launch_bounds__(HM_PX_THREADS) hm_px_prep(const double* __rest
     }
     __syncthreads();
     const unsigned P = min(n, piv_max);
-    if (n <= HM_PREP_RANK_MAX) {
-        // rank of (key, position): distinct by construction
-        for (unsigned i = threadIdx.x; i < n; i += HM_PX_THREADS) {
-            const double k = key[i];
-            unsigned r = 0;
-            for (unsigned j = 0; j < n; ++j) {
-                const double kj = key[j];
-                r += (kj < k || (kj == k && j < i)) ? 1u : 0u;
-            }
-            if (r < P) {
-#pragma unroll
-                for (int d = 0; d < M; ++d) pivots[(size_t)r * M + d] = __ldcg(piv_raw + (size_t)i * M + d);
-            }
-        }
-    } else {
-        for (unsigned i = threadIdx.x; i < n2; i += HM_PX_THREADS) ord[i] = (unsigned short)i;
-        __syncthreads();
-        for (unsigned k = 2; k <= n2; k <<= 1) {
-            for (unsigned j = k >> 1; j > 0; j >>= 1) {
-                for (unsigned i = threadIdx.x; i < n2; i += HM_PX_THREADS) {
-                    const unsigned l = i ^ j;
-                    if (l > i) {
-                        const bool up = (i & k) == 0;
-                        const double a = key[i], b = key[l];
-                        const unsigned short oa = ord[i], ob = ord[l];
-                        const bool gt = (a > b) || (a == b && oa > ob);
-                        if (gt == up) {
-                            key[i] = b;
-                            key[l] = a;
-                            ord[i] = ob;
-                            ord[l] = oa;
-                        }
+    for (unsigned i = threadIdx.x; i < n2; i += HM_PX_THREADS) ord[i] = (unsigned short)i;
+    __syncthreads();
+    for (unsigned k = 2; k <= n2; k <<= 1) {
+        for (unsigned j = k >> 1; j > 0; j >>= 1) {
+            for (unsigned i = threadIdx.x; i < n2; i += HM_PX_THREADS) {
+                const unsigned l = i ^ j;
+                if (l > i) {
+                    const bool up = (i & k) == 0;
+                    const double a = key[i], b = key[l];
+                    const unsigned short oa = ord[i], ob = ord[l];
+                    const bool gt = (a > b) || (a == b && oa > ob);
+                    if (gt == up) {
+                        key[i] = b;
+                        key[l] = a;
+                        ord[i] = ob;
+                        ord[l] = oa;
                     }
                 }
-                __syncthreads();
             }
+            __syncthreads();
         }
-        for (unsigned i = threadIdx.x; i < P; i += HM_PX_THREADS) {
-            const unsigned src = ord[i];
+    }
+    for (unsigned i = threadIdx.x; i < P; i += HM_PX_THREADS) {
+        const unsigned src = ord[i];
 #pragma unroll
-            for (int d = 0; d < M; ++d) pivots[(size_t)i * M + d] = __ldcg(piv_raw + (size_t)src * M + d);
-        }
+        for (int d = 0; d < M; ++d) pivots[(size_t)i * M + d] = __ldcg(piv_raw + (size_t)src * M + d);
     }
     if (threadIdx.x == 0) {
         ctl->n_piv = P;
         ctl->n_piv_raw = 0;          // ready for the next level
         ctl->prep_ticket = 0;
-        ctl->n_sample = S;
     }
 }
 
@@ -596,12 +542,35 @@ __global__ void __launch_bounds__(HM_PX_THREADS, 3) hm_px_stream(const double* _
 #pragma unroll
         for (int d = 0; d < M; ++d) c2[d] = have ? __ldg(costs + (size_t)sidx * M + d) : 0.0;
         bool dead = !have;
+        if (ITEMS == HM_PS_ITEMS2) {
+            // level 2 (few points, long pivot list, most of the batch survives for a long time): the batch's points one
+            // after the other, the LANES over the pivots -- a survivor costs P / 32 iterations instead of P, a killed
+            // point usually one (the pivots are sorted strongest first)
+            unsigned deadmask = 0;                         // warp uniform
+            for (unsigned q = 0; q < m; ++q) {
+                double cq[M];
+#pragma unroll
+                for (int d = 0; d < M; ++d) cq[d] = __shfl_sync(0xffffffffu, c2[d], (int)q);
+                for (unsigned p0 = K1; p0 < P; p0 += 32) {
+                    const unsigned p = p0 + lane;
+                    bool all = p < P;
+#pragma unroll
+                    for (int d = 0; d < M; ++d) all = all && (cq[d] > sp[(size_t)d * HM_PIV_MAX + (p < P ? p : 0)]);
+                    if (__any_sync(0xffffffffu, all)) {
+                        deadmask |= 1u << q;
+                        break;
+                    }
+                }
+            }
+            dead = dead || ((deadmask >> lane) & 1u);
+        } else {
         for (unsigned p = K1; p < P; ++p) {
             if (__all_sync(0xffffffffu, dead)) break;
             bool all = true;
 #pragma unroll
             for (int d = 0; d < M; ++d) all = all && (c2[d] > sp[(size_t)d * HM_PIV_MAX + p]);
             dead = dead || all;
+        }
         }
         n1 -= m;
         const unsigned ballot = __ballot_sync(0xffffffffu, !dead);
@@ -836,11 +805,15 @@ __global__ void __launch_bounds__(HM_TAIL_SMALL, 1) hm_px_tail_small(const doubl
     const unsigned n = ctl->n_front1;
     if (n > HM_TAIL_SMALL) return;          // sort_front / pass2_a / pass2_b (grid-wide) take it
     const unsigned t = threadIdx.x;
+    if (n == 0) {
+        if (t == 0) ctl->tail_done = 1;
+        return;
+    }
     if (t == 0) n_dead = 0;
     if (t < n) key[t] = list[t];
     __syncthreads();
-    if (t < n) {                            // rank sort: the indices are distinct
-        const unsigned k = key[t];
+    if (t < n) {                            // rank sort: the indices are distinct (one barrier; a bitonic network's 28
+        const unsigned k = key[t];          // barriers for 128 entries cost more than the n reads per thread)
         unsigned r = 0;
         for (unsigned j = 0; j < n; ++j) r += key[j] < k ? 1u : 0u;
         HM_DEV_ASSERT(r < n);
@@ -916,6 +889,7 @@ struct HmParetoWs {
     double* pivots;              // exact path: batch pivots; fast path: sorted pivots   [HM_PB][M]
     unsigned char* state;
     HmParetoRound* round;
+    double* sample;              // [HM_SAMPLE2][M]
     double* piv_raw;             // [HM_SAMPLE2][M]
     HmParetoCtl* ctl;
 };
@@ -938,6 +912,7 @@ static size_t hm_pareto_layout(int64_t N, int M, unsigned char* base, HmParetoWs
     unsigned char* pv = take((size_t)HM_PB * M * 8);
     unsigned char* stt = take(n);
     unsigned char* rd = take(sizeof(HmParetoRound));
+    unsigned char* sm = take((size_t)HM_SAMPLE2 * M * 8);
     unsigned char* pr = take((size_t)HM_SAMPLE2 * M * 8);
     unsigned char* ct = take(sizeof(HmParetoCtl));
     if (ws) {
@@ -948,6 +923,7 @@ static size_t hm_pareto_layout(int64_t N, int M, unsigned char* base, HmParetoWs
         ws->pivots = (double*)pv;
         ws->state = stt;
         ws->round = (HmParetoRound*)rd;
+        ws->sample = (double*)sm;
         ws->piv_raw = (double*)pr;
         ws->ctl = (HmParetoCtl*)ct;
     }
@@ -1120,19 +1096,19 @@ static int hm_pareto_run_fast(const double* costs, int64_t N, uint8_t* mask, voi
     const size_t stream_smem1 = sizeof(double) * M * HM_PIV_MAX + sizeof(unsigned) * HM_PX_WARPS * (HM_PS_Q1 + HM_PS_Q2);
     const size_t stream_smem2 = stream_smem1;
     static_assert(HM_SAMPLE1 == HM_SAMPLE2, "one pivot-preparation geometry for both levels");
-    // the whole sample in shared memory when it fits 128 KB, else 1024-point tiles; the last CTA's sort needs 10 B / point
-    const unsigned prep_tile = (size_t)M * HM_SAMPLE1 * 8 <= 128 * 1024 ? HM_SAMPLE1 : HM_PX_TILE;
-    const size_t prep_smem = std::max<size_t>((size_t)M * prep_tile * 8, (size_t)HM_SAMPLE1 * 10);
-    const unsigned prep_grid = (HM_SAMPLE1 + HM_PX_WARPS * (M <= 4 ? 4 : 2) - 1) / (HM_PX_WARPS * (M <= 4 ? 4 : 2));
-    // level 1 keeps only its strongest pivots: every stage-1 survivor batch walks ALL of them (it nearly always holds a
-    // final survivor), and that walk is time the warp is not streaming; what the weaker pivots would have killed is left
-    // to level 2, whose pivots are stronger anyway
-    unsigned piv1_max = HM_PIV1_MAX;
+    const size_t exact_smem = sizeof(double) * M * HM_PX_TILE;
+    // 1024-point tiles; the last CTA's sort needs 10 B per sample point
+    const size_t prep_smem = std::max<size_t>(exact_smem, (size_t)HM_SAMPLE1 * 10);
+    const unsigned prep_grid = (HM_SAMPLE1 + HM_PX_GROUP - 1) / HM_PX_GROUP;
+    // level-1 pivot cap (experiments: HM_B200_PARETO_PIV1).  Measured on C4 (profiles/r02_exp_pareto3.log): 1024 / 128 / 64 /
+    // 32 / 16 pivots -> level-1 stream 54.9 / 55.0 / 55.8 / 54.2 / 49.5 us, but level-2 stream 17.1 / 15.5 / 15.3 / 17.3 /
+    // 25.6 us: what the weaker pivots leave alive comes back at level 2, so the cap stays at HM_PIV_MAX.
+    unsigned piv1_max = HM_PIV_MAX;
     if (const char* e = getenv("HM_B200_PARETO_PIV1")) piv1_max = (unsigned)std::min(std::max(atoi(e), 8), HM_PIV_MAX);
     int dev = 0;
     HM_CUDA_TRY(cudaGetDevice(&dev));
     if (dev >= 32 || !(HmPxSetup<M>::done_mask >> dev & 1u)) {
-        HM_CUDA_TRY(cudaFuncSetAttribute(hm_px_exact<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem));
+        HM_CUDA_TRY(cudaFuncSetAttribute(hm_px_exact<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)exact_smem));
         HM_CUDA_TRY(cudaFuncSetAttribute(hm_px_prep<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem));
         HM_CUDA_TRY(cudaFuncSetAttribute(hm_px_stream<M, IT1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_smem1));
         HM_CUDA_TRY(cudaFuncSetAttribute(hm_px_stream<M, HM_PS_ITEMS2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_smem2));
@@ -1157,8 +1133,8 @@ static int hm_pareto_run_fast(const double* costs, int64_t N, uint8_t* mask, voi
     hm_px_ctl_init<<<1, 32, 0, s>>>(ctl);
     HM_CUDA_TRY(cudaMemsetAsync(mask, 0, (size_t)N, s));
     // ---- level 1: pivots from a strided sample of everything, stream the whole cost matrix ----
-    hm_px_prep<M><<<prep_grid, HM_PX_THREADS, prep_smem, s>>>(costs, nullptr, nullptr, n, HM_SAMPLE1, prep_tile, piv1_max,
-                                                               ws.piv_raw, ws.pivots, ctl);
+    hm_px_gather_sample<M><<<(HM_SAMPLE1 + 255) / 256, 256, 0, s>>>(costs, nullptr, nullptr, n, HM_SAMPLE1, ws.sample, ctl);
+    hm_px_prep<M><<<prep_grid, HM_PX_THREADS, prep_smem, s>>>(ws.sample, piv1_max, ws.piv_raw, ws.pivots, ctl);
     {
         const unsigned chunk = HM_PX_THREADS * IT1;
         const unsigned chunks = (n + chunk - 1) / chunk;
@@ -1169,12 +1145,12 @@ static int hm_pareto_run_fast(const double* costs, int64_t N, uint8_t* mask, voi
                                                                               list1, &ctl->n_list1);
     }
     // ---- level 2: pivots sampled from the survivors, re-filter the survivors ----
-    hm_px_prep<M><<<prep_grid, HM_PX_THREADS, prep_smem, s>>>(costs, list1, &ctl->n_list1, 0, HM_SAMPLE2, prep_tile, HM_PIV_MAX,
-                                                               ws.piv_raw, ws.pivots, ctl);
+    hm_px_gather_sample<M><<<(HM_SAMPLE2 + 255) / 256, 256, 0, s>>>(costs, list1, &ctl->n_list1, 0, HM_SAMPLE2, ws.sample, ctl);
+    hm_px_prep<M><<<prep_grid, HM_PX_THREADS, prep_smem, s>>>(ws.sample, HM_PIV_MAX, ws.piv_raw, ws.pivots, ctl);
     hm_px_stream<M, HM_PS_ITEMS2><<<sms * 4, HM_PX_THREADS, stream_smem2, s>>>(costs, list1, &ctl->n_list1, 0, ws.pivots,
                                                                              ctl, list2, &ctl->n_list2);
     // ---- exact all-pairs on what is left -> mask, and the front's indices into list1 ----
-    hm_px_exact<M><<<sms * 2, HM_PX_THREADS, prep_smem, s>>>(costs, list2, &ctl->n_list2, prep_tile, list1, mask,
+    hm_px_exact<M><<<sms * 4, HM_PX_THREADS, exact_smem, s>>>(costs, list2, &ctl->n_list2, list1, mask,
                                                                      &ctl->n_front1, &ctl->nan_flag);
     HM_CUDA_TRY(cudaGetLastError());
     if (pass2) {

@@ -29,8 +29,11 @@ static int hm_check_desc(const hm_param_desc_t& p, long long n_tables, int j) {
                    "ordinal value table out of range");
     }
     if (p.kind == HM_P_CATEGORICAL) HM_REQUIRE(p.n_values >= 1, "categorical size");
-    if (p.kind == HM_P_INTEGER && p.prior_kind == HM_PRIOR_TABLE)
-        HM_REQUIRE(p.n_prior == (int)(p.hi - p.lo) + 1, "integer distribution length");
+    if (p.kind == HM_P_INTEGER) {
+        // the uniform draw is a 32-bit multiply-high on the range size, the value index an int
+        HM_REQUIRE(p.hi >= p.lo && p.hi - p.lo + 1.0 <= 2147483647.0, "integer parameter: at most 2^31 - 1 values");
+        if (p.prior_kind == HM_PRIOR_TABLE) HM_REQUIRE(p.n_prior == (int)(p.hi - p.lo) + 1, "integer distribution length");
+    }
     if (p.prior_kind == HM_PRIOR_TABLE)
         HM_REQUIRE(p.n_prior >= 1 && p.prior_off >= 0 && p.prior_off + 2ll * p.n_prior <= n_tables,
                    "prior table out of range ([probabilities | cumulative])");

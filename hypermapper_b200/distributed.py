@@ -67,7 +67,9 @@ def pareto_mask_sharded(costs_local, filter_fn=None, group=None):
     are all-gathered in rank order = global index order; (3) every rank runs the full filter on that union: pass 1
     removes the points dominated from another block, pass 2 -- sequential and index-order dependent -- then sees
     exactly the rows and the order it sees in the single-process run; (4) every rank keeps the verdicts of its own rows.
-    NaN costs break the transitivity argument: they are detected and rejected.
+    NaN costs break the transitivity argument: they are detected (the count headers carry the flag, so every rank
+    decides the same way) and the call falls back to filtering the whole gathered matrix on every rank
+    (_pareto_all_rows_fallback).
 
     costs_local: CUDA (nccl, or gloo with the collectives staged through the host) or CPU tensor [n_local][M] fp64.
     filter_fn(costs, pass2) -> uint8/bool mask tensor on the same device; default: the K4 kernels."""
@@ -85,14 +87,9 @@ def pareto_mask_sharded(costs_local, filter_fn=None, group=None):
     rows = torch.nonzero(alive).view(-1)
     mine = costs_local[rows].contiguous()
     out = torch.zeros((n_local,), dtype=torch.uint8, device=dev)
-    nan_msg = ("pareto_mask_sharded: NaN costs (the dominance relation is not transitive with NaNs; filter them on one "
-               "rank with sequential_is_pareto_efficient)")
     if world == 1:
         if float(has_nan.item()):
-            raise ValueError(nan_msg)
-        keep = filter_fn(mine, True).to(torch.bool) if len(rows) else alive[:0]
-        out[rows[keep]] = 1
-        return out
+            return filter_fn(costs_local, True).to(torch.uint8)            # the full filter handles NaNs in index order
     # ONE collective in the common case: every rank contributes a fixed-capacity block [1 + cap][M] whose header row
     # carries its survivor count (+0.5 if it saw a NaN); a second round with the exact capacity only if a rank overflows.
     # On the tensors' device with nccl, through the host otherwise (gloo).
@@ -108,8 +105,8 @@ def pareto_mask_sharded(costs_local, filter_fn=None, group=None):
         dist.all_gather_into_tensor(gathered, block, group=group)
         gathered = gathered.view(world, 1 + cap, M)
         heads = gathered[:, 0, 0].cpu().tolist()
-        if any(h != int(h) for h in heads):
-            raise ValueError(nan_msg)                    # every rank sees the same headers and raises together
+        if any(h != int(h) for h in heads):              # every rank sees the same headers and takes the same branch
+            return _pareto_all_rows_fallback(costs_local, filter_fn, group, cdev)
         counts = [int(h) for h in heads]
         if max(counts) <= cap:
             break
@@ -119,6 +116,31 @@ def pareto_mask_sharded(costs_local, filter_fn=None, group=None):
     start = sum(counts[:rank])
     out[rows[keep[start: start + counts[rank]]]] = 1
     return out
+
+
+def _pareto_all_rows_fallback(costs_local, filter_fn, group, cdev):
+    """NaN costs: the dominance relation is no longer transitive, so the local pre-filter is not valid and the sweep's
+    order matters (compute_pareto.py:89-117 takes the rows in index order).  Every rank gathers ALL rows (padded
+    all-gather, rank order = global index order), runs the full filter on the whole matrix -- the K4 kernels take their
+    exact NaN path -- and keeps its own slice.  Correct, not fast: NaN costs are the exception."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    dev = costs_local.device
+    n_local, M = costs_local.shape
+    sizes = torch.zeros((world,), dtype=torch.int64, device=cdev)
+    dist.all_gather_into_tensor(sizes, torch.tensor([n_local], dtype=torch.int64, device=cdev), group=group)
+    sizes = [int(v) for v in sizes.cpu().tolist()]
+    nmax = max(max(sizes), 1)
+    block = torch.zeros((nmax, M), dtype=torch.float64, device=cdev)
+    block[:n_local] = costs_local.to(cdev)
+    gathered = torch.empty((world * nmax, M), dtype=torch.float64, device=cdev)
+    dist.all_gather_into_tensor(gathered, block, group=group)
+    full = torch.cat([gathered[r * nmax: r * nmax + sizes[r]] for r in range(world)], dim=0).to(dev).contiguous()
+    mask = filter_fn(full, True).to(torch.uint8)
+    start = sum(sizes[:rank])
+    return mask[start: start + n_local].contiguous()
 
 
 def _pareto_mask_sharded_device(costs_local, group=None):
@@ -135,15 +157,13 @@ def _pareto_mask_sharded_device(costs_local, group=None):
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     dev = costs_local.device
     n_local, M = costs_local.shape
-    nan_msg = ("pareto_mask_sharded: NaN costs (the dominance relation is not transitive with NaNs; filter them on one "
-               "rank with sequential_is_pareto_efficient)")
     out = torch.zeros((n_local,), dtype=torch.uint8, device=dev)
     cap = _PARETO_EXCHANGE_ROWS
     costs_local = costs_local.contiguous()
     if world == 1:
         _, rows, idx, n_alive, saw_nan = pareto_pass1_compact(costs_local, cap)
         if saw_nan:
-            raise ValueError(nan_msg)
+            return pareto_mask_device(costs_local, True)
         if n_alive > cap:
             _, rows, idx, n_alive, saw_nan = pareto_pass1_compact(costs_local, n_alive)
         if n_alive:
@@ -162,8 +182,8 @@ def _pareto_mask_sharded_device(costs_local, group=None):
         dist.all_gather_into_tensor(gathered, block.to(cdev), group=group)
         gathered = gathered.view(world, 1 + cap, M)
         heads = gathered[:, 0, 0].cpu().tolist()
-        if any(h != int(h) for h in heads):
-            raise ValueError(nan_msg)                    # every rank sees the same headers and raises together
+        if any(h != int(h) for h in heads):              # every rank sees the same headers and takes the same branch
+            return _pareto_all_rows_fallback(costs_local, pareto_mask_device, group, cdev)
         counts = [int(h) for h in heads]
         if max(counts) <= cap:
             break

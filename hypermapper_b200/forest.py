@@ -283,3 +283,35 @@ def topk_merge(values, indices, k):
                          _lib.dptr(ws), _lib.stream_ptr())
     _lib.check(rc, "hm_topk_merge")
     return ov, oi
+
+
+_ST_WS = {}
+
+
+def score_topk(forests, X, acq, k, feas=None):
+    """hm_rf_score_topk / hm_rf_score_topk_packed: the k best candidates (values ascending, ties -> lowest index, NaN
+    first: get_min_configurations, utility_functions.py:295-316) of a pool without materialising its score array.
+    X: CUDA float32 [D_enc][N] (column-major encoded candidates) or CUDA int64 [N] (packed codes; the forests must have
+    been through attach_packing).  -> (values fp64 [k], indices int64 [k]) on the device."""
+    torch = _lib.require_cuda()
+    L = _lib.lib()
+    M = len(forests)
+    handles = (ctypes.c_void_p * M)(*[f.handle for f in forests])
+    packed = X.dtype == torch.int64
+    assert X.is_cuda and X.is_contiguous() and (X.dim() == 1 if packed else (X.dim() == 2 and X.dtype == torch.float32))
+    N = X.shape[0] if packed else X.shape[1]
+    dev = X.device
+    key = (dev.index, int(k))
+    ws = _ST_WS.get(key)
+    if ws is None:
+        ws = _ST_WS[key] = torch.empty((int(L.hm_rf_score_topk_workspace_bytes(int(k))),), dtype=torch.uint8, device=dev)
+    vals = torch.empty((k,), dtype=torch.float64, device=dev)
+    idx = torch.empty((k,), dtype=torch.int64, device=dev)
+    if packed:
+        rc = L.hm_rf_score_topk_packed(handles, M, _lib.dptr(X), N, ctypes.byref(acq), _lib.dptr(feas), int(k),
+                                       _lib.dptr(vals), _lib.dptr(idx), _lib.dptr(ws), _lib.stream_ptr())
+    else:
+        rc = L.hm_rf_score_topk(handles, M, _lib.dptr(X), N, N, ctypes.byref(acq), _lib.dptr(feas), int(k),
+                                _lib.dptr(vals), _lib.dptr(idx), _lib.dptr(ws), _lib.stream_ptr())
+    _lib.check(rc, "hm_rf_score_topk")
+    return vals, idx

@@ -131,6 +131,22 @@ int hm_rf_eval_packed(const hm_forest_t* const* forests, int M, const uint64_t* 
                       int32_t* const* leaf_out, double* mean_out, double* var_out, double* pred_out,
                       const hm_acq_params_t* acq, const double* feas, double* score_out, void* stream);
 
+/* Fused scoring + selection: the k best candidates of a pool (the stable (value, index) order of hm_topk =
+ * utility_functions.get_min_configurations, utility_functions.py:295-316) WITHOUT the score array ever being written:
+ * what local_search needs from its random pools (the seeds of the hill climb, local_search.py:625-645).
+ * The forest kernel's epilogue appends a candidate to a short list only if it can still be among the k best (its
+ * score beats the k-th best of a 65 536-candidate prefix, or ties it from inside the prefix, or is NaN); hm_topk_merge
+ * on that list is the top-k of the pool.  Identical to hm_rf_eval + hm_topk for every input (a list overflow falls
+ * back to exactly that).  out_vals[k], out_idx[k]: device; workspace: hm_rf_score_topk_workspace_bytes(k) device bytes.
+ * The call synchronises the stream once (the list length decides about the fall-back). */
+int64_t hm_rf_score_topk_workspace_bytes(int k);
+int hm_rf_score_topk(const hm_forest_t* const* forests, int M, const float* Xcm, int64_t ldx, int64_t N,
+                     const hm_acq_params_t* acq, const double* feas, int k, double* out_vals, int64_t* out_idx,
+                     void* workspace, void* stream);
+int hm_rf_score_topk_packed(const hm_forest_t* const* forests, int M, const uint64_t* codes, int64_t N,
+                            const hm_acq_params_t* acq, const double* feas, int k, double* out_vals,
+                            int64_t* out_idx, void* workspace, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * K3  scalarised acquisition on precomputed mean/variance (GP path, or RF mean/var API users)
  * replaces: EI / ucb / thompson_sampling arithmetic (random_scalarizations.py:160-506)

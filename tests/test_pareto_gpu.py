@@ -123,7 +123,8 @@ rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
 dist.init_process_group("gloo", rank=rank, world_size=world)      # both ranks share cuda:0; collectives via the host
 rng = np.random.default_rng(5)
 cases = {"uniform3": rng.random((400_000, 3)), "ties3": np.floor(rng.random((200_000, 3)) * 64) / 64,
-         "uniform2": rng.random((300_001, 2))}
+         "uniform2": rng.random((300_001, 2)), "nan3": rng.random((50_001, 3))}
+cases["nan3"][[7, 30_000, 49_999], [0, 2, 1]] = np.nan          # NaN costs: the all-rows fallback (exact path on every rank)
 for name, c in cases.items():
     whole = pareto_mask_device(torch.from_numpy(c).cuda()).cpu().numpy()
     lo, hi = shard_bounds(len(c), rank, world)

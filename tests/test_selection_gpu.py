@@ -163,3 +163,50 @@ def test_final_pick_when_the_best_of_a_pool_is_already_evaluated():
                                        config["scalarization_key"], 1, previous_points=data)
     assert best["a"] == 32 and best["d"] == 2
     assert space.get_unique_hash_string_from_values(best) not in fast
+
+
+@pytest.mark.parametrize("case", ["c3_packed", "f32_ties", "nan_scores", "overflow", "short_pool", "k1024"])
+def test_fused_score_topk_equals_eval_then_topk(case):
+    """hm_rf_score_topk(_packed) -- threshold filter in the forest kernel's epilogue, no score array -- returns exactly
+    what hm_rf_eval + hm_topk returns: tie classes larger than k, NaN scores (np.argmin order: NaN first), a pool whose
+    scores keep improving (list overflow -> fall-back), pools shorter than the prefix, k = 1024."""
+    import torch
+    from hypermapper_b200 import forest, _lib
+    from test_packed_gpu import _make, _raw
+    from test_rf_gpu import _synthetic_forest
+    rng = np.random.default_rng(11)
+    k, feas = 20, None
+    if case in ("c3_packed", "k1024"):
+        space, ds = _make("c3")
+        N = 700_001
+        raw = _raw(space, N, rng)
+        X = ds.encode_packed(raw)
+        x32, _ = ds.encode(raw)
+        fs = [_synthetic_forest(rng, 24, ds.n_encoded, 5, 9) for _ in range(2)]       # shallow: huge tie classes
+        dfs = [forest.DeviceForest(forest.tables_from_arrays(**f)) for f in fs]
+        forest.attach_packing(dfs, ds)
+        k = 1024 if case == "k1024" else 20
+        plain = lambda acq, fe: forest.rf_eval_packed(dfs, X, acq=acq, feas=fe)["score"]
+    else:
+        D = 5
+        N = 1000 if case == "short_pool" else 500_003
+        Xh = rng.random((N, D))
+        if case == "f32_ties":
+            Xh = np.round(Xh * 3) / 3                                                  # 4^5 distinct candidates
+        X = torch.from_numpy(np.ascontiguousarray(Xh.astype(np.float32).T)).cuda()
+        fs = [_synthetic_forest(rng, 12, D, 3, 8) for _ in range(2)]
+        dfs = [forest.DeviceForest(forest.tables_from_arrays(**f)) for f in fs]
+        if case == "nan_scores":
+            fe = np.ones(N)
+            fe[[5, 70_000, 70_001, 400_000, N - 1]] = np.nan                           # NaN scores inside and beyond the prefix
+            feas = torch.from_numpy(fe).cuda()
+        if case == "overflow":
+            feas = torch.linspace(1.0, 50.0, N, dtype=torch.float64).cuda()             # -EI * feas: ever better scores
+        plain = lambda acq, fe: forest.rf_eval(dfs, X, acq=acq, feas=fe)["score"]
+    for kind, scal in (("EI", "tchebyshev"), ("TS", "linear"), ("UCB", "modified_tchebyshev")):
+        acq = _lib.make_acq_params(kind, scal, [0.3, 0.7], [0.1, 0.2], 0.5)
+        want_v, want_i = forest.topk(plain(acq, feas), k)
+        got_v, got_i = forest.score_topk(dfs, X, acq, k, feas=feas)
+        torch.cuda.synchronize()
+        assert torch.equal(got_i, want_i), (case, kind)
+        assert torch.equal(got_v.view(torch.int64), want_v.view(torch.int64)), (case, kind)

@@ -72,6 +72,15 @@ def test_device_encode_api_forms_and_errors():
     with pytest.raises(ValueError):
         models.encode_to_device(bad, space, "float32")
     assert models.encode_to_device(cand[:0], space, "float32").shape == (want.shape[1], 0)
+    # an integer parameter with 2^31 or more values: the device generator draws value indices with 32-bit arithmetic, so
+    # the space is refused when its handle is built instead of sampling garbage
+    from hypermapper_b200 import _lib
+    from hypermapper_b200.space_device import DeviceSpace
+    from bench_support.space_lite import SpaceLite
+    huge = SpaceLite({"optimization_objectives": ["v"], "input_parameters": {
+        "i": {"parameter_type": "integer", "values": [0, 2 ** 31]}, "x": {"parameter_type": "real", "values": [0, 1]}}})
+    with pytest.raises(_lib.HmError):
+        DeviceSpace(huge)
 
 
 def test_device_encode_zscore_matches_host_encoder():

@@ -31,6 +31,7 @@ def main():
     import test_packed_gpu as pk
     import test_space_gpu as sp
     import test_api_gpu as api
+    import test_selection_gpu as sel
     cases = [
         (rf.test_forest_kernel_vs_oracle_synthetic, (3, 2, 1, 3, 5000)),
         (rf.test_forest_kernel_vs_oracle_synthetic, (64, 23, 4, 11, 20000)),
@@ -52,6 +53,8 @@ def main():
         (pk.test_malformed_codes_stay_inside_the_forest, ("pow2", 50_000, 12)),
         (pk.test_malformed_codes_stay_inside_the_forest, ("wide", 50_000, 12)),
         (pk.test_packed_host_entry_and_errors, ()),
+        (sel.test_fused_score_topk_equals_eval_then_topk, ("c3_packed",)),
+        (sel.test_fused_score_topk_equals_eval_then_topk, ("overflow",)),
         (gp.test_gp_mean_var_vs_oracle, (256, 6, 1e-4, 20000, "matern52")),
         (gp.test_gp_mean_var_vs_oracle, (512, 32, 1e-4, 4000, "matern52")),
         (gp.test_gp_mean_var_vs_oracle, (700, 10, 1e-3, 2000, "matern52")),
