@@ -72,7 +72,8 @@
 #define HM_WALK_LEVELS 2
 #endif
 #ifndef HM_LOOP_LEVELS
-#define HM_LOOP_LEVELS 2             // the same for the self-looping-leaf walk (packed kind 3)
+#define HM_LOOP_LEVELS 1             // the same for the self-looping-leaf walk (packed kind 3): 1 (C3 51.7 -> 51.1 ms: an
+                                     // arrived chain re-loads its leaf, so a level too many costs L1-pipe wavefronts)
 #endif
 #define HM_PACKED_CTAS (1024 / HM_PACKED_BLOCK)          // CTAs per SM of the packed kernel
 #define HM_PACKED_NODEBUF (((HM_SMEM_TOTAL - 1024 * HM_PACKED_CTAS) / HM_PACKED_CTAS - HM_SMEM_HEADER) / 2 / 16 * 16)
@@ -235,7 +236,7 @@ static int hm_build_blob(const HmHostTrees& trees, int layout, int nodebuf, int 
         size_t nodes = 0;
         while (t1 < n_trees) {
             size_t nn = nodes + trees[t1].size();
-            size_t hdr = (((size_t)(t1 - t + 1) * 4) + 15) & ~(size_t)15;
+            size_t hdr = (((size_t)(t1 - t + 1) * 8) + 15) & ~(size_t)15;
             size_t bytes = (hdr + nn * 8 + 15) & ~(size_t)15;
             if (t1 > t && (!staged || bytes > (size_t)nodebuf)) break;
             nodes = nn;
@@ -243,7 +244,7 @@ static int hm_build_blob(const HmHostTrees& trees, int layout, int nodebuf, int 
             if (!staged) break;
         }
         const int ng = t1 - t;
-        const size_t hdr = (((size_t)ng * 4) + 15) & ~(size_t)15;
+        const size_t hdr = (((size_t)ng * 8) + 15) & ~(size_t)15;
         const size_t bytes = (hdr + nodes * 8 + 15) & ~(size_t)15;
         HM_REQUIRE(nodes <= HM_LEFT_MASK, "group too large");
         HM_REQUIRE(layout != HM_LAYOUT_F32_SMEM || nodes < (1u << 14), "shared-memory group too large for the packed-word node layout");
@@ -255,12 +256,13 @@ static int hm_build_blob(const HmHostTrees& trees, int layout, int nodebuf, int 
         g.nodes_off = (unsigned)hdr;
         blob.resize(blob.size() + bytes, 0);
         unsigned char* gp = blob.data() + g.blob_off;
+        // header: a copy of every tree's root node, so a round starts with ONE uniform load per chain (no root index ->
+        // node dependency); the key-tree walkers of the pre-pass keep the group-relative root index (tree_root)
         uint32_t* roots = (uint32_t*)gp;
         uint32_t* nd32 = (uint32_t*)(gp + hdr);
         uint32_t base = 0;
         for (int tt = t; tt < t1; ++tt) {
             const std::vector<HmHostNode>& T = trees[tt];
-            roots[tt - t] = base;
             tree_root[tt] = base;
             tree_nodes_off[tt] = (long long)(g.blob_off + hdr);
             for (size_t h = 0; h < T.size(); ++h) {
@@ -280,6 +282,8 @@ static int hm_build_blob(const HmHostTrees& trees, int layout, int nodebuf, int 
                     slot[1] = (((base + T[h].left) * 8u) << 6) | (uint32_t)T[h].feat;
                 }
             }
+            roots[2 * (tt - t)] = nd32[2 * (size_t)base];
+            roots[2 * (tt - t) + 1] = nd32[2 * (size_t)base + 1];
             base += (uint32_t)T.size();
         }
         groups.push_back(g);
@@ -625,6 +629,17 @@ extern "C" int hm_forest_packed_groups(const hm_forest_t* f) { return (f && f->p
 #ifndef HM_MAX_CHAINS
 #define HM_MAX_CHAINS 3
 #endif
+// Leaf records are 32 bytes (q, s, u, value).  When `value` is not needed they are fetched as 128 + 64 bits, or -- kernel
+// instantiation NVM = 2 -- with ONE 256-bit load whose last column ptxas masks off (LDG.E.ENL2.256 with a 0x3f register
+// mask).  Measured: the single load wins where the kernel is issue-bound (resident forests; C1 2.97 -> 2.79 ms) and loses
+// where the L1 data pipe is the limit (streamed forests: C3 +0.9 %, C5-RF +1.9 %); a run-time switch between the two forms
+// inside one kernel costs the streamed forests 1-4 % (both loads are emitted predicated), hence the template parameter.
+#ifndef HM_LEAF256
+#define HM_LEAF256 0
+#endif
+#ifndef HM_LEAF_LD
+#define HM_LEAF_LD "ld.global.nc"      // experiments: "ld.global.cg" (L2 only), "ld.global.nc.L1::evict_last" ...
+#endif
 struct HmAcc {
     double q, s, u, v;
     double pq[HM_MAX_CHAINS], ps[HM_MAX_CHAINS], pu[HM_MAX_CHAINS], pv[HM_MAX_CHAINS];
@@ -632,14 +647,20 @@ struct HmAcc {
 // All HM_MAX_CHAINS pending slots are added on every flush, in slot (= tree) order; a slot that holds no record holds
 // +0.0, and x + 0.0 == x bit for bit (only -0.0 becomes +0.0, which compares equal), so the sums are those of the
 // reference's tree-order loop without a data-dependent slot count in the instruction stream.
-template <bool NEED_V>
+#ifndef HM_KEEP_PV
+#define HM_KEEP_PV 1
+#endif
+template <int NVM>
 __device__ __forceinline__ void hm_acc_flush(HmAcc& acc) {
 #pragma unroll
     for (int c = 0; c < HM_MAX_CHAINS; ++c) {
         acc.q = hm_add(acc.q, acc.pq[c]);
         acc.s = hm_add(acc.s, acc.ps[c]);
         acc.u = hm_add(acc.u, acc.pu[c]);
-        if (NEED_V) acc.v = hm_add(acc.v, acc.pv[c]);
+        if (NVM == 1) acc.v = hm_add(acc.v, acc.pv[c]);
+        // NVM == 2: the record arrived as ONE 256-bit load; its unused fourth column is kept "live" until here (no
+        // instruction is emitted) -- measured on C1: 2.79 ms with this line, 3.03 ms without it
+        if (NVM == 2 && HM_KEEP_PV) asm volatile("" ::"d"(acc.pv[c]));
     }
 }
 __device__ __forceinline__ void hm_acc_clear_pending(HmAcc& acc) {
@@ -654,13 +675,14 @@ __device__ __forceinline__ void hm_acc_clear_pending(HmAcc& acc) {
 // ...); the chains of different trees are independent, so their loads overlap; a chain that has reached its leaf
 // idles (predicated off) until the slowest of the NCH is done.  The leaf records are then added in tree order, so the
 // fp64 sums are unchanged.
-template <bool APPLY, bool NEED_V, bool SMEM, int NCH, int PACKED>
-__device__ __forceinline__ void hm_walk_round(const uint32_t* __restrict__ roots, const uint2* __restrict__ nodes,
+template <bool APPLY, int NVM, bool SMEM, int NCH, int PACKED>
+__device__ __forceinline__ void hm_walk_round(const unsigned long long* __restrict__ roots, const uint2* __restrict__ nodes,
                                               int t0, const float* __restrict__ xs_t, int BD,
                                               unsigned long long code, HmRtConst k,
                                               const double* __restrict__ leaf_tab, const int* __restrict__ leaf_node,
                                               HmAcc& acc, int* __restrict__ leaf_out, long long N, long long i,
                                               bool valid, int first_tree) {
+    constexpr bool NEED_V = NVM == 1;      // NVM: 0 = records as 128 + 64 bits, 1 = all four columns, 2 = one masked 256-bit load
     uint2 nd[NCH];
     if (SMEM && PACKED) {
         // packed candidates: the split is a shift and an unsigned compare on the 64-bit code held in a register pair
@@ -677,7 +699,7 @@ __device__ __forceinline__ void hm_walk_round(const uint32_t* __restrict__ roots
         uint32_t yy[NCH];
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
-            nq[c] = reinterpret_cast<const unsigned long long*>(nodes)[roots[t0 + c]];
+            nq[c] = roots[t0 + c];
             asm volatile("{\n\t.reg .b32 lo;\n\tmov.b64 {lo, %0}, %1;\n\t}" : "=r"(yy[c]) : "l"(nq[c]));
         }
         if (PACKED == 3) {
@@ -770,7 +792,7 @@ __device__ __forceinline__ void hm_walk_round(const uint32_t* __restrict__ roots
         // packed candidates, trees too large for a node buffer: walked in L2
         const unsigned char* nb = reinterpret_cast<const unsigned char*>(nodes);
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) nd[c] = nodes[roots[t0 + c]];
+        for (int c = 0; c < NCH; ++c) nd[c] = reinterpret_cast<const uint2*>(roots)[t0 + c];
         bool any = false;
 #pragma unroll
         for (int c = 0; c < NCH; ++c) any = any || ((nd[c].y & k.leaf_and) != k.leaf_eq);
@@ -792,7 +814,7 @@ __device__ __forceinline__ void hm_walk_round(const uint32_t* __restrict__ roots
         const uint32_t xs_a = hm_smem_u32(xs_t), nodes_a = hm_smem_u32(nodes);
         unsigned long long nq[NCH];
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) nq[c] = reinterpret_cast<const unsigned long long*>(nodes)[roots[t0 + c]];
+        for (int c = 0; c < NCH; ++c) nq[c] = roots[t0 + c];
         bool any = false;
 #pragma unroll
         for (int c = 0; c < NCH; ++c) any = any || ((uint32_t)(nq[c] >> 32) & HM_PK_LEFT_MASK);
@@ -833,7 +855,7 @@ __device__ __forceinline__ void hm_walk_round(const uint32_t* __restrict__ roots
         for (int c = 0; c < NCH; ++c) nd[c] = make_uint2((uint32_t)nq[c], (uint32_t)(nq[c] >> 32));
     } else {
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) nd[c] = nodes[roots[t0 + c]];
+        for (int c = 0; c < NCH; ++c) nd[c] = reinterpret_cast<const uint2*>(roots)[t0 + c];
         bool any = false;
 #pragma unroll
         for (int c = 0; c < NCH; ++c) any = any || (nd[c].y & HM_LEFT_MASK);
@@ -856,18 +878,18 @@ __device__ __forceinline__ void hm_walk_round(const uint32_t* __restrict__ roots
 #endif
     // add the previous round's leaf records (they had this whole walk to arrive), then put this round's in flight:
     // one 256-bit load per 32-byte record (LDG.E.256), or 128 + 64 bits when the `value` column is not needed
-    hm_acc_flush<NEED_V>(acc);
+    hm_acc_flush<NVM>(acc);
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
-        const double* rec = reinterpret_cast<const double*>(reinterpret_cast<const unsigned char*>(leaf_tab) +
-                                                            (unsigned long long)nd[c].x * 32ull);
-        if (NEED_V) {
-            asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+        const double* rec;
+        asm("mad.wide.u32 %0, %1, 32, %2;" : "=l"(rec) : "r"(nd[c].x), "l"(leaf_tab));
+        if (NEED_V || HM_LEAF256 || NVM == 2) {
+            asm volatile(HM_LEAF_LD ".v4.f64 {%0,%1,%2,%3}, [%4];"
                          : "=d"(acc.pq[c]), "=d"(acc.ps[c]), "=d"(acc.pu[c]), "=d"(acc.pv[c])
                          : "l"(rec));
         } else {
-            asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(acc.pq[c]), "=d"(acc.ps[c]) : "l"(rec));
-            asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(acc.pu[c]) : "l"(rec + 2));
+            asm volatile(HM_LEAF_LD ".v2.f64 {%0,%1}, [%2];" : "=d"(acc.pq[c]), "=d"(acc.ps[c]) : "l"(rec));
+            asm volatile(HM_LEAF_LD ".f64 %0, [%1];" : "=d"(acc.pu[c]) : "l"(rec + 2));
         }
         if (APPLY) {
             if (valid && leaf_out)
@@ -881,15 +903,15 @@ __device__ __forceinline__ void hm_walk_round(const uint32_t* __restrict__ roots
 
 // Walk `ntrees` trees whose roots/nodes are at the given pointers (shared or global), in tree order: rounds of 3,
 // then what is left as a round of 2 and/or 1 (4 = 2 + 2).
-template <bool APPLY, bool NEED_V, bool SMEM, int PACKED>
-__device__ __forceinline__ void hm_walk_group(const uint32_t* __restrict__ roots, const uint2* __restrict__ nodes,
+template <bool APPLY, int NVM, bool SMEM, int PACKED>
+__device__ __forceinline__ void hm_walk_group(const unsigned long long* __restrict__ roots, const uint2* __restrict__ nodes,
                                               int ntrees, const float* __restrict__ xs_t, int BD, unsigned long long code,
                                               HmRtConst k,
                                               const double* __restrict__ leaf_tab, const int* __restrict__ leaf_node,
                                               HmAcc& acc, int* __restrict__ leaf_out, long long N, long long i,
                                               bool valid, int first_tree) {
     int t = 0;
-#define HM_ROUND(K) hm_walk_round<APPLY, NEED_V, SMEM, K, PACKED>(roots, nodes, t, xs_t, BD, code, k, leaf_tab, leaf_node, acc, leaf_out, N, i, valid, first_tree)
+#define HM_ROUND(K) hm_walk_round<APPLY, NVM, SMEM, K, PACKED>(roots, nodes, t, xs_t, BD, code, k, leaf_tab, leaf_node, acc, leaf_out, N, i, valid, first_tree)
 #if HM_FOREST_MAXCH >= 5
     while (ntrees - t >= 5) { HM_ROUND(5); t += 5; }
 #endif
@@ -902,7 +924,7 @@ __device__ __forceinline__ void hm_walk_group(const uint32_t* __restrict__ roots
 #undef HM_ROUND
 }
 
-template <bool APPLY, bool NEED_V, int BDT, int PACKED>
+template <bool APPLY, int NVM, int BDT, int PACKED>
 __global__ void __launch_bounds__(BDT, (PACKED && BDT < 1024) ? 1024 / BDT : 1) hm_forest_kernel(const __grid_constant__ HmEvalArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
@@ -951,7 +973,6 @@ __global__ void __launch_bounds__(BDT, (PACKED && BDT < 1024) ? 1024 / BDT : 1) 
 
     long long step = 0;
     float* xs_t = xs + tid;
-    const double filter_tau = a.filter_tau ? __ldg(a.filter_tau) : 0.0;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long long slot = tile * BD + tid;
         const bool valid = slot < a.N;
@@ -998,7 +1019,7 @@ __global__ void __launch_bounds__(BDT, (PACKED && BDT < 1024) ? 1024 / BDT : 1) 
                     const unsigned ntr = __ldg(&F.groups[g].n_trees);
                     const unsigned noff = __ldg(&F.groups[g].nodes_off);
                     const unsigned ft = __ldg(&F.groups[g].first_tree);
-                    hm_walk_group<APPLY, NEED_V, true, PACKED>(reinterpret_cast<const uint32_t*>(gb),
+                    hm_walk_group<APPLY, NVM, true, PACKED>(reinterpret_cast<const unsigned long long*>(gb),
                                          reinterpret_cast<const uint2*>(gb + noff), (int)ntr, xs_t, BD, code, a.k, F.leaf_tab,
                                          F.leaf_node, acc, lo, a.N, i, valid, (int)ft);
                     if (!resident) {
@@ -1012,12 +1033,12 @@ __global__ void __launch_bounds__(BDT, (PACKED && BDT < 1024) ? 1024 / BDT : 1) 
                 for (int g = 0; g < F.n_groups; ++g) {
                     const HmGroupDesc gd = F.groups[g];
                     const unsigned char* gb = F.blob + gd.blob_off;
-                    hm_walk_group<APPLY, NEED_V, false, PACKED>(reinterpret_cast<const uint32_t*>(gb),
+                    hm_walk_group<APPLY, NVM, false, PACKED>(reinterpret_cast<const unsigned long long*>(gb),
                                          reinterpret_cast<const uint2*>(gb + gd.nodes_off), (int)gd.n_trees, xs_t, BD,
                                          code, a.k, F.leaf_tab, F.leaf_node, acc, lo, a.N, i, valid, (int)gd.first_tree);
                 }
             }
-            hm_acc_flush<NEED_V>(acc);
+            hm_acc_flush<NVM>(acc);
             // models.py:266-273
             const double mean = acc.q;
             double vom = fabs(hm_sub(acc.s, hm_mul(mean, mean)));
@@ -1043,6 +1064,7 @@ __global__ void __launch_bounds__(BDT, (PACKED && BDT < 1024) ? 1024 / BDT : 1) 
             const double feas = a.feas ? __ldg(a.feas + i) : 1.0;
             const double sc = hm_acq_value(a.acq, mean_l, var_l, feas);
             if (a.filter_tau) {
+                const double filter_tau = __ldg(a.filter_tau);
                 if (sc < filter_tau || sc != sc || (sc == filter_tau && i < a.filter_n0)) {
                     const unsigned pos = atomicAdd(a.list_count, 1u);
                     if (pos < a.list_cap) {
@@ -1283,7 +1305,7 @@ static int hm_forest_build_perm(const hm_forest_t* const* forests, int M, const 
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel instantiation, device) instead of on every call
 // (the hill climb issues thousands of small launches)
-template <bool AP, bool NV, int B, int PK>
+template <bool AP, int NV, int B, int PK>
 static cudaError_t hm_forest_kernel_attr() {
     static unsigned done_mask = 0;
     int dev = 0;
@@ -1390,7 +1412,11 @@ static int hm_rf_eval_impl(const hm_forest_t* const* forests, int M, const float
     const long long n_tiles = (N + block - 1) / block;
     const int grid = (int)std::min<long long>(n_tiles, (long long)hm_num_sms() * (packed ? HM_PACKED_CTAS : 1));
     // the plain-predict column of the leaf records is only read for pred_out and Thompson sampling
-    const bool need_v = pred_out != nullptr || (acq && a.acq.kind == HM_ACQ_TS);
+#ifndef HM_FORCE_V
+#define HM_FORCE_V 0
+#endif
+    const bool need_v = HM_FORCE_V || pred_out != nullptr || (acq && a.acq.kind == HM_ACQ_TS);
+    const bool leaf256 = steps <= 2;   // forests resident in shared memory: issue-bound, one load per leaf record
     cudaError_t attr_err = cudaSuccess;
 #define HM_LAUNCH_B(AP, NV, B, PK)                                                                                     \
     do {                                                                                                               \
@@ -1408,9 +1434,9 @@ static int hm_rf_eval_impl(const hm_forest_t* const* forests, int M, const float
         else HM_LAUNCH_B(AP, NV, 128, 0);                                                                              \
     } while (0)
     if (any_leaf) {
-        if (need_v) HM_LAUNCH(true, true); else HM_LAUNCH(true, false);
+        if (need_v) HM_LAUNCH(true, 1); else HM_LAUNCH(true, 0);
     } else {
-        if (need_v) HM_LAUNCH(false, true); else HM_LAUNCH(false, false);
+        if (need_v) HM_LAUNCH(false, 1); else if (leaf256) HM_LAUNCH(false, 2); else HM_LAUNCH(false, 0);
     }
 #undef HM_LAUNCH
 #undef HM_LAUNCH_B

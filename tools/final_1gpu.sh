@@ -22,9 +22,9 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${T}_launches_c4.csv python bench.py --workload c4 --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > /dev/null 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${T}_launches_c1.csv python bench.py --workload c1 --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > /dev/null 2>&1
 # full captures of the dominant kernels
-ncu --set full --clock-control none --import-source on -k regex:hm_forest_kernel -c 1 -o $O/${T}_forest_c3 -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:hm_forest_kernel --launch-skip 1 -c 1 -o $O/${T}_forest_c3 -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > /dev/null 2>&1
 ncu -i $O/${T}_forest_c3.ncu-rep --page raw --csv > $O/${T}_forest_c3_ncu_raw.csv 2>/dev/null
-ncu --set full --clock-control none --import-source on -k regex:hm_forest_kernel -c 1 -o $O/${T}_forest_c1 -f python bench.py --workload c1 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:hm_forest_kernel --launch-skip 1 -c 1 -o $O/${T}_forest_c1 -f python bench.py --workload c1 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > /dev/null 2>&1
 ncu -i $O/${T}_forest_c1.ncu-rep --page raw --csv > $O/${T}_forest_c1_ncu_raw.csv 2>/dev/null
 ncu --set full --clock-control none --import-source on -k regex:hm_px_stream -c 1 -o $O/${T}_pareto_stream -f python bench.py --workload c4 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > /dev/null 2>&1
 ncu -i $O/${T}_pareto_stream.ncu-rep --page raw --csv > $O/${T}_pareto_stream_ncu_raw.csv 2>/dev/null
