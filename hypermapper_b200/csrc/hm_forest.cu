@@ -84,6 +84,8 @@ struct HmGroupDesc {
     unsigned int first_tree;
     unsigned int n_trees;
     unsigned int nodes_off;   // byte offset of the node array inside the group
+    unsigned int leaf_off;    // byte offset of the group's own copy of its trees' leaf records (0: the group carries none)
+    unsigned int leaf_base;   // forest-wide ordinal of the first of those records
 };
 
 struct HmForestDev {
@@ -130,6 +132,8 @@ struct hm_forest {
     HmKeyTree key[2];
     HmHostTrees* host_trees;
     std::vector<long long>* tree_leaf_base;
+    std::vector<double>* host_leaf_tab;   // kept for small forests only (the packed groups may carry their leaf records too)
+    int leaf_smem, leaf_smem_p;           // every group of the fp32 / packed layout carries its leaf records (resident forests)
     int sort_mode;                 // coherence pre-pass: -1 auto, 0 off, 1 on
     // packed layout (hm_forest_attach_packing)
     int packed;                    // once the packed node arrays exist: 1 = FAST layout (every shift <= 31), 2 = wide,
@@ -226,7 +230,22 @@ enum { HM_LAYOUT_F32_SMEM = 0, HM_LAYOUT_F32_L2 = 1, HM_LAYOUT_PACKED = 2, HM_LA
 static int hm_build_blob(const HmHostTrees& trees, int layout, int nodebuf, int block, bool staged,
                          std::vector<unsigned char>& blob, std::vector<HmGroupDesc>& groups,
                          std::vector<unsigned>& tree_root, std::vector<long long>& tree_nodes_off,
-                         unsigned loop_shift = 0, unsigned loop_bound = 0) {
+                         unsigned loop_shift = 0, unsigned loop_bound = 0, const double* leaf_rows = nullptr,
+                         const std::vector<long long>* leaf_base = nullptr) {
+    // leaf_rows (4 doubles per forest-wide leaf ordinal) + leaf_base (first ordinal of every tree): every group also
+    // carries the records of its trees' leaves, 32-byte aligned behind the node array -- for forests small enough to stay
+    // resident in shared memory the kernel then never gathers a leaf record from global memory (mode NVM = 2)
+    const bool with_leaves = leaf_rows != nullptr && leaf_base != nullptr && staged;
+    auto group_bytes = [&](int t0, int t1x, size_t nn, size_t* leaf_off_out) {
+        const size_t hdr = (((size_t)(t1x - t0) * 8) + 15) & ~(size_t)15;
+        size_t bytes = (hdr + nn * 8 + 15) & ~(size_t)15;
+        if (with_leaves) {
+            bytes = (bytes + 31) & ~(size_t)31;
+            if (leaf_off_out) *leaf_off_out = bytes;
+            bytes += (size_t)((*leaf_base)[t1x] - (*leaf_base)[t0]) * 32;
+        }
+        return bytes;
+    };
     const int n_trees = (int)trees.size();
     tree_root.assign(n_trees, 0);
     tree_nodes_off.assign(n_trees, 0);
@@ -236,8 +255,7 @@ static int hm_build_blob(const HmHostTrees& trees, int layout, int nodebuf, int 
         size_t nodes = 0;
         while (t1 < n_trees) {
             size_t nn = nodes + trees[t1].size();
-            size_t hdr = (((size_t)(t1 - t + 1) * 8) + 15) & ~(size_t)15;
-            size_t bytes = (hdr + nn * 8 + 15) & ~(size_t)15;
+            const size_t bytes = group_bytes(t, t1 + 1, nn, nullptr);
             if (t1 > t && (!staged || bytes > (size_t)nodebuf)) break;
             nodes = nn;
             ++t1;
@@ -245,7 +263,8 @@ static int hm_build_blob(const HmHostTrees& trees, int layout, int nodebuf, int 
         }
         const int ng = t1 - t;
         const size_t hdr = (((size_t)ng * 8) + 15) & ~(size_t)15;
-        const size_t bytes = (hdr + nodes * 8 + 15) & ~(size_t)15;
+        size_t leaf_off = 0;
+        const size_t bytes = group_bytes(t, t1, nodes, &leaf_off);
         HM_REQUIRE(nodes <= HM_LEFT_MASK, "group too large");
         HM_REQUIRE(layout != HM_LAYOUT_F32_SMEM || nodes < (1u << 14), "shared-memory group too large for the packed-word node layout");
         HmGroupDesc g;
@@ -254,8 +273,12 @@ static int hm_build_blob(const HmHostTrees& trees, int layout, int nodebuf, int 
         g.first_tree = (unsigned)t;
         g.n_trees = (unsigned)ng;
         g.nodes_off = (unsigned)hdr;
+        g.leaf_off = with_leaves ? (unsigned)leaf_off : 0u;
+        g.leaf_base = with_leaves ? (unsigned)(*leaf_base)[t] : 0u;
         blob.resize(blob.size() + bytes, 0);
         unsigned char* gp = blob.data() + g.blob_off;
+        if (with_leaves)
+            memcpy(gp + leaf_off, leaf_rows + 4 * (size_t)(*leaf_base)[t], (size_t)((*leaf_base)[t1] - (*leaf_base)[t]) * 32);
         // header: a copy of every tree's root node, so a round starts with ONE uniform load per chain (no root index ->
         // node dependency); the key-tree walkers of the pre-pass keep the group-relative root index (tree_root)
         uint32_t* roots = (uint32_t*)gp;
@@ -399,12 +422,31 @@ extern "C" int hm_forest_create(int n_trees, int n_features, const int64_t* off,
                                groups, tree_root, tree_nodes_off);
         if (rc) return rc;
     }
+    // a forest that stays resident in shared memory (<= 2 groups) takes its leaf records along if they fit too
+    int leaf_smem = 0;
+    if (staged && groups.size() <= 2 && !getenv("HM_B200_NO_LEAF_SMEM")) {
+        std::vector<HmGroupDesc> g2;
+        std::vector<unsigned char> b2;
+        std::vector<unsigned> r2;
+        std::vector<long long> o2;
+        int rc = hm_build_blob(*trees, HM_LAYOUT_F32_SMEM, nodebuf, block, true, b2, g2, r2, o2, 0, 0, leaf_tab.data(), leaf_base);
+        if (rc) return rc;
+        if (g2.size() <= 2) {
+            groups.swap(g2);
+            blob.swap(b2);
+            tree_root.swap(r2);
+            tree_nodes_off.swap(o2);
+            leaf_smem = 1;
+        }
+    }
 
     hm_forest* F = new (std::nothrow) hm_forest();
     if (!F) return HM_E_NOMEM;
     memset(F, 0, sizeof(*F));
     F->host_trees = trees;
     F->tree_leaf_base = leaf_base;
+    F->leaf_smem = leaf_smem;
+    if (leaf_tab.size() * sizeof(double) <= (size_t)HM_SMEM_TOTAL) F->host_leaf_tab = new (std::nothrow) std::vector<double>(leaf_tab);
     guard.a = nullptr;
     guard.b = nullptr;
     F->sort_mode = hm_forest_default_sort_mode();
@@ -567,6 +609,23 @@ extern "C" int hm_forest_attach_packing(hm_forest_t* F, const hm_space_t* S) {
     int rc = hm_build_blob(dst, loop ? HM_LAYOUT_PACKED_LOOP : HM_LAYOUT_PACKED, nodebuf_p, 0, staged != 0, blob, groups,
                            tree_root, tree_nodes_off, loop_shift, loop_bound);
     if (rc) return rc;
+    F->leaf_smem_p = 0;
+    if (staged && groups.size() <= 2 && F->host_leaf_tab && !getenv("HM_B200_NO_LEAF_SMEM")) {
+        std::vector<HmGroupDesc> g2;
+        std::vector<unsigned char> b2;
+        std::vector<unsigned> r2;
+        std::vector<long long> o2;
+        rc = hm_build_blob(dst, loop ? HM_LAYOUT_PACKED_LOOP : HM_LAYOUT_PACKED, nodebuf_p, 0, true, b2, g2, r2, o2, loop_shift,
+                           loop_bound, F->host_leaf_tab->data(), F->tree_leaf_base);
+        if (rc) return rc;
+        if (g2.size() <= 2) {
+            groups.swap(g2);
+            blob.swap(b2);
+            tree_root.swap(r2);
+            tree_nodes_off.swap(o2);
+            F->leaf_smem_p = 1;
+        }
+    }
     HM_CUDA_TRY(cudaMalloc(&F->d_blob_p, blob.size()));
     HM_CUDA_TRY(cudaMalloc(&F->d_groups_p, groups.size() * sizeof(HmGroupDesc)));
     HM_CUDA_TRY(cudaMemcpy(F->d_blob_p, blob.data(), blob.size(), cudaMemcpyHostToDevice));
@@ -613,6 +672,7 @@ extern "C" void hm_forest_destroy(hm_forest_t* F) {
     cudaFree(F->d_groups_p);
     delete F->host_trees;
     delete F->tree_leaf_base;
+    delete F->host_leaf_tab;
     delete F;
 }
 extern "C" int hm_forest_n_trees(const hm_forest_t* f) { return f ? f->n_trees : 0; }
@@ -629,11 +689,12 @@ extern "C" int hm_forest_packed_groups(const hm_forest_t* f) { return (f && f->p
 #ifndef HM_MAX_CHAINS
 #define HM_MAX_CHAINS 3
 #endif
-// Leaf records are 32 bytes (q, s, u, value).  When `value` is not needed they are fetched as 128 + 64 bits, or -- kernel
-// instantiation NVM = 2 -- with ONE 256-bit load whose last column ptxas masks off (LDG.E.ENL2.256 with a 0x3f register
-// mask).  Measured: the single load wins where the kernel is issue-bound (resident forests; C1 2.97 -> 2.79 ms) and loses
-// where the L1 data pipe is the limit (streamed forests: C3 +0.9 %, C5-RF +1.9 %); a run-time switch between the two forms
-// inside one kernel costs the streamed forests 1-4 % (both loads are emitted predicated), hence the template parameter.
+// Leaf records are 32 bytes (q, s, u, value), gathered from global memory through L1: 128 + 64 bits when `value` is not
+// needed.  HM_LEAF256 = 1 fetches them with ONE 256-bit load whose last column ptxas masks off (LDG.E.ENL2.256, register mask
+// 0x3f) -- measured: wins where the kernel is issue-bound (small resident forests; C1 3.04 -> 2.77 ms), loses where the L1
+// data pipe is the limit (streamed forests: C3 +0.9 %, C5-RF +1.9 %); a run-time switch between the two forms inside one
+// kernel costs the streamed forests 1-4 % (both loads are emitted predicated).  Resident forests therefore got their own
+// kernel mode (NVM = 2) that does not gather at all: their groups carry the leaf records into shared memory.
 #ifndef HM_LEAF256
 #define HM_LEAF256 0
 #endif
@@ -647,9 +708,6 @@ struct HmAcc {
 // All HM_MAX_CHAINS pending slots are added on every flush, in slot (= tree) order; a slot that holds no record holds
 // +0.0, and x + 0.0 == x bit for bit (only -0.0 becomes +0.0, which compares equal), so the sums are those of the
 // reference's tree-order loop without a data-dependent slot count in the instruction stream.
-#ifndef HM_KEEP_PV
-#define HM_KEEP_PV 1
-#endif
 template <int NVM>
 __device__ __forceinline__ void hm_acc_flush(HmAcc& acc) {
 #pragma unroll
@@ -658,9 +716,6 @@ __device__ __forceinline__ void hm_acc_flush(HmAcc& acc) {
         acc.s = hm_add(acc.s, acc.ps[c]);
         acc.u = hm_add(acc.u, acc.pu[c]);
         if (NVM == 1) acc.v = hm_add(acc.v, acc.pv[c]);
-        // NVM == 2: the record arrived as ONE 256-bit load; its unused fourth column is kept "live" until here (no
-        // instruction is emitted) -- measured on C1: 2.79 ms with this line, 3.03 ms without it
-        if (NVM == 2 && HM_KEEP_PV) asm volatile("" ::"d"(acc.pv[c]));
     }
 }
 __device__ __forceinline__ void hm_acc_clear_pending(HmAcc& acc) {
@@ -682,7 +737,8 @@ __device__ __forceinline__ void hm_walk_round(const unsigned long long* __restri
                                               const double* __restrict__ leaf_tab, const int* __restrict__ leaf_node,
                                               HmAcc& acc, int* __restrict__ leaf_out, long long N, long long i,
                                               bool valid, int first_tree) {
-    constexpr bool NEED_V = NVM == 1;      // NVM: 0 = records as 128 + 64 bits, 1 = all four columns, 2 = one masked 256-bit load
+    constexpr bool NEED_V = NVM == 1;      // NVM: 0 = leaf records as 128 + 64 bits, 1 = all four columns, 2 = the groups carry
+                                           // their leaf records: 128 + 64 bits from SHARED memory (`leaf_tab` = shared address)
     uint2 nd[NCH];
     if (SMEM && PACKED) {
         // packed candidates: the split is a shift and an unsigned compare on the 64-bit code held in a register pair
@@ -881,15 +937,22 @@ __device__ __forceinline__ void hm_walk_round(const unsigned long long* __restri
     hm_acc_flush<NVM>(acc);
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
+        if (NVM == 2) {
+            const uint32_t ra = (uint32_t)reinterpret_cast<uintptr_t>(leaf_tab) + nd[c].x * 32u;
+            HM_DEV_ASSERT(ra >= hm_smem_u32(nodes) && ra + 32u <= hm_smem_u32(nodes) + (unsigned)k.nodebuf);
+            asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(acc.pq[c]), "=d"(acc.ps[c]) : "r"(ra));
+            asm volatile("ld.shared.f64 %0, [%1+16];" : "=d"(acc.pu[c]) : "r"(ra));
+        } else {
         const double* rec;
         asm("mad.wide.u32 %0, %1, 32, %2;" : "=l"(rec) : "r"(nd[c].x), "l"(leaf_tab));
-        if (NEED_V || HM_LEAF256 || NVM == 2) {
+        if (NEED_V || HM_LEAF256) {
             asm volatile(HM_LEAF_LD ".v4.f64 {%0,%1,%2,%3}, [%4];"
                          : "=d"(acc.pq[c]), "=d"(acc.ps[c]), "=d"(acc.pu[c]), "=d"(acc.pv[c])
                          : "l"(rec));
         } else {
             asm volatile(HM_LEAF_LD ".v2.f64 {%0,%1}, [%2];" : "=d"(acc.pq[c]), "=d"(acc.ps[c]) : "l"(rec));
             asm volatile(HM_LEAF_LD ".f64 %0, [%1];" : "=d"(acc.pu[c]) : "l"(rec + 2));
+        }
         }
         if (APPLY) {
             if (valid && leaf_out)
@@ -1019,8 +1082,16 @@ __global__ void __launch_bounds__(BDT, (PACKED && BDT < 1024) ? 1024 / BDT : 1) 
                     const unsigned ntr = __ldg(&F.groups[g].n_trees);
                     const unsigned noff = __ldg(&F.groups[g].nodes_off);
                     const unsigned ft = __ldg(&F.groups[g].first_tree);
+                    const double* lt = F.leaf_tab;
+                    if (NVM == 2) {
+                        // the group's own leaf records: shared-memory address of the (virtual) record of ordinal 0
+                        // (kind 3: of ordinal -loop_bound, as word 0 of a self-looping leaf is bound + ordinal)
+                        const unsigned loff = __ldg(&F.groups[g].leaf_off), lbase = __ldg(&F.groups[g].leaf_base);
+                        HM_DEV_ASSERT(loff != 0u);
+                        lt = reinterpret_cast<const double*>((uintptr_t)(hm_smem_u32(gb) + loff - (lbase + a.k.loop_bound) * 32u));
+                    }
                     hm_walk_group<APPLY, NVM, true, PACKED>(reinterpret_cast<const unsigned long long*>(gb),
-                                         reinterpret_cast<const uint2*>(gb + noff), (int)ntr, xs_t, BD, code, a.k, F.leaf_tab,
+                                         reinterpret_cast<const uint2*>(gb + noff), (int)ntr, xs_t, BD, code, a.k, lt,
                                          F.leaf_node, acc, lo, a.N, i, valid, (int)ft);
                     if (!resident) {
                         __syncthreads();   // everyone is done reading this buffer
@@ -1416,7 +1487,10 @@ static int hm_rf_eval_impl(const hm_forest_t* const* forests, int M, const float
 #define HM_FORCE_V 0
 #endif
     const bool need_v = HM_FORCE_V || pred_out != nullptr || (acq && a.acq.kind == HM_ACQ_TS);
-    const bool leaf256 = steps <= 2;   // forests resident in shared memory: issue-bound, one load per leaf record
+    // forests resident in shared memory whose groups carry their leaf records: no leaf gather from global memory at all
+    bool leaf_smem = steps <= 2;
+    for (int m = 0; m < M; ++m)
+        leaf_smem = leaf_smem && a.f[m].staged && (packed ? forests[m]->leaf_smem_p : forests[m]->leaf_smem);
     cudaError_t attr_err = cudaSuccess;
 #define HM_LAUNCH_B(AP, NV, B, PK)                                                                                     \
     do {                                                                                                               \
@@ -1436,7 +1510,7 @@ static int hm_rf_eval_impl(const hm_forest_t* const* forests, int M, const float
     if (any_leaf) {
         if (need_v) HM_LAUNCH(true, 1); else HM_LAUNCH(true, 0);
     } else {
-        if (need_v) HM_LAUNCH(false, 1); else if (leaf256) HM_LAUNCH(false, 2); else HM_LAUNCH(false, 0);
+        if (need_v) HM_LAUNCH(false, 1); else if (leaf_smem) HM_LAUNCH(false, 2); else HM_LAUNCH(false, 0);
     }
 #undef HM_LAUNCH
 #undef HM_LAUNCH_B
