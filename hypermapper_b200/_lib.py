@@ -20,7 +20,7 @@ SCALARIZATIONS = {"linear": 0, "tchebyshev": 1, "modified_tchebyshev": 2}
 EXPORTED_SYMBOLS = [
     "hm_last_error", "hm_device_sm_count", "hm_version", "hm_fp64_peak_tflops", "hm_checked_failures",
     "hm_forest_create", "hm_forest_destroy", "hm_forest_n_trees", "hm_forest_n_features", "hm_forest_staged",
-    "hm_forest_set_coherence", "hm_forest_n_groups",
+    "hm_forest_set_coherence", "hm_forest_n_groups", "hm_forest_leaf_resident",
     "hm_forest_attach_packing", "hm_forest_packed", "hm_forest_packed_groups", "hm_rf_eval_packed",
     "hm_rf_eval", "hm_acq_score",
     "hm_rf_score_topk_workspace_bytes", "hm_rf_score_topk", "hm_rf_score_topk_packed",
@@ -104,6 +104,7 @@ def lib():
         getattr(L, f).argtypes = [vp]
     for f in ("hm_forest_packed", "hm_forest_packed_groups"):
         getattr(L, f).argtypes = [vp]
+    L.hm_forest_leaf_resident.argtypes = [vp, i32]
     L.hm_forest_set_coherence.argtypes = [vp, i32]
     L.hm_forest_attach_packing.argtypes = [vp, vp]
     L.hm_rf_eval_packed.argtypes = [ctypes.POINTER(vp), i32, vp, i64, ctypes.POINTER(vp), vp, vp, vp,

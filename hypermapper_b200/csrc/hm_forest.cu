@@ -681,6 +681,9 @@ extern "C" int hm_forest_staged(const hm_forest_t* f) { return f ? f->staged : 0
 extern "C" int hm_forest_n_groups(const hm_forest_t* f) { return f ? f->dev.n_groups : 0; }
 extern "C" int hm_forest_packed(const hm_forest_t* f) { return f ? f->packed : 0; }
 extern "C" int hm_forest_packed_groups(const hm_forest_t* f) { return (f && f->packed) ? f->devp.n_groups : 0; }
+extern "C" int hm_forest_leaf_resident(const hm_forest_t* f, int packed) {
+    return f ? (packed ? (f->packed ? f->leaf_smem_p : 0) : f->leaf_smem) : 0;
+}
 
 // ------------------------------------------------------------------------------------------------------------
 // Running sums of one objective + the leaf records of the previous round of trees, still in flight: a round's leaf

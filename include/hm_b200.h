@@ -80,6 +80,10 @@ int hm_forest_staged(const hm_forest_t* f);
 /* number of shared-memory tree groups of the device layout (<= 2 summed over the forests of a call: the forests
  * stay resident in shared memory; more: they stream through it and large pools take the coherence pre-pass) */
 int hm_forest_n_groups(const hm_forest_t* f);
+/* 1 if the groups of the fp32 layout (packed == 0) / of the packed layout (packed != 0) carry their trees' leaf records:
+ * a call whose forests all do and stay resident in shared memory (<= 2 groups in total) never gathers a leaf record from
+ * global memory (models.py:225-275's per-leaf dictionaries live next to the nodes) */
+int hm_forest_leaf_resident(const hm_forest_t* f, int packed);
 
 /* acquisition parameters, one struct for all kinds (unused fields ignored) */
 typedef struct hm_acq_params {

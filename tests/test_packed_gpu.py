@@ -119,6 +119,10 @@ def test_packed_path_is_bit_identical_to_fp32_path(name, N, T, dlo, dhi):
         sa = forest.rf_eval(dfs, x32, acq=p)["score"]
         sb = forest.rf_eval_packed(dfs, codes, acq=p)["score"]
         assert torch.equal(sa.view(torch.int64), sb.view(torch.int64)), kind
+        # ... and a launch that also returns leaves never takes the resident-forest mode that reads the leaf records from
+        # shared memory (NVM = 2), so this pins that mode's scores as well wherever the small cases above select it
+        sc = forest.rf_eval_packed(dfs, codes, want_leaves=True, acq=p)["score"]
+        assert torch.equal(sb.view(torch.int64), sc.view(torch.int64)), kind
 
 
 @pytest.mark.parametrize("name,N,T", [("c3", 200_000, 24), ("odd", 50_000, 12), ("pow2", 50_000, 12), ("wide", 50_000, 12)])

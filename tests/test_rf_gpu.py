@@ -349,3 +349,47 @@ def test_full_size_pool_properties():
         fa = oracle.ForestArrays(f["tree_off"], f["left"], f["right"], f["feature"], f["threshold"], f["leaf_mean"],
                                  f["leaf_var"], f["value"], D)
         assert np.array_equal(out["mean"][m].cpu().numpy()[sub], oracle.rf_prediction(fa, oracle.rf_apply(fa, Xs)))
+
+
+def test_resident_forests_with_leaf_records_in_shared_memory():
+    """Forests that stay resident in shared memory (<= 2 groups over the whole call) carry their leaf records in their
+    groups and are scored by a kernel mode that reads them from there (hm_forest.cu, NVM = 2).  That mode only runs
+    when neither leaves nor the plain prediction are requested, so its means / variances / scores are compared bit for
+    bit with the same call made WITH leaves (global-memory records) and with the C oracle: one single-group forest,
+    two single-group forests (the second lands in the second buffer), one two-group forest, and a three-forest call
+    that is no longer resident (falls back to the gathers)."""
+    from hypermapper_b200 import forest, _lib
+    from oracle import oracle
+    torch = _torch()
+    L = _lib.lib()
+    rng = np.random.default_rng(2024)
+    D, N = 3, 40_000
+    X = rng.random((N, D))
+    Xd = torch.from_numpy(np.ascontiguousarray(X.astype(np.float32).T)).cuda()
+    small = [_synthetic_forest(rng, 10, D, 1, 5) for _ in range(3)]
+    two_group = None
+    for T in (12, 16, 20, 24, 28, 32, 40):                      # the first size whose fp32 layout needs exactly two groups
+        cand = _synthetic_forest(rng, T, D, 9, 10)
+        df = forest.DeviceForest(forest.tables_from_arrays(**cand))
+        if int(L.hm_forest_n_groups(df.handle)) == 2 and int(L.hm_forest_leaf_resident(df.handle, 0)) == 1:
+            two_group = cand
+            break
+    assert two_group is not None, "no two-group resident forest among the sizes tried"
+    seen_groups = set()
+    for fs, resident in (([small[0]], True), ([small[0], small[1]], True), ([two_group], True), (small, False)):
+        dfs = [forest.DeviceForest(forest.tables_from_arrays(**f)) for f in fs]
+        groups = sum(int(L.hm_forest_n_groups(d.handle)) for d in dfs)
+        assert (groups <= 2) == resident and all(int(L.hm_forest_leaf_resident(d.handle, 0)) == 1 for d in dfs)
+        seen_groups.add(groups)
+        M = len(fs)
+        acq = _lib.make_acq_params("EI", "tchebyshev", [1.0 / M] * M, [0.3] * M, 0.0)
+        fast = forest.rf_eval(dfs, Xd, want_mean=True, want_var=True, acq=acq)
+        slow = forest.rf_eval(dfs, Xd, want_leaves=True, want_mean=True, want_var=True, acq=acq)
+        for k in ("mean", "var", "score"):
+            assert np.array_equal(fast[k].cpu().numpy(), slow[k].cpu().numpy(), equal_nan=True), (k, groups)
+        for m, f in enumerate(fs):
+            fa = oracle.ForestArrays(f["tree_off"], f["left"], f["right"], f["feature"], f["threshold"], f["leaf_mean"],
+                                     f["leaf_var"], f["value"], D)
+            leaf = oracle.rf_apply(fa, X.astype(np.float32).astype(np.float64))
+            assert np.array_equal(fast["mean"][m].cpu().numpy(), oracle.rf_prediction(fa, leaf))
+    assert {1, 2} <= seen_groups

@@ -5,7 +5,7 @@ GPU pool where compute-sanitizer is closed (profiles/r02_sanitizer_unavailable.t
 
     HM_B200_LIB=hypermapper_b200/csrc/libhm_b200_checked.so python tools/checked_run.py
 
-Coverage: forest kernel (resident / streamed through the TMA double buffer + coherence pre-pass / walked in L2; fp32,
+Coverage: forest kernel (resident with leaf records in shared memory / streamed through the TMA double buffer + coherence pre-pass / walked in L2; fp32,
 packed-fast, packed-wide and self-looping-leaf layouts, malformed codes), top-k (k = 20 and k = 1024, heavy ties: the roll-back path), GP (4- and 8-warp
 plans, per-warp TMA rings; the large-n path), Pareto (fast path with warp queues, exact NaN path), encode / sample,
 device hill climb.  Every case also checks its results against the oracle / goldens (they are the GPU tests' own
@@ -39,6 +39,8 @@ def main():
         (rf.test_forest_kernel_vs_oracle_synthetic, (4, 5, 13, 15, 4000)),
         (rf.test_coherence_prepass_is_invisible, (24, 32, 200_001)),
         (rf.test_forest_edge_cases_empty_single_leaf_mixed_layouts_eight_objectives, ()),
+        (rf.test_resident_forests_with_leaf_records_in_shared_memory, ()),
+        (pk.test_packed_path_is_bit_identical_to_fp32_path, ("c3", 5000, 7, 3, 9)),
         (rf.test_topk_vs_oracle_ties_nan, (100000, 20)),
         (rf.test_topk_vs_oracle_ties_nan, (3_000_000, 1024)),
         (rf.test_topk_descending_input_worst_case, ()),
