@@ -1191,20 +1191,55 @@ __global__ void __launch_bounds__(256) hm_forest_sortkey(const HmKeyArgs a, unsi
 }
 
 // exclusive scan of `n` counters in place, one CTA (n <= 2^22: a few passes over an L2-resident array)
-__global__ void __launch_bounds__(1024, 1) hm_forest_scan(unsigned* __restrict__ v, unsigned n) {
+// Exclusive scan of the bucket histogram, one launch over up to hm_num_sms() CTAs: a CTA takes a ticket (CTAs with a lower
+// ticket are therefore already running -- no co-residency assumption), sums its chunk, publishes the sum, adds up the sums
+// of the lower tickets as they appear, and scans its chunk with that carry.  `sync` = [ticket, flags[grid], sums[grid]], zeroed.
+__global__ void __launch_bounds__(1024, 1) hm_forest_scan(unsigned* __restrict__ v, unsigned n, unsigned* __restrict__ sync) {
     __shared__ unsigned warp_sums[32];
-    __shared__ unsigned carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
+    __shared__ unsigned carry, ticket;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (unsigned base = 0; base < n; base += 4096) {
+    if (threadIdx.x == 0) ticket = atomicAdd(sync, 1u);
+    __syncthreads();
+    const unsigned b = ticket, nb = gridDim.x;
+    volatile unsigned* flags = sync + 1;
+    volatile unsigned* sums = sync + 1 + nb;
+    const unsigned chunk = ((n + nb - 1) / nb + 4095u) & ~4095u;
+    const unsigned lo = min(n, b * chunk), hi = min(n, lo + chunk);
+    auto block_sum = [&](unsigned x) {            // sum over the CTA, returned to every thread
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        __syncthreads();
+        if (lane == 0) warp_sums[warp] = x;
+        __syncthreads();
+        unsigned s = warp_sums[lane];
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        return s;
+    };
+    unsigned mine = 0;
+    for (unsigned i = lo + threadIdx.x; i < hi; i += 1024) mine += v[i];
+    const unsigned total = block_sum(mine);
+    if (threadIdx.x == 0) {
+        sums[b] = total;
+        __threadfence();
+        flags[b] = 1u;
+    }
+    unsigned prev = 0;
+    if (threadIdx.x < b) {
+        while (flags[threadIdx.x] == 0u) {}
+        __threadfence();
+        prev = sums[threadIdx.x];
+    }
+    const unsigned before = block_sum(prev);
+    __syncthreads();
+    if (threadIdx.x == 0) carry = before;
+    __syncthreads();
+    for (unsigned base = lo; base < hi; base += 4096) {
         // 4 consecutive counters per thread
         const unsigned i0 = base + threadIdx.x * 4;
         unsigned c[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) c[q] = (i0 + q < n) ? v[i0 + q] : 0;
-        const unsigned mine = c[0] + c[1] + c[2] + c[3];
-        unsigned x = mine;
+        for (int q = 0; q < 4; ++q) c[q] = (i0 + q < hi) ? v[i0 + q] : 0;
+        const unsigned own = c[0] + c[1] + c[2] + c[3];
+        unsigned x = own;
         for (int o = 1; o < 32; o <<= 1) {
             const unsigned y = __shfl_up_sync(0xffffffffu, x, o);
             if (lane >= o) x += y;
@@ -1220,10 +1255,10 @@ __global__ void __launch_bounds__(1024, 1) hm_forest_scan(unsigned* __restrict__
             warp_sums[lane] = s;
         }
         __syncthreads();
-        unsigned run = carry + (warp ? warp_sums[warp - 1] : 0) + (x - mine);
+        unsigned run = carry + (warp ? warp_sums[warp - 1] : 0) + (x - own);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            if (i0 + q < n) v[i0 + q] = run;
+            if (i0 + q < hi) v[i0 + q] = run;
             run += c[q];
         }
         __syncthreads();
@@ -1346,21 +1381,24 @@ static int hm_forest_build_perm(const hm_forest_t* const* forests, int M, const 
     unsigned* buf = nullptr;
     const int D = forests[0]->n_features, Dp = packed ? 2 : (D + 3) & ~3;      // words per candidate in the sorted copy
     const size_t rows_words = (size_t)N * Dp;                       // 16-byte aligned rows at the front
-    const size_t words = rows_words + (size_t)N * 2 + bins;
+    const int scan_grid = (int)std::min<size_t>((size_t)std::min(hm_num_sms(), 512), (bins + 4095) / 4096);
+    const size_t sync_words = 1 + 2 * (size_t)scan_grid;               // ticket, flags, sums of hm_forest_scan
+    const size_t words = rows_words + (size_t)N * 2 + bins + sync_words;
     HM_CUDA_TRY(cudaMallocAsync((void**)&buf, words * sizeof(unsigned), st));
     unsigned* key = buf + rows_words;
     unsigned* perm = key + N;
     unsigned* hist = perm + N;
-    HM_CUDA_TRY(cudaMemsetAsync(hist, 0, bins * sizeof(unsigned), st));
+    unsigned* scan_sync = hist + bins;
+    HM_CUDA_TRY(cudaMemsetAsync(hist, 0, (bins + sync_words) * sizeof(unsigned), st));
     const unsigned grid = (unsigned)((N + 255) / 256);
     if (packed) {
         hm_forest_sortkey_packed<<<grid, 256, 0, st>>>(ka, codes, key, hist);
-        hm_forest_scan<<<1, 1024, 0, st>>>(hist, (unsigned)bins);
+        hm_forest_scan<<<scan_grid, 1024, 0, st>>>(hist, (unsigned)bins, scan_sync);
         hm_forest_scatter_codes<<<grid, 256, 0, st>>>(key, hist, codes, N, perm, reinterpret_cast<unsigned long long*>(buf));
         *codes_out = reinterpret_cast<unsigned long long*>(buf);
     } else {
         hm_forest_sortkey<<<grid, 256, 0, st>>>(ka, key, hist);
-        hm_forest_scan<<<1, 1024, 0, st>>>(hist, (unsigned)bins);
+        hm_forest_scan<<<scan_grid, 1024, 0, st>>>(hist, (unsigned)bins, scan_sync);
         hm_forest_scatter_rows<<<grid, 256, 0, st>>>(key, hist, Xcm, ldx, N, D, Dp, perm, reinterpret_cast<float*>(buf));
         *rows_out = reinterpret_cast<float*>(buf);
         *Dp_out = Dp;

@@ -368,8 +368,9 @@ def test_resident_forests_with_leaf_records_in_shared_memory():
     Xd = torch.from_numpy(np.ascontiguousarray(X.astype(np.float32).T)).cuda()
     small = [_synthetic_forest(rng, 10, D, 1, 5) for _ in range(3)]
     two_group = None
-    for T in (12, 16, 20, 24, 28, 32, 40):                      # the first size whose fp32 layout needs exactly two groups
-        cand = _synthetic_forest(rng, T, D, 9, 10)
+    # ~220 leaves per tree: 3.5 KB of nodes + 7 KB of leaf records against a node buffer of 107 KB (D = 3)
+    for T in (12, 14, 16, 18, 10, 20, 8, 24):                   # the first size whose groups (records included) are exactly two
+        cand = _synthetic_forest(rng, T, D, 7, 8)
         df = forest.DeviceForest(forest.tables_from_arrays(**cand))
         if int(L.hm_forest_n_groups(df.handle)) == 2 and int(L.hm_forest_leaf_resident(df.handle, 0)) == 1:
             two_group = cand
