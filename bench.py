@@ -45,14 +45,17 @@ WORKLOADS = ["c3", "c3f32", "c1", "c5rf", "c2", "c5gp", "c4", "c3raw", "c3pool"]
 # `ncu --set full` capture of the same command at the same size (profiles/<file>); None where no capture at that size exists
 # on-chip utilisation of the same launch in the same capture (per cent of peak): what actually bounds the kernel
 NCU_ONCHIP = {
+    ("c3", 1 << 24): {"l1tex_data_pipe_pct": 76.1, "issue_slots_pct": 55.3, "dram_pct": 0.3,
+                      "source": "profiles/r02_final_forest_c3_ncu_raw.csv"},
     ("c3f32", 1 << 24): {"l1tex_data_pipe_pct": 87.9, "issue_slots_pct": 63.5, "dram_pct": 0.7,
                          "source": "profiles/r01_forest_c3_default_ncu_raw.csv"},
-    ("c1", 1 << 26): {"l1tex_data_pipe_pct": 71.0, "issue_slots_pct": 83.9, "dram_pct": 4.8,
-                      "source": "profiles/r01_forest_c1_ncu_raw.csv"},
+    ("c1", 1 << 26): {"l1tex_data_pipe_pct": 88.3, "issue_slots_pct": 77.0, "dram_pct": 5.1,
+                      "source": "profiles/r02_final_forest_c1_ncu_raw.csv"},
 }
 NCU_TRAFFIC = {
+    ("c3", 1 << 24): (0.661674e9 + 0.496786e9, "profiles/r02_final_forest_c3_ncu_raw.csv"),
     ("c3f32", 1 << 24): (2.234378e9 + 0.545148e9, "profiles/r01_forest_c3_default_ncu_raw.csv"),
-    ("c1", 1 << 26): (0.537153e9 + 0.501310e9, "profiles/r01_forest_c1_ncu_raw.csv"),
+    ("c1", 1 << 26): (0.538545e9 + 0.498207e9, "profiles/r02_final_forest_c1_ncu_raw.csv"),
 }
 
 
