@@ -71,6 +71,9 @@
 #ifndef HM_WALK_LEVELS
 #define HM_WALK_LEVELS 2
 #endif
+#ifndef HM_NODE_ORDER_DEFAULT
+#define HM_NODE_ORDER_DEFAULT 0      // 0 = breadth-first node arrays, 1 = depth-first (hm_forest_node_order)
+#endif
 #ifndef HM_LOOP_LEVELS
 #define HM_LOOP_LEVELS 1             // the same for the self-looping-leaf walk (packed kind 3): 1 (C3 51.7 -> 51.1 ms: an
                                      // arrived chain re-loads its leaf, so a level too many costs L1-pipe wavefronts)
@@ -227,6 +230,20 @@ enum { HM_LAYOUT_F32_SMEM = 0, HM_LAYOUT_F32_L2 = 1, HM_LAYOUT_PACKED = 2, HM_LA
 
 // Groups the trees (as many consecutive trees as fit one node buffer when the forest is staged through shared memory, one
 // tree per group when it is walked in L2) and lays the node words out for `layout`.
+// Order of a tree's child PAIRS in its node array.  The kernels only need the two children of a node to be adjacent; where a
+// pair sits is free.  Breadth-first (0) keeps the nodes of one depth together; depth-first (1) keeps every SUBTREE contiguous:
+// its m descendants occupy m consecutive slots right behind its child pair, so the nodes -- and, as leaf ordinals follow the
+// same order, the 32-byte leaf records -- that the coherent candidates of a warp touch late in a walk are neighbours in
+// memory whatever their depth: distinct shared-memory banks for the node loads and shared 128-byte lines for the record gathers.
+static int hm_forest_node_order() {
+    static int order = -1;
+    if (order < 0) {
+        const char* e = getenv("HM_B200_NODE_ORDER");
+        order = (e && e[0] == 'b') ? 0 : (e && e[0] == 'd') ? 1 : HM_NODE_ORDER_DEFAULT;
+    }
+    return order;
+}
+
 static int hm_build_blob(const HmHostTrees& trees, int layout, int nodebuf, int block, bool staged,
                          std::vector<unsigned char>& blob, std::vector<HmGroupDesc>& groups,
                          std::vector<unsigned>& tree_root, std::vector<long long>& tree_nodes_off,
@@ -328,7 +345,8 @@ extern "C" int hm_forest_create(int n_trees, int n_features, const int64_t* off,
     hm_forest_geometry(n_features, &block, &nodebuf);
     HM_REQUIRE((size_t)block * n_features * 4 <= 160 * 1024, "n_features too large for the shared-memory tile");
 
-    // pass 1: per-tree breadth-first relayout (children adjacent), leaf ordinals in (tree, breadth-first) order
+    // pass 1: per-tree relayout (children adjacent; breadth- or depth-first, hm_forest_node_order), leaf ordinals in
+    // (tree, layout) order
     long long n_leaves_total = 0;
     for (int t = 0; t < n_trees; ++t) {
         HM_REQUIRE(off[t + 1] > off[t], "empty tree");
@@ -359,8 +377,18 @@ extern "C" int hm_forest_create(int n_trees, int n_features, const int64_t* off,
         order.reserve(n);
         order.push_back(0);
         newidx[0] = 0;
-        for (size_t h = 0; h < order.size(); ++h) {
-            const int nd = order[h];
+        // work list of placed nodes whose child pair is still to be placed: a queue (breadth-first) or a stack (depth-first)
+        const bool dfs = hm_forest_node_order() == 1;
+        std::vector<int> work(1, 0);
+        size_t head = 0;
+        while (dfs ? !work.empty() : head < work.size()) {
+            int nd;
+            if (dfs) {
+                nd = work.back();
+                work.pop_back();
+            } else {
+                nd = work[head++];
+            }
             const int l = left[b + nd], r = right[b + nd];
             if (l >= 0 && l != r) {
                 HM_REQUIRE(l < n && r >= 0 && r < n, "child index out of range");
@@ -371,6 +399,13 @@ extern "C" int hm_forest_create(int n_trees, int n_features, const int64_t* off,
                 order.push_back(l);
                 newidx[r] = (int)order.size();
                 order.push_back(r);
+                if (dfs) {                 // the left subtree is laid out first
+                    work.push_back(r);
+                    work.push_back(l);
+                } else {
+                    work.push_back(l);
+                    work.push_back(r);
+                }
             }
         }
         HM_REQUIRE((int)order.size() == n, "unreachable nodes in tree");
@@ -575,8 +610,41 @@ extern "C" int hm_forest_attach_packing(hm_forest_t* F, const hm_space_t* S) {
             while (T[h].feat >= 0 && fixed[h]) h = T[h].left + (fixed[h] == 2 ? 1u : 0u);
             return h;
         };
-        std::vector<uint32_t> order;
+        // placement order of the surviving nodes (hm_forest_node_order): order[pos] = node of the fp32 tree, first_child[pos]
+        // = position of its child pair
+        std::vector<uint32_t> order, first_child;
         order.push_back(resolve(0));
+        first_child.push_back(0);
+        {
+            const bool dfs = hm_forest_node_order() == 1;
+            std::vector<uint32_t> work(1, 0u);
+            size_t head = 0;
+            while (dfs ? !work.empty() : head < work.size()) {
+                uint32_t pos;
+                if (dfs) {
+                    pos = work.back();
+                    work.pop_back();
+                } else {
+                    pos = work[head++];
+                }
+                const uint32_t h = order[pos];
+                if (T[h].feat < 0) continue;
+                const uint32_t at = (uint32_t)order.size();
+                first_child[pos] = at;
+                // first slot: taken when the test fails = sklearn's left child, unless the test is the swapped one
+                order.push_back(resolve(T[h].left + (swapped[h] ? 1u : 0u)));
+                order.push_back(resolve(T[h].left + (swapped[h] ? 0u : 1u)));
+                first_child.push_back(0);
+                first_child.push_back(0);
+                if (dfs) {
+                    work.push_back(at + 1);
+                    work.push_back(at);
+                } else {
+                    work.push_back(at);
+                    work.push_back(at + 1);
+                }
+            }
+        }
         std::vector<HmHostNode>& O = dst[t];
         for (size_t k = 0; k < order.size(); ++k) {
             const uint32_t h = order[k];
@@ -586,10 +654,7 @@ extern "C" int hm_forest_attach_packing(hm_forest_t* F, const hm_space_t* S) {
             } else {
                 nd.w0 = cmp[h];
                 nd.feat = (int32_t)shift[h];
-                nd.left = (uint32_t)order.size();
-                // first slot: taken when the test fails = sklearn's left child, unless the test is the swapped one
-                order.push_back(resolve(T[h].left + (swapped[h] ? 1u : 0u)));
-                order.push_back(resolve(T[h].left + (swapped[h] ? 0u : 1u)));
+                nd.left = first_child[k];
             }
             O.push_back(nd);
         }
