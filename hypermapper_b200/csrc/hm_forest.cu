@@ -8,12 +8,13 @@
 //   EI / ucb / thompson_sampling             random_scalarizations.py:160-506 (via hm_acq.cuh)
 //
 // Layout in HBM (built once per fitted model by hm_forest_create):
-//   blob      : tree groups, each 16 B aligned:  [uint32 root[n_trees_g] (padded to 16 B)] [uint2 node[...]]
+//   blob      : tree groups, each 16 B aligned:  [uint2 root_node_copy[n_trees_g] (padded to 16 B)] [uint2 node[...]]
+//               [+ 32-byte leaf records of the group's trees, 32 B aligned, when the forest stays resident in shared memory]
 //               node.x = float32 threshold bits (internal)  |  forest-wide leaf ordinal (leaf)
 //               node.y = feature << 22 | left   (left = group-relative index of the left child, right = left+1;
 //                        left == 0  <=>  leaf)
-//               trees are re-laid out breadth-first so the two children are adjacent and the hot top levels
-//               share a few shared-memory lines.
+//               trees are re-laid out breadth-first (hm_forest_node_order) so the two children are adjacent and the hot
+//               top levels share a few shared-memory lines.
 //   groups    : descriptor per group (offset/bytes/first tree/#trees)
 //   leaf_tab  : 4 fp64 per leaf  [q = m/T, s = m**2/T, u = v/T, value]  (32 B -> one sector, one 256-bit load per leaf visit)
 //   leaf_node : sklearn node id per leaf (for the apply output)
